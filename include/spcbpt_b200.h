@@ -1,0 +1,350 @@
+/*
+ * spcbpt_b200.h -- C ABI of libspcbpt_b200.so, the B200-native (sm_100a) SPCBPT render core.
+ *
+ * This header is the drop-in boundary for the render path of ssufujia/SPCBPT-OptiX7.  Every entry
+ * point names the reference interface it stands in for (paths relative to the reference tree,
+ * src/OptiXPathTracer/ unless stated otherwise).  Plain C: pointers, sizes and POD structs only.
+ *
+ * The POD structs below keep the reference's byte layout (sizes/offsets are static_assert-ed in
+ * csrc/layout_check.cu and tested in tests/test_layout.py) so a reference host can pass its own
+ * `MyParams`, `BDPTVertex`, `Light`, `MaterialData::Pbr`, `classTree::tree_node` memory unchanged.
+ *
+ * Error model: every call returns 0 on success or a negative spc_status; spc_last_error() returns
+ * a human-readable message for the calling thread's last failure (the reference throws
+ * sutil::Exception from CUDA_CHECK / OPTIX_CHECK, sutil/Exception.h:82-115).  There is no CPU
+ * fallback: without a CUDA device spc_create fails with SPC_ERR_NO_DEVICE.
+ */
+#ifndef SPCBPT_B200_H
+#define SPCBPT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SPC_API __attribute__((visibility("default")))
+#else
+#define SPC_API
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* status codes                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+typedef enum spc_status {
+    SPC_OK              = 0,
+    SPC_ERR_INVALID     = -1, /* bad argument / call order                                      */
+    SPC_ERR_CUDA        = -2, /* a CUDA runtime call failed (message has the CUDA error string) */
+    SPC_ERR_NO_DEVICE   = -3, /* no CUDA device: there is deliberately no CPU fallback          */
+    SPC_ERR_NO_SCENE    = -4, /* launch/trace before spc_scene_upload                           */
+    SPC_ERR_CAPACITY    = -5  /* a caller-provided buffer is too small                          */
+} spc_status;
+
+/* ------------------------------------------------------------------------------------------ */
+/* POD mirrors of the reference's host<->device contract (layout kept)   */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct spc_float2 { float x, y; } spc_float2;          /* NB: CUDA float2 is 8-aligned  */
+typedef struct spc_float3 { float x, y, z; } spc_float3;
+typedef struct spc_float4 { float x, y, z, w; } spc_float4;
+typedef struct spc_int2   { int32_t x, y; } spc_int2;
+
+/* src/cuda/MaterialData.h:67-76 (MaterialData::Texture, 40 B).  `tex` is a cudaTextureObject_t in
+ * the reference; here it is 1 + index into the texture table given to spc_scene_upload (0 = none):
+ * textures are sampled by our own bilinear/wrap fetch so that host oracle and GPU agree. */
+typedef struct spc_texture_ref {
+    int32_t    texcoord;
+    int32_t    _pad0;
+    uint64_t   tex;
+    float      texcoord_offset[2];
+    float      texcoord_rotation[2];   /* sin, cos */
+    float      texcoord_scale[2];
+} spc_texture_ref;
+
+/* src/cuda/MaterialData.h:78-97 (MaterialData::Pbr, 144 B, 16-aligned) */
+typedef struct
+#if defined(__GNUC__)
+__attribute__((aligned(16)))
+#endif
+spc_pbr {
+    float           base_color[4];
+    float           metallic;
+    float           roughness;
+    float           specular;
+    float           specularTint;
+    float           subsurface;
+    float           anisotropic;
+    float           sheen;
+    float           sheenTint;
+    float           clearcoat;
+    float           clearcoatGloss;
+    spc_texture_ref base_color_tex;
+    spc_texture_ref metallic_roughness_tex;
+    uint8_t         brdf;               /* "glass" flag; unfinished in the reference (readme.md:28) */
+    uint8_t         _pad1[7];
+} spc_pbr;
+
+/* src/cuda/Light.h:30-92 (Light, 80 B).  Only QUAD lights are live on the SPCBPT path. */
+enum { SPC_LIGHT_POINT = 0, SPC_LIGHT_AMBIENT = 1, SPC_LIGHT_QUAD = 2, SPC_LIGHT_DIRECTIONAL = 3, SPC_LIGHT_ENV = 4 };
+typedef struct spc_light {
+    int32_t    type;
+    int32_t    id;
+    int32_t    divLevel;
+    int32_t    ssBase;
+    /* union member `quad` (Light.h:70-78); note u and v are corner+u, corner+v (scene_shift.cpp:127-129) */
+    spc_float3 corner;
+    spc_float3 u;
+    spc_float3 v;
+    spc_float3 emission;
+    spc_float3 normal;
+    float      area;
+} spc_light;
+
+/* BDPTVertex.h:9-70 (BDPTVertex, 120 B, 8-aligned) */
+enum { SPC_VTYPE_SPHERE = 0, SPC_VTYPE_QUAD = 1, SPC_VTYPE_DIRECTION = 2, SPC_VTYPE_ENV = 3,
+       SPC_VTYPE_HIT_LIGHT_SOURCE = 4, SPC_VTYPE_ENV_MISS = 5, SPC_VTYPE_NORMALHIT = 6 };  /* light_parameters.h:8-11 LightType */
+typedef struct
+#if defined(__GNUC__)
+__attribute__((aligned(8)))
+#endif
+spc_vertex {
+    spc_float3 position;
+    spc_float3 normal;
+    spc_float3 flux;
+    spc_float3 color;
+    spc_float3 lastPosition;
+    spc_float3 RMIS_pointer_3;
+    spc_float2 uv;
+    float      RMIS_pointer;
+    float      last_lum;
+    float      lastNormalProjection;
+    float      pdf;
+    float      singlePdf;
+    float      lastSinglePdf;
+    int16_t    materialId;
+    int16_t    subspaceId;
+    int16_t    depth;
+    int16_t    lastZoneId;
+    int16_t    type;
+    uint8_t    isOrigin;
+    uint8_t    inBrdf;
+    uint8_t    lastBrdf;
+    uint8_t    isBrdf;
+    uint8_t    isLastVertex_direction;
+    uint8_t    _pad;
+} spc_vertex;
+
+/* decisionTree/classTree_common.h:11-38 (classTree::tree_node, 56 B) */
+typedef struct spc_tree_node {
+    spc_float3 mid;
+    int32_t    child[8];
+    int32_t    label;
+    int32_t    type;      /* 0 position, 1 normal, 2 direction (unused: DIR_JUDGE 0) */
+    uint8_t    leaf;
+    uint8_t    _pad[3];
+} spc_tree_node;
+
+/* decisionTree/classTree_common.h:77-91 (classTree::divide_weight, 40 B) */
+typedef struct spc_divide_weight {
+    spc_float3 position;
+    spc_float3 dir;
+    spc_float3 normal;
+    float      weight;
+} spc_divide_weight;
+
+/* optixPathTracer.h:43-51 (Subspace, 20 B) */
+typedef struct spc_subspace {
+    int32_t jump_bias;
+    int32_t id;
+    int32_t size;
+    float   sum_pmf;
+    float   Q;
+} spc_subspace;
+
+/* src/cuda/BufferView.h:35-63 (BufferView<T>, 16 B) */
+typedef struct spc_buffer_view {
+    uint64_t data;
+    uint32_t count;
+    uint16_t byte_stride;
+    uint16_t elmt_byte_size;
+} spc_buffer_view;
+
+/* optixPathTracer.h:52-66 (LightTraceParams, 40 B) */
+typedef struct spc_light_trace_params {
+    int32_t     num_core;
+    int32_t     core_padding;
+    int32_t     M;
+    int32_t     M_per_core;
+    spc_vertex* ans;          /* device: BDPTVertex[num_core*core_padding]                     */
+    uint8_t*    validState;   /* device: bool[num_core*core_padding]                           */
+    int32_t     launch_frame;
+    int32_t     _pad;
+} spc_light_trace_params;
+
+/* optixPathTracer.h:76-88 (PreTraceParams, 32 B) */
+typedef struct spc_pretrace_params {
+    int32_t num_core;
+    int32_t padding;
+    int32_t iteration;
+    int32_t _pad;
+    void*   paths;            /* device: TrainData::pathInfo_sample[num_core]          (48 B)  */
+    void*   conns;            /* device: TrainData::pathInfo_node[num_core*padding]    (92 B)  */
+} spc_pretrace_params;
+
+/* optixPathTracer.h:89-97 (SubspaceSampler, 40 B) */
+typedef struct spc_subspace_sampler {
+    const spc_vertex* LVC;
+    spc_subspace*     subspace;
+    float*            cmfs;
+    int32_t*          jump_buffer;
+    int32_t           vertex_count;
+    int32_t           path_count;
+} spc_subspace_sampler;
+
+/* optixPathTracer.h:166-190 (subspaceMacroInfo, 40 B).  `subspaceNum` is unused by the reference
+ * (NUM_SUBSPACE is a #define, optixPathTracer.h:31); here it carries the runtime K (0 -> ctx K). */
+typedef struct spc_subspace_macro_info {
+    int32_t        subspaceNum;
+    int32_t        _pad;
+    spc_tree_node* eye_tree;
+    spc_tree_node* light_tree;
+    float*         Q;
+    float*         CMFGamma;
+} spc_subspace_macro_info;
+
+/* optixPathTracer.h:98-137 (envInfo, 56 B) -- environment lighting is unfinished in the reference
+ * (readme.md:28) and out of scope; the block is carried for layout only and `valid` must be 0. */
+typedef struct spc_env_info {
+    uint64_t   tex;
+    float*     cmf;
+    float      r;
+    spc_float3 center;
+    int32_t    size, width, height, divLevel, ssBase;
+    uint8_t    valid;
+    uint8_t    _pad[3];
+} spc_env_info;
+
+/* optixPathTracer.h:191-199 (PTParams = MyParams : whitted::LaunchParams, whitted.h:64-84), 352 B */
+typedef struct spc_params {
+    uint32_t                width;
+    uint32_t                height;
+    uint32_t                subframe_index;
+    uint32_t                _pad0;
+    spc_float4*             accum_buffer;   /* device float4[W*H], caller-allocated               */
+    uint32_t*               frame_buffer;   /* device uchar4[W*H], caller-allocated (may be NULL) */
+    int32_t                 max_depth;      /* 0 -> the reference's literal 50 (raygen.cu:361)    */
+    spc_float3              eye, U, V, W;
+    uint32_t                _pad1;
+    spc_buffer_view         lights;         /* ignored: lights come from spc_scene_upload         */
+    spc_buffer_view         materials;      /* ignored: materials come from spc_scene_upload      */
+    spc_float3              miss_color;
+    uint32_t                _pad2;
+    uint64_t                handle;         /* OptixTraversableHandle: ignored                    */
+    spc_light_trace_params  lt;
+    spc_subspace_sampler    sampler;
+    spc_pretrace_params     pre_tracer;
+    spc_subspace_macro_info subspace_info;
+    spc_env_info            sky;
+} spc_params;
+
+/* ------------------------------------------------------------------------------------------ */
+/* scene ingest (replaces sutil::Scene::finalize -> buildMeshAccels/buildInstanceAccel,        */
+/* sutil/Scene.cpp:731,943,1260, and the HostToDeviceBuffer uploads of scene_shift.cpp:187-328)*/
+/* ------------------------------------------------------------------------------------------ */
+typedef struct spc_mesh {
+    const float*    positions;    /* float3[n_vertices], stride 12 B (scene_shift.cpp:214)        */
+    const uint32_t* indices;      /* uint32[3*n_triangles], stride 12 B per triangle (:217)       */
+    const float*    texcoords;    /* float2[n_vertices] or NULL (reference zero-fills, :203-206)  */
+    uint32_t        n_vertices;
+    uint32_t        n_triangles;
+    int32_t         material_id;  /* index into materials[]; ignored when light_id >= 0           */
+    int32_t         light_id;     /* >= 0: this mesh is the 2-triangle quad of lights[light_id]
+                                     (single sided, back-face culled for closest-hit rays,
+                                     sutil/Scene.cpp:1030,1085 + cuProg.h:402); -1 otherwise       */
+} spc_mesh;
+
+typedef struct spc_texture {
+    const uint8_t* rgba;          /* RGBA8, row-major, as decoded by stbi_load(...,STBI_rgb_alpha) */
+    int32_t        width, height;
+} spc_texture;
+
+/* one ray of a wavefront batch: 32 B in */
+typedef struct spc_ray {
+    float ox, oy, oz, tmin;
+    float dx, dy, dz, tmax;
+} spc_ray;
+
+/* closest-hit record: 16 B out.  prim = global triangle index in upload order (mesh order, then
+ * triangle order inside the mesh), -1 on a miss (then t,u,v are 0). */
+typedef struct spc_hit {
+    float   t, u, v;
+    int32_t prim;
+} spc_hit;
+
+typedef struct spc_bvh_stats {
+    uint32_t n_triangles;
+    uint32_t n_nodes;           /* 8-wide compressed nodes (80 B each)                            */
+    uint32_t n_bvh2_nodes;
+    uint32_t max_depth;         /* of the 8-wide tree                                              */
+    float    sah_cost;          /* SAH cost of the 8-wide tree (c_node=1, c_tri=0.3)               */
+    float    build_ms;          /* device time of the whole build                                  */
+    uint64_t bytes_nodes;
+    uint64_t bytes_triangles;
+} spc_bvh_stats;
+
+/* traversal work counters for the roofline's algorithmic bytes */
+typedef struct spc_trace_counters {
+    uint64_t rays;
+    uint64_t nodes_visited;     /* 8-wide nodes fetched (80 B each)                                */
+    uint64_t tris_tested;       /* triangles fetched+tested (48 B each)                            */
+} spc_trace_counters;
+
+typedef struct spc_context spc_context;
+
+enum { SPC_RAYFLAG_NONE = 0, SPC_RAYFLAG_CULL_BACK_FACING = 1 };
+
+/* -------------------------------- lifetime ------------------------------------------------- */
+/* Replaces Scene::createContext (sutil/Scene.cpp:856-880).  K = number of subspaces
+ * (NUM_SUBSPACE, optixPathTracer.h:31), K_light = emitter subspaces (NUM_SUBSPACE_LIGHTSOURCE,
+ * :32), connections = CONNECTION_N (:37).  Pass 0 for the reference defaults (1000, int(0.2*K), 3). */
+SPC_API int  spc_create(int device, int K, int K_light, int connections, spc_context** out);
+SPC_API void spc_destroy(spc_context* ctx);
+SPC_API const char* spc_last_error(void);
+SPC_API const char* spc_version(void);
+/* All work of `ctx` is enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default
+ * stream the reference uses everywhere, optixPathTracer.cpp:506). */
+SPC_API int  spc_set_stream(spc_context* ctx, void* cuda_stream);
+SPC_API int  spc_synchronize(spc_context* ctx);   /* CUDA_SYNC_CHECK, sutil/Exception.h:115 */
+
+/* -------------------------------- scene + BVH ---------------------------------------------- */
+/* Host pointers in, device copies + BVH out.  Triangle order defines the prim ids used everywhere. */
+SPC_API int  spc_scene_upload(spc_context* ctx,
+                              const spc_mesh* meshes, int n_meshes,
+                              const spc_pbr* materials, int n_materials,
+                              const spc_light* lights, int n_lights,
+                              const spc_texture* textures, int n_textures);
+SPC_API int  spc_bvh_stats_get(spc_context* ctx, spc_bvh_stats* out);
+
+/* -------------------------------- wavefront ray batches ------------------------------------ */
+/* Replaces optixTrace for closest-hit rays (cuProg.h:384-461): nearest hit with tmin < t < tmax,
+ * ties -> lowest prim id; ray_flags SPC_RAYFLAG_CULL_BACK_FACING culls back faces of single-sided
+ * (emitter) triangles only, like OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES with the reference's
+ * per-instance DISABLE_TRIANGLE_FACE_CULLING.  Host-buffer variant copies H2D/D2H inside. */
+SPC_API int  spc_trace_batch(spc_context* ctx, const spc_ray* rays_host, int64_t n, int ray_flags, spc_hit* hits_host);
+SPC_API int  spc_trace_batch_device(spc_context* ctx, const spc_ray* rays_dev, int64_t n, int ray_flags, spc_hit* hits_dev);
+/* Replaces visibilityTest's optixTrace (cuProg.h:463-487): out[i] = 1 when NO triangle is hit on
+ * (tmin, tmax) (i.e. "visible"), else 0.  No face culling (OPTIX_RAY_FLAG_TERMINATE_ON_FIRST_HIT). */
+SPC_API int  spc_occlusion_batch(spc_context* ctx, const spc_ray* rays_host, int64_t n, uint8_t* visible_host);
+SPC_API int  spc_occlusion_batch_device(spc_context* ctx, const spc_ray* rays_dev, int64_t n, uint8_t* visible_dev);
+/* Instrumented (slower) copies of the two kernels above that also count nodes/triangles fetched;
+ * results are identical.  Used only to state the algorithmic bytes per ray. */
+SPC_API int  spc_trace_batch_counted(spc_context* ctx, const spc_ray* rays_dev, int64_t n, int ray_flags, spc_hit* hits_dev, spc_trace_counters* out_host);
+SPC_API int  spc_occlusion_batch_counted(spc_context* ctx, const spc_ray* rays_dev, int64_t n, uint8_t* visible_dev, spc_trace_counters* out_host);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+SPC_API int64_t spc_launch_count(spc_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPCBPT_B200_H */

@@ -1,0 +1,267 @@
+"""spcbpt-optix7_b200 -- host-side Python mirror of the C ABI in include/spcbpt_b200.h.
+
+The product is libspcbpt_b200.so (hand-written sm_100a CUDA + C ABI); this module only binds it
+with ctypes and describes the POD structs as numpy dtypes.  There is no Python/CPU compute path:
+importing works anywhere (so CPU-only tests can check symbols and layouts), but creating a
+Context without a CUDA device raises.
+
+The directory name has a hyphen (contract of the build), so import it through
+``spcbpt_loader.load()`` at the repo root, which registers it as ``spcbpt_optix7_b200``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspcbpt_b200.so")
+
+# --------------------------------------------------------------------------------------------
+# numpy dtypes of the POD structs (byte-identical to include/spcbpt_b200.h)
+# --------------------------------------------------------------------------------------------
+RAY = np.dtype([("ox", "f4"), ("oy", "f4"), ("oz", "f4"), ("tmin", "f4"),
+                ("dx", "f4"), ("dy", "f4"), ("dz", "f4"), ("tmax", "f4")])
+HIT = np.dtype([("t", "f4"), ("u", "f4"), ("v", "f4"), ("prim", "i4")])
+TEXREF = np.dtype([("texcoord", "i4"), ("_pad0", "i4"), ("tex", "u8"), ("texcoord_offset", "f4", 2),
+                   ("texcoord_rotation", "f4", 2), ("texcoord_scale", "f4", 2)])
+PBR = np.dtype([("base_color", "f4", 4), ("metallic", "f4"), ("roughness", "f4"), ("specular", "f4"),
+                ("specularTint", "f4"), ("subsurface", "f4"), ("anisotropic", "f4"), ("sheen", "f4"),
+                ("sheenTint", "f4"), ("clearcoat", "f4"), ("clearcoatGloss", "f4"),
+                ("base_color_tex", TEXREF), ("metallic_roughness_tex", TEXREF), ("brdf", "u1"), ("_pad1", "u1", 7)])
+LIGHT = np.dtype([("type", "i4"), ("id", "i4"), ("divLevel", "i4"), ("ssBase", "i4"), ("corner", "f4", 3),
+                  ("u", "f4", 3), ("v", "f4", 3), ("emission", "f4", 3), ("normal", "f4", 3), ("area", "f4")])
+VERTEX = np.dtype([("position", "f4", 3), ("normal", "f4", 3), ("flux", "f4", 3), ("color", "f4", 3),
+                   ("lastPosition", "f4", 3), ("RMIS_pointer_3", "f4", 3), ("uv", "f4", 2), ("RMIS_pointer", "f4"),
+                   ("last_lum", "f4"), ("lastNormalProjection", "f4"), ("pdf", "f4"), ("singlePdf", "f4"),
+                   ("lastSinglePdf", "f4"), ("materialId", "i2"), ("subspaceId", "i2"), ("depth", "i2"),
+                   ("lastZoneId", "i2"), ("type", "i2"), ("isOrigin", "u1"), ("inBrdf", "u1"), ("lastBrdf", "u1"),
+                   ("isBrdf", "u1"), ("isLastVertex_direction", "u1"), ("_pad", "u1")])
+TREE_NODE = np.dtype([("mid", "f4", 3), ("child", "i4", 8), ("label", "i4"), ("type", "i4"), ("leaf", "u1"), ("_pad", "u1", 3)])
+DIVIDE_WEIGHT = np.dtype([("position", "f4", 3), ("dir", "f4", 3), ("normal", "f4", 3), ("weight", "f4")])
+SUBSPACE = np.dtype([("jump_bias", "i4"), ("id", "i4"), ("size", "i4"), ("sum_pmf", "f4"), ("Q", "f4")])
+MESH = np.dtype([("positions", "u8"), ("indices", "u8"), ("texcoords", "u8"), ("n_vertices", "u4"),
+                 ("n_triangles", "u4"), ("material_id", "i4"), ("light_id", "i4")])
+TEXTURE = np.dtype([("rgba", "u8"), ("width", "i4"), ("height", "i4")])
+BVH_STATS = np.dtype([("n_triangles", "u4"), ("n_nodes", "u4"), ("n_bvh2_nodes", "u4"), ("max_depth", "u4"),
+                      ("sah_cost", "f4"), ("build_ms", "f4"), ("bytes_nodes", "u8"), ("bytes_triangles", "u8")])
+TRACE_COUNTERS = np.dtype([("rays", "u8"), ("nodes_visited", "u8"), ("tris_tested", "u8")])
+BUFFER_VIEW = np.dtype([("data", "u8"), ("count", "u4"), ("byte_stride", "u2"), ("elmt_byte_size", "u2")])
+LT_PARAMS = np.dtype([("num_core", "i4"), ("core_padding", "i4"), ("M", "i4"), ("M_per_core", "i4"), ("ans", "u8"),
+                      ("validState", "u8"), ("launch_frame", "i4"), ("_pad", "i4")])
+PRETRACE_PARAMS = np.dtype([("num_core", "i4"), ("padding", "i4"), ("iteration", "i4"), ("_pad", "i4"),
+                            ("paths", "u8"), ("conns", "u8")])
+SAMPLER = np.dtype([("LVC", "u8"), ("subspace", "u8"), ("cmfs", "u8"), ("jump_buffer", "u8"),
+                    ("vertex_count", "i4"), ("path_count", "i4")])
+SUBSPACE_INFO = np.dtype([("subspaceNum", "i4"), ("_pad", "i4"), ("eye_tree", "u8"), ("light_tree", "u8"),
+                          ("Q", "u8"), ("CMFGamma", "u8")])
+ENV_INFO = np.dtype([("tex", "u8"), ("cmf", "u8"), ("r", "f4"), ("center", "f4", 3), ("size", "i4"), ("width", "i4"),
+                     ("height", "i4"), ("divLevel", "i4"), ("ssBase", "i4"), ("valid", "u1"), ("_pad", "u1", 3)])
+PARAMS = np.dtype([("width", "u4"), ("height", "u4"), ("subframe_index", "u4"), ("_pad0", "u4"),
+                   ("accum_buffer", "u8"), ("frame_buffer", "u8"), ("max_depth", "i4"), ("eye", "f4", 3),
+                   ("U", "f4", 3), ("V", "f4", 3), ("W", "f4", 3), ("_pad1", "u4"), ("lights", BUFFER_VIEW),
+                   ("materials", BUFFER_VIEW), ("miss_color", "f4", 3), ("_pad2", "u4"), ("handle", "u8"),
+                   ("lt", LT_PARAMS), ("sampler", SAMPLER), ("pre_tracer", PRETRACE_PARAMS),
+                   ("subspace_info", SUBSPACE_INFO), ("sky", ENV_INFO)])
+
+EXPECTED_SIZES = {"RAY": 32, "HIT": 16, "TEXREF": 40, "PBR": 144, "LIGHT": 80, "VERTEX": 120, "TREE_NODE": 56,
+                  "DIVIDE_WEIGHT": 40, "SUBSPACE": 20, "MESH": 40, "TEXTURE": 16, "BUFFER_VIEW": 16,
+                  "LT_PARAMS": 40, "PRETRACE_PARAMS": 32, "SAMPLER": 40, "SUBSPACE_INFO": 40, "ENV_INFO": 56,
+                  "PARAMS": 352}
+
+RAYFLAG_NONE = 0
+RAYFLAG_CULL_BACK_FACING = 1
+LIGHT_QUAD = 2
+VTYPE_QUAD = 1
+VTYPE_HIT_LIGHT_SOURCE = 4
+VTYPE_NORMALHIT = 6
+
+
+class SpcError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def declared_symbols():
+    """Every SPC_API function declared in include/spcbpt_b200.h (parsed from the header)."""
+    import re
+    hdr = os.path.join(_HERE, "..", "include", "spcbpt_b200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"SPC_API\s+[\w\s\*]+?\b(spc_\w+)\s*\(", txt)))
+
+
+def lib():
+    """Load libspcbpt_b200.so (built in-tree by build.py); fail loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SpcError("libspcbpt_b200.so is not built: run `python spcbpt-optix7_b200/build.py` "
+                       "(there is no Python or CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    L.spc_last_error.restype = ctypes.c_char_p
+    L.spc_version.restype = ctypes.c_char_p
+    L.spc_create.argtypes = [i32, i32, i32, i32, ctypes.POINTER(vp)]
+    L.spc_destroy.argtypes = [vp]
+    L.spc_destroy.restype = None
+    L.spc_set_stream.argtypes = [vp, vp]
+    L.spc_synchronize.argtypes = [vp]
+    L.spc_scene_upload.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, i32]
+    L.spc_bvh_stats_get.argtypes = [vp, vp]
+    L.spc_trace_batch.argtypes = [vp, vp, i64, i32, vp]
+    L.spc_trace_batch_device.argtypes = [vp, vp, i64, i32, vp]
+    L.spc_occlusion_batch.argtypes = [vp, vp, i64, vp]
+    L.spc_occlusion_batch_device.argtypes = [vp, vp, i64, vp]
+    L.spc_trace_batch_counted.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.spc_occlusion_batch_counted.argtypes = [vp, vp, i64, vp, vp]
+    L.spc_launch_count.argtypes = [vp]
+    L.spc_launch_count.restype = i64
+    _bind_optional(L)
+    _lib = L
+    return L
+
+
+def _bind_optional(L):
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    table = {
+        "spc_gen_camera_rays": [vp, vp, i32, i32, i32, vp],
+        "spc_gen_bench_rays": [vp, i32, vp, vp, i64, vp, vp],
+    }
+    for name, args in table.items():
+        if hasattr(L, name):
+            getattr(L, name).argtypes = args
+
+
+def _ptr(a):
+    """Address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def pack_scene(scene):
+    """Turn a scenes.SceneData into the (meshes, materials, lights, textures) struct arrays of the
+    C ABI.  Returns (arrays, keepalive): keepalive must outlive the call that consumes the arrays."""
+    keep = []
+    meshes = np.zeros(len(scene.meshes), MESH)
+    for i, m in enumerate(scene.meshes):
+        pos = np.ascontiguousarray(m["positions"], np.float32)
+        idx = np.ascontiguousarray(m["indices"], np.uint32)
+        uv = None if m.get("texcoords") is None else np.ascontiguousarray(m["texcoords"], np.float32)
+        keep += [pos, idx, uv]
+        meshes[i]["positions"] = pos.ctypes.data
+        meshes[i]["indices"] = idx.ctypes.data
+        meshes[i]["texcoords"] = 0 if uv is None else uv.ctypes.data
+        meshes[i]["n_vertices"] = pos.shape[0]
+        meshes[i]["n_triangles"] = idx.shape[0]
+        meshes[i]["material_id"] = m.get("material_id", 0)
+        meshes[i]["light_id"] = m.get("light_id", -1)
+    textures = np.zeros(max(len(scene.textures), 1), TEXTURE)
+    for i, t in enumerate(scene.textures):
+        px = np.ascontiguousarray(t, np.uint8)
+        keep.append(px)
+        textures[i]["rgba"] = px.ctypes.data
+        textures[i]["height"], textures[i]["width"] = px.shape[0], px.shape[1]
+    mats = np.ascontiguousarray(scene.materials)
+    lights = np.ascontiguousarray(scene.lights)
+    keep += [meshes, textures, mats, lights]
+    return (meshes, mats, lights, textures, len(scene.textures)), keep
+
+
+class Context:
+    """RAII wrapper of spc_context.  Mirrors the calls a reference host makes at its two seams
+    (sutil::Scene launch seam and MyThrustOp post-processing seam)."""
+
+    def __init__(self, device=0, K=0, K_light=0, connections=0):
+        self._L = lib()
+        h = ctypes.c_void_p()
+        rc = self._L.spc_create(device, K, K_light, connections, ctypes.byref(h))
+        if rc != 0:
+            raise SpcError("spc_create failed (%d): %s" % (rc, self._L.spc_last_error().decode()))
+        self.h = h
+        self.device = device
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.spc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise SpcError("%s failed (%d): %s" % (what, rc, self._L.spc_last_error().decode()))
+
+    def call(self, name, *args):
+        """Generic checked call: ctx.call('spc_xxx', ...) -> raises SpcError on non-zero status."""
+        fn = getattr(self._L, name)
+        self._ck(fn(self.h, *[_ptr(a) if not isinstance(a, (int, float)) else a for a in args]), name)
+
+    # -- plumbing -------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._ck(self._L.spc_set_stream(self.h, ctypes.c_void_p(cuda_stream)), "spc_set_stream")
+
+    def synchronize(self):
+        self._ck(self._L.spc_synchronize(self.h), "spc_synchronize")
+
+    def launch_count(self):
+        return int(self._L.spc_launch_count(self.h))
+
+    # -- scene ----------------------------------------------------------------------------
+    def upload_scene(self, scene):
+        (meshes, mats, lights, textures, ntex), keep = pack_scene(scene)
+        self._ck(self._L.spc_scene_upload(self.h, meshes.ctypes.data, len(meshes), mats.ctypes.data, len(mats),
+                                          lights.ctypes.data, len(lights), textures.ctypes.data, ntex),
+                 "spc_scene_upload")
+        del keep
+
+    def bvh_stats(self):
+        s = np.zeros(1, BVH_STATS)
+        self._ck(self._L.spc_bvh_stats_get(self.h, s.ctypes.data), "spc_bvh_stats_get")
+        return {k: s[0][k].item() for k in BVH_STATS.names}
+
+    # -- ray batches (host buffers: the e2e path) --------------------------------------------
+    def trace(self, rays, flags=RAYFLAG_CULL_BACK_FACING):
+        rays = np.ascontiguousarray(rays, RAY)
+        hits = np.zeros(rays.shape[0], HIT)
+        self._ck(self._L.spc_trace_batch(self.h, rays.ctypes.data, rays.shape[0], flags, hits.ctypes.data), "spc_trace_batch")
+        return hits
+
+    def occlusion(self, rays):
+        rays = np.ascontiguousarray(rays, RAY)
+        vis = np.zeros(rays.shape[0], np.uint8)
+        self._ck(self._L.spc_occlusion_batch(self.h, rays.ctypes.data, rays.shape[0], vis.ctypes.data), "spc_occlusion_batch")
+        return vis
+
+    # -- ray batches (device pointers: torch tensors or raw addresses) -----------------------
+    def trace_device(self, rays_dev, n, hits_dev, flags=RAYFLAG_CULL_BACK_FACING):
+        self._ck(self._L.spc_trace_batch_device(self.h, _ptr(rays_dev), n, flags, _ptr(hits_dev)), "spc_trace_batch_device")
+
+    def occlusion_device(self, rays_dev, n, vis_dev):
+        self._ck(self._L.spc_occlusion_batch_device(self.h, _ptr(rays_dev), n, _ptr(vis_dev)), "spc_occlusion_batch_device")
+
+    def trace_counted(self, rays_dev, n, hits_dev, flags=RAYFLAG_CULL_BACK_FACING):
+        c = np.zeros(1, TRACE_COUNTERS)
+        self._ck(self._L.spc_trace_batch_counted(self.h, _ptr(rays_dev), n, flags, _ptr(hits_dev), c.ctypes.data), "spc_trace_batch_counted")
+        return {k: int(c[0][k]) for k in TRACE_COUNTERS.names}
+
+    def occlusion_counted(self, rays_dev, n, vis_dev):
+        c = np.zeros(1, TRACE_COUNTERS)
+        self._ck(self._L.spc_occlusion_batch_counted(self.h, _ptr(rays_dev), n, _ptr(vis_dev), c.ctypes.data), "spc_occlusion_batch_counted")
+        return {k: int(c[0][k]) for k in TRACE_COUNTERS.names}
+
+
+from . import scenes  # noqa: E402,F401

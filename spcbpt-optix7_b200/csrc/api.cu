@@ -1,0 +1,272 @@
+// api.cu -- the extern "C" surface of libspcbpt_b200.so (declared in include/spcbpt_b200.h).
+#include <cstdarg>
+#include <cstring>
+#include "common.cuh"
+
+namespace spc {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace spc
+
+struct spc_context {
+    spc::Context c;
+};
+
+using spc::Context;
+
+#define SPC_API_BEGIN                                                                            \
+    if (!ctx) {                                                                                  \
+        spc::set_error("null context");                                                          \
+        return SPC_ERR_INVALID;                                                                  \
+    }                                                                                            \
+    Context& c = ctx->c;                                                                         \
+    (void)c;                                                                                     \
+    try {                                                                                        \
+        cudaSetDevice(c.device);
+
+#define SPC_API_END                                                                              \
+    }                                                                                            \
+    catch (const spc::CudaFailure& f) { return f.code; }                                         \
+    catch (const std::exception& e) {                                                            \
+        spc::set_error("exception: %s", e.what());                                               \
+        return SPC_ERR_INVALID;                                                                  \
+    }                                                                                            \
+    return SPC_OK;
+
+extern "C" {
+
+const char* spc_last_error(void) { return spc::g_err; }
+const char* spc_version(void) { return "spcbpt_b200 0.1 (sm_100a)"; }
+
+int spc_create(int device, int K, int K_light, int connections, spc_context** out) {
+    if (!out) {
+        spc::set_error("spc_create: out is null");
+        return SPC_ERR_INVALID;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        spc::set_error("spc_create: no CUDA device (%s); this library has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return SPC_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) {
+        spc::set_error("spc_create: device %d out of range [0,%d)", device, ndev);
+        return SPC_ERR_INVALID;
+    }
+    if (K == 0) K = 1000;
+    if (K_light == 0) K_light = int(0.2 * K);
+    if (connections == 0) connections = 3;
+    if (K < 2 || K > 32767 || K_light < 1 || K_light >= K || connections < 1 || connections > 16) {
+        spc::set_error("spc_create: bad K=%d K_light=%d connections=%d (subspace ids are int16)", K, K_light, connections);
+        return SPC_ERR_INVALID;
+    }
+    spc_context* ctx = new spc_context();
+    ctx->c.device = device;
+    ctx->c.K = K;
+    ctx->c.K_light = K_light;
+    ctx->c.connections = connections;
+    try {
+        SPC_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        SPC_CUDA(cudaGetDeviceProperties(&prop, device));
+        ctx->c.sm_count = prop.multiProcessorCount;
+        ctx->c.counters.alloc(8);
+    } catch (const spc::CudaFailure& f) {
+        delete ctx;
+        return f.code;
+    }
+    *out = ctx;
+    return SPC_OK;
+}
+
+void spc_destroy(spc_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    delete ctx;
+}
+
+int spc_set_stream(spc_context* ctx, void* cuda_stream) {
+    SPC_API_BEGIN
+    c.stream = (cudaStream_t)cuda_stream;
+    SPC_API_END
+}
+
+int spc_synchronize(spc_context* ctx) {
+    SPC_API_BEGIN
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    SPC_API_END
+}
+
+int64_t spc_launch_count(spc_context* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int spc_scene_upload(spc_context* ctx, const spc_mesh* meshes, int n_meshes, const spc_pbr* materials,
+                     int n_materials, const spc_light* lights, int n_lights, const spc_texture* textures,
+                     int n_textures) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(meshes && n_meshes > 0, SPC_ERR_INVALID, "spc_scene_upload: no meshes");
+    SPC_REQUIRE(n_materials >= 0 && n_lights >= 0 && n_textures >= 0, SPC_ERR_INVALID, "spc_scene_upload: negative count");
+    SPC_REQUIRE(n_materials < 32768, SPC_ERR_INVALID, "spc_scene_upload: material ids are int16 (BDPTVertex.h:49)");
+    uint64_t total = 0;
+    for (int m = 0; m < n_meshes; m++) {
+        const spc_mesh& me = meshes[m];
+        SPC_REQUIRE(me.positions && me.indices, SPC_ERR_INVALID, "spc_scene_upload: mesh %d has null arrays", m);
+        SPC_REQUIRE(me.light_id >= 0 ? me.light_id < n_lights : (me.material_id >= 0 && me.material_id < n_materials),
+                    SPC_ERR_INVALID, "spc_scene_upload: mesh %d references material %d / light %d out of range", m,
+                    me.material_id, me.light_id);
+        total += me.n_triangles;
+    }
+    SPC_REQUIRE(total >= 1 && total < 0x7fffffffull, SPC_ERR_INVALID, "spc_scene_upload: %llu triangles", (unsigned long long)total);
+    const uint32_t n = (uint32_t)total;
+    std::vector<float4> tri_pos((size_t)n * 3);
+    std::vector<float2> tri_uv((size_t)n * 3);
+    size_t p = 0;
+    for (int m = 0; m < n_meshes; m++) {
+        const spc_mesh& me = meshes[m];
+        // per-mesh id words carried in the .w lanes: material (or -1), light id (or -1), mesh index
+        const int mat = me.light_id >= 0 ? -1 : me.material_id;
+        for (uint32_t t = 0; t < me.n_triangles; t++, p++) {
+            for (int k = 0; k < 3; k++) {
+                const uint32_t vi = me.indices[3 * (size_t)t + k];
+                SPC_REQUIRE(vi < me.n_vertices, SPC_ERR_INVALID, "spc_scene_upload: mesh %d triangle %u index %u >= %u", m, t, vi, me.n_vertices);
+                const float* q = me.positions + 3 * (size_t)vi;
+                int wbits = k == 0 ? mat : (k == 1 ? me.light_id : m);
+                float w;
+                memcpy(&w, &wbits, 4);
+                tri_pos[3 * p + k] = make_float4(q[0], q[1], q[2], w);
+                tri_uv[3 * p + k] = me.texcoords ? make_float2(me.texcoords[2 * (size_t)vi], me.texcoords[2 * (size_t)vi + 1])
+                                                 : make_float2(0.f, 0.f);
+            }
+        }
+    }
+    spc::SceneGeom& g = c.geom;
+    g.n_prims = n;
+    g.tri_pos.alloc(tri_pos.size());
+    g.tri_uv.alloc(tri_uv.size());
+    SPC_CUDA(cudaMemcpyAsync(g.tri_pos.p, tri_pos.data(), tri_pos.size() * sizeof(float4), cudaMemcpyHostToDevice, c.stream));
+    SPC_CUDA(cudaMemcpyAsync(g.tri_uv.p, tri_uv.data(), tri_uv.size() * sizeof(float2), cudaMemcpyHostToDevice, c.stream));
+    g.n_materials = n_materials;
+    g.n_lights = n_lights;
+    g.n_textures = n_textures;
+    g.materials.alloc(n_materials);
+    g.lights.alloc(n_lights);
+    if (n_materials) SPC_CUDA(cudaMemcpyAsync(g.materials.p, materials, n_materials * sizeof(spc_pbr), cudaMemcpyHostToDevice, c.stream));
+    if (n_lights) SPC_CUDA(cudaMemcpyAsync(g.lights.p, lights, n_lights * sizeof(spc_light), cudaMemcpyHostToDevice, c.stream));
+    {
+        std::vector<int4> desc(n_textures > 0 ? n_textures : 1);
+        size_t bytes = 0;
+        for (int t = 0; t < n_textures; t++) {
+            SPC_REQUIRE(textures[t].rgba && textures[t].width > 0 && textures[t].height > 0, SPC_ERR_INVALID, "spc_scene_upload: texture %d is empty", t);
+            desc[t] = make_int4((int)bytes, textures[t].width, textures[t].height, 0);
+            bytes += (size_t)textures[t].width * textures[t].height * 4;
+            SPC_REQUIRE(bytes < 0x7fffffffull, SPC_ERR_CAPACITY, "spc_scene_upload: textures exceed 2 GiB");
+        }
+        g.tex_data.alloc(bytes);
+        g.tex_desc.alloc(desc.size());
+        for (int t = 0; t < n_textures; t++)
+            SPC_CUDA(cudaMemcpyAsync(g.tex_data.p + desc[t].x, textures[t].rgba, (size_t)textures[t].width * textures[t].height * 4,
+                                     cudaMemcpyHostToDevice, c.stream));
+        SPC_CUDA(cudaMemcpyAsync(g.tex_desc.p, desc.data(), desc.size() * sizeof(int4), cudaMemcpyHostToDevice, c.stream));
+    }
+    SPC_CUDA(cudaStreamSynchronize(c.stream));  // host staging vectors die at scope exit
+    spc::build_bvh(c, g.tri_pos.p, n);
+    c.has_scene = true;
+    SPC_API_END
+}
+
+int spc_bvh_stats_get(spc_context* ctx, spc_bvh_stats* out) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(out, SPC_ERR_INVALID, "spc_bvh_stats_get: out is null");
+    SPC_REQUIRE(c.has_scene, SPC_ERR_NO_SCENE, "spc_bvh_stats_get: no scene uploaded");
+    *out = c.bvh_stats;
+    SPC_API_END
+}
+
+int spc_trace_batch_device(spc_context* ctx, const spc_ray* rays_dev, int64_t n, int ray_flags, spc_hit* hits_dev) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(c.has_scene, SPC_ERR_NO_SCENE, "spc_trace_batch: no scene uploaded");
+    SPC_REQUIRE(n >= 0 && (n == 0 || (rays_dev && hits_dev)), SPC_ERR_INVALID, "spc_trace_batch: bad arguments");
+    spc::launch_trace_closest(c, rays_dev, n, ray_flags, hits_dev, nullptr);
+    SPC_API_END
+}
+
+int spc_trace_batch(spc_context* ctx, const spc_ray* rays_host, int64_t n, int ray_flags, spc_hit* hits_host) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(c.has_scene, SPC_ERR_NO_SCENE, "spc_trace_batch: no scene uploaded");
+    SPC_REQUIRE(n >= 0 && (n == 0 || (rays_host && hits_host)), SPC_ERR_INVALID, "spc_trace_batch: bad arguments");
+    if (n > 0) {
+        c.scratch_rays.alloc(n);
+        c.scratch_hits.alloc(n);
+        SPC_CUDA(cudaMemcpyAsync(c.scratch_rays.p, rays_host, n * sizeof(spc_ray), cudaMemcpyHostToDevice, c.stream));
+        spc::launch_trace_closest(c, c.scratch_rays.p, n, ray_flags, c.scratch_hits.p, nullptr);
+        SPC_CUDA(cudaMemcpyAsync(hits_host, c.scratch_hits.p, n * sizeof(spc_hit), cudaMemcpyDeviceToHost, c.stream));
+        SPC_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    SPC_API_END
+}
+
+int spc_occlusion_batch_device(spc_context* ctx, const spc_ray* rays_dev, int64_t n, uint8_t* visible_dev) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(c.has_scene, SPC_ERR_NO_SCENE, "spc_occlusion_batch: no scene uploaded");
+    SPC_REQUIRE(n >= 0 && (n == 0 || (rays_dev && visible_dev)), SPC_ERR_INVALID, "spc_occlusion_batch: bad arguments");
+    spc::launch_trace_occlusion(c, rays_dev, n, visible_dev, nullptr);
+    SPC_API_END
+}
+
+int spc_occlusion_batch(spc_context* ctx, const spc_ray* rays_host, int64_t n, uint8_t* visible_host) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(c.has_scene, SPC_ERR_NO_SCENE, "spc_occlusion_batch: no scene uploaded");
+    SPC_REQUIRE(n >= 0 && (n == 0 || (rays_host && visible_host)), SPC_ERR_INVALID, "spc_occlusion_batch: bad arguments");
+    if (n > 0) {
+        c.scratch_rays.alloc(n);
+        c.scratch_vis.alloc(n);
+        SPC_CUDA(cudaMemcpyAsync(c.scratch_rays.p, rays_host, n * sizeof(spc_ray), cudaMemcpyHostToDevice, c.stream));
+        spc::launch_trace_occlusion(c, c.scratch_rays.p, n, c.scratch_vis.p, nullptr);
+        SPC_CUDA(cudaMemcpyAsync(visible_host, c.scratch_vis.p, n, cudaMemcpyDeviceToHost, c.stream));
+        SPC_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    SPC_API_END
+}
+
+static int counted_finish(Context& c, int64_t n, spc_trace_counters* out) {
+    unsigned long long h[2];
+    SPC_CUDA(cudaMemcpyAsync(h, c.counters.p, sizeof(h), cudaMemcpyDeviceToHost, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    out->rays = (uint64_t)n;
+    out->nodes_visited = h[0];
+    out->tris_tested = h[1];
+    return 0;
+}
+
+int spc_trace_batch_counted(spc_context* ctx, const spc_ray* rays_dev, int64_t n, int ray_flags, spc_hit* hits_dev,
+                            spc_trace_counters* out_host) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(c.has_scene, SPC_ERR_NO_SCENE, "spc_trace_batch_counted: no scene uploaded");
+    SPC_REQUIRE(n >= 0 && out_host && (n == 0 || (rays_dev && hits_dev)), SPC_ERR_INVALID, "spc_trace_batch_counted: bad arguments");
+    SPC_CUDA(cudaMemsetAsync(c.counters.p, 0, 16, c.stream));
+    spc::launch_trace_closest(c, rays_dev, n, ray_flags, hits_dev, c.counters.p);
+    counted_finish(c, n, out_host);
+    SPC_API_END
+}
+
+int spc_occlusion_batch_counted(spc_context* ctx, const spc_ray* rays_dev, int64_t n, uint8_t* visible_dev,
+                                spc_trace_counters* out_host) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(c.has_scene, SPC_ERR_NO_SCENE, "spc_occlusion_batch_counted: no scene uploaded");
+    SPC_REQUIRE(n >= 0 && out_host && (n == 0 || (rays_dev && visible_dev)), SPC_ERR_INVALID, "spc_occlusion_batch_counted: bad arguments");
+    SPC_CUDA(cudaMemsetAsync(c.counters.p, 0, 16, c.stream));
+    spc::launch_trace_occlusion(c, rays_dev, n, visible_dev, c.counters.p);
+    counted_finish(c, n, out_host);
+    SPC_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// common.cuh -- shared declarations of libspcbpt_b200 (sm_100a only; no CPU fallback anywhere).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/spcbpt_b200.h"
+
+namespace spc {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: C ABI returns codes, message kept per thread (spc_last_error)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+struct CudaFailure { int code; };
+
+#define SPC_CUDA(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            spc::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                  \
+                           cudaGetErrorString(e__));                                             \
+            throw spc::CudaFailure{SPC_ERR_CUDA};                                                \
+        }                                                                                        \
+    } while (0)
+
+#define SPC_REQUIRE(cond, code, ...)                                                             \
+    do {                                                                                         \
+        if (!(cond)) {                                                                           \
+            spc::set_error(__VA_ARGS__);                                                         \
+            throw spc::CudaFailure{code};                                                        \
+        }                                                                                        \
+    } while (0)
+
+// RAII device buffer (cudaMalloc; buffers are sized for B200's 180 GB, no pooling needed)
+template <typename T>
+struct DevBuf {
+    T*     p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        if (count <= n && p) return;
+        release();
+        if (count == 0) count = 1;
+        SPC_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// compressed 8-wide BVH (80-byte nodes) + 48-byte triangles, single flattened level
+// ---------------------------------------------------------------------------------------------
+// Node = 5 x float4 (all loads are 128-bit):
+//   n0 = { p.x, p.y, p.z, bits(ex | ey<<8 | ez<<16 | imask<<24) }     box origin, biased exponents
+//   n1 = { bits(child_base), bits(tri_base), bits(meta[0..3]), bits(meta[4..7]) }
+//   n2 = { qlox[0..3], qlox[4..7], qloy[0..3], qloy[4..7] }           8-bit quantised child boxes
+//   n3 = { qloz[0..3], qloz[4..7], qhix[0..3], qhix[4..7] }
+//   n4 = { qhiy[0..3], qhiy[4..7], qhiz[0..3], qhiz[4..7] }
+// meta[slot]: 0 = empty; internal child = 0x20 | (24+slot); leaf = (unary tri count << 5) | tri offset.
+// Triangle = 3 x float4: { v0.xyz, bits(prim) }, { e1.xyz, bits(flags) }, { e2.xyz, 0 } with
+// e1 = v1-v0, e2 = v2-v0 (one IEEE subtraction each, as the intersection contract prescribes).
+struct Bvh8 {
+    DevBuf<float4> nodes;      // 5 per node
+    DevBuf<float4> tris;       // 3 per triangle, BVH order
+    uint32_t       n_nodes = 0;
+    uint32_t       n_tris  = 0;
+};
+
+enum : uint32_t { TRI_FLAG_SINGLE_SIDED = 1u };
+
+// de-indexed shading geometry in global prim order (gathered once per hit)
+struct SceneGeom {
+    DevBuf<float4>   tri_pos;     // 3 per prim: {P0, bits(material)}, {P1, bits(light_id)}, {P2, bits(mesh)}
+    DevBuf<float2>   tri_uv;      // 3 per prim
+    DevBuf<spc_pbr>  materials;
+    DevBuf<spc_light> lights;
+    DevBuf<uint8_t>  tex_data;    // all textures, RGBA8, concatenated
+    DevBuf<int4>     tex_desc;    // {offset_bytes, width, height, 0} per texture
+    uint32_t         n_prims = 0;
+    int              n_materials = 0, n_lights = 0, n_textures = 0;
+    float            scene_lo[3], scene_hi[3];
+};
+
+struct Context {
+    int           device = 0;
+    int           K = 1000, K_light = 200, connections = 3;
+    cudaStream_t  stream = 0;
+    int           sm_count = 148;
+    bool          has_scene = false;
+    SceneGeom     geom;
+    Bvh8          bvh;
+    spc_bvh_stats bvh_stats = {};
+    int64_t       launches = 0;
+    // scratch for host-buffer entry points
+    DevBuf<spc_ray> scratch_rays;
+    DevBuf<spc_hit> scratch_hits;
+    DevBuf<uint8_t> scratch_vis;
+    DevBuf<unsigned long long> counters;
+};
+
+void build_bvh(Context& ctx, const float4* d_tri_pos /*3 per prim*/, uint32_t n_prims);
+
+void launch_trace_closest(Context& ctx, const spc_ray* rays, int64_t n, int flags, spc_hit* hits,
+                          unsigned long long* counters /*nullable*/);
+void launch_trace_occlusion(Context& ctx, const spc_ray* rays, int64_t n, uint8_t* visible,
+                            unsigned long long* counters /*nullable*/);
+
+}  // namespace spc

@@ -1,0 +1,207 @@
+// traverse.cuh -- device-side traversal of the compressed 8-wide BVH (replaces optixTrace,
+// reference call sites cuProg.h:395,420,445 (closest hit) and cuProg.h:470 (occlusion)).
+//
+// Intersection contract (must stay bit-identical to oracle/spc_oracle.cpp: orc_tri_test):
+//   dot(a,b)   = fma(a.z,b.z, fma(a.y,b.y, a.x*b.x))
+//   cross(a,b) = ( fma(a.y,b.z, -(a.z*b.y)), fma(a.z,b.x, -(a.x*b.z)), fma(a.x,b.y, -(a.y*b.x)) )
+//   e1 = v1-v0, e2 = v2-v0;  pvec = cross(d,e2);  det = dot(e1,pvec)
+//   miss when det == 0 (single-sided triangles under CULL_BACK_FACING: miss unless det > 0)
+//   inv = 1/det; tvec = o-v0; u = dot(tvec,pvec)*inv; miss unless 0 <= u <= 1
+//   qvec = cross(tvec,e1); v = dot(d,qvec)*inv; miss unless v >= 0 and u+v <= 1
+//   t = dot(e2,qvec)*inv;  hit when tmin < t < tmax; nearest t wins, equal t -> lowest prim id.
+// Every operation is a single IEEE-754 binary32 op (explicit intrinsics: no contraction, no ftz).
+// The result is therefore independent of BVH shape and traversal order.
+#pragma once
+#include "common.cuh"
+
+namespace spc {
+
+constexpr int kSmStack  = 8;    // per-thread stack entries kept in shared memory
+constexpr int kLocStack = 24;   // overflow entries in local memory
+constexpr int kMaxBvhDepth = kSmStack + kLocStack;
+
+__device__ __forceinline__ float c_dot(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
+}
+__device__ __forceinline__ void c_cross(float ax, float ay, float az, float bx, float by, float bz,
+                                        float& cx, float& cy, float& cz) {
+    cx = __fmaf_rn(ay, bz, -__fmul_rn(az, by));
+    cy = __fmaf_rn(az, bx, -__fmul_rn(ax, bz));
+    cz = __fmaf_rn(ax, by, -__fmul_rn(ay, bx));
+}
+
+// byte j of w as an exact float, without I2F: splice the byte into the mantissa of 2^23.
+template <int J>
+__device__ __forceinline__ float byte_to_float(uint32_t w) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "n"(0x7650 + J));
+    return __uint_as_float(r) - 8388608.0f;
+}
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int j) { return (w >> (8 * j)) & 0xffu; }
+
+struct TravRay {
+    float ox, oy, oz, dx, dy, dz, tmin, tmax;
+};
+struct TravHit {
+    float t, u, v;
+    int   prim;
+};
+
+// one child quad (4 of the 8 slots) of a node
+#define SPC_CHILD_TEST(J)                                                                         \
+    {                                                                                             \
+        float lx = __fmaf_rn(byte_to_float<J>(slox), adjx, orgx);                                 \
+        float ly = __fmaf_rn(byte_to_float<J>(sloy), adjy, orgy);                                 \
+        float lz = __fmaf_rn(byte_to_float<J>(sloz), adjz, orgz);                                 \
+        float hx = __fmaf_rn(byte_to_float<J>(shix), adjx, orgx);                                 \
+        float hy = __fmaf_rn(byte_to_float<J>(shiy), adjy, orgy);                                 \
+        float hz = __fmaf_rn(byte_to_float<J>(shiz), adjz, orgz);                                 \
+        float cmin = fmaxf(fmaxf(lx, ly), fmaxf(lz, r.tmin));                                     \
+        float cmax = fminf(fminf(hx, hy), fminf(hz, tcur));                                       \
+        if (cmin <= cmax) hitmask |= byte_of(child_bits4, J) << byte_of(bit_index4, J);           \
+    }
+
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ bool traverse_bvh8(const float4* __restrict__ nodes,
+                                              const float4* __restrict__ tris, const TravRay& r,
+                                              bool cull_back, uint2* sstack, int sstride,
+                                              TravHit& hit, unsigned& cnt_nodes, unsigned& cnt_tris) {
+    const float eps = 1.0e-24f;
+    const float idx = 1.0f / (fabsf(r.dx) > eps ? r.dx : copysignf(eps, r.dx));
+    const float idy = 1.0f / (fabsf(r.dy) > eps ? r.dy : copysignf(eps, r.dy));
+    const float idz = 1.0f / (fabsf(r.dz) > eps ? r.dz : copysignf(eps, r.dz));
+    const uint32_t oct      = (r.dx < 0.f ? 1u : 0u) | (r.dy < 0.f ? 2u : 0u) | (r.dz < 0.f ? 4u : 0u);
+    const uint32_t oct_inv  = 7u ^ oct;
+    const uint32_t oct_inv4 = oct_inv * 0x01010101u;
+
+    float tcur      = r.tmax;
+    int   best_prim = -1;
+    float best_u = 0.f, best_v = 0.f;
+
+    uint2 lstack[kLocStack];
+    int   sp = 0;
+
+    uint2 ngroup = make_uint2(0u, 0x80000000u);
+    uint2 tgroup = make_uint2(0u, 0u);
+
+    while (true) {
+        if (ngroup.y > 0x00ffffffu) {
+            const uint32_t hits  = ngroup.y;
+            const uint32_t imask = ngroup.y & 0xffu;
+            const uint32_t bit   = 31u - __clz(hits);
+            ngroup.y &= ~(1u << bit);
+            if (ngroup.y > 0x00ffffffu) {
+                if (sp < kSmStack) sstack[sp * sstride] = ngroup;
+                else lstack[sp - kSmStack] = ngroup;
+                sp++;
+            }
+            const uint32_t slot = (bit - 24u) ^ oct_inv;
+            const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
+            const float4*  np   = nodes + (size_t)(ngroup.x + rel) * 5;
+            const float4 n0 = __ldg(np + 0);
+            const float4 n1 = __ldg(np + 1);
+            const float4 n2 = __ldg(np + 2);
+            const float4 n3 = __ldg(np + 3);
+            const float4 n4 = __ldg(np + 4);
+            if (COUNT) cnt_nodes++;
+
+            const uint32_t e_im = __float_as_uint(n0.w);
+            const float adjx = __uint_as_float((e_im & 0xffu) << 23) * idx;
+            const float adjy = __uint_as_float(((e_im >> 8) & 0xffu) << 23) * idy;
+            const float adjz = __uint_as_float(((e_im >> 16) & 0xffu) << 23) * idz;
+            const float orgx = (n0.x - r.ox) * idx;
+            const float orgy = (n0.y - r.oy) * idy;
+            const float orgz = (n0.z - r.oz) * idz;
+
+            uint32_t hitmask = 0;
+            {
+                const uint32_t meta4       = __float_as_uint(n1.z);
+                const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+                const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlox = __float_as_uint(n2.x), qloy = __float_as_uint(n2.z), qloz = __float_as_uint(n3.x);
+                const uint32_t qhix = __float_as_uint(n3.z), qhiy = __float_as_uint(n4.x), qhiz = __float_as_uint(n4.z);
+                const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
+                const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
+                const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
+                SPC_CHILD_TEST(0) SPC_CHILD_TEST(1) SPC_CHILD_TEST(2) SPC_CHILD_TEST(3)
+            }
+            {
+                const uint32_t meta4       = __float_as_uint(n1.w);
+                const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+                const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlox = __float_as_uint(n2.y), qloy = __float_as_uint(n2.w), qloz = __float_as_uint(n3.y);
+                const uint32_t qhix = __float_as_uint(n3.w), qhiy = __float_as_uint(n4.y), qhiz = __float_as_uint(n4.w);
+                const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
+                const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
+                const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
+                SPC_CHILD_TEST(0) SPC_CHILD_TEST(1) SPC_CHILD_TEST(2) SPC_CHILD_TEST(3)
+            }
+            ngroup.x = __float_as_uint(n1.x);
+            ngroup.y = (hitmask & 0xff000000u) | (e_im >> 24);
+            tgroup.x = __float_as_uint(n1.y);
+            tgroup.y = hitmask & 0x00ffffffu;
+        } else {
+            tgroup = ngroup;
+            ngroup = make_uint2(0u, 0u);
+        }
+
+        while (tgroup.y != 0u) {
+            const uint32_t ti = 31u - __clz(tgroup.y);
+            tgroup.y &= ~(1u << ti);
+            const float4* tp = tris + (size_t)(tgroup.x + ti) * 3;
+            const float4 a = __ldg(tp + 0);
+            const float4 b = __ldg(tp + 1);
+            const float4 c = __ldg(tp + 2);
+            if (COUNT) cnt_tris++;
+            float px, py, pz;
+            c_cross(r.dx, r.dy, r.dz, c.x, c.y, c.z, px, py, pz);
+            const float det = c_dot(b.x, b.y, b.z, px, py, pz);
+            const bool  single = cull_back && (__float_as_uint(b.w) & TRI_FLAG_SINGLE_SIDED);
+            if (single ? !(det > 0.0f) : !(det != 0.0f)) continue;
+            const float inv = __fdiv_rn(1.0f, det);
+            const float tx = __fsub_rn(r.ox, a.x), ty = __fsub_rn(r.oy, a.y), tz = __fsub_rn(r.oz, a.z);
+            const float u = __fmul_rn(c_dot(tx, ty, tz, px, py, pz), inv);
+            if (!(u >= 0.0f && u <= 1.0f)) continue;
+            float qx, qy, qz;
+            c_cross(tx, ty, tz, b.x, b.y, b.z, qx, qy, qz);
+            const float v = __fmul_rn(c_dot(r.dx, r.dy, r.dz, qx, qy, qz), inv);
+            if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) continue;
+            const float t = __fmul_rn(c_dot(c.x, c.y, c.z, qx, qy, qz), inv);
+            if (!(t > r.tmin)) continue;
+            const int prim = (int)__float_as_uint(a.w);
+            if (ANYHIT) {
+                if (t < r.tmax) return true;
+            } else {
+                if (t < tcur || (t == tcur && prim < best_prim)) {
+                    tcur = t;
+                    best_prim = prim;
+                    best_u = u;
+                    best_v = v;
+                }
+            }
+        }
+
+        if (ngroup.y <= 0x00ffffffu) {
+            if (sp == 0) break;
+            sp--;
+            ngroup = (sp < kSmStack) ? sstack[sp * sstride] : lstack[sp - kSmStack];
+        }
+    }
+    if (ANYHIT) return false;
+    hit.t = best_prim >= 0 ? tcur : 0.0f;
+    hit.u = best_u;
+    hit.v = best_v;
+    hit.prim = best_prim;
+    return best_prim >= 0;
+}
+
+}  // namespace spc

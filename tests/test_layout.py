@@ -1,0 +1,82 @@
+"""CPU tests: struct layouts, exported symbols, loader behaviour (no compute calls)."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_numpy_dtypes_match_header_sizes(pkg):
+    for name, size in pkg.EXPECTED_SIZES.items():
+        assert getattr(pkg, name).itemsize == size, name
+
+
+def test_params_offsets(pkg):
+    # field offsets of MyParams probed from the reference headers (SURVEY.md section 8 intro)
+    want = dict(width=0, height=4, subframe_index=8, accum_buffer=16, frame_buffer=24, max_depth=32, eye=36,
+                U=48, V=60, W=72, lights=88, materials=104, miss_color=120, handle=136, lt=144, sampler=184,
+                pre_tracer=224, subspace_info=256, sky=296)
+    for k, off in want.items():
+        assert pkg.PARAMS.fields[k][1] == off, k
+
+
+def test_vertex_offsets(pkg):
+    want = dict(position=0, normal=12, flux=24, color=36, lastPosition=48, RMIS_pointer_3=60, uv=72,
+                RMIS_pointer=80, last_lum=84, lastNormalProjection=88, pdf=92, singlePdf=96, lastSinglePdf=100,
+                materialId=104, subspaceId=106, depth=108, lastZoneId=110, type=112, isOrigin=114, inBrdf=115,
+                lastBrdf=116, isBrdf=117, isLastVertex_direction=118)
+    for k, off in want.items():
+        assert pkg.VERTEX.fields[k][1] == off, k
+
+
+def test_layout_matches_reference_headers(pkg):
+    """golden/ref_layout.json is produced by oracle/_ref/libref_host.so = sizeof/offsetof evaluated on
+    the reference's own headers (tests/golden/make_golden.py)."""
+    ref = json.load(open(os.path.join(GOLD, "ref_layout.json")))
+    assert ref["sizeof"]["BDPTVertex"] == pkg.VERTEX.itemsize
+    assert ref["sizeof"]["MyParams"] == pkg.PARAMS.itemsize
+    assert ref["sizeof"]["Light"] == pkg.LIGHT.itemsize
+    assert ref["sizeof"]["MaterialData::Pbr"] == pkg.PBR.itemsize
+    assert ref["sizeof"]["tree_node"] == pkg.TREE_NODE.itemsize
+    assert ref["sizeof"]["Subspace"] == pkg.SUBSPACE.itemsize
+    assert ref["sizeof"]["divide_weight"] == pkg.DIVIDE_WEIGHT.itemsize
+    for k, off in ref["offsetof"]["MyParams"].items():
+        assert pkg.PARAMS.fields[k][1] == off, k
+    for k, off in ref["offsetof"]["BDPTVertex"].items():
+        assert pkg.VERTEX.fields[k][1] == off, k
+    for k, off in ref["offsetof"]["Light"].items():
+        assert pkg.LIGHT.fields[k][1] == off, k
+    for k, off in ref["offsetof"]["Pbr"].items():
+        assert pkg.PBR.fields[k][1] == off, k
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    assert os.path.exists(pkg.LIB_PATH), "build the extension first (python spcbpt-optix7_b200/build.py)"
+    L = ctypes.CDLL(pkg.LIB_PATH)
+    syms = pkg.declared_symbols()
+    assert len(syms) >= 15
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device the product must refuse to run (no oracle, no CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.SpcError) as e:
+        pkg.Context(0)
+    assert "no CUDA device" in str(e.value) or "NO_DEVICE" in str(e.value) or "-3" in str(e.value)
+
+
+def test_product_does_not_reference_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkgdir = os.path.join(root, "spcbpt-optix7_b200")
+    for dp, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "orc_" not in txt and "liborc" not in txt and "oracle/" not in txt.replace("oracle/spc_oracle.cpp", "").replace("oracle/orc_scene.cpp", "").replace("oracle/ref_shim", "").replace("oracle/orc_", "X"), f
