@@ -341,6 +341,17 @@ SPC_API int  spc_occlusion_batch_device(spc_context* ctx, const spc_ray* rays_de
  * results are identical.  Used only to state the algorithmic bytes per ray. */
 SPC_API int  spc_trace_batch_counted(spc_context* ctx, const spc_ray* rays_dev, int64_t n, int ray_flags, spc_hit* hits_dev, spc_trace_counters* out_host);
 SPC_API int  spc_occlusion_batch_counted(spc_context* ctx, const spc_ray* rays_dev, int64_t n, uint8_t* visible_dev, spc_trace_counters* out_host);
+/* -------------------------------- ray-batch producers ---------------------------------------- */
+/* Pinhole primaries of one subframe (the raygen part of __raygen__SPCBPT / __raygen__pinhole,
+ * raygen.cu:321-344): seed = tea<4>(y*W+x, subframe), jitter (0.5,0.5) at subframe 0 else two rnd
+ * draws, dir = normalize(d.x*U + d.y*V + W), tmin 1e-3 (SCENE_EPSILON, cuProg.h:39), tmax 1e16.
+ * cam12 = eye,U,V,W (MyParams fields, whitted.h:75-78).  rays_dev: device spc_ray[width*height]. */
+SPC_API int  spc_gen_camera_rays(spc_context* ctx, const float* cam12, int width, int height, int subframe, spc_ray* rays_dev);
+/* Traversal-microbench ray sets derived from a primary batch and its hits (BASELINE.md section 3,
+ * config 2): kind 1 = cosine-hemisphere bounce rays (seed tea<4>(i,1)), kind 2 = shadow rays to a
+ * uniform point of light 0 (seed tea<4>(i,2), interval [1e-3, len-1e-3] as cuProg.h:466-475). */
+SPC_API int  spc_gen_bench_rays(spc_context* ctx, int kind, const spc_ray* rays_in_dev, const spc_hit* hits_in_dev, int64_t n,
+                                spc_ray* rays_out_dev, void* reserved);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 SPC_API int64_t spc_launch_count(spc_context* ctx);
 

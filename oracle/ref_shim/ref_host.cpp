@@ -21,6 +21,7 @@
 
 thread_local RefShimState g_shim;
 
+#include "rmis_patched.h"   // see oracle/Makefile: rmis.h with getMat() returning by value
 #include "hit_program.cu"
 #include "raygen.cu"
 #include "decisionTree/classTree_host.h"
@@ -32,7 +33,8 @@ namespace {
 
 struct RefScene {
     orc::Scene* geo = nullptr;                       // intersection only
-    std::vector<whitted::HitGroupData> records;      // one per mesh (radiance ray type)
+    std::vector<unsigned char> record_bytes;         // one whitted::HitGroupData per mesh (radiance ray type)
+    whitted::HitGroupData* record(int m) { return reinterpret_cast<whitted::HitGroupData*>(record_bytes.data()) + m; }
     std::vector<int> prim_mesh, prim_local;          // global prim -> (mesh, local prim)
     std::vector<bool> mesh_is_light;
     std::vector<MaterialData::Pbr> pbr;              // params.materials
@@ -85,7 +87,7 @@ void ref_shim_trace(float3 o, float3 d, float tmin, float tmax, unsigned int fla
         const bool cull = (flags & OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES) != 0;
         if (g_scene->geo->closest(oo, dd, tmin, tmax, cull, h)) {
             const int mesh = g_scene->prim_mesh[h.prim];
-            g_shim.sbt_data = &g_scene->records[mesh];
+            g_shim.sbt_data = g_scene->record(mesh);
             g_shim.prim_index = (unsigned)g_scene->prim_local[h.prim];
             g_shim.bary = make_float2(h.u, h.v);
             g_shim.ray_tmax = h.t;
@@ -232,7 +234,7 @@ REF_API int ref_scene_create(const spc_mesh* meshes, int n_meshes, const spc_pbr
         s->pbr[n_materials + i] = mtl.pbr;
     }
     s->pos.resize(n_meshes); s->idx.resize(n_meshes); s->uv.resize(n_meshes);
-    s->records.resize(n_meshes);
+    s->record_bytes.assign((size_t)n_meshes * sizeof(whitted::HitGroupData) + 16, 0);
     s->mesh_is_light.resize(n_meshes);
     for (int m = 0; m < n_meshes; m++) {
         const spc_mesh& me = meshes[m];
@@ -244,8 +246,7 @@ REF_API int ref_scene_create(const spc_mesh* meshes, int n_meshes, const spc_pbr
             s->uv[m][v].x = me.texcoords ? me.texcoords[2 * v] : 0.f;       // zero fill: scene_shift.cpp:203-206
             s->uv[m][v].y = me.texcoords ? me.texcoords[2 * v + 1] : 0.f;
         }
-        whitted::HitGroupData& rec = s->records[m];
-        memset((void*)&rec, 0, sizeof(rec));
+        whitted::HitGroupData& rec = *s->record(m);
         rec.geometry_data.type = GeometryData::TRIANGLE_MESH;
         GeometryData::TriangleMesh& tm = rec.geometry_data.triangle_mesh;
         tm.positions.data = (CUdeviceptr)s->pos[m].data(); tm.positions.count = me.n_vertices;

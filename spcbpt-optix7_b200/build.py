@@ -17,9 +17,11 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "--shared",
-    # parity: IEEE div/sqrt, denormals kept; contraction happens only where written (explicit fma
-    # intrinsics in the contract arithmetic), never --use_fast_math.
-    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    # parity: IEEE div/sqrt, denormals kept, no implicit a*b+c contraction (-fmad=false) so that
+    # plain fp32 expressions round exactly like the host oracle built with -ffp-contract=off; fused
+    # ops appear only where written (explicit __fmaf_rn in the traversal and the contract
+    # arithmetic).  Never --use_fast_math.
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-fmad=false",
     "-Xptxas", "-v",
     "-diag-suppress", "177,550",
 ]

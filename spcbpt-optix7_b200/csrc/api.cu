@@ -16,10 +16,6 @@ void set_error(const char* fmt, ...) {
 
 }  // namespace spc
 
-struct spc_context {
-    spc::Context c;
-};
-
 using spc::Context;
 
 #define SPC_API_BEGIN                                                                            \

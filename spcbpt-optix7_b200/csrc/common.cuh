@@ -116,3 +116,8 @@ void launch_trace_occlusion(Context& ctx, const spc_ray* rays, int64_t n, uint8_
                             unsigned long long* counters /*nullable*/);
 
 }  // namespace spc
+
+// the opaque handle of the C ABI
+struct spc_context {
+    spc::Context c;
+};
