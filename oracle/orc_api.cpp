@@ -102,3 +102,89 @@ ORC_API void orc_occlusion_batch(void* sc, const spc_ray* rays, int64_t n, uint8
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// render path (orc_render.cpp)
+// ---------------------------------------------------------------------------------------------
+#include "orc_render.h"
+
+static Frame make_frame(void* sc, const spc_params* p, int K, int connections, int max_depth) {
+    Frame fr;
+    fr.sc = (const Scene*)sc;
+    fr.p = *p;
+    fr.K = K;
+    fr.connections = connections;
+    fr.max_depth = max_depth > 0 ? max_depth : 50;
+    return fr;
+}
+
+extern "C" {
+
+ORC_API void orc_set_jitter_rtl(int v) { g_jitter_rtl = v; }
+
+// optixLaunch of "light trace" (optixPathTracer.cpp:491-514): one sequential core per launch index
+ORC_API void orc_light_trace(void* sc, const spc_params* p, int K, int max_depth, int threads) {
+    const Frame fr = make_frame(sc, p, K, 3, max_depth);
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            const int c = next.fetch_add(1);
+            if (c >= fr.p.lt.num_core) break;
+            light_trace_core(fr, c);
+        }
+    };
+    if (threads <= 1) worker();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++) pool.emplace_back(worker);
+        for (auto& th : pool) th.join();
+    }
+}
+
+// MyThrustOp::LVC_Process (device_thrust.cu:241-332)
+ORC_API void orc_lvc_process(const spc_vertex* lvc, const uint8_t* valid, int n, int K, spc_subspace* subspace, float* cmfs,
+                             int* jump, int* vertex_count, int* path_count) {
+    lvc_process(lvc, valid, n, K, subspace, cmfs, jump, vertex_count, path_count);
+}
+
+// optixLaunch of "SPCBPT_eye" (optixPathTracer.cpp:609-635); optional per-pixel bounce-0 prim / subspace ids
+ORC_API void orc_eye_pass(void* sc, const spc_params* p, int K, int connections, int max_depth, int threads, int* first_prim,
+                          int* first_label) {
+    const Frame fr = make_frame(sc, p, K, connections, max_depth);
+    const int W = (int)p->width, H = (int)p->height;
+    parallel_for((int64_t)W * H, threads, [&](int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; i++)
+            eye_pixel(fr, (int)(i % W), (int)(i / W), first_prim ? first_prim + i : nullptr, first_label ? first_label + i : nullptr);
+    });
+}
+
+// stage-wise entry points -----------------------------------------------------------------------
+ORC_API void orc_bsdf(void* sc, int material_id, const float* color3, const float* N, const float* V, const float* L, uint32_t* seed,
+                      float* eval3, float* pdf1, float* sample3) {
+    Pbr m = load_pbr(*(const Scene*)sc, material_id);
+    if (color3) m.base_color = mk3(color3[0], color3[1], color3[2]);
+    const f3 n = mk3(N[0], N[1], N[2]), v = mk3(V[0], V[1], V[2]), l = mk3(L[0], L[1], L[2]);
+    const f3 e = bsdf_eval(m, n, v, l);
+    eval3[0] = e.x; eval3[1] = e.y; eval3[2] = e.z;
+    *pdf1 = bsdf_pdf(m, n, v, l);
+    const f3 s = bsdf_sample(m, n, v, *seed);
+    sample3[0] = s.x; sample3[1] = s.y; sample3[2] = s.z;
+}
+
+ORC_API void orc_classify(const spc_tree_node* tree, const float* pos, const float* nrm, int n, int* labels) {
+    for (int i = 0; i < n; i++)
+        labels[i] = tree_label(tree, mk3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), mk3(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]));
+}
+
+// connectVertex_SPCBPT (raygen.cu:253-303) on caller-provided vertex pairs: out3 = contribution, w = MIS weight
+ORC_API void orc_connect(void* sc, const spc_params* p, int K, int connections, const spc_vertex* eye, const spc_vertex* light, int n,
+                         float* out3, float* w) {
+    const Frame fr = make_frame(sc, p, K, connections, 0);
+    for (int i = 0; i < n; i++) {
+        f3 c;
+        w[i] = connect_mis_and_eval(fr, eye[i], light[i], c);
+        out3[3 * i] = c.x; out3[3 * i + 1] = c.y; out3[3 * i + 2] = c.z;
+    }
+}
+
+}  // extern "C"

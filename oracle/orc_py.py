@@ -104,3 +104,84 @@ class Scene:
         vis = np.zeros(rays.shape[0], np.uint8)
         lib().orc_occlusion_batch(self.h, rays.ctypes.data, rays.shape[0], vis.ctypes.data, int(brute), threads)
         return vis
+
+
+# ---- render path -----------------------------------------------------------------------------
+def _bind_render(L):
+    vp, i32 = ctypes.c_void_p, ctypes.c_int
+    L.orc_light_trace.argtypes = [vp, vp, i32, i32, i32]
+    L.orc_light_trace.restype = None
+    L.orc_lvc_process.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.orc_lvc_process.restype = None
+    L.orc_eye_pass.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    L.orc_eye_pass.restype = None
+    L.orc_bsdf.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.orc_bsdf.restype = None
+    L.orc_classify.argtypes = [vp, vp, vp, i32, vp]
+    L.orc_classify.restype = None
+    L.orc_connect.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, vp]
+    L.orc_connect.restype = None
+
+
+def light_trace(scene, params, K, max_depth=0, threads=8):
+    L = lib(); _bind_render(L)
+    L.orc_light_trace(scene.h, params.ctypes.data, K, max_depth, threads)
+
+
+def lvc_process(pkg, lvc, valid, K):
+    L = lib(); _bind_render(L)
+    n = lvc.shape[0]
+    sub = np.zeros(K, pkg.SUBSPACE)
+    cmfs = np.zeros(n, np.float32)
+    jump = np.zeros(n, np.int32)
+    vc, pc = ctypes.c_int(0), ctypes.c_int(0)
+    L.orc_lvc_process(lvc.ctypes.data, valid.ctypes.data, n, K, sub.ctypes.data, cmfs.ctypes.data, jump.ctypes.data,
+                      ctypes.byref(vc), ctypes.byref(pc))
+    return sub, cmfs[:vc.value].copy(), jump[:vc.value].copy(), vc.value, pc.value
+
+
+def eye_pass(scene, params, K, connections=3, max_depth=0, threads=8, want_first=False):
+    L = lib(); _bind_render(L)
+    n = int(params["width"][0]) * int(params["height"][0])
+    fp = np.zeros(n, np.int32) if want_first else None
+    fl = np.zeros(n, np.int32) if want_first else None
+    L.orc_eye_pass(scene.h, params.ctypes.data, K, connections, max_depth, threads,
+                   fp.ctypes.data if want_first else None, fl.ctypes.data if want_first else None)
+    return fp, fl
+
+
+def bsdf(scene, material_id, color, N, V, Ldir, seed):
+    L = lib(); _bind_render(L)
+    N, V, Ldir = (np.ascontiguousarray(a, np.float32) for a in (N, V, Ldir))
+    col = None if color is None else np.ascontiguousarray(color, np.float32)
+    st = np.array([seed], np.uint32)
+    e, p, s = np.zeros(3, np.float32), np.zeros(1, np.float32), np.zeros(3, np.float32)
+    L.orc_bsdf(scene.h, material_id, None if col is None else col.ctypes.data, N.ctypes.data, V.ctypes.data, Ldir.ctypes.data,
+               st.ctypes.data, e.ctypes.data, p.ctypes.data, s.ctypes.data)
+    return e, float(p[0]), s, int(st[0])
+
+
+def classify(pkg, tree, pos, nrm):
+    L = lib(); _bind_render(L)
+    tree = np.ascontiguousarray(tree, pkg.TREE_NODE)
+    pos = np.ascontiguousarray(pos, np.float32)
+    nrm = np.ascontiguousarray(nrm, np.float32)
+    lab = np.zeros(pos.shape[0], np.int32)
+    L.orc_classify(tree.ctypes.data, pos.ctypes.data, nrm.ctypes.data, pos.shape[0], lab.ctypes.data)
+    return lab
+
+
+def connect(pkg, scene, params, K, connections, eye, light):
+    L = lib(); _bind_render(L)
+    eye = np.ascontiguousarray(eye, pkg.VERTEX)
+    light = np.ascontiguousarray(light, pkg.VERTEX)
+    n = eye.shape[0]
+    out = np.zeros((n, 3), np.float32)
+    w = np.zeros(n, np.float32)
+    L.orc_connect(scene.h, params.ctypes.data, K, connections, eye.ctypes.data, light.ctypes.data, n, out.ctypes.data, w.ctypes.data)
+    return out, w
+
+
+def set_jitter_rtl(v):
+    """reproduce g++'s right-to-left evaluation of make_float2(rnd,rnd) (pinning vs libref_host only)"""
+    lib().orc_set_jitter_rtl(int(v))
