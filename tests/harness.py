@@ -57,9 +57,71 @@ def random_trees_and_gamma(pkg, points, normals, K, K_light, builder, seed=0):
     eye_tree, _ = builder(pkg, s, K, 0)
     s["weight"] = rng.uniform(0.2, 1.0, points.shape[0]).astype(np.float32)
     light_tree, _ = builder(pkg, s, K - K_light, 0)
+    Q, cmf = random_q_gamma(K, seed + 1000)
+    return eye_tree, light_tree, Q, cmf
+
+
+def random_q_gamma(K, seed):
+    """a random positive Q vector and a row-CDF Gamma matrix (seeded: regenerated, not stored, by the golden tests)"""
+    rng = np.random.default_rng(seed)
     Q = rng.uniform(0.05, 2.0, K).astype(np.float32)
     G = rng.uniform(0.01, 1.0, (K, K)).astype(np.float32)
     G /= G.sum(1, keepdims=True)
     cmf = np.cumsum(G, axis=1, dtype=np.float32)
     cmf[:, -1] = 1.0
-    return eye_tree, light_tree, Q, cmf
+    return Q, cmf
+
+
+GOLDEN_CFG = dict(w=48, h=40, num_core=16, core_padding=120, M_per_core=20, launch_frame=3, subframes=(0, 1, 2))
+
+
+def golden_scene(pkg):
+    """the 682-triangle Cornell fixture of tests/golden/render.npz"""
+    return pkg.scenes.cornell_scene(wall_cells=6, box_cells=4)
+
+
+def golden_render_setup(pkg, builder):
+    """scene + trees + Q/Gamma used by tests/golden/make_golden.py (trees need the reference's builder)"""
+    sc = golden_scene(pkg)
+    K, K_light = 1000, 200
+    rays = pkg.scenes.camera_rays(sc, 64, 64)
+    # sample points for the trees: a deterministic cloud on the scene surfaces (vertex positions + face normals)
+    P, N = [], []
+    for m in sc.meshes:
+        tri = m["positions"][m["indices"].astype(np.int64)]
+        c = tri.mean(1)
+        n = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+        n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-30)
+        P.append(c.astype(np.float32))
+        N.append(n.astype(np.float32))
+    del rays
+    P, N = np.concatenate(P), np.concatenate(N)
+    eye_tree, light_tree, Q, cmf = random_trees_and_gamma(pkg, P, N, K, K_light, builder)
+    return sc, K, K_light, eye_tree, light_tree, Q, cmf, dict(GOLDEN_CFG)
+
+
+UNDEFINED_ON_ORIGIN = ("color", "lastPosition", "RMIS_pointer_3", "last_lum", "lastNormalProjection", "lastSinglePdf",
+                       "lastZoneId", "inBrdf", "lastBrdf", "isLastVertex_direction", "_pad")
+
+
+def compare_lvc(pkg, a, valid_a, b, valid_b, exact=True, rtol=1e-5):
+    """field-wise comparison of two LVCs on the fields the reference defines (depth-0 emitter vertices
+    leave most fields as stack garbage, raygen.cu:172-195).  Returns a list of mismatch strings."""
+    bad = []
+    if not np.array_equal(valid_a, valid_b):
+        return ["validState differs on %d slots" % int((valid_a != valid_b).sum())]
+    v = valid_a.astype(bool)
+    origin = a["depth"] == 0
+    for name in pkg.VERTEX.names:
+        if name in ("_pad", "inBrdf", "RMIS_pointer_3"):   # RMIS_pointer_3 is eye-side state: never written on light paths
+            continue
+        m = v & ~origin if name in UNDEFINED_ON_ORIGIN else v
+        x, y = a[name][m], b[name][m]
+        if exact or x.dtype.kind in "iu":
+            if not np.array_equal(x.view(np.uint8), y.view(np.uint8)):
+                bad.append("%s: %d of %d differ" % (name, int((x != y).sum()), x.size))
+        else:
+            err = np.abs(x - y) / np.maximum(np.abs(y), 1e-20)
+            if not (err <= rtol).all():
+                bad.append("%s: max rel err %g" % (name, float(err.max())))
+    return bad

@@ -73,10 +73,14 @@ def test_no_cpu_fallback(pkg):
 
 
 def test_product_does_not_reference_oracle():
+    """the product (package + C ABI sources) must not include, link, load or import anything under oracle/"""
+    import re
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    pkgdir = os.path.join(root, "spcbpt-optix7_b200")
-    for dp, _, files in os.walk(pkgdir):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
-                txt = open(os.path.join(dp, f), errors="ignore").read()
-                assert "orc_" not in txt and "liborc" not in txt and "oracle/" not in txt.replace("oracle/spc_oracle.cpp", "").replace("oracle/orc_scene.cpp", "").replace("oracle/ref_shim", "").replace("oracle/orc_", "X"), f
+    bad = re.compile(r'liborc|libref_host|orc_py|ref_py|load_oracle|#\s*include\s*[<"][^">]*(oracle|orc_)[^">]*[">]|dlopen|import\s+oracle|from\s+oracle')
+    for sub in ("spcbpt-optix7_b200", "include", "host"):
+        for dp, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    m = bad.search(txt)
+                    assert not m, "%s: %s" % (f, m.group(0))

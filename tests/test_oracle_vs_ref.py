@@ -1,0 +1,114 @@
+"""CPU tests that need the reference tree (skipped on the GPU box): the oracle against the reference's
+own sources compiled for the host (oracle/_ref/libref_host.so) on fresh seeded inputs -- larger and more
+varied than the committed golden files (textured + metallic materials, two lights, several subframes)."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from harness import HostFrame, compare_lvc, random_trees_and_gamma
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    spec = importlib.util.spec_from_file_location("ref_py", os.path.join(ROOT, "oracle", "ref_py.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    if not m.available():
+        pytest.skip("reference tree absent and oracle/_ref not prebuilt")
+    return m
+
+
+def _varied_cornell(pkg):
+    sc = pkg.scenes.cornell_scene(wall_cells=8, box_cells=5)
+    rng = np.random.default_rng(5)
+    mats = pkg.scenes.make_pbr(5)
+    mats[:3] = sc.materials
+    mats["base_color"][3] = (0.9, 0.8, 0.3, 1); mats["metallic"][3] = 1.0; mats["roughness"][3] = 0.15
+    mats["base_color"][4] = (1, 1, 1, 1); mats["roughness"][4] = 0.6
+    tex = rng.integers(0, 256, (16, 24, 4), dtype=np.uint8)
+    sc.textures = [tex]
+    mats["base_color_tex"]["tex"][4] = 1
+    sc.materials = mats
+    sc.meshes[3]["material_id"] = 3     # short box: metal
+    sc.meshes[4]["material_id"] = 4     # tall box: textured
+    L2 = pkg.scenes.make_quad_light(1, (20.0, 300.0, 100.0), (20.0, 300.0, 200.0), (20.0, 400.0, 100.0), (6.0, 8.0, 12.0), 3, 4)
+    sc.lights = np.concatenate([sc.lights, L2])
+    sc.meshes.append(pkg.scenes.light_mesh(L2, 1))
+    return sc
+
+
+def test_render_path_bit_exact(pkg, orc, ref):
+    sc = _varied_cornell(pkg)
+    K, KL = 1000, 200
+    osc = orc.Scene(pkg, sc)
+    ref.scene_create(pkg, sc)
+    P = np.concatenate([m["positions"][m["indices"].astype(np.int64)].mean(1) for m in sc.meshes]).astype(np.float32)
+    N = np.tile(np.array([[0, 1, 0]], np.float32), (P.shape[0], 1))
+    eye_tree, light_tree, Q, cmf = random_trees_and_gamma(pkg, P, N, K, KL, ref.tree_build, seed=9)
+    w, h = 64, 48
+
+    def run(kind):
+        fr = HostFrame(pkg, sc, w, h, K=K, num_core=24, core_padding=150, M_per_core=25)
+        fr.set_trees(eye_tree, light_tree)
+        fr.set_q_gamma(Q, cmf)
+        fr.P["lt"]["launch_frame"] = 7
+        if kind == "ref":
+            ref.launch(fr.P, ref.KIND_LIGHT_TRACE, 24, 1, threads=8)
+        else:
+            orc.light_trace(osc, fr.P, K, threads=8)
+        sub, cmfs, jump, vc, pc = orc.lvc_process(pkg, fr.lvc, fr.valid, K)
+        fr.set_sampler(sub, cmfs, jump, vc, pc)
+        outs = []
+        for sf in (0, 1, 5):
+            fr.P["subframe_index"] = sf
+            if kind == "ref":
+                ref.launch(fr.P, ref.KIND_SPCBPT_EYE, w, h, threads=8)
+            else:
+                orc.eye_pass(osc, fr.P, K, 3, 0, threads=8)
+            outs.append((fr.accum.copy(), fr.frame.copy()))
+        return fr, outs
+
+    orc.set_jitter_rtl(1)
+    try:
+        fa, oa = run("ref")
+        fb, ob = run("orc")
+    finally:
+        orc.set_jitter_rtl(0)
+        ref.lib().ref_scene_destroy()
+    bad = compare_lvc(pkg, fb.lvc, fb.valid, fa.lvc, fa.valid, exact=True)
+    assert not bad, bad
+    assert fa.valid.sum() > 1000
+    for (xa, fa_), (xb, fb_) in zip(oa, ob):
+        assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32))
+        assert np.array_equal(fa_, fb_)
+    assert oa[0][0][:, :3].mean() > 0.01
+
+
+def test_bsdf_random(pkg, orc, ref):
+    rng = np.random.default_rng(77)
+    n = 400
+    m = pkg.scenes.make_pbr(n)
+    m["base_color"][:, :3] = rng.uniform(0, 1, (n, 3))
+    m["metallic"] = rng.uniform(0, 1, n); m["roughness"] = rng.uniform(0, 1, n)
+    m["clearcoat"] = rng.uniform(0, 1, n); m["clearcoatGloss"] = rng.uniform(0, 1, n)
+    m["sheen"] = rng.uniform(0, 1, n); m["subsurface"] = rng.uniform(0, 1, n)
+    sc = pkg.scenes.cornell_scene(wall_cells=1, box_cells=1)
+    sc.materials = m
+    osc = orc.Scene(pkg, sc)
+
+    def unit():
+        v = rng.normal(0, 1, 3)
+        return (v / np.linalg.norm(v)).astype(np.float32)
+    for i in range(n):
+        N, V, L = unit(), unit(), unit()
+        if np.dot(N, V) < 0:
+            V = -V
+        seed = int(rng.integers(0, 2 ** 32))
+        a = ref.bsdf(pkg, m[i:i + 1], N, V, L, seed)
+        b = orc.bsdf(osc, i, None, N, V, L, seed)
+        assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.float32(a[1]).view(np.uint32) == np.float32(b[1]).view(np.uint32)
+        assert np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32)) and a[3] == b[3]
