@@ -352,6 +352,33 @@ SPC_API int  spc_gen_camera_rays(spc_context* ctx, const float* cam12, int width
  * uniform point of light 0 (seed tea<4>(i,2), interval [1e-3, len-1e-3] as cuProg.h:466-475). */
 SPC_API int  spc_gen_bench_rays(spc_context* ctx, int kind, const spc_ray* rays_in_dev, const spc_hit* hits_in_dev, int64_t n,
                                 spc_ray* rays_out_dev, void* reserved);
+/* -------------------------------- launch seam ----------------------------------------------- */
+/* The reference copies its MyParams to the device before every launch (optixPathTracer.cpp:495-500,
+ * 527-532,616-621) and reads it from the `params` module symbol (cuProg.h:65-67).  spc_set_params takes
+ * the same 352-byte struct by value; every pointer inside is a DEVICE pointer owned by the caller
+ * (accum_buffer, frame_buffer, lt.ans, lt.validState, pre_tracer.paths/conns, subspace_info.*, sampler.*).
+ * `lights`, `materials` and `handle` are ignored (they come from spc_scene_upload). */
+SPC_API int  spc_set_params(spc_context* ctx, const spc_params* params);
+/* Replaces Scene::switchRaygen(name) + optixLaunch(pipeline, 0, d_params, sizeof(MyParams), sbt, w, h, 1)
+ * (sutil/Scene.cpp:1642-1789; optixPathTracer.cpp:502-512, 534-544, 612-632).  Launch sizes as in the
+ * reference: SPCBPT_EYE / PT (width, height) = image size; LIGHT_TRACE (lt.num_core, 1); PRETRACE
+ * (pre_tracer.num_core, 1).  Asynchronous on the context's stream. */
+enum { SPC_LAUNCH_PT = 0, SPC_LAUNCH_SPCBPT_EYE = 1, SPC_LAUNCH_LIGHT_TRACE = 2, SPC_LAUNCH_PRETRACE = 3 };
+SPC_API int  spc_launch(spc_context* ctx, int kind, int width, int height);
+/* by-name form of the same call: "pt" | "SPCBPT_eye" | "light trace" | "pretrace" (optixPathTracer.cpp:88,502,534,612) */
+SPC_API int  spc_launch_named(spc_context* ctx, const char* raygen_name, int width, int height);
+/* optional parity dumps of the eye pass: per pixel, the primitive id of the primary hit (-1 miss) and the
+ * subspace id of the first eye vertex (-1 none).  Device int[W*H] each, or NULL to disable. */
+SPC_API int  spc_set_debug_outputs(spc_context* ctx, int32_t* first_prim_dev, int32_t* first_label_dev);
+
+/* -------------------------------- post-processing seam (MyThrustOp) -------------------------- */
+/* MyThrustOp::LVC_Process(vertices, validState, countRange) (cuda_thrust/device_thrust.cu:241-332): bins the
+ * valid light vertices by subspace id in slot order and builds the per-subspace cmf tables, entirely on the
+ * device.  The arrays behind out->subspace / cmfs / jump_buffer are owned by the context and stay valid
+ * until the next call (the reference's function-static device_vectors behave the same way). */
+SPC_API int  spc_lvc_process(spc_context* ctx, const spc_vertex* lvc_dev, const uint8_t* valid_dev, int count_range,
+                             spc_subspace_sampler* out_host);
+
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 SPC_API int64_t spc_launch_count(spc_context* ctx);
 

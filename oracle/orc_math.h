@@ -51,6 +51,19 @@ static inline f3 c_cross(f3 a, f3 b) {
     return f3{orc_fma(a.y, b.z, -(a.z * b.y)), orc_fma(a.z, b.x, -(a.x * b.z)), orc_fma(a.x, b.y, -(a.y * b.x))};
 }
 
+// ---- contract transcendental functions -------------------------------------------------------------
+// sin/cos/log/pow/exp of a float = the fp64 libm function rounded once to fp32.  CUDA's fp64 functions
+// (<= 2 ulp) and glibc's (< 1 ulp) then agree bit-for-bit in fp32 except when the exact value lies within
+// ~2 fp64-ulp of an fp32 rounding boundary (probability ~1e-8 per call), so the product's kernels
+// (csrc/shade.cuh cm_*) and this oracle produce identical bits.  The reference itself uses
+// --use_fast_math intrinsics (__sinf, __powf, ...), which no host build can reproduce; its host-shim build
+// (oracle/ref_shim/ref_host.cpp) is given the same definitions.
+static inline float cm_sinf(float x) { return (float)std::sin((double)x); }
+static inline float cm_cosf(float x) { return (float)std::cos((double)x); }
+static inline float cm_logf(float x) { return (float)std::log((double)x); }
+static inline float cm_expf(float x) { return (float)std::exp((double)x); }
+static inline float cm_powf(float x, float y) { return (float)std::pow((double)x, (double)y); }
+
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 

@@ -61,7 +61,7 @@ static Pbr shade_pbr(const Scene& sc, int id, float uvx, float uvy) {
         const float tv = (sx * (-rx) + sy * ry) + tr.texcoord_offset[1];
         float c[4];
         tex_fetch(sc.textures[(size_t)tr.tex - 1], tu, tv, c);
-        m.base_color = f3{std::pow(c[0], 2.2f), std::pow(c[1], 2.2f), std::pow(c[2], 2.2f)};
+        m.base_color = f3{cm_powf(c[0], 2.2f), cm_powf(c[1], 2.2f), cm_powf(c[2], 2.2f)};
     }
     m.roughness *= 1.0f;
     m.metallic *= 1.0f;
@@ -81,7 +81,7 @@ static inline float GTR1(float NDotH, float a) {            // cuProg.h:693-699
     if (a >= 1.0f) return (1.0f / PIf);
     const float a2 = a * a;
     const float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return (a2 - 1.0f) / (PIf * std::log(a2) * t);
+    return (a2 - 1.0f) / (PIf * cm_logf(a2) * t);
 }
 static inline float GTR2(float NDotH, float a) {            // cuProg.h:701-706
     const float a2 = a * a;
@@ -142,8 +142,8 @@ static inline f3 cosine_sample_hemisphere(float u1, float u2) {   // cuProg.h:11
     const float r = std::sqrt(u1);
     const float phi = 2.0f * PIf * u2;
     f3 p;
-    p.x = r * std::cos(phi);
-    p.y = r * std::sin(phi);
+    p.x = r * cm_cosf(phi);
+    p.y = r * cm_sinf(phi);
     p.z = std::sqrt(std::fmax(0.0f, 1.0f - p.x * p.x - p.y * p.y));
     return p;
 }
@@ -162,8 +162,8 @@ f3 bsdf_sample(const Pbr& mat, f3 N, f3 V, uint32_t& seed) {   // Tracer::Sample
         const float phi = r1 * 2.0f * PIf;
         const float cosTheta = std::sqrt((1.0f - r2) / (1.0f + (a * a - 1.0f) * r2));
         const float sinTheta = std::sqrt(1.0f - (cosTheta * cosTheta));
-        const float sinPhi = std::sin(phi);
-        const float cosPhi = std::cos(phi);
+        const float sinPhi = cm_sinf(phi);
+        const float cosPhi = cm_cosf(phi);
         f3 half = f3{sinTheta * cosPhi, sinTheta * sinPhi, cosTheta};
         half = onb.inverse_transform(half);
         dir = 2.0f * dot(V, half) * half - V;
@@ -625,7 +625,7 @@ static inline uint8_t quantize8(float x) {
 }
 static inline float to_srgb(float c) {
     const float invGamma = 1.0f / 2.4f;
-    const float powed = std::pow(c, invGamma);
+    const float powed = cm_powf(c, invGamma);
     return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
 }
 static uint32_t tonemap_pack(f3 accum) {

@@ -21,6 +21,28 @@
 
 thread_local RefShimState g_shim;
 
+// Transcendentals: the reference is built with --use_fast_math (__sinf, __powf, ...), which a host build cannot
+// reproduce.  The shim gives sinf/cosf/logf/powf/expf the "contract" definition used by the oracle and by the
+// product's kernels: the fp64 libm function rounded once to fp32 (oracle/orc_math.h cm_*).  All standard
+// headers the reference pulls in are included above, before these macros.
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <map>
+#include <set>
+#include <queue>
+#include <random>
+static inline float ref_cm_sinf(float x) { return (float)::sin((double)x); }
+static inline float ref_cm_cosf(float x) { return (float)::cos((double)x); }
+static inline float ref_cm_logf(float x) { return (float)::log((double)x); }
+static inline float ref_cm_expf(float x) { return (float)::exp((double)x); }
+static inline float ref_cm_powf(float x, float y) { return (float)::pow((double)x, (double)y); }
+#define sinf ref_cm_sinf
+#define cosf ref_cm_cosf
+#define logf ref_cm_logf
+#define expf ref_cm_expf
+#define powf ref_cm_powf
+
 #include "rmis_patched.h"   // see oracle/Makefile: rmis.h with getMat() returning by value
 #include "hit_program.cu"
 #include "raygen.cu"

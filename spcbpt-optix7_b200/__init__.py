@@ -68,6 +68,7 @@ EXPECTED_SIZES = {"RAY": 32, "HIT": 16, "TEXREF": 40, "PBR": 144, "LIGHT": 80, "
                   "LT_PARAMS": 40, "PRETRACE_PARAMS": 32, "SAMPLER": 40, "SUBSPACE_INFO": 40, "ENV_INFO": 56,
                   "PARAMS": 352}
 
+LAUNCH_PT, LAUNCH_SPCBPT_EYE, LAUNCH_LIGHT_TRACE, LAUNCH_PRETRACE = 0, 1, 2, 3
 RAYFLAG_NONE = 0
 RAYFLAG_CULL_BACK_FACING = 1
 LIGHT_QUAD = 2
@@ -128,6 +129,11 @@ def _bind_optional(L):
     table = {
         "spc_gen_camera_rays": [vp, vp, i32, i32, i32, vp],
         "spc_gen_bench_rays": [vp, i32, vp, vp, i64, vp, vp],
+        "spc_set_params": [vp, vp],
+        "spc_launch": [vp, i32, i32, i32],
+        "spc_launch_named": [vp, ctypes.c_char_p, i32, i32],
+        "spc_set_debug_outputs": [vp, vp, vp],
+        "spc_lvc_process": [vp, vp, vp, i32, vp],
     }
     for name, args in table.items():
         if hasattr(L, name):
@@ -232,6 +238,27 @@ class Context:
         s = np.zeros(1, BVH_STATS)
         self._ck(self._L.spc_bvh_stats_get(self.h, s.ctypes.data), "spc_bvh_stats_get")
         return {k: s[0][k].item() for k in BVH_STATS.names}
+
+    # -- launch seam (sutil::Scene::switchRaygen + optixLaunch) and MyThrustOp seam -----------
+    def set_params(self, params):
+        """params: numpy array of dtype PARAMS (1 element) whose pointers are device addresses"""
+        assert params.dtype == PARAMS and params.size == 1
+        self._ck(self._L.spc_set_params(self.h, params.ctypes.data), "spc_set_params")
+
+    def launch(self, kind, width, height):
+        if isinstance(kind, str):
+            self._ck(self._L.spc_launch_named(self.h, kind.encode(), width, height), "spc_launch_named")
+        else:
+            self._ck(self._L.spc_launch(self.h, kind, width, height), "spc_launch")
+
+    def set_debug_outputs(self, first_prim_dev, first_label_dev):
+        self._ck(self._L.spc_set_debug_outputs(self.h, _ptr(first_prim_dev), _ptr(first_label_dev)), "spc_set_debug_outputs")
+
+    def lvc_process(self, lvc_dev, valid_dev, n):
+        """MyThrustOp::LVC_Process -> numpy SAMPLER record (device pointers owned by the context)"""
+        s = np.zeros(1, SAMPLER)
+        self._ck(self._L.spc_lvc_process(self.h, _ptr(lvc_dev), _ptr(valid_dev), n, s.ctypes.data), "spc_lvc_process")
+        return s
 
     # -- ray batches (host buffers: the e2e path) --------------------------------------------
     def trace(self, rays, flags=RAYFLAG_CULL_BACK_FACING):

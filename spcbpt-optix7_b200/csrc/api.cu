@@ -88,6 +88,7 @@ int spc_create(int device, int K, int K_light, int connections, spc_context** ou
 void spc_destroy(spc_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->c.device);
+    if (ctx->c.h_pinned) cudaFreeHost(ctx->c.h_pinned);
     delete ctx;
 }
 

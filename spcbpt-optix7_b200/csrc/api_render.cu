@@ -1,0 +1,85 @@
+// api_render.cu -- extern "C" entry points of the render path (launch seam + MyThrustOp seam).
+#include <cstring>
+#include "common.cuh"
+
+using spc::Context;
+
+#define SPC_API_BEGIN                                                                            \
+    if (!ctx) {                                                                                  \
+        spc::set_error("null context");                                                          \
+        return SPC_ERR_INVALID;                                                                  \
+    }                                                                                            \
+    Context& c = ctx->c;                                                                         \
+    (void)c;                                                                                     \
+    try {                                                                                        \
+        cudaSetDevice(c.device);
+
+#define SPC_API_END                                                                              \
+    }                                                                                            \
+    catch (const spc::CudaFailure& f) { return f.code; }                                         \
+    catch (const std::exception& e) {                                                            \
+        spc::set_error("exception: %s", e.what());                                               \
+        return SPC_ERR_INVALID;                                                                  \
+    }                                                                                            \
+    return SPC_OK;
+
+extern "C" {
+
+int spc_set_params(spc_context* ctx, const spc_params* params) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(params, SPC_ERR_INVALID, "spc_set_params: params is null");
+    SPC_REQUIRE(!params->sky.valid, SPC_ERR_INVALID, "spc_set_params: environment lighting (sky.valid) is not supported (unfinished in the reference, readme.md:28)");
+    c.params = *params;
+    c.has_params = true;
+    SPC_API_END
+}
+
+int spc_launch(spc_context* ctx, int kind, int width, int height) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(c.has_scene, SPC_ERR_NO_SCENE, "spc_launch: no scene uploaded");
+    switch (kind) {
+        case SPC_LAUNCH_LIGHT_TRACE:
+            SPC_REQUIRE(c.has_params && width == c.params.lt.num_core && height == 1, SPC_ERR_INVALID,
+                        "spc_launch(light trace): launch size must be (lt.num_core, 1)");
+            spc::launch_light_trace(c);
+            break;
+        case SPC_LAUNCH_SPCBPT_EYE:
+            spc::launch_eye_pass(c, width, height);
+            break;
+        default:
+            SPC_REQUIRE(false, SPC_ERR_INVALID, "spc_launch: raygen kind %d is not available in this build", kind);
+    }
+    SPC_API_END
+}
+
+int spc_launch_named(spc_context* ctx, const char* name, int width, int height) {
+    if (!name) {
+        spc::set_error("spc_launch_named: null name");
+        return SPC_ERR_INVALID;
+    }
+    int kind = -1;
+    if (!strcmp(name, "pt")) kind = SPC_LAUNCH_PT;
+    else if (!strcmp(name, "SPCBPT_eye")) kind = SPC_LAUNCH_SPCBPT_EYE;
+    else if (!strcmp(name, "light trace")) kind = SPC_LAUNCH_LIGHT_TRACE;
+    else if (!strcmp(name, "pretrace")) kind = SPC_LAUNCH_PRETRACE;
+    if (kind < 0) {
+        spc::set_error("spc_launch_named: unknown raygen '%s'", name);   // the reference throws (Scene.cpp:1693-1696)
+        return SPC_ERR_INVALID;
+    }
+    return spc_launch(ctx, kind, width, height);
+}
+
+int spc_set_debug_outputs(spc_context* ctx, int32_t* first_prim_dev, int32_t* first_label_dev) {
+    SPC_API_BEGIN
+    c.dbg_first_prim = first_prim_dev;
+    c.dbg_first_label = first_label_dev;
+    SPC_API_END
+}
+
+int spc_lvc_process(spc_context* ctx, const spc_vertex* lvc_dev, const uint8_t* valid_dev, int count_range, spc_subspace_sampler* out_host) {
+    SPC_API_BEGIN
+    spc::lvc_process(c, lvc_dev, valid_dev, count_range, out_host);
+    SPC_API_END
+}
+
+}  // extern "C"

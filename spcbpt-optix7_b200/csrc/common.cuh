@@ -91,6 +91,37 @@ struct SceneGeom {
     float            scene_lo[3], scene_hi[3];
 };
 
+// per-pixel path state + wavefront queues of the eye pass (render.cu), sized on first use
+struct EyeBuffers {
+    DevBuf<spc_vertex> ev;        // current eye vertex of every path (indexed by pixel)
+    DevBuf<float4>     pre;       // {pre-loaded BSDF value toward the sampled direction, pre-loaded singlePdf}
+    DevBuf<float4>     res;       // {radiance estimate of this subframe, seed bits}
+    DevBuf<spc_ray>    rays[2];   // ping-pong ray queues (queue order)
+    DevBuf<int>        queue[2];  // ping-pong pixel ids (queue order)
+    DevBuf<spc_hit>    hits;
+    DevBuf<spc_ray>    shadow;    // `connections` shadow rays per queue entry
+    DevBuf<uint8_t>    visible;
+    DevBuf<int>        conn_lvc;  // LVC index of every connection (-1: none)
+    DevBuf<float>      conn_pmf;  // path_count * pmf_1 * pmf_2
+    DevBuf<float4>     contrib;   // per connection: contribution / pmf / CONNECTION_N (0 when rejected)
+    DevBuf<int>        counts;    // counts[b] = live paths entering bounce b
+    size_t             pixels = 0;
+    int                conns = 0;
+};
+
+// outputs of the LVC binning (lvc.cu) = MyThrustOp::LVC_Process's SubspaceSampler arrays, owned by the context
+struct LvcBuffers {
+    DevBuf<spc_subspace> subspace;
+    DevBuf<float>        cmfs;
+    DevBuf<int>          jump;
+    DevBuf<float>        weight;      // per LVC slot
+    DevBuf<int>          key;         // per LVC slot: subspace id or -1
+    DevBuf<float>        wsorted;
+    DevBuf<int>          hist;        // [chunks][K]
+    DevBuf<int>          totals;      // [K] + counters
+    int                  n = 0;
+};
+
 struct Context {
     int           device = 0;
     int           K = 1000, K_light = 200, connections = 3;
@@ -106,6 +137,14 @@ struct Context {
     DevBuf<spc_hit> scratch_hits;
     DevBuf<uint8_t> scratch_vis;
     DevBuf<unsigned long long> counters;
+    // render path
+    spc_params    params = {};
+    bool          has_params = false;
+    EyeBuffers    eye;
+    LvcBuffers    lvc;
+    int*          dbg_first_prim = nullptr;    // optional device outputs of the eye pass (parity dumps)
+    int*          dbg_first_label = nullptr;
+    int*          h_pinned = nullptr;          // small pinned staging block for counter read-backs
 };
 
 void build_bvh(Context& ctx, const float4* d_tri_pos /*3 per prim*/, uint32_t n_prims);
@@ -114,6 +153,13 @@ void launch_trace_closest(Context& ctx, const spc_ray* rays, int64_t n, int flag
                           unsigned long long* counters /*nullable*/);
 void launch_trace_occlusion(Context& ctx, const spc_ray* rays, int64_t n, uint8_t* visible,
                             unsigned long long* counters /*nullable*/);
+
+void launch_trace_closest_q(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits);
+void launch_trace_occlusion_q(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, uint8_t* visible);
+
+void launch_light_trace(Context& ctx);                       // "light trace" raygen
+void launch_eye_pass(Context& ctx, int width, int height);   // "SPCBPT_eye" raygen
+void lvc_process(Context& ctx, const spc_vertex* lvc, const uint8_t* valid, int n, spc_subspace_sampler* out);
 
 }  // namespace spc
 

@@ -1,0 +1,190 @@
+// lvc.cu -- light-vertex-cache binning on the device.  Replaces MyThrustOp::LVC_Process
+// (cuda_thrust/device_thrust.cu:241-332), which copies the validity flags, subspace ids and weights of all
+// 800 k LVC slots to the host, buckets and prefix-sums them in a serial host loop and uploads three arrays
+// again every frame.  Here the same result is produced by five small kernels without leaving the GPU:
+//
+//   k_lvc_keys     per slot: key = subspace id (or -1 when invalid), weight = (flux.x+flux.y+flux.z)/pdf with
+//                  Inf/NaN -> 0 (device_thrust.cu:200-207); per-chunk histogram of the keys in shared memory
+//   k_lvc_colscan  per subspace: exclusive scan of its counts over the chunks (stable order = slot order)
+//   k_lvc_bias     exclusive scan over subspaces -> Subspace{jump_bias,id,size}; vertex_count
+//   k_lvc_scatter  stable counting-sort scatter (warp match-any ranks) -> jump_buffer + sorted weights
+//   k_lvc_cmf      per subspace (one warp): running fp32 sum IN SLOT ORDER -- the summation order of the
+//                  reference's host loop, so the cmf values are bit-identical -- then division by the total
+#include "shade.cuh"
+
+namespace spc {
+
+constexpr int kChunk = 2048;   // slots per warp-chunk
+
+__global__ void k_lvc_keys(const spc_vertex* __restrict__ lvc, const uint8_t* __restrict__ valid, int n, int K, int n_chunks,
+                           int* __restrict__ key, float* __restrict__ weight, int* __restrict__ hist, int* __restrict__ counters) {
+    extern __shared__ int s_hist[];   // [warps][K]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    int* h = s_hist + (size_t)warp * K;
+    for (int chunk = blockIdx.x * wpb + warp; chunk < n_chunks; chunk += gridDim.x * wpb) {
+        for (int k = lane; k < K; k += 32) h[k] = 0;
+        __syncwarp();
+        int n_begin = 0;
+        const int lo = chunk * kChunk, hi = min(n, lo + kChunk);
+        for (int i = lo + lane; i < hi; i += 32) {
+            int k = -1;
+            float w = 0.f;
+            if (valid[i]) {
+                const spc_vertex* v = lvc + i;
+                const int sid = v->subspaceId;
+                if (sid >= 0 && sid < K) {
+                    k = sid;
+                    float res = (v->flux.x + v->flux.y + v->flux.z) / v->pdf;
+                    res = isinf(res) ? 0 : res;
+                    w = isnan(res) ? 0 : res;
+                    if (v->depth == 0) n_begin++;
+                    atomicAdd(h + k, 1);
+                }
+            }
+            key[i] = k;
+            weight[i] = w;
+        }
+        __syncwarp();
+        for (int k = lane; k < K; k += 32) hist[(size_t)chunk * K + k] = h[k];
+        for (int o = 16; o > 0; o >>= 1) n_begin += __shfl_xor_sync(0xffffffffu, n_begin, o);
+        if (lane == 0 && n_begin) atomicAdd(counters + 1, n_begin);   // path_count = #valid depth-0 vertices
+        __syncwarp();
+    }
+}
+
+// hist[chunk][k] -> exclusive prefix over chunks (in place); totals[k] = size of subspace k
+__global__ void k_lvc_colscan(int* __restrict__ hist, int n_chunks, int K, int* __restrict__ totals) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    int run = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        const int v = hist[(size_t)c * K + k];
+        hist[(size_t)c * K + k] = run;
+        run += v;
+    }
+    totals[k] = run;
+}
+
+// one block: exclusive scan of totals -> Subspace records; counters[0] = vertex_count
+__global__ void k_lvc_bias(const int* __restrict__ totals, int K, spc_subspace* __restrict__ sub, int* __restrict__ counters) {
+    __shared__ int s_part[1024];
+    const int t = threadIdx.x, T = blockDim.x;
+    const int per = (K + T - 1) / T;
+    const int lo = min(K, t * per), hi = min(K, lo + per);
+    int s = 0;
+    for (int k = lo; k < hi; k++) s += totals[k];
+    s_part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int run = 0;
+        for (int i = 0; i < T; i++) { const int v = s_part[i]; s_part[i] = run; run += v; }
+        counters[0] = run;
+    }
+    __syncthreads();
+    int run = s_part[t];
+    for (int k = lo; k < hi; k++) {
+        sub[k].jump_bias = run;
+        sub[k].id = k;
+        sub[k].size = totals[k];
+        sub[k].Q = 0.f;
+        run += totals[k];
+    }
+}
+
+__global__ void k_lvc_scatter(const int* __restrict__ key, const float* __restrict__ weight, int n, int K, int n_chunks,
+                              const int* __restrict__ hist, const spc_subspace* __restrict__ sub, int* __restrict__ jump,
+                              float* __restrict__ wsorted) {
+    extern __shared__ int s_cur[];   // [warps][K] write cursors
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    int* cur = s_cur + (size_t)warp * K;
+    for (int chunk = blockIdx.x * wpb + warp; chunk < n_chunks; chunk += gridDim.x * wpb) {
+        for (int k = lane; k < K; k += 32) cur[k] = sub[k].jump_bias + hist[(size_t)chunk * K + k];
+        __syncwarp();
+        const int lo = chunk * kChunk, hi = min(n, lo + kChunk);
+        for (int base = lo; base < hi; base += 32) {
+            const int i = base + lane;
+            const int k = i < hi ? key[i] : -1;
+            const unsigned active = __ballot_sync(0xffffffffu, k >= 0);
+            if (k >= 0) {
+                const unsigned peers = __match_any_sync(active, k);
+                const int rank = __popc(peers & ((1u << lane) - 1u));
+                const int pos = cur[k] + rank;
+                jump[pos] = i;
+                wsorted[pos] = weight[i];
+                __syncwarp(active);
+                if (rank == 0) cur[k] += __popc(peers);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// one warp per subspace: sequential running sum in slot order, then normalise
+__global__ void k_lvc_cmf(spc_subspace* __restrict__ sub, int K, const float* __restrict__ wsorted, float* __restrict__ cmfs) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= K) return;
+    const int bias = sub[warp].jump_bias, size = sub[warp].size;
+    float run = 0.f;
+    bool first = true;
+    for (int base = 0; base < size; base += 32) {
+        const int i = base + lane;
+        const float w = i < size ? wsorted[bias + i] : 0.f;
+        float mine = 0.f;
+        const int m = min(32, size - base);
+        for (int j = 0; j < m; j++) {
+            const float wj = __shfl_sync(0xffffffffu, w, j);
+            // the reference's first element is the weight itself, later ones `w + previous` (device_thrust.cu:281-286)
+            run = first ? wj : wj + run;
+            first = false;
+            if (j == lane) mine = run;
+        }
+        if (i < size) cmfs[bias + i] = mine;
+    }
+    // Q_subspace_vertex[s] += w accumulates the same sequence starting from 0: 0 + w0 = w0, so it equals the last running sum
+    const float total = size > 0 ? run : 0.f;
+    if (lane == 0) sub[warp].sum_pmf = total;
+    __syncwarp();
+    for (int i = lane; i < size; i += 32) cmfs[bias + i] = cmfs[bias + i] / total;
+}
+
+void lvc_process(Context& c, const spc_vertex* lvc, const uint8_t* valid, int n, spc_subspace_sampler* out) {
+    SPC_REQUIRE(lvc && valid && n > 0 && out, SPC_ERR_INVALID, "spc_lvc_process: bad arguments");
+    const int K = c.K;
+    LvcBuffers& b = c.lvc;
+    const int n_chunks = (n + kChunk - 1) / kChunk;
+    b.subspace.alloc(K); b.cmfs.alloc(n); b.jump.alloc(n); b.weight.alloc(n); b.key.alloc(n); b.wsorted.alloc(n);
+    b.hist.alloc((size_t)n_chunks * K); b.totals.alloc(K + 8);
+    b.n = n;
+    if (!c.h_pinned) SPC_CUDA(cudaMallocHost((void**)&c.h_pinned, 64 * sizeof(int)));
+    cudaStream_t st = c.stream;
+    int* counters = b.totals.p + K;
+    SPC_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(int), st));
+    // shared memory: K ints per warp; as many warps per block as fit in 160 KB (K = 1000 -> 8 warps, 32 KB)
+    int wpb = (int)std::min<size_t>(8, (160 * 1024) / ((size_t)K * 4));
+    SPC_REQUIRE(wpb >= 1, SPC_ERR_CAPACITY, "spc_lvc_process: K=%d does not fit the shared-memory histogram", K);
+    const size_t smem = (size_t)wpb * K * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPC_CUDA(cudaFuncSetAttribute(k_lvc_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SPC_CUDA(cudaFuncSetAttribute(k_lvc_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const int grid = std::max(1, std::min((n_chunks + wpb - 1) / wpb, c.sm_count * 4));
+    k_lvc_keys<<<grid, wpb * 32, smem, st>>>(lvc, valid, n, K, n_chunks, b.key.p, b.weight.p, b.hist.p, counters);
+    k_lvc_colscan<<<(K + 127) / 128, 128, 0, st>>>(b.hist.p, n_chunks, K, b.totals.p);
+    k_lvc_bias<<<1, 1024, 0, st>>>(b.totals.p, K, b.subspace.p, counters);
+    k_lvc_scatter<<<grid, wpb * 32, smem, st>>>(b.key.p, b.weight.p, n, K, n_chunks, b.hist.p, b.subspace.p, b.jump.p, b.wsorted.p);
+    k_lvc_cmf<<<(K * 32 + 127) / 128, 128, 0, st>>>(b.subspace.p, K, b.wsorted.p, b.cmfs.p);
+    c.launches += 5;
+    SPC_CUDA(cudaGetLastError());
+    SPC_CUDA(cudaMemcpyAsync(c.h_pinned, counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SPC_CUDA(cudaStreamSynchronize(st));
+    out->LVC = lvc;
+    out->subspace = b.subspace.p;
+    out->cmfs = b.cmfs.p;
+    out->jump_buffer = b.jump.p;
+    out->vertex_count = c.h_pinned[0];
+    out->path_count = c.h_pinned[1];
+}
+
+}  // namespace spc

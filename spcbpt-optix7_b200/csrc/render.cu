@@ -1,0 +1,419 @@
+// render.cu -- the two per-frame passes of SPCBPT as hand-written CUDA for sm_100a:
+//   * light trace  (replaces optixLaunch of __raygen__lightTrace, raygen.cu:620-685, + the closest-hit programs
+//                   __closesthit__lightSubpath / __closesthit__lightSource_subpath, hit_program.cu:341-438,239-244)
+//   * eye pass     (replaces optixLaunch of __raygen__SPCBPT, raygen.cu:319-443, + __closesthit__eyeSubpath /
+//                   __closesthit__eyeSubpath_LightSource, hit_program.cu:246-340,62-147)
+// The eye pass is a wavefront: per bounce  trace -> shade+classify+sample connections -> shadow rays ->
+// connection eval + MIS -> ordered gather, with queue sizes kept on the device (no host round trip per stage).
+#include <algorithm>
+#include "shade.cuh"
+#include "traverse.cuh"
+
+namespace spc {
+
+static DevFrame make_frame(Context& c) {
+    DevFrame fr;
+    fr.sc.tri_pos = c.geom.tri_pos.p;
+    fr.sc.tri_uv = c.geom.tri_uv.p;
+    fr.sc.materials = c.geom.materials.p;
+    fr.sc.lights = c.geom.lights.p;
+    fr.sc.tex_data = c.geom.tex_data.p;
+    fr.sc.tex_desc = c.geom.tex_desc.p;
+    fr.sc.nodes = c.bvh.nodes.p;
+    fr.sc.tris = c.bvh.tris.p;
+    fr.sc.n_lights = c.geom.n_lights;
+    fr.sc.n_materials = c.geom.n_materials;
+    fr.p = c.params;
+    fr.K = c.K;
+    fr.connections = c.connections;
+    fr.max_depth = c.params.max_depth > 0 ? c.params.max_depth : 50;
+    return fr;
+}
+
+// =============================================================================================
+// light trace, reference streams: one sequential "core" per launch index.  The reference's two RNG
+// streams per core (raygen side: 5 draws per path; hit side: 4 draws per bounce, both started from the same
+// state, raygen.cu:624-628) make path j of a core depend on the bounce counts of paths < j, so a core is
+// inherently serial; the 1000 cores run one per warp (lane 0) to keep every SM scheduler busy without
+// intra-warp divergence.  This kernel is latency-bound by construction and is meant to run on a side
+// stream under the previous frame's eye pass.
+// =============================================================================================
+constexpr int kLtWarps = 4;
+
+__global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFrame fr) {
+    __shared__ uint2 s_stack[kSmStack * kLtWarps];
+    const int warp = threadIdx.x >> 5;
+    const int core = blockIdx.x * kLtWarps + warp;
+    const spc_light_trace_params& lt = fr.p.lt;
+    if ((threadIdx.x & 31) != 0 || core >= lt.num_core) return;
+
+    uint32_t seed = tea<4>((uint32_t)core, (uint32_t)lt.launch_frame);
+    uint32_t hit_seed = seed;   // payload.seed: a copy taken once (raygen.cu:628)
+    const unsigned bias = (unsigned)lt.core_padding * (unsigned)core;
+    unsigned n_vert = 0, n_path = 0;
+    const unsigned cap = (unsigned)lt.core_padding;
+    unsigned cn = 0, ct = 0;
+
+    while (true) {
+        const int li = pick_light(fr, seed);
+        LightSample ls;
+        {
+            const float r1 = rnd(seed);
+            const float r2 = rnd(seed);
+            light_reverse_sample(fr, li, r1, r2, ls);   // lightSample::operator(), cuProg.h:602-621
+        }
+        light_trace_mode(ls, seed);
+        float3 ray_direction = ls.direction;
+        float3 ray_origin = ls.position;
+        Vtx cur;
+        vtx_zero(cur);
+        init_vertex_from_light_sample(ls, cur);
+        float3 pre_flux = f3(0.f);
+        float pre_singlePdf = ls.dir_pdf;   // init_lightSubPath_from_lightSample, raygen.cu:196-213
+        vtx_store(lt.ans + bias + n_vert, cur);
+        lt.validState[bias + n_vert] = 1;
+        n_vert++;
+        if (!(n_vert < cap)) break;
+        bool done = false;
+        int depth = 0;
+        while (true) {
+            TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
+            TravHit h;
+            bool pushed = false;
+            if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, s_stack + warp, kLtWarps, h, cn, ct)) {
+                done = true;                                   // __miss__BDPTVertex, raygen.cu:699-704
+            } else {
+                const LocalGeom g = hit_geometry(fr.sc, h.prim, h.u, h.v);
+                if (g.light >= 0) {
+                    done = true;                               // __closesthit__lightSource_subpath, hit_program.cu:239-244
+                } else {
+                    Vtx mid;
+                    SurfaceOut so;
+                    surface_hit(fr, cur, pre_flux, pre_singlePdf, g, h.t, ray_direction, true, hit_seed, mid, so);
+                    cur = mid;
+                    pre_flux = so.next_flux;
+                    pre_singlePdf = so.next_singlePdf;
+                    ray_direction = so.dir;
+                    ray_origin = g.P;
+                    done = so.done;
+                    pushed = true;
+                }
+            }
+            if (pushed) {
+                vtx_store(lt.ans + bias + n_vert, cur);
+                lt.validState[bias + n_vert] = 1;
+                n_vert++;
+                if (!(n_vert < cap)) break;
+            }
+            if (done || depth > fr.max_depth) break;
+            depth += 1;
+        }
+        n_path++;
+        if (n_path >= (unsigned)lt.M_per_core) break;
+        if (!(n_vert < cap)) break;
+    }
+    for (unsigned i = n_vert; i < cap; i++) lt.validState[bias + i] = 0;
+}
+
+void launch_light_trace(Context& c) {
+    SPC_REQUIRE(c.has_params, SPC_ERR_INVALID, "spc_launch: spc_set_params has not been called");
+    const spc_light_trace_params& lt = c.params.lt;
+    SPC_REQUIRE(lt.num_core > 0 && lt.core_padding > 0 && lt.ans && lt.validState, SPC_ERR_INVALID, "spc_launch(light trace): MyParams::lt is not set up");
+    SPC_REQUIRE(c.geom.n_lights > 0, SPC_ERR_NO_SCENE, "spc_launch(light trace): the scene has no lights");
+    const DevFrame fr = make_frame(c);
+    k_light_trace_cores<<<(lt.num_core + kLtWarps - 1) / kLtWarps, kLtWarps * 32, 0, c.stream>>>(fr);
+    SPC_CUDA(cudaGetLastError());
+    c.launches++;
+}
+
+// =============================================================================================
+// eye pass
+// =============================================================================================
+struct EyeArgs {
+    spc_vertex* ev;
+    float4*     pre;
+    float4*     res;
+    float4*     rays_cur;
+    float4*     rays_next;
+    int*        queue_cur;
+    int*        queue_next;
+    const float4* hits;
+    float4*     shadow;
+    const uint8_t* visible;
+    int*        conn_lvc;
+    float*      conn_pmf;
+    float4*     contrib;
+    int*        counts;     // counts[bounce] in, counts[bounce+1] out
+    int*        first_prim;
+    int*        first_label;
+    int         bounce;
+};
+
+// raygen part of __raygen__SPCBPT (raygen.cu:321-353) + init_EyeSubpath (:216-231)
+__global__ void k_eye_init(const DevFrame fr, const EyeArgs a, int n_pix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const unsigned W = fr.p.width, H = fr.p.height;
+    const unsigned x = (unsigned)i % W, y = (unsigned)i / W;
+    uint32_t seed = tea<4>((uint32_t)i, fr.p.subframe_index);
+    float jx = 0.5f, jy = 0.5f;
+    if (fr.p.subframe_index != 0) {   // make_float2(rnd(seed), rnd(seed)): nvcc evaluates left to right
+        jx = rnd(seed);
+        jy = rnd(seed);
+    }
+    const float dx = 2.0f * (((float)x + jx) / (float)W) - 1.0f;
+    const float dy = 2.0f * (((float)y + jy) / (float)H) - 1.0f;
+    const float3 eye = ld3(fr.p.eye);
+    const float3 d = normalize(dx * ld3(fr.p.U) + dy * ld3(fr.p.V) + ld3(fr.p.W));
+    Vtx v;
+    vtx_zero(v);
+    v.position = eye;
+    v.flux = f3(1.0f);
+    v.pdf = 1.0f;
+    v.RMIS_pointer = 0;
+    v.normal = d;
+    v.isOrigin = 1;
+    v.depth = 0;
+    v.singlePdf = 1.0f;
+    vtx_store(a.ev + i, v);
+    a.pre[i] = make_float4(0.f, 0.f, 0.f, 1.0f);
+    a.res[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(seed));
+    a.queue_cur[i] = i;
+    a.rays_cur[2 * (size_t)i] = make_float4(eye.x, eye.y, eye.z, SPC_SCENE_EPS);
+    a.rays_cur[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, 1e16f);
+    if (a.first_prim) a.first_prim[i] = -1;
+    if (a.first_label) a.first_label[i] = -1;
+    if (i == 0) a.counts[0] = n_pix;
+}
+
+// closest-hit programs + connection sampling of one bounce; one lane per live path
+__global__ void __launch_bounds__(128) k_eye_shade(const DevFrame fr, const EyeArgs a) {
+    const int n = a.counts[a.bounce];
+    const int C = fr.connections;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool alive = false;
+        float4 nro, nrd;
+        int pix = 0;
+        if (i < n) {
+            pix = a.queue_cur[i];
+            const float4 hit = a.hits[i];
+            const int prim = __float_as_int(hit.w);
+            for (int j = 0; j < C; j++) {   // default: no connection in this slot (an empty-interval shadow ray)
+                a.conn_lvc[(size_t)i * C + j] = -1;
+                a.shadow[2 * ((size_t)i * C + j)] = make_float4(0.f, 0.f, 0.f, 1.0f);
+                a.shadow[2 * ((size_t)i * C + j) + 1] = make_float4(0.f, 0.f, 1.f, -1.0f);
+            }
+            if (a.bounce == 0 && a.first_prim) a.first_prim[pix] = prim;
+            if (prim >= 0) {
+                const float4 rd4 = a.rays_cur[2 * (size_t)i + 1];
+                const float3 ray_direction = f3(rd4.x, rd4.y, rd4.z);
+                const Vtx last = vtx_load(a.ev + pix);
+                const float4 pre = a.pre[pix];
+                float4 res = a.res[pix];
+                uint32_t seed = __float_as_uint(res.w);
+                const LocalGeom g = hit_geometry(fr.sc, prim, hit.y, hit.z);
+                Vtx mid;
+                if (g.light >= 0) {
+                    // __closesthit__eyeSubpath_LightSource + lightStraghtHit (raygen.cu:305-317, :383-388)
+                    if (eye_hits_light(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, hit.x, ray_direction, mid)) {
+                        if (a.bounce == 0 && a.first_label) a.first_label[pix] = mid.subspaceId;
+                        const float3 ans = mid.flux / mid.pdf / mid.RMIS_pointer;
+                        if (!invalid3(ans)) {
+                            res.x += ans.x; res.y += ans.y; res.z += ans.z;
+                            a.res[pix] = res;
+                        }
+                    }
+                } else {
+                    SurfaceOut so;
+                    surface_hit(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, hit.x, ray_direction, false, seed, mid, so);
+                    if (a.bounce == 0 && a.first_label) a.first_label[pix] = mid.subspaceId;
+                    vtx_store(a.ev + pix, mid);
+                    a.pre[pix] = make_float4(so.next_flux.x, so.next_flux.y, so.next_flux.z, so.next_singlePdf);
+                    // CONNECTION_N probabilistic connections (raygen.cu:390-419): stage 1 picks a light subspace from
+                    // row eye-subspace of the Gamma CDF, stage 2 a vertex of that subspace from its cmf
+                    const spc_subspace_sampler& S = fr.p.sampler;
+                    for (int j = 0; j < C; j++) {
+                        int light_id = 0;
+                        float pmf1 = 1;
+                        if (fr.p.subspace_info.light_tree)
+                            light_id = binary_sample(fr.p.subspace_info.CMFGamma + (size_t)mid.subspaceId * fr.K, fr.K, seed, pmf1);
+                        const spc_subspace sub = S.subspace[light_id];
+                        if (sub.size != 0) {
+                            float pmf2;
+                            const int index = binary_sample(S.cmfs + sub.jump_bias, sub.size, seed, pmf2) + sub.jump_bias;
+                            const int lv = S.jump_buffer[index];
+                            const spc_vertex* L = S.LVC + lv;
+                            const float3 lp = f3(L->position.x, L->position.y, L->position.z);
+                            // visibilityTest (cuProg.h:489-502 -> :463-487)
+                            const float3 bias_pos = lp - mid.position;
+                            const float len = length(bias_pos);
+                            const float3 dir = bias_pos / len;
+                            a.shadow[2 * ((size_t)i * C + j)] = make_float4(mid.position.x, mid.position.y, mid.position.z, SPC_SCENE_EPS);
+                            a.shadow[2 * ((size_t)i * C + j) + 1] = make_float4(dir.x, dir.y, dir.z, len - SPC_SCENE_EPS);
+                            a.conn_lvc[(size_t)i * C + j] = lv;
+                            a.conn_pmf[(size_t)i * C + j] = (float)S.path_count * pmf2 * pmf1;
+                        }
+                    }
+                    res.w = __uint_as_float(seed);
+                    a.res[pix] = res;
+                    // loop head of the next iteration (raygen.cu:361): payload.done || payload.depth > 50
+                    alive = !so.done && !(a.bounce + 1 > fr.max_depth);
+                    nro = make_float4(g.P.x, g.P.y, g.P.z, SPC_SCENE_EPS);
+                    nrd = make_float4(so.dir.x, so.dir.y, so.dir.z, 1e16f);
+                }
+            }
+        }
+        // warp-vote compaction of the survivors into the next queue
+        const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+        if (ballot) {
+            const int lane = threadIdx.x & 31;
+            int slot0 = 0;
+            if (lane == (__ffs(ballot) - 1)) slot0 = atomicAdd(a.counts + a.bounce + 1, __popc(ballot));
+            slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(ballot) - 1);
+            if (alive) {
+                const int slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
+                a.queue_next[slot] = pix;
+                a.rays_next[2 * (size_t)slot] = nro;
+                a.rays_next[2 * (size_t)slot + 1] = nrd;
+            }
+        }
+    }
+}
+
+// connectVertex_SPCBPT (raygen.cu:253-303) for every visible connection; one lane per connection
+__global__ void __launch_bounds__(128) k_eye_connect(const DevFrame fr, const EyeArgs a) {
+    const int C = fr.connections;
+    const int64_t n = (int64_t)a.counts[a.bounce] * C;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        float3 term = f3(0.f);
+        const int lv = a.conn_lvc[k];
+        if (lv >= 0 && a.visible[k]) {
+            const int pix = a.queue_cur[k / C];
+            const Vtx eye = vtx_load(a.ev + pix);
+            const Vtx light = vtx_load(fr.p.sampler.LVC + lv);
+            const float3 c = connect_vertices(fr, eye, light, nullptr);
+            const float3 res = c / a.conn_pmf[k];
+            if (!invalid3(res)) term = res / (float)C;
+        }
+        a.contrib[k] = make_float4(term.x, term.y, term.z, 0.f);
+    }
+}
+
+// result += res / CONNECTION_N, in connection order (raygen.cu:415)
+__global__ void k_eye_gather(const DevFrame fr, const EyeArgs a) {
+    const int C = fr.connections;
+    const int n = a.counts[a.bounce];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pix = a.queue_cur[i];
+        float4 r = a.res[pix];
+        bool any = false;
+        for (int j = 0; j < C; j++) {
+            if (a.conn_lvc[(size_t)i * C + j] < 0) continue;
+            const float4 t = a.contrib[(size_t)i * C + j];
+            r.x += t.x; r.y += t.y; r.z += t.z;
+            any = true;
+        }
+        if (any) a.res[pix] = r;
+    }
+}
+
+// running mean + ToneMap (raygen.cu:50-58, :430-442) + make_color (src/cuda/helpers.h:35-67)
+__device__ __forceinline__ unsigned quantize8(float x) {
+    x = clampf(x, 0.0f, 1.0f);
+    return min((unsigned)(x * 256.0f), 255u);
+}
+__device__ __forceinline__ float to_srgb(float c) {
+    const float invGamma = 1.0f / 2.4f;
+    const float powed = cm_powf(c, invGamma);
+    return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
+}
+__global__ void k_accumulate(const DevFrame fr, const float4* __restrict__ res, int n_pix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const float4 r = res[i];
+    float3 c = f3(r.x, r.y, r.z);
+    if (fr.p.subframe_index > 0) {
+        const float t = 1.0f / (float)(int)(fr.p.subframe_index + 1);
+        const spc_float4 prev = fr.p.accum_buffer[i];
+        c = lerp3(f3(prev.x, prev.y, prev.z), c, t);
+    }
+    fr.p.accum_buffer[i] = spc_float4{c.x, c.y, c.z, 1.0f};
+    if (fr.p.frame_buffer) {
+        const float lum = 0.3f * c.x + 0.6f * c.y + 0.1f * c.z;
+        const float s = 1.0f + 1 * lum / 1.5f;
+        const float inv = 1.0f / s;   // `c * 1.0f / s` on a float4 multiplies by the reciprocal (sutil/vec_math.h:720-724)
+        const float3 v = f3(clampf(c.x * 1.0f * inv, 0.f, 1.f), clampf(c.y * 1.0f * inv, 0.f, 1.f), clampf(c.z * 1.0f * inv, 0.f, 1.f));
+        fr.p.frame_buffer[i] = quantize8(to_srgb(v.x)) | (quantize8(to_srgb(v.y)) << 8) | (quantize8(to_srgb(v.z)) << 16) | (255u << 24);
+    }
+}
+
+void launch_eye_pass(Context& c, int width, int height) {
+    SPC_REQUIRE(c.has_params, SPC_ERR_INVALID, "spc_launch: spc_set_params has not been called");
+    SPC_REQUIRE(width > 0 && height > 0 && (unsigned)width == c.params.width && (unsigned)height == c.params.height, SPC_ERR_INVALID,
+                "spc_launch(SPCBPT_eye): launch size %dx%d differs from MyParams %ux%u", width, height, c.params.width, c.params.height);
+    SPC_REQUIRE(c.params.accum_buffer, SPC_ERR_INVALID, "spc_launch(SPCBPT_eye): MyParams::accum_buffer is null");
+    const spc_subspace_sampler& S = c.params.sampler;
+    SPC_REQUIRE(S.LVC && S.subspace && S.cmfs && S.jump_buffer, SPC_ERR_INVALID, "spc_launch(SPCBPT_eye): MyParams::sampler is not set (run LVC_Process first)");
+    SPC_REQUIRE(!c.params.subspace_info.light_tree || c.params.subspace_info.CMFGamma, SPC_ERR_INVALID,
+                "spc_launch(SPCBPT_eye): light_tree without CMFGamma");
+    const size_t P = (size_t)width * height;
+    SPC_REQUIRE(P < 0x7fffffffull / 16, SPC_ERR_INVALID, "spc_launch: image too large");
+    const DevFrame fr = make_frame(c);
+    const int C = c.connections;
+    EyeBuffers& e = c.eye;
+    if (e.pixels < P || e.conns != C) {
+        e.ev.alloc(P); e.pre.alloc(P); e.res.alloc(P);
+        for (int k = 0; k < 2; k++) { e.rays[k].alloc(P); e.queue[k].alloc(P); }
+        e.hits.alloc(P);
+        e.shadow.alloc(P * C); e.visible.alloc(P * C); e.conn_lvc.alloc(P * C); e.conn_pmf.alloc(P * C); e.contrib.alloc(P * C);
+        e.pixels = P; e.conns = C;
+    }
+    const int n_counts = fr.max_depth + 4;
+    e.counts.alloc(n_counts);
+    if (!c.h_pinned) SPC_CUDA(cudaMallocHost((void**)&c.h_pinned, 64 * sizeof(int)));
+    cudaStream_t st = c.stream;
+    SPC_CUDA(cudaMemsetAsync(e.counts.p, 0, n_counts * sizeof(int), st));
+
+    EyeArgs a;
+    a.ev = e.ev.p; a.pre = e.pre.p; a.res = e.res.p;
+    a.hits = (const float4*)e.hits.p; a.shadow = (float4*)e.shadow.p; a.visible = e.visible.p;
+    a.conn_lvc = e.conn_lvc.p; a.conn_pmf = e.conn_pmf.p; a.contrib = e.contrib.p; a.counts = e.counts.p;
+    a.first_prim = c.dbg_first_prim; a.first_label = c.dbg_first_label;
+    a.bounce = 0;
+    a.rays_cur = (float4*)e.rays[0].p; a.rays_next = (float4*)e.rays[1].p;
+    a.queue_cur = e.queue[0].p; a.queue_next = e.queue[1].p;
+
+    const int nP = (int)P;
+    k_eye_init<<<(nP + 255) / 256, 256, 0, st>>>(fr, a, nP);
+    c.launches++;
+    const int grid_cap = c.sm_count * 16;
+    int64_t n_max = nP;   // host-side upper bound on the live paths (refreshed by the occasional read-back)
+    // loop of raygen.cu:357-421: a path is traced while !done && depth <= max_depth, i.e. bounces 0..max_depth
+    for (int b = 0; b <= fr.max_depth; b++) {
+        a.bounce = b;
+        a.rays_cur = (float4*)e.rays[b & 1].p; a.rays_next = (float4*)e.rays[(b + 1) & 1].p;
+        a.queue_cur = e.queue[b & 1].p; a.queue_next = e.queue[(b + 1) & 1].p;
+        launch_trace_closest_q(c, (const spc_ray*)a.rays_cur, e.counts.p + b, 1, n_max, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);
+        const int g1 = (int)std::min<int64_t>((n_max + 127) / 128, grid_cap);
+        k_eye_shade<<<g1, 128, 0, st>>>(fr, a);
+        launch_trace_occlusion_q(c, (const spc_ray*)a.shadow, e.counts.p + b, C, n_max * C, e.visible.p);
+        const int g2 = (int)std::min<int64_t>((n_max * C + 127) / 128, grid_cap);
+        k_eye_connect<<<g2, 128, 0, st>>>(fr, a);
+        k_eye_gather<<<g1, 128, 0, st>>>(fr, a);
+        c.launches += 3;
+        SPC_CUDA(cudaGetLastError());
+        // every 4th bounce: read the next queue size back to shrink the grids / stop early
+        if ((b & 3) == 3 && b < fr.max_depth) {
+            SPC_CUDA(cudaMemcpyAsync(c.h_pinned, e.counts.p + b + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            SPC_CUDA(cudaStreamSynchronize(st));
+            n_max = c.h_pinned[0];
+            if (n_max == 0) break;
+        }
+    }
+    k_accumulate<<<(nP + 255) / 256, 256, 0, st>>>(fr, e.res.p, nP);
+    c.launches++;
+    SPC_CUDA(cudaGetLastError());
+}
+
+}  // namespace spc

@@ -118,10 +118,92 @@ def compare_lvc(pkg, a, valid_a, b, valid_b, exact=True, rtol=1e-5):
         m = v & ~origin if name in UNDEFINED_ON_ORIGIN else v
         x, y = a[name][m], b[name][m]
         if exact or x.dtype.kind in "iu":
-            if not np.array_equal(x.view(np.uint8), y.view(np.uint8)):
-                bad.append("%s: %d of %d differ" % (name, int((x != y).sum()), x.size))
+            if x.dtype.kind == "f":
+                # bit-exact, except that NaNs only have to be NaNs on both sides (x86 and CUDA produce different NaN payloads)
+                ne = (x.view(np.uint32) != y.view(np.uint32)) & ~(np.isnan(x) & np.isnan(y))
+            else:
+                ne = x != y
+            if ne.any():
+                bad.append("%s: %d of %d differ" % (name, int(ne.sum()), x.size))
         else:
             err = np.abs(x - y) / np.maximum(np.abs(y), 1e-20)
             if not (err <= rtol).all():
                 bad.append("%s: max rel err %g" % (name, float(err.max())))
     return bad
+
+
+class DeviceFrame:
+    """The same buffers as HostFrame, in device memory (torch tensors are only the allocator here), with a
+    MyParams whose pointers are device addresses -- what a reference host hands to the launch seam."""
+
+    def __init__(self, pkg, scene, width, height, K=1000, num_core=1000, core_padding=800, M_per_core=100):
+        import torch
+        self.torch, self.pkg, self.scene, self.K = torch, pkg, scene, K
+        self.w, self.h = width, height
+        self.P = np.zeros(1, pkg.PARAMS)
+        P = self.P
+        eye, U, V, W = scene.camera_frame(width, height)
+        P["width"], P["height"] = width, height
+        P["eye"], P["U"], P["V"], P["W"] = eye, U, V, W
+        dev = "cuda"
+        self.accum = torch.zeros((width * height, 4), dtype=torch.float32, device=dev)
+        self.frame = torch.zeros(width * height, dtype=torch.int32, device=dev)
+        P["accum_buffer"], P["frame_buffer"] = self.accum.data_ptr(), self.frame.data_ptr()
+        n = num_core * core_padding
+        self.n_lvc = n
+        self.lvc = torch.zeros(n * pkg.VERTEX.itemsize, dtype=torch.uint8, device=dev)
+        self.valid = torch.zeros(n, dtype=torch.uint8, device=dev)
+        lt = P["lt"]
+        lt["num_core"], lt["core_padding"], lt["M_per_core"], lt["M"] = num_core, core_padding, M_per_core, num_core * M_per_core
+        lt["ans"], lt["validState"] = self.lvc.data_ptr(), self.valid.data_ptr()
+        P["subspace_info"]["subspaceNum"] = K
+        self.keep = {}
+
+    def _up(self, arr):
+        return self.torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).cuda()
+
+    def set_trees(self, eye_tree, light_tree):
+        self.keep["eye_tree"] = self._up(np.ascontiguousarray(eye_tree, self.pkg.TREE_NODE))
+        self.keep["light_tree"] = self._up(np.ascontiguousarray(light_tree, self.pkg.TREE_NODE))
+        self.P["subspace_info"]["eye_tree"] = self.keep["eye_tree"].data_ptr()
+        self.P["subspace_info"]["light_tree"] = self.keep["light_tree"].data_ptr()
+
+    def set_q_gamma(self, Q, cmf_gamma):
+        self.keep["Q"] = self._up(np.ascontiguousarray(Q, np.float32))
+        self.keep["CMF"] = self._up(np.ascontiguousarray(cmf_gamma, np.float32))
+        self.P["subspace_info"]["Q"] = self.keep["Q"].data_ptr()
+        self.P["subspace_info"]["CMFGamma"] = self.keep["CMF"].data_ptr()
+
+    def upload_lvc(self, lvc, valid):
+        self.lvc.copy_(self._up(lvc))
+        self.valid.copy_(self._up(valid))
+
+    def lvc_host(self):
+        return self.lvc.cpu().numpy().view(self.pkg.VERTEX).copy(), self.valid.cpu().numpy().copy()
+
+    def set_sampler_record(self, rec):
+        self.P["sampler"] = rec[0]
+
+    def sampler_host(self):
+        """download the SubspaceSampler arrays the record points at (through torch's raw-pointer free path: cudaMemcpy via ctypes)"""
+        import ctypes
+        s = self.P["sampler"][0]
+        vc = int(s["vertex_count"])
+        rt = ctypes.CDLL("libcudart.so.12")
+        rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        self.torch.cuda.synchronize()
+        sub = np.zeros(self.K, self.pkg.SUBSPACE)
+        cmfs = np.zeros(max(vc, 1), np.float32)
+        jump = np.zeros(max(vc, 1), np.int32)
+        assert rt.cudaMemcpy(sub.ctypes.data, int(s["subspace"]), sub.nbytes, 2) == 0
+        if vc:
+            assert rt.cudaMemcpy(cmfs.ctypes.data, int(s["cmfs"]), vc * 4, 2) == 0
+            assert rt.cudaMemcpy(jump.ctypes.data, int(s["jump_buffer"]), vc * 4, 2) == 0
+        return sub, cmfs[:vc], jump[:vc], vc, int(s["path_count"])
+
+
+def float_bits_differ(x, y):
+    """boolean mask: fp32 arrays differ bitwise, NaN == NaN regardless of payload (x86 and CUDA NaNs differ)"""
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.ascontiguousarray(y, np.float32)
+    return (x.view(np.uint32) != y.view(np.uint32)) & ~(np.isnan(x) & np.isnan(y))
