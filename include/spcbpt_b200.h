@@ -192,6 +192,32 @@ typedef struct spc_pretrace_params {
     void*   conns;            /* device: TrainData::pathInfo_node[num_core*padding]    (92 B)  */
 } spc_pretrace_params;
 
+/* optixPathTracer.h:372-383 (TrainData::pathInfo_sample = preTracePath, 48 B): one NEE training path */
+typedef struct spc_train_path {
+    spc_float3 contri;
+    float      sample_pdf;
+    float      fix_pdf;
+    int32_t    begin_ind;     /* [begin_ind, end_ind) into the connection array */
+    int32_t    end_ind;
+    int32_t    choice_id;
+    int32_t    pixel_x, pixel_y;   /* int2 pixel_id (8-aligned) */
+    uint8_t    valid;
+    uint8_t    _pad[7];
+} spc_train_path;
+
+/* optixPathTracer.h:325-371 (TrainData::pathInfo_node = preTraceConnection, 92 B): one split of a training path
+ * into an eye prefix ending at A and a light suffix starting at B */
+typedef struct spc_train_conn {
+    spc_float3 A_position, B_position, A_dir, B_dir, A_normal, B_normal;
+    float      peak_pdf;      /* pdf(eye prefix) * contribution(light suffix) */
+    int32_t    path_id;
+    int32_t    label_A;       /* eye depth until node_label() writes the eye subspace id */
+    int32_t    label_B;
+    uint8_t    valid;
+    uint8_t    light_source;
+    uint8_t    _pad[2];
+} spc_train_conn;
+
 /* optixPathTracer.h:89-97 (SubspaceSampler, 40 B) */
 typedef struct spc_subspace_sampler {
     const spc_vertex* LVC;
@@ -378,6 +404,48 @@ SPC_API int  spc_set_debug_outputs(spc_context* ctx, int32_t* first_prim_dev, in
  * until the next call (the reference's function-static device_vectors behave the same way). */
 SPC_API int  spc_lvc_process(spc_context* ctx, const spc_vertex* lvc_dev, const uint8_t* valid_dev, int count_range,
                              spc_subspace_sampler* out_host);
+
+/* ---- subspace training (the rest of the MyThrustOp seam, cuda_thrust/device_thrust.h:109-135).  Like the reference's
+ * library these calls are stateful: the context owns the accumulated training set (neat_paths / neat_conns), Q, Gamma
+ * and the trainer's arrays; returned device pointers stay valid until the next call of the same function. ---- */
+/* valid_sample_gather(raw_paths, maxPathSize, raw_conns, maxConns) (:457-493): appends the valid paths of one pretrace
+ * launch (and their connections) to the training set; *sample_count = number appended. */
+SPC_API int  spc_valid_sample_gather(spc_context* ctx, const spc_train_path* raw_paths_dev, int max_paths,
+                                     const spc_train_conn* raw_conns_dev, int max_conns, int* sample_count);
+SPC_API int  spc_sample_reweight(spc_context* ctx);                                                 /* sample_reweight() (:574-623) */
+/* get_weighted_point_for_tree_building(eye_side, max_size) (:494-527) -> host array; *n = required count */
+SPC_API int  spc_get_tree_points(spc_context* ctx, int eye_side, int max_size, spc_divide_weight* out_host, int cap, int* n);
+/* eye_tree_to_device / light_tree_to_device (:539-552): uploads a host tree, returns the device copy owned by the context */
+SPC_API int  spc_tree_to_device(spc_context* ctx, int eye_side, const spc_tree_node* nodes_host, int n, spc_tree_node** dev_out);
+/* preprocess_getQ(vertices, validState, countRange, Q) (:347-409): folds one light-trace launch into the running Q
+ * estimate (reset != 0 restarts it, like passing a null Q); *acc_paths = accumulated light-path count */
+SPC_API int  spc_preprocess_getQ(spc_context* ctx, const spc_vertex* lvc_dev, const uint8_t* valid_dev, int count_range, int reset,
+                                 float** Q_dev, int* acc_paths);
+SPC_API int  spc_Q_zero_handle(spc_context* ctx);                                                   /* Q_zero_handle (:335-346) */
+SPC_API int  spc_node_label(spc_context* ctx, const spc_tree_node* eye_tree_dev, const spc_tree_node* light_tree_dev);   /* node_label (:569-573) */
+SPC_API int  spc_build_optimal_E_train_data(spc_context* ctx, int n_samples);                       /* (:3261-3325) */
+SPC_API int  spc_preprocess_getGamma(spc_context* ctx, float** gamma_dev);                          /* (:627-667) */
+/* train_optimal_E(E_ptr) (:3327-3344): lr 0.01, batch 20000, 1 epoch when the arguments are 0 */
+SPC_API int  spc_train_optimal_E(spc_context* ctx, int batch_size, int epochs, float lr, float** gamma_dev,
+                                 float* loss_per_batch_host, int loss_cap, int* n_batches);
+SPC_API int  spc_Gamma2CMFGamma(spc_context* ctx, const float* gamma_dev, float** cmf_dev);          /* (:3406-3433) */
+/* parity dumps / bookkeeping of the training set */
+SPC_API int  spc_train_set_size(spc_context* ctx, int* n_paths, int* n_conns);
+SPC_API int  spc_train_set_read(spc_context* ctx, spc_train_path* paths_host, spc_train_conn* conns_host);
+SPC_API int  spc_train_data_read(spc_context* ctx, int* N, int* M, float* outlier_threshold, float* f_square, float* pdf0, int* P2N,
+                                 float* peak, int* label_E, int* label_P);
+SPC_API int  spc_train_reset(spc_context* ctx);
+/* plain device<->host copies on the context's device (so that a C host needs no CUDA runtime of its own) */
+SPC_API int  spc_device_alloc(spc_context* ctx, size_t bytes, void** dev_out);
+SPC_API int  spc_device_free(spc_context* ctx, void* dev);
+SPC_API int  spc_upload(spc_context* ctx, void* dev, const void* host, size_t bytes);
+SPC_API int  spc_download(spc_context* ctx, void* host, const void* dev, size_t bytes);
+
+/* classTree::buildTreeBaseOnExistSample()(samples, subspaceSize, labelBias) (decisionTree/classTree_host.h:302-431):
+ * host-side build of a classification tree from weighted sample points (the reference runs it on the host as well,
+ * optixPathTracer.cpp:563-567).  Writes at most `cap` nodes to `out` and returns the node count (nothing is
+ * written when it exceeds cap) or a negative spc_status; *max_label receives the largest label used. */
+SPC_API int  spc_build_tree(const spc_divide_weight* samples, int n, int K, int label_bias, spc_tree_node* out, int cap, int* max_label);
 
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 SPC_API int64_t spc_launch_count(spc_context* ctx);

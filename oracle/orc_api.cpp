@@ -188,3 +188,81 @@ ORC_API void orc_connect(void* sc, const spc_params* p, int K, int connections, 
 }
 
 }  // extern "C"
+
+
+// ---------------------------------------------------------------------------------------------
+// training path (orc_train.cpp)
+// ---------------------------------------------------------------------------------------------
+#include "orc_train.h"
+
+extern "C" {
+
+// optixLaunch of "pretrace" (optixPathTracer.cpp:523-545): one training path per launch index
+ORC_API void orc_pretrace(void* sc, const spc_params* p, int K, int max_depth, int threads) {
+    const Frame fr = make_frame(sc, p, K, 3, max_depth);
+    parallel_for(fr.p.pre_tracer.num_core, threads > 1 && fr.p.pre_tracer.num_core >= 1024 ? threads : 1,
+                 [&](int64_t b, int64_t e) { for (int64_t i = b; i < e; i++) pretrace_core(fr, (int)i); });
+}
+
+ORC_API void* orc_ts_create() { return new TrainSet(); }
+ORC_API void orc_ts_destroy(void* ts) { delete (TrainSet*)ts; }
+ORC_API int orc_ts_gather(void* ts, const spc_train_path* paths, int n_paths, const spc_train_conn* conns, int n_conns) {
+    return ((TrainSet*)ts)->gather(paths, n_paths, conns, n_conns);
+}
+ORC_API int orc_ts_sizes(void* ts, int* n_paths, int* n_conns) {
+    *n_paths = (int)((TrainSet*)ts)->paths.size();
+    *n_conns = (int)((TrainSet*)ts)->conns.size();
+    return 0;
+}
+ORC_API void orc_ts_read(void* ts, spc_train_path* paths, spc_train_conn* conns) {
+    TrainSet* t = (TrainSet*)ts;
+    if (paths) memcpy(paths, t->paths.data(), t->paths.size() * sizeof(spc_train_path));
+    if (conns) memcpy(conns, t->conns.data(), t->conns.size() * sizeof(spc_train_conn));
+}
+ORC_API void orc_ts_reweight(void* ts) { ((TrainSet*)ts)->reweight(); }
+ORC_API int orc_ts_tree_points(void* ts, int eye_side, int max_size, spc_divide_weight* out, int cap) {
+    const std::vector<spc_divide_weight> v = ((TrainSet*)ts)->tree_points(eye_side != 0, max_size);
+    if ((int)v.size() <= cap) memcpy(out, v.data(), v.size() * sizeof(spc_divide_weight));
+    return (int)v.size();
+}
+ORC_API void orc_ts_label(void* ts, const spc_tree_node* eye_tree, const spc_tree_node* light_tree) { ((TrainSet*)ts)->label(eye_tree, light_tree); }
+ORC_API void* orc_q_create(int K) { return new QEstimator(K); }
+ORC_API void orc_q_destroy(void* q) { delete (QEstimator*)q; }
+ORC_API int orc_q_add(void* q, const spc_vertex* lvc, const uint8_t* valid, int n) { return ((QEstimator*)q)->add(lvc, valid, n); }
+ORC_API void orc_q_zero_handle(void* q) { ((QEstimator*)q)->zero_handle(); }
+ORC_API void orc_q_read(void* q, float* out) { memcpy(out, ((QEstimator*)q)->Q.data(), ((QEstimator*)q)->K * sizeof(float)); }
+
+struct OrcTrainData { TrainData td; };
+ORC_API void* orc_ts_build_train_data(void* ts, int n_samples, const float* Q, int K) {
+    OrcTrainData* d = new OrcTrainData();
+    ((TrainSet*)ts)->build_train_data(n_samples, Q, K, d->td);
+    return d;
+}
+ORC_API void orc_td_destroy(void* td) { delete (OrcTrainData*)td; }
+ORC_API void orc_td_sizes(void* td, int* N, int* M, float* threshold) {
+    *N = ((OrcTrainData*)td)->td.N; *M = ((OrcTrainData*)td)->td.M; *threshold = ((OrcTrainData*)td)->td.outlier_threshold;
+}
+ORC_API void orc_td_read(void* td, float* f_square, float* pdf0, int* P2N, float* peak, int* label_E, int* label_P) {
+    const TrainData& t = ((OrcTrainData*)td)->td;
+    memcpy(f_square, t.f_square.data(), t.N * 4); memcpy(pdf0, t.pdf0.data(), t.N * 4); memcpy(P2N, t.P2N.data(), t.N * 4);
+    memcpy(peak, t.peak.data(), t.M * 4); memcpy(label_E, t.label_E.data(), t.M * 4); memcpy(label_P, t.label_P.data(), t.M * 4);
+}
+ORC_API void orc_ts_gamma_histogram(void* ts, int K, float* G) {
+    std::vector<float> g;
+    ((TrainSet*)ts)->gamma_histogram(K, g);
+    memcpy(G, g.data(), g.size() * 4);
+}
+ORC_API void orc_train_gamma(void* td, int K, float* G, int batch_size, int epochs, float lr, float* loss_log, int loss_cap, int* n_loss) {
+    std::vector<float> g(G, G + (size_t)K * K), loss;
+    train_gamma(((OrcTrainData*)td)->td, K, g, batch_size, epochs, lr, 0.2, &loss);
+    memcpy(G, g.data(), g.size() * 4);
+    if (n_loss) *n_loss = (int)loss.size();
+    if (loss_log) memcpy(loss_log, loss.data(), std::min((size_t)loss_cap, loss.size()) * 4);
+}
+ORC_API void orc_gamma_to_cmf(const float* G, int K, float* cmf) {
+    std::vector<float> g(G, G + (size_t)K * K), c;
+    gamma_to_cmf(g, K, 0.2f, c);
+    memcpy(cmf, c.data(), c.size() * 4);
+}
+
+}  // extern "C"

@@ -185,3 +185,123 @@ def connect(pkg, scene, params, K, connections, eye, light):
 def set_jitter_rtl(v):
     """reproduce g++'s right-to-left evaluation of make_float2(rnd,rnd) (pinning vs libref_host only)"""
     lib().orc_set_jitter_rtl(int(v))
+
+
+# ---- training path ---------------------------------------------------------------------------
+def _bind_train(L):
+    vp, i32, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    L.orc_pretrace.argtypes = [vp, vp, i32, i32, i32]
+    L.orc_pretrace.restype = None
+    for name, args, res in (("orc_ts_create", [], vp), ("orc_ts_destroy", [vp], None), ("orc_ts_gather", [vp, vp, i32, vp, i32], i32),
+                            ("orc_ts_sizes", [vp, vp, vp], i32), ("orc_ts_read", [vp, vp, vp], None), ("orc_ts_reweight", [vp], None),
+                            ("orc_ts_tree_points", [vp, i32, i32, vp, i32], i32), ("orc_ts_label", [vp, vp, vp], None),
+                            ("orc_q_create", [i32], vp), ("orc_q_destroy", [vp], None), ("orc_q_add", [vp, vp, vp, i32], i32),
+                            ("orc_q_zero_handle", [vp], None), ("orc_q_read", [vp, vp], None),
+                            ("orc_ts_build_train_data", [vp, i32, vp, i32], vp), ("orc_td_destroy", [vp], None),
+                            ("orc_td_sizes", [vp, vp, vp, vp], None), ("orc_td_read", [vp, vp, vp, vp, vp, vp, vp], None),
+                            ("orc_ts_gamma_histogram", [vp, i32, vp], None),
+                            ("orc_train_gamma", [vp, i32, vp, i32, i32, f32, vp, i32, vp], None), ("orc_gamma_to_cmf", [vp, i32, vp], None)):
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+
+
+def pretrace(scene, params, K, max_depth=0, threads=8):
+    L = lib(); _bind_train(L)
+    L.orc_pretrace(scene.h, params.ctypes.data, K, max_depth, threads)
+
+
+class TrainSet:
+    """the accumulated training set (neat_paths / neat_conns of device_thrust.cu:428-429) and its MyThrustOp operations"""
+
+    def __init__(self, pkg):
+        self.pkg = pkg
+        self.L = lib(); _bind_train(self.L)
+        self.h = self.L.orc_ts_create()
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.orc_ts_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def gather(self, paths, conns):
+        paths = np.ascontiguousarray(paths, self.pkg.TRAIN_PATH)
+        conns = np.ascontiguousarray(conns, self.pkg.TRAIN_CONN)
+        return self.L.orc_ts_gather(self.h, paths.ctypes.data, paths.shape[0], conns.ctypes.data, conns.shape[0])
+
+    def read(self):
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        self.L.orc_ts_sizes(self.h, ctypes.byref(a), ctypes.byref(b))
+        paths = np.zeros(a.value, self.pkg.TRAIN_PATH)
+        conns = np.zeros(b.value, self.pkg.TRAIN_CONN)
+        self.L.orc_ts_read(self.h, paths.ctypes.data, conns.ctypes.data)
+        return paths, conns
+
+    def reweight(self):
+        self.L.orc_ts_reweight(self.h)
+
+    def tree_points(self, eye_side, max_size):
+        cap = 1 << 22
+        out = np.zeros(cap, self.pkg.DIVIDE_WEIGHT)
+        n = self.L.orc_ts_tree_points(self.h, int(eye_side), max_size, out.ctypes.data, cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def label(self, eye_tree, light_tree):
+        e = np.ascontiguousarray(eye_tree, self.pkg.TREE_NODE)
+        l = np.ascontiguousarray(light_tree, self.pkg.TREE_NODE)
+        self.L.orc_ts_label(self.h, e.ctypes.data, l.ctypes.data)
+
+    def build_train_data(self, n_samples, Q, K):
+        Q = np.ascontiguousarray(Q, np.float32)
+        td = self.L.orc_ts_build_train_data(self.h, n_samples, Q.ctypes.data, K)
+        N, M, th = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_float(0)
+        self.L.orc_td_sizes(td, ctypes.byref(N), ctypes.byref(M), ctypes.byref(th))
+        out = dict(N=N.value, M=M.value, threshold=th.value, handle=td,
+                   f_square=np.zeros(N.value, np.float32), pdf0=np.zeros(N.value, np.float32), P2N=np.zeros(N.value, np.int32),
+                   peak=np.zeros(M.value, np.float32), label_E=np.zeros(M.value, np.int32), label_P=np.zeros(M.value, np.int32))
+        self.L.orc_td_read(td, *(out[k].ctypes.data for k in ("f_square", "pdf0", "P2N", "peak", "label_E", "label_P")))
+        return out
+
+    def gamma_histogram(self, K):
+        G = np.zeros((K, K), np.float32)
+        self.L.orc_ts_gamma_histogram(self.h, K, G.ctypes.data)
+        return G
+
+
+class QEstimator:
+    def __init__(self, K):
+        self.K = K
+        self.L = lib(); _bind_train(self.L)
+        self.h = self.L.orc_q_create(K)
+
+    def add(self, lvc, valid):
+        return self.L.orc_q_add(self.h, lvc.ctypes.data, valid.ctypes.data, lvc.shape[0])
+
+    def zero_handle(self):
+        self.L.orc_q_zero_handle(self.h)
+
+    def read(self):
+        q = np.zeros(self.K, np.float32)
+        self.L.orc_q_read(self.h, q.ctypes.data)
+        return q
+
+
+def train_gamma(td, K, G, batch_size=20000, epochs=1, lr=0.01):
+    L = lib(); _bind_train(L)
+    G = np.ascontiguousarray(G, np.float32).copy()
+    loss = np.zeros(4096, np.float32)
+    n = ctypes.c_int(0)
+    L.orc_train_gamma(td["handle"], K, G.ctypes.data, batch_size, epochs, lr, loss.ctypes.data, loss.shape[0], ctypes.byref(n))
+    return G, loss[:n.value].copy()
+
+
+def gamma_to_cmf(G, K):
+    L = lib(); _bind_train(L)
+    G = np.ascontiguousarray(G, np.float32)
+    out = np.zeros_like(G)
+    L.orc_gamma_to_cmf(G.ctypes.data, K, out.ctypes.data)
+    return out

@@ -1,5 +1,6 @@
 // orc_render.cpp -- CPU oracle of the SPCBPT render path (see orc_render.h).  TEST INFRASTRUCTURE ONLY.
 #include "orc_render.h"
+#include "orc_internal.h"
 #include <algorithm>
 #include <cfloat>
 #include <cstring>
@@ -11,8 +12,6 @@ static const float PIf = 3.14159265358979323846f;   // M_PIf, sutil/vec_math.h
 static const double PId = 3.14159265358979323846;   // M_PI
 static const float SCENE_EPS = 1e-3f;               // cuProg.h:39
 
-static inline f3 ld(const spc_float3& v) { return f3{v.x, v.y, v.z}; }
-static inline void st(spc_float3& d, f3 v) { d.x = v.x; d.y = v.y; d.z = v.z; }
 static inline float absf(float x) { return std::fabs(x); }
 static inline f3 operator+(f3 a, float b) { return f3{a.x + b, a.y + b, a.z + b}; }   // sutil/vec_math.h float3+float
 
@@ -223,13 +222,7 @@ static LocalGeom local_geometry(const Tri& tr, float bu, float bv) {
 // ============================================================================================
 // light sampling: Tracer::lightSample (cuProg.h:554-666), QUAD lights only
 // ============================================================================================
-struct LightSample {
-    f3 position, emission, direction;
-    float uvx, uvy, pdf, dir_pdf;
-    int subspaceId;
-    const spc_light* light;
-};
-static void light_reverse_sample(const Frame& fr, const spc_light& L, float r1, float r2, LightSample& s) {   // cuProg.h:571-601
+void light_reverse_sample(const Frame& fr, const spc_light& L, float r1, float r2, LightSample& s) {   // cuProg.h:571-601
     s.light = &L;
     const float r3 = 1 - r1 - r2;
     s.position = ld(L.u) * r1 + ld(L.v) * r2 + ld(L.corner) * r3;
@@ -242,7 +235,7 @@ static void light_reverse_sample(const Frame& fr, const spc_light& L, float r1, 
     const int lightSpaceId = L.ssBase + xb * L.divLevel + yb;
     s.subspaceId = fr.K - lightSpaceId - 1;
 }
-static void light_sample_pos(const Frame& fr, const spc_light& L, uint32_t& seed, LightSample& s) {           // cuProg.h:602-621
+void light_sample_pos(const Frame& fr, const spc_light& L, uint32_t& seed, LightSample& s) {           // cuProg.h:602-621
     const float r1 = rnd(seed);
     const float r2 = rnd(seed);
     light_reverse_sample(fr, L, r1, r2, s);
@@ -254,11 +247,11 @@ static void light_trace_mode(LightSample& s, uint32_t& seed) {                  
     s.direction = onb.inverse_transform(cosine_sample_hemisphere(r1, r2));
     s.dir_pdf = absf(dot(s.direction, ld(s.light->normal))) / PIf;
 }
-static int pick_light(const Frame& fr, uint32_t& seed) {                                                      // raygen.cu:639, cuProg.h:624
+int pick_light(const Frame& fr, uint32_t& seed) {                                                      // raygen.cu:639, cuProg.h:624
     const int n = (int)fr.sc->lights.size();
     return std::max(0, std::min((int)std::floor(rnd(seed) * (float)(unsigned)n), n - 1));
 }
-static void init_vertex_from_light_sample(const LightSample& s, spc_vertex& v) {                              // raygen.cu:172-195
+void init_vertex_from_light_sample(const LightSample& s, spc_vertex& v) {                              // raygen.cu:172-195
     st(v.position, s.position);
     st(v.normal, ld(s.light->normal));
     st(v.flux, s.emission);
@@ -277,7 +270,7 @@ static void init_vertex_from_light_sample(const LightSample& s, spc_vertex& v) {
 // ============================================================================================
 // recursive MIS (rmis.h)
 // ============================================================================================
-static Pbr vertex_mat(const Frame& fr, const spc_vertex& v) {                       // rmis::getMat, rmis.h:16-21
+Pbr vertex_mat(const Frame& fr, const spc_vertex& v) {                       // rmis::getMat, rmis.h:16-21
     Pbr m = load_pbr(*fr.sc, v.materialId);
     m.base_color = ld(v.color);
     return m;
@@ -434,24 +427,7 @@ static float light_hit(const Frame& fr, const spc_vertex& eye, const spc_vertex&
 // touch current/last/next, and `next` carries the two values pre-loaded by the previous hit
 // (flux = BSDF value, singlePdf), hit_program.cu:286-287 + :335
 // ============================================================================================
-struct Path {
-    spc_vertex v[3];
-    int size;
-    spc_vertex& cur() { return v[(size - 1) % 3]; }
-    spc_vertex& next() { return v[size % 3]; }
-    spc_vertex& last() { return v[(size - 2) % 3]; }
-};
-struct Payload {                                     // Tracer::PayloadBDPTVertex, cuProg.h:303-323
-    Path path;
-    f3 origin, ray_direction;
-    float pdf;
-    uint32_t seed;
-    int depth;
-    bool done;
-    void clear() { path.size = 0; depth = 0; done = false; }
-};
-
-static inline bool invalid3(f3 a) {                 // ISINVALIDVALUE, raygen.cu:43
+bool invalid3(f3 a) {                 // ISINVALIDVALUE, raygen.cu:43
     return a.x > 100000.0f || std::isnan(a.x) || a.y > 100000.0f || std::isnan(a.y) || a.z > 100000.0f || std::isnan(a.z);
 }
 
@@ -557,7 +533,7 @@ static void closesthit_eye_light(const Frame& fr, Payload& prd, const Tri& tr, c
 
 // traceEyeSubPath / traceLightSubPath (cuProg.h:409-461): closest hit with back-face culling of
 // emitter quads, then the hit/miss program of the active raygen (sutil/Scene.cpp:1648-1691)
-static void trace_subpath(const Frame& fr, Payload& prd, f3 o, f3 d, bool light_side) {
+void trace_subpath(const Frame& fr, Payload& prd, f3 o, f3 d, bool light_side) {
     Hit h;
     if (!fr.sc->closest(o, d, SCENE_EPS, 1e16f, true, h)) {
         prd.done = true;                                   // __miss__BDPTVertex, raygen.cu:699-704
@@ -573,7 +549,7 @@ static void trace_subpath(const Frame& fr, Payload& prd, f3 o, f3 d, bool light_
 }
 
 // visibilityTest (cuProg.h:463-502)
-static bool visibility_test(const Frame& fr, f3 pos_A, f3 pos_B) {
+bool visibility_test(const Frame& fr, f3 pos_A, f3 pos_B) {
     const f3 bias_pos = pos_B - pos_A;
     const float len = length(bias_pos);
     const f3 dir = bias_pos / len;

@@ -145,6 +145,9 @@ REF_API const char* ref_layout_json() {
         "\"tree_node\": %zu, \"Subspace\": %zu, \"divide_weight\": %zu, \"pathInfo_node\": %zu, \"pathInfo_sample\": %zu, "
         "\"nVertex\": %zu, \"HitGroupData\": %zu, \"LightTraceParams\": %zu, \"PreTraceParams\": %zu, \"SubspaceSampler\": %zu, "
         "\"subspaceMacroInfo\": %zu, \"envInfo\": %zu, \"BDPTPath\": %zu},"
+        " \"train\": {\"sample.sample_pdf\": %d, \"sample.fix_pdf\": %d, \"sample.begin_ind\": %d, \"sample.end_ind\": %d, \"sample.choice_id\": %d, "
+        "\"sample.pixel_id\": %d, \"sample.valid\": %d, \"node.B_position\": %d, \"node.A_dir_d\": %d, \"node.B_dir_d\": %d, \"node.A_normal_d\": %d, "
+        "\"node.B_normal_d\": %d, \"node.peak_pdf\": %d, \"node.path_id\": %d, \"node.label_A\": %d, \"node.label_B\": %d, \"node.valid\": %d, \"node.light_source\": %d},"
         " \"offsetof\": {\"MyParams\": {\"width\": %d, \"height\": %d, \"subframe_index\": %d, \"accum_buffer\": %d, \"frame_buffer\": %d, "
         "\"max_depth\": %d, \"eye\": %d, \"U\": %d, \"V\": %d, \"W\": %d, \"lights\": %d, \"materials\": %d, \"miss_color\": %d, "
         "\"handle\": %d, \"lt\": %d, \"sampler\": %d, \"pre_tracer\": %d, \"subspace_info\": %d, \"sky\": %d},"
@@ -163,6 +166,12 @@ REF_API const char* ref_layout_json() {
         sizeof(classTree::tree_node), sizeof(Subspace), sizeof(classTree::divide_weight), sizeof(TrainData::pathInfo_node),
         sizeof(TrainData::pathInfo_sample), sizeof(TrainData::nVertex), sizeof(whitted::HitGroupData), sizeof(LightTraceParams),
         sizeof(PreTraceParams), sizeof(SubspaceSampler), sizeof(subspaceMacroInfo), sizeof(envInfo), sizeof(BDPTPath),
+        OFF(TrainData::pathInfo_sample, sample_pdf), OFF(TrainData::pathInfo_sample, fix_pdf), OFF(TrainData::pathInfo_sample, begin_ind),
+        OFF(TrainData::pathInfo_sample, end_ind), OFF(TrainData::pathInfo_sample, choice_id), OFF(TrainData::pathInfo_sample, pixel_id),
+        OFF(TrainData::pathInfo_sample, valid), OFF(TrainData::pathInfo_node, B_position), OFF(TrainData::pathInfo_node, A_dir_d),
+        OFF(TrainData::pathInfo_node, B_dir_d), OFF(TrainData::pathInfo_node, A_normal_d), OFF(TrainData::pathInfo_node, B_normal_d),
+        OFF(TrainData::pathInfo_node, peak_pdf), OFF(TrainData::pathInfo_node, path_id), OFF(TrainData::pathInfo_node, label_A),
+        OFF(TrainData::pathInfo_node, label_B), OFF(TrainData::pathInfo_node, valid), OFF(TrainData::pathInfo_node, light_source),
         OFF(MyParams, width), OFF(MyParams, height), OFF(MyParams, subframe_index), OFF(MyParams, accum_buffer), OFF(MyParams, frame_buffer),
         OFF(MyParams, max_depth), OFF(MyParams, eye), OFF(MyParams, U), OFF(MyParams, V), OFF(MyParams, W), OFF(MyParams, lights),
         OFF(MyParams, materials), OFF(MyParams, miss_color), OFF(MyParams, handle), OFF(MyParams, lt), OFF(MyParams, sampler),

@@ -38,6 +38,11 @@ VERTEX = np.dtype([("position", "f4", 3), ("normal", "f4", 3), ("flux", "f4", 3)
                    ("isBrdf", "u1"), ("isLastVertex_direction", "u1"), ("_pad", "u1")])
 TREE_NODE = np.dtype([("mid", "f4", 3), ("child", "i4", 8), ("label", "i4"), ("type", "i4"), ("leaf", "u1"), ("_pad", "u1", 3)])
 DIVIDE_WEIGHT = np.dtype([("position", "f4", 3), ("dir", "f4", 3), ("normal", "f4", 3), ("weight", "f4")])
+TRAIN_PATH = np.dtype([("contri", "f4", 3), ("sample_pdf", "f4"), ("fix_pdf", "f4"), ("begin_ind", "i4"), ("end_ind", "i4"),
+                       ("choice_id", "i4"), ("pixel_id", "i4", 2), ("valid", "u1"), ("_pad", "u1", 7)])
+TRAIN_CONN = np.dtype([("A_position", "f4", 3), ("B_position", "f4", 3), ("A_dir", "f4", 3), ("B_dir", "f4", 3),
+                       ("A_normal", "f4", 3), ("B_normal", "f4", 3), ("peak_pdf", "f4"), ("path_id", "i4"), ("label_A", "i4"),
+                       ("label_B", "i4"), ("valid", "u1"), ("light_source", "u1"), ("_pad", "u1", 2)])
 SUBSPACE = np.dtype([("jump_bias", "i4"), ("id", "i4"), ("size", "i4"), ("sum_pmf", "f4"), ("Q", "f4")])
 MESH = np.dtype([("positions", "u8"), ("indices", "u8"), ("texcoords", "u8"), ("n_vertices", "u4"),
                  ("n_triangles", "u4"), ("material_id", "i4"), ("light_id", "i4")])
@@ -64,7 +69,7 @@ PARAMS = np.dtype([("width", "u4"), ("height", "u4"), ("subframe_index", "u4"), 
                    ("subspace_info", SUBSPACE_INFO), ("sky", ENV_INFO)])
 
 EXPECTED_SIZES = {"RAY": 32, "HIT": 16, "TEXREF": 40, "PBR": 144, "LIGHT": 80, "VERTEX": 120, "TREE_NODE": 56,
-                  "DIVIDE_WEIGHT": 40, "SUBSPACE": 20, "MESH": 40, "TEXTURE": 16, "BUFFER_VIEW": 16,
+                  "DIVIDE_WEIGHT": 40, "SUBSPACE": 20, "TRAIN_PATH": 48, "TRAIN_CONN": 92, "MESH": 40, "TEXTURE": 16, "BUFFER_VIEW": 16,
                   "LT_PARAMS": 40, "PRETRACE_PARAMS": 32, "SAMPLER": 40, "SUBSPACE_INFO": 40, "ENV_INFO": 56,
                   "PARAMS": 352}
 
@@ -134,6 +139,26 @@ def _bind_optional(L):
         "spc_launch_named": [vp, ctypes.c_char_p, i32, i32],
         "spc_set_debug_outputs": [vp, vp, vp],
         "spc_lvc_process": [vp, vp, vp, i32, vp],
+        "spc_build_tree": [vp, i32, i32, i32, vp, i32, vp],
+        "spc_valid_sample_gather": [vp, vp, i32, vp, i32, vp],
+        "spc_sample_reweight": [vp],
+        "spc_get_tree_points": [vp, i32, i32, vp, i32, vp],
+        "spc_tree_to_device": [vp, i32, vp, i32, vp],
+        "spc_preprocess_getQ": [vp, vp, vp, i32, i32, vp, vp],
+        "spc_Q_zero_handle": [vp],
+        "spc_node_label": [vp, vp, vp],
+        "spc_build_optimal_E_train_data": [vp, i32],
+        "spc_preprocess_getGamma": [vp, vp],
+        "spc_train_optimal_E": [vp, i32, i32, f32, vp, vp, i32, vp],
+        "spc_Gamma2CMFGamma": [vp, vp, vp],
+        "spc_train_set_size": [vp, vp, vp],
+        "spc_train_set_read": [vp, vp, vp],
+        "spc_train_data_read": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "spc_train_reset": [vp],
+        "spc_device_alloc": [vp, ctypes.c_size_t, vp],
+        "spc_device_free": [vp, vp],
+        "spc_upload": [vp, vp, vp, ctypes.c_size_t],
+        "spc_download": [vp, vp, vp, ctypes.c_size_t],
     }
     for name, args in table.items():
         if hasattr(L, name):
@@ -180,6 +205,22 @@ def pack_scene(scene):
     lights = np.ascontiguousarray(scene.lights)
     keep += [meshes, textures, mats, lights]
     return (meshes, mats, lights, textures, len(scene.textures)), keep
+
+
+def build_tree(samples, K, label_bias=0):
+    """classTree::buildTreeBaseOnExistSample()(samples, K, labelBias) on the host -> (tree_node[], max_label)"""
+    L = lib()
+    samples = np.ascontiguousarray(samples, DIVIDE_WEIGHT)
+    cap = 1 << 16
+    while True:
+        out = np.zeros(cap, TREE_NODE)
+        ml = ctypes.c_int(0)
+        n = L.spc_build_tree(samples.ctypes.data, samples.shape[0], K, label_bias, out.ctypes.data, cap, ctypes.byref(ml))
+        if n < 0:
+            raise SpcError("spc_build_tree failed (%d): %s" % (n, L.spc_last_error().decode()))
+        if n <= cap:
+            return out[:n].copy(), ml.value
+        cap = n
 
 
 class Context:
@@ -259,6 +300,82 @@ class Context:
         s = np.zeros(1, SAMPLER)
         self._ck(self._L.spc_lvc_process(self.h, _ptr(lvc_dev), _ptr(valid_dev), n, s.ctypes.data), "spc_lvc_process")
         return s
+
+    # -- subspace training (MyThrustOp seam, part 2) ------------------------------------------
+    def download(self, dev_ptr, dtype, count):
+        out = np.zeros(count, dtype)
+        self._ck(self._L.spc_download(self.h, out.ctypes.data, ctypes.c_void_p(int(dev_ptr)), out.nbytes), "spc_download")
+        return out
+
+    def valid_sample_gather(self, paths_dev, n_paths, conns_dev, n_conns):
+        n = ctypes.c_int(0)
+        self._ck(self._L.spc_valid_sample_gather(self.h, _ptr(paths_dev), n_paths, _ptr(conns_dev), n_conns, ctypes.byref(n)), "spc_valid_sample_gather")
+        return n.value
+
+    def sample_reweight(self):
+        self._ck(self._L.spc_sample_reweight(self.h), "spc_sample_reweight")
+
+    def get_tree_points(self, eye_side, max_size):
+        n = ctypes.c_int(0)
+        self._ck(self._L.spc_get_tree_points(self.h, int(eye_side), max_size, None, 0, ctypes.byref(n)), "spc_get_tree_points")
+        out = np.zeros(max(n.value, 1), DIVIDE_WEIGHT)
+        self._ck(self._L.spc_get_tree_points(self.h, int(eye_side), max_size, out.ctypes.data, out.shape[0], ctypes.byref(n)), "spc_get_tree_points")
+        return out[:n.value]
+
+    def tree_to_device(self, eye_side, nodes):
+        nodes = np.ascontiguousarray(nodes, TREE_NODE)
+        p = ctypes.c_void_p()
+        self._ck(self._L.spc_tree_to_device(self.h, int(eye_side), nodes.ctypes.data, nodes.shape[0], ctypes.byref(p)), "spc_tree_to_device")
+        return p.value
+
+    def preprocess_getQ(self, lvc_dev, valid_dev, n, reset=False):
+        q, acc = ctypes.c_void_p(), ctypes.c_int(0)
+        self._ck(self._L.spc_preprocess_getQ(self.h, _ptr(lvc_dev), _ptr(valid_dev), n, int(reset), ctypes.byref(q), ctypes.byref(acc)), "spc_preprocess_getQ")
+        return q.value, acc.value
+
+    def Q_zero_handle(self):
+        self._ck(self._L.spc_Q_zero_handle(self.h), "spc_Q_zero_handle")
+
+    def node_label(self, eye_tree_dev, light_tree_dev):
+        self._ck(self._L.spc_node_label(self.h, ctypes.c_void_p(eye_tree_dev), ctypes.c_void_p(light_tree_dev)), "spc_node_label")
+
+    def build_optimal_E_train_data(self, n_samples):
+        self._ck(self._L.spc_build_optimal_E_train_data(self.h, n_samples), "spc_build_optimal_E_train_data")
+
+    def preprocess_getGamma(self):
+        g = ctypes.c_void_p()
+        self._ck(self._L.spc_preprocess_getGamma(self.h, ctypes.byref(g)), "spc_preprocess_getGamma")
+        return g.value
+
+    def train_optimal_E(self, batch_size=0, epochs=0, lr=0.0):
+        g, nb = ctypes.c_void_p(), ctypes.c_int(0)
+        loss = np.zeros(8192, np.float32)
+        self._ck(self._L.spc_train_optimal_E(self.h, batch_size, epochs, lr, ctypes.byref(g), loss.ctypes.data, loss.shape[0], ctypes.byref(nb)), "spc_train_optimal_E")
+        return g.value, loss[:nb.value].copy()
+
+    def Gamma2CMFGamma(self, gamma_dev):
+        p = ctypes.c_void_p()
+        self._ck(self._L.spc_Gamma2CMFGamma(self.h, ctypes.c_void_p(gamma_dev), ctypes.byref(p)), "spc_Gamma2CMFGamma")
+        return p.value
+
+    def train_set_read(self):
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        self._ck(self._L.spc_train_set_size(self.h, ctypes.byref(a), ctypes.byref(b)), "spc_train_set_size")
+        paths, conns = np.zeros(a.value, TRAIN_PATH), np.zeros(b.value, TRAIN_CONN)
+        self._ck(self._L.spc_train_set_read(self.h, paths.ctypes.data, conns.ctypes.data), "spc_train_set_read")
+        return paths, conns
+
+    def train_data_read(self):
+        N, M, th = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_float(0)
+        self._ck(self._L.spc_train_data_read(self.h, ctypes.byref(N), ctypes.byref(M), ctypes.byref(th), None, None, None, None, None, None), "spc_train_data_read")
+        out = dict(N=N.value, M=M.value, threshold=th.value,
+                   f_square=np.zeros(N.value, np.float32), pdf0=np.zeros(N.value, np.float32), P2N=np.zeros(N.value, np.int32),
+                   peak=np.zeros(M.value, np.float32), label_E=np.zeros(M.value, np.int32), label_P=np.zeros(M.value, np.int32))
+        self._ck(self._L.spc_train_data_read(self.h, None, None, None, *(out[k].ctypes.data for k in ("f_square", "pdf0", "P2N", "peak", "label_E", "label_P"))), "spc_train_data_read")
+        return out
+
+    def train_reset(self):
+        self._ck(self._L.spc_train_reset(self.h), "spc_train_reset")
 
     # -- ray batches (host buffers: the e2e path) --------------------------------------------
     def trace(self, rays, flags=RAYFLAG_CULL_BACK_FACING):

@@ -43,6 +43,11 @@ int spc_launch(spc_context* ctx, int kind, int width, int height) {
                         "spc_launch(light trace): launch size must be (lt.num_core, 1)");
             spc::launch_light_trace(c);
             break;
+        case SPC_LAUNCH_PRETRACE:
+            SPC_REQUIRE(c.has_params && width == c.params.pre_tracer.num_core && height == 1, SPC_ERR_INVALID,
+                        "spc_launch(pretrace): launch size must be (pre_tracer.num_core, 1)");
+            spc::launch_pretrace(c);
+            break;
         case SPC_LAUNCH_SPCBPT_EYE:
             spc::launch_eye_pass(c, width, height);
             break;

@@ -1,0 +1,161 @@
+// api_train.cu -- extern "C" entry points of the subspace-training path (MyThrustOp seam, part 2) and the
+// plain memory helpers.
+#include <cstring>
+#include "common.cuh"
+
+using spc::Context;
+
+#define SPC_API_BEGIN                                                                            \
+    if (!ctx) {                                                                                  \
+        spc::set_error("null context");                                                          \
+        return SPC_ERR_INVALID;                                                                  \
+    }                                                                                            \
+    Context& c = ctx->c;                                                                         \
+    (void)c;                                                                                     \
+    try {                                                                                        \
+        cudaSetDevice(c.device);
+
+#define SPC_API_END                                                                              \
+    }                                                                                            \
+    catch (const spc::CudaFailure& f) { return f.code; }                                         \
+    catch (const std::exception& e) {                                                            \
+        spc::set_error("exception: %s", e.what());                                               \
+        return SPC_ERR_INVALID;                                                                  \
+    }                                                                                            \
+    return SPC_OK;
+
+extern "C" {
+
+int spc_valid_sample_gather(spc_context* ctx, const spc_train_path* raw_paths_dev, int max_paths, const spc_train_conn* raw_conns_dev,
+                            int max_conns, int* sample_count) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(raw_paths_dev && raw_conns_dev && max_paths > 0 && max_conns > 0, SPC_ERR_INVALID, "spc_valid_sample_gather: bad arguments");
+    const int n = spc::train_gather(c, raw_paths_dev, max_paths, raw_conns_dev, max_conns);
+    if (sample_count) *sample_count = n;
+    SPC_API_END
+}
+int spc_sample_reweight(spc_context* ctx) {
+    SPC_API_BEGIN
+    spc::train_reweight(c);
+    SPC_API_END
+}
+int spc_get_tree_points(spc_context* ctx, int eye_side, int max_size, spc_divide_weight* out_host, int cap, int* n) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(n, SPC_ERR_INVALID, "spc_get_tree_points: n is null");
+    *n = spc::train_tree_points(c, eye_side, max_size, out_host, cap);
+    SPC_API_END
+}
+int spc_tree_to_device(spc_context* ctx, int eye_side, const spc_tree_node* nodes_host, int n, spc_tree_node** dev_out) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(nodes_host && n > 0 && dev_out, SPC_ERR_INVALID, "spc_tree_to_device: bad arguments");
+    spc::DevBuf<spc_tree_node>& b = eye_side ? c.train.eye_tree : c.train.light_tree;
+    b.alloc(n);
+    SPC_CUDA(cudaMemcpyAsync(b.p, nodes_host, (size_t)n * sizeof(spc_tree_node), cudaMemcpyHostToDevice, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    *dev_out = b.p;
+    SPC_API_END
+}
+int spc_preprocess_getQ(spc_context* ctx, const spc_vertex* lvc_dev, const uint8_t* valid_dev, int count_range, int reset, float** Q_dev, int* acc_paths) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(lvc_dev && valid_dev && count_range > 0, SPC_ERR_INVALID, "spc_preprocess_getQ: bad arguments");
+    const int acc = spc::train_get_Q(c, lvc_dev, valid_dev, count_range, reset);
+    if (acc_paths) *acc_paths = acc;
+    if (Q_dev) *Q_dev = c.train.Q.p;
+    SPC_API_END
+}
+int spc_Q_zero_handle(spc_context* ctx) {
+    SPC_API_BEGIN
+    spc::train_Q_zero_handle(c);
+    SPC_API_END
+}
+int spc_node_label(spc_context* ctx, const spc_tree_node* eye_tree_dev, const spc_tree_node* light_tree_dev) {
+    SPC_API_BEGIN
+    spc::train_node_label(c, eye_tree_dev, light_tree_dev);
+    SPC_API_END
+}
+int spc_build_optimal_E_train_data(spc_context* ctx, int n_samples) {
+    SPC_API_BEGIN
+    spc::train_build_data(c, n_samples);
+    SPC_API_END
+}
+int spc_preprocess_getGamma(spc_context* ctx, float** gamma_dev) {
+    SPC_API_BEGIN
+    float* g = spc::train_get_gamma(c);
+    if (gamma_dev) *gamma_dev = g;
+    SPC_API_END
+}
+int spc_train_optimal_E(spc_context* ctx, int batch_size, int epochs, float lr, float** gamma_dev, float* loss_host, int loss_cap, int* n_batches) {
+    SPC_API_BEGIN
+    float* g = spc::train_optimal_E(c, batch_size > 0 ? batch_size : 20000, epochs > 0 ? epochs : 1, lr > 0 ? lr : 0.01f, loss_host, loss_cap, n_batches);
+    if (gamma_dev) *gamma_dev = g;
+    SPC_API_END
+}
+int spc_Gamma2CMFGamma(spc_context* ctx, const float* gamma_dev, float** cmf_dev) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(gamma_dev && cmf_dev, SPC_ERR_INVALID, "spc_Gamma2CMFGamma: bad arguments");
+    *cmf_dev = spc::train_gamma_to_cmf(c, gamma_dev);
+    SPC_API_END
+}
+int spc_train_set_size(spc_context* ctx, int* n_paths, int* n_conns) {
+    SPC_API_BEGIN
+    if (n_paths) *n_paths = (int)c.train.n_paths;
+    if (n_conns) *n_conns = (int)c.train.n_conns;
+    SPC_API_END
+}
+int spc_train_set_read(spc_context* ctx, spc_train_path* paths_host, spc_train_conn* conns_host) {
+    SPC_API_BEGIN
+    if (paths_host && c.train.n_paths) SPC_CUDA(cudaMemcpyAsync(paths_host, c.train.paths.p, c.train.n_paths * sizeof(spc_train_path), cudaMemcpyDeviceToHost, c.stream));
+    if (conns_host && c.train.n_conns) SPC_CUDA(cudaMemcpyAsync(conns_host, c.train.conns.p, c.train.n_conns * sizeof(spc_train_conn), cudaMemcpyDeviceToHost, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    SPC_API_END
+}
+int spc_train_data_read(spc_context* ctx, int* N, int* M, float* outlier_threshold, float* f_square, float* pdf0, int* P2N, float* peak, int* label_E, int* label_P) {
+    SPC_API_BEGIN
+    spc::TrainBuffers& t = c.train;
+    if (N) *N = t.N;
+    if (M) *M = t.M;
+    if (outlier_threshold) *outlier_threshold = t.outlier_threshold;
+    auto dl = [&](void* h, const void* d, size_t bytes) {
+        if (h && bytes) SPC_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c.stream));
+    };
+    dl(f_square, t.f_square.p, (size_t)t.N * 4); dl(pdf0, t.pdf0.p, (size_t)t.N * 4); dl(P2N, t.P2N.p, (size_t)t.N * 4);
+    dl(peak, t.peak.p, (size_t)t.M * 4); dl(label_E, t.label_E.p, (size_t)t.M * 4); dl(label_P, t.label_P.p, (size_t)t.M * 4);
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    SPC_API_END
+}
+int spc_train_reset(spc_context* ctx) {
+    SPC_API_BEGIN
+    c.train.n_paths = c.train.n_conns = 0;
+    c.train.has_Q = false;
+    c.train.acc_valid_path = 0;
+    c.train.N = c.train.M = 0;
+    SPC_API_END
+}
+int spc_device_alloc(spc_context* ctx, size_t bytes, void** dev_out) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(dev_out, SPC_ERR_INVALID, "spc_device_alloc: dev_out is null");
+    SPC_CUDA(cudaMalloc(dev_out, bytes ? bytes : 1));
+    SPC_CUDA(cudaMemsetAsync(*dev_out, 0, bytes ? bytes : 1, c.stream));
+    SPC_API_END
+}
+int spc_device_free(spc_context* ctx, void* dev) {
+    SPC_API_BEGIN
+    if (dev) SPC_CUDA(cudaFree(dev));
+    SPC_API_END
+}
+int spc_upload(spc_context* ctx, void* dev, const void* host, size_t bytes) {
+    SPC_API_BEGIN
+    SPC_REQUIRE((dev && host) || !bytes, SPC_ERR_INVALID, "spc_upload: null pointer");
+    if (bytes) SPC_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    SPC_API_END
+}
+int spc_download(spc_context* ctx, void* host, const void* dev, size_t bytes) {
+    SPC_API_BEGIN
+    SPC_REQUIRE((dev && host) || !bytes, SPC_ERR_INVALID, "spc_download: null pointer");
+    if (bytes) SPC_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    SPC_API_END
+}
+
+}  // extern "C"

@@ -122,6 +122,26 @@ struct LvcBuffers {
     int                  n = 0;
 };
 
+// the accumulated training set and everything derived from it (train.cu): the file-static state of
+// cuda_thrust/device_thrust.cu (neat_paths/neat_conns :428-429, Q_vec :333-334, Gamma_vec :624-625, E_td :3109)
+struct TrainBuffers {
+    DevBuf<spc_train_path> paths;
+    DevBuf<spc_train_conn> conns;
+    size_t n_paths = 0, n_conns = 0;
+    DevBuf<int> flag_p, flag_c, pos_p, pos_c, scan_sums, scan_sums2, totals;
+    DevBuf<spc_divide_weight> tree_pts;
+    DevBuf<spc_tree_node> eye_tree, light_tree;
+    DevBuf<float> Q;
+    int   acc_valid_path = 0;
+    bool  has_Q = false;
+    int   N = 0, M = 0;
+    float outlier_threshold = 0.f;
+    DevBuf<float> outlier, f_square, pdf0, peak;
+    DevBuf<int>   P2N, label_E, label_P;
+    std::vector<int> h_P2N;
+    DevBuf<float> gamma, cmf, theta, adam_m, adam_v, E, dE, Esum, loss;
+};
+
 struct Context {
     int           device = 0;
     int           K = 1000, K_light = 200, connections = 3;
@@ -145,6 +165,9 @@ struct Context {
     int*          dbg_first_prim = nullptr;    // optional device outputs of the eye pass (parity dumps)
     int*          dbg_first_label = nullptr;
     int*          h_pinned = nullptr;          // small pinned staging block for counter read-backs
+    DevBuf<spc_vertex> pretrace_scratch;       // per-lane eye-vertex buffers of the training tracer
+    TrainBuffers  train;
+    LvcBuffers    bins_tmp;                    // ordered-binning scratch of getQ / sample_reweight
 };
 
 void build_bvh(Context& ctx, const float4* d_tri_pos /*3 per prim*/, uint32_t n_prims);
@@ -159,7 +182,21 @@ void launch_trace_occlusion_q(Context& ctx, const spc_ray* rays, const int* n_de
 
 void launch_light_trace(Context& ctx);                       // "light trace" raygen
 void launch_eye_pass(Context& ctx, int width, int height);   // "SPCBPT_eye" raygen
+void launch_pretrace(Context& ctx);                          // "pretrace" raygen
 void lvc_process(Context& ctx, const spc_vertex* lvc, const uint8_t* valid, int n, spc_subspace_sampler* out);
+void bin_ordered(Context& c, LvcBuffers& b, int n, int K, int* counters);
+int* lvc_bin(Context& c, LvcBuffers& b, const spc_vertex* lvc, const uint8_t* valid, int n);
+
+int    train_gather(Context& c, const spc_train_path* raw_paths, int max_paths, const spc_train_conn* raw_conns, int max_conns);
+void   train_reweight(Context& c);
+int    train_tree_points(Context& c, int eye_side, int max_size, spc_divide_weight* out_host, int cap);
+void   train_node_label(Context& c, const spc_tree_node* eye_tree, const spc_tree_node* light_tree);
+int    train_get_Q(Context& c, const spc_vertex* lvc, const uint8_t* valid, int n, int reset);
+void   train_Q_zero_handle(Context& c);
+void   train_build_data(Context& c, int n_samples);
+float* train_get_gamma(Context& c);
+float* train_optimal_E(Context& c, int batch_size, int epochs, float lr, float* loss_out_host, int loss_cap, int* n_loss);
+float* train_gamma_to_cmf(Context& c, const float* gamma_dev);
 
 }  // namespace spc
 

@@ -38,3 +38,8 @@ static_assert(offsetof(spc_params, width) == 0 && offsetof(spc_params, height) =
                   offsetof(spc_params, sampler) == 184 && offsetof(spc_params, pre_tracer) == 224 &&
                   offsetof(spc_params, subspace_info) == 256 && offsetof(spc_params, sky) == 296, "MyParams fields");
 static_assert(sizeof(spc_ray) == 32 && sizeof(spc_hit) == 16, "ray batch records");
+static_assert(sizeof(spc_train_path) == 48 && offsetof(spc_train_path, sample_pdf) == 12 && offsetof(spc_train_path, begin_ind) == 20 &&
+                  offsetof(spc_train_path, pixel_x) == 32 && offsetof(spc_train_path, valid) == 40, "TrainData::pathInfo_sample");
+static_assert(sizeof(spc_train_conn) == 92 && offsetof(spc_train_conn, peak_pdf) == 72 && offsetof(spc_train_conn, path_id) == 76 &&
+                  offsetof(spc_train_conn, label_A) == 80 && offsetof(spc_train_conn, label_B) == 84 && offsetof(spc_train_conn, valid) == 88 &&
+                  offsetof(spc_train_conn, light_source) == 89, "TrainData::pathInfo_node");

@@ -1,10 +1,11 @@
 // lvc.cu -- light-vertex-cache binning on the device.  Replaces MyThrustOp::LVC_Process
 // (cuda_thrust/device_thrust.cu:241-332), which copies the validity flags, subspace ids and weights of all
 // 800 k LVC slots to the host, buckets and prefix-sums them in a serial host loop and uploads three arrays
-// again every frame.  Here the same result is produced by five small kernels without leaving the GPU:
+// again every frame.  Here the same result is produced by six small kernels without leaving the GPU:
 //
 //   k_lvc_keys     per slot: key = subspace id (or -1 when invalid), weight = (flux.x+flux.y+flux.z)/pdf with
-//                  Inf/NaN -> 0 (device_thrust.cu:200-207); per-chunk histogram of the keys in shared memory
+//                  Inf/NaN -> 0 (device_thrust.cu:200-207)
+//   k_bin_hist     per-chunk histogram of the keys in shared memory
 //   k_lvc_colscan  per subspace: exclusive scan of its counts over the chunks (stable order = slot order)
 //   k_lvc_bias     exclusive scan over subspaces -> Subspace{jump_bias,id,size}; vertex_count
 //   k_lvc_scatter  stable counting-sort scatter (warp match-any ranks) -> jump_buffer + sorted weights
@@ -16,38 +17,47 @@ namespace spc {
 
 constexpr int kChunk = 2048;   // slots per warp-chunk
 
-__global__ void k_lvc_keys(const spc_vertex* __restrict__ lvc, const uint8_t* __restrict__ valid, int n, int K, int n_chunks,
-                           int* __restrict__ key, float* __restrict__ weight, int* __restrict__ hist, int* __restrict__ counters) {
+// per slot: bin key + weight of an LVC vertex; counters[1] += #valid depth-0 vertices (path_count)
+__global__ void k_lvc_keys(const spc_vertex* __restrict__ lvc, const uint8_t* __restrict__ valid, int n, int K,
+                           int* __restrict__ key, float* __restrict__ weight, int* __restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_begin = 0;
+    if (i < n) {
+        int k = -1;
+        float w = 0.f;
+        if (valid[i]) {
+            const spc_vertex* v = lvc + i;
+            const int sid = v->subspaceId;
+            if (sid >= 0 && sid < K) {
+                k = sid;
+                float res = (v->flux.x + v->flux.y + v->flux.z) / v->pdf;
+                res = isinf(res) ? 0 : res;
+                w = isnan(res) ? 0 : res;
+                if (v->depth == 0) n_begin = 1;
+            }
+        }
+        key[i] = k;
+        weight[i] = w;
+    }
+    for (int o = 16; o > 0; o >>= 1) n_begin += __shfl_xor_sync(0xffffffffu, n_begin, o);
+    if ((threadIdx.x & 31) == 0 && n_begin) atomicAdd(counters + 1, n_begin);
+}
+
+// generic: per-chunk histogram of bin keys (key < 0: not binned) in shared memory, one warp per chunk
+__global__ void k_bin_hist(const int* __restrict__ key, int n, int K, int n_chunks, int* __restrict__ hist) {
     extern __shared__ int s_hist[];   // [warps][K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     int* h = s_hist + (size_t)warp * K;
     for (int chunk = blockIdx.x * wpb + warp; chunk < n_chunks; chunk += gridDim.x * wpb) {
         for (int k = lane; k < K; k += 32) h[k] = 0;
         __syncwarp();
-        int n_begin = 0;
         const int lo = chunk * kChunk, hi = min(n, lo + kChunk);
         for (int i = lo + lane; i < hi; i += 32) {
-            int k = -1;
-            float w = 0.f;
-            if (valid[i]) {
-                const spc_vertex* v = lvc + i;
-                const int sid = v->subspaceId;
-                if (sid >= 0 && sid < K) {
-                    k = sid;
-                    float res = (v->flux.x + v->flux.y + v->flux.z) / v->pdf;
-                    res = isinf(res) ? 0 : res;
-                    w = isnan(res) ? 0 : res;
-                    if (v->depth == 0) n_begin++;
-                    atomicAdd(h + k, 1);
-                }
-            }
-            key[i] = k;
-            weight[i] = w;
+            const int k = key[i];
+            if (k >= 0) atomicAdd(h + k, 1);
         }
         __syncwarp();
         for (int k = lane; k < K; k += 32) hist[(size_t)chunk * K + k] = h[k];
-        for (int o = 16; o > 0; o >>= 1) n_begin += __shfl_xor_sync(0xffffffffu, n_begin, o);
-        if (lane == 0 && n_begin) atomicAdd(counters + 1, n_begin);   // path_count = #valid depth-0 vertices
         __syncwarp();
     }
 }
@@ -147,38 +157,55 @@ __global__ void k_lvc_cmf(spc_subspace* __restrict__ sub, int K, const float* __
     for (int i = lane; i < size; i += 32) cmfs[bias + i] = cmfs[bias + i] / total;
 }
 
-void lvc_process(Context& c, const spc_vertex* lvc, const uint8_t* valid, int n, spc_subspace_sampler* out) {
-    SPC_REQUIRE(lvc && valid && n > 0 && out, SPC_ERR_INVALID, "spc_lvc_process: bad arguments");
-    const int K = c.K;
-    LvcBuffers& b = c.lvc;
+// Generic ordered binning: given per-element bin keys (-1 = skip) and weights, produce the stable bucket order
+// (jump), Subspace{jump_bias,id,size,sum_pmf} per bin with sum_pmf = the fp32 sum of the bin's weights IN ELEMENT
+// ORDER, and (optionally normalised) running sums.  Used by LVC_Process, preprocess_getQ and sample_reweight,
+// whose reference implementations are serial host loops with exactly this summation order.
+void bin_ordered(Context& c, LvcBuffers& b, int n, int K, int* counters /* [0] <- number of binned elements */) {
     const int n_chunks = (n + kChunk - 1) / kChunk;
-    b.subspace.alloc(K); b.cmfs.alloc(n); b.jump.alloc(n); b.weight.alloc(n); b.key.alloc(n); b.wsorted.alloc(n);
-    b.hist.alloc((size_t)n_chunks * K); b.totals.alloc(K + 8);
-    b.n = n;
-    if (!c.h_pinned) SPC_CUDA(cudaMallocHost((void**)&c.h_pinned, 64 * sizeof(int)));
+    b.subspace.alloc(K); b.cmfs.alloc(n); b.jump.alloc(n); b.wsorted.alloc(n);
+    b.hist.alloc((size_t)n_chunks * K);
     cudaStream_t st = c.stream;
-    int* counters = b.totals.p + K;
-    SPC_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(int), st));
     // shared memory: K ints per warp; as many warps per block as fit in 160 KB (K = 1000 -> 8 warps, 32 KB)
-    int wpb = (int)std::min<size_t>(8, (160 * 1024) / ((size_t)K * 4));
-    SPC_REQUIRE(wpb >= 1, SPC_ERR_CAPACITY, "spc_lvc_process: K=%d does not fit the shared-memory histogram", K);
+    const int wpb = (int)std::min<size_t>(8, (160 * 1024) / ((size_t)K * 4));
+    SPC_REQUIRE(wpb >= 1, SPC_ERR_CAPACITY, "ordered binning: %d bins do not fit the shared-memory histogram", K);
     const size_t smem = (size_t)wpb * K * 4;
     static bool attr_set = false;
     if (!attr_set) {
-        SPC_CUDA(cudaFuncSetAttribute(k_lvc_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SPC_CUDA(cudaFuncSetAttribute(k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SPC_CUDA(cudaFuncSetAttribute(k_lvc_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
     const int grid = std::max(1, std::min((n_chunks + wpb - 1) / wpb, c.sm_count * 4));
-    k_lvc_keys<<<grid, wpb * 32, smem, st>>>(lvc, valid, n, K, n_chunks, b.key.p, b.weight.p, b.hist.p, counters);
+    k_bin_hist<<<grid, wpb * 32, smem, st>>>(b.key.p, n, K, n_chunks, b.hist.p);
     k_lvc_colscan<<<(K + 127) / 128, 128, 0, st>>>(b.hist.p, n_chunks, K, b.totals.p);
     k_lvc_bias<<<1, 1024, 0, st>>>(b.totals.p, K, b.subspace.p, counters);
     k_lvc_scatter<<<grid, wpb * 32, smem, st>>>(b.key.p, b.weight.p, n, K, n_chunks, b.hist.p, b.subspace.p, b.jump.p, b.wsorted.p);
-    k_lvc_cmf<<<(K * 32 + 127) / 128, 128, 0, st>>>(b.subspace.p, K, b.wsorted.p, b.cmfs.p);
+    k_lvc_cmf<<<(int)(((size_t)K * 32 + 127) / 128), 128, 0, st>>>(b.subspace.p, K, b.wsorted.p, b.cmfs.p);
     c.launches += 5;
     SPC_CUDA(cudaGetLastError());
-    SPC_CUDA(cudaMemcpyAsync(c.h_pinned, counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    SPC_CUDA(cudaStreamSynchronize(st));
+}
+
+// keys + weights of an LVC, then ordered binning; counters (device, 2 ints after totals) = {vertex_count, path_count}
+int* lvc_bin(Context& c, LvcBuffers& b, const spc_vertex* lvc, const uint8_t* valid, int n) {
+    const int K = c.K;
+    b.weight.alloc(n); b.key.alloc(n); b.totals.alloc(K + 8);
+    b.n = n;
+    int* counters = b.totals.p + K;
+    SPC_CUDA(cudaMemsetAsync(counters, 0, 8 * sizeof(int), c.stream));
+    k_lvc_keys<<<(n + 255) / 256, 256, 0, c.stream>>>(lvc, valid, n, K, b.key.p, b.weight.p, counters);
+    c.launches++;
+    bin_ordered(c, b, n, K, counters);
+    return counters;
+}
+
+void lvc_process(Context& c, const spc_vertex* lvc, const uint8_t* valid, int n, spc_subspace_sampler* out) {
+    SPC_REQUIRE(lvc && valid && n > 0 && out, SPC_ERR_INVALID, "spc_lvc_process: bad arguments");
+    LvcBuffers& b = c.lvc;
+    if (!c.h_pinned) SPC_CUDA(cudaMallocHost((void**)&c.h_pinned, 64 * sizeof(int)));
+    int* counters = lvc_bin(c, b, lvc, valid, n);
+    SPC_CUDA(cudaMemcpyAsync(c.h_pinned, counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
     out->LVC = lvc;
     out->subspace = b.subspace.p;
     out->cmfs = b.cmfs.p;

@@ -11,7 +11,7 @@
 
 namespace spc {
 
-static DevFrame make_frame(Context& c) {
+DevFrame make_dev_frame(Context& c) {
     DevFrame fr;
     fr.sc.tri_pos = c.geom.tri_pos.p;
     fr.sc.tri_uv = c.geom.tri_uv.p;
@@ -120,7 +120,7 @@ void launch_light_trace(Context& c) {
     const spc_light_trace_params& lt = c.params.lt;
     SPC_REQUIRE(lt.num_core > 0 && lt.core_padding > 0 && lt.ans && lt.validState, SPC_ERR_INVALID, "spc_launch(light trace): MyParams::lt is not set up");
     SPC_REQUIRE(c.geom.n_lights > 0, SPC_ERR_NO_SCENE, "spc_launch(light trace): the scene has no lights");
-    const DevFrame fr = make_frame(c);
+    const DevFrame fr = make_dev_frame(c);
     k_light_trace_cores<<<(lt.num_core + kLtWarps - 1) / kLtWarps, kLtWarps * 32, 0, c.stream>>>(fr);
     SPC_CUDA(cudaGetLastError());
     c.launches++;
@@ -359,7 +359,7 @@ void launch_eye_pass(Context& c, int width, int height) {
                 "spc_launch(SPCBPT_eye): light_tree without CMFGamma");
     const size_t P = (size_t)width * height;
     SPC_REQUIRE(P < 0x7fffffffull / 16, SPC_ERR_INVALID, "spc_launch: image too large");
-    const DevFrame fr = make_frame(c);
+    const DevFrame fr = make_dev_frame(c);
     const int C = c.connections;
     EyeBuffers& e = c.eye;
     if (e.pixels < P || e.conns != C) {

@@ -1,0 +1,589 @@
+// train.cu -- the subspace-training plumbing behind the MyThrustOp seam (cuda_thrust/device_thrust.cu), on the
+// device.  The reference does most of these steps in serial host loops after copying the whole training set
+// (~600 MB of structs) to the host and back; here the set never leaves HBM.
+//
+//   valid_sample_gather         (:457-493)   flag scan + order-preserving scatter + index fix-up, appended to the set
+//   sample_reweight             (:574-623)   ordered binning on the 10x10-pixel grid, then a per-path division
+//   get_weighted_point_...      (:494-527)   one lane per connection
+//   node_label                  (:554-573)   classification of both endpoints of every connection
+//   preprocess_getQ / Q_zero    (:347-409, :335-346)  ordered binning of the LVC (same order as the host loop)
+//   build_optimal_E_train_data  (:3261-3325) outlier clamp + SoA training arrays
+//   preprocess_getGamma         (:627-667)   K x K scatter-add histogram (fp32 atomics) + row normalise
+//   train_optimal_E             (:3327-3344 -> matrix_parameter::fit :1615-1655, matrix_optimal_operator :923-1190,
+//                                adam_step_func :1437-1470): three fused kernels per batch instead of ~25 thrust calls
+//   Gamma2CMFGamma              (:3406-3433) one lane per row, sequential fp32 prefix (the reference's order)
+// Not a dense contraction anywhere: CUDA cores + fp32 atomics, no tensor cores.
+#include <algorithm>
+#include <cfloat>
+#include "shade.cuh"
+
+namespace spc {
+
+// ---------------------------------------------------------------------------------------------
+// small device-wide exclusive scan of int flags (three kernels; n up to 2^31)
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanBlock = 256, kScanPer = 8, kScanTile = kScanBlock * kScanPer;
+
+__global__ void k_scan_local(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ sums) {
+    __shared__ int s_warp[kScanBlock / 32];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanPer;
+    int v[kScanPer], tot = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; k++) {
+        v[k] = base + k < n ? in[base + k] : 0;
+        tot += v[k];
+    }
+    int inc = tot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < kScanBlock / 32 ? s_warp[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        if (lane < kScanBlock / 32) s_warp[lane] = w;
+    }
+    __syncthreads();
+    int run = inc - tot + (warp ? s_warp[warp - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < kScanPer; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == kScanBlock - 1) sums[blockIdx.x] = s_warp[kScanBlock / 32 - 1];
+}
+__global__ void k_scan_sums(int* __restrict__ sums, int nb, int* __restrict__ total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < nb; i++) { const int v = sums[i]; sums[i] = run; run += v; }
+        *total = run;
+    }
+}
+__global__ void k_scan_add(int* __restrict__ out, int n, const int* __restrict__ sums) {
+    const int i = blockIdx.x * kScanTile + threadIdx.x * kScanPer;
+    const int add = sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanPer; k++)
+        if (i + k < n) out[i + k] += add;
+}
+static void exclusive_scan(Context& c, const int* in, int* out, int n, DevBuf<int>& sums, int* total_dev) {
+    const int nb = (n + kScanTile - 1) / kScanTile;
+    sums.alloc(nb + 1);
+    k_scan_local<<<nb, kScanBlock, 0, c.stream>>>(in, out, n, sums.p);
+    k_scan_sums<<<1, 32, 0, c.stream>>>(sums.p, nb, total_dev);
+    k_scan_add<<<nb, kScanBlock, 0, c.stream>>>(out, n, sums.p);
+    c.launches += 3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// valid_sample_gather
+// ---------------------------------------------------------------------------------------------
+__global__ void k_path_flags(const spc_train_path* __restrict__ p, int n, int* __restrict__ f) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f[i] = p[i].valid ? 1 : 0;
+}
+__global__ void k_conn_flags(const spc_train_conn* __restrict__ p, int n, int* __restrict__ f) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f[i] = p[i].valid ? 1 : 0;
+}
+__global__ void k_gather_conns(const spc_train_conn* __restrict__ raw, int n, const int* __restrict__ pos, spc_train_conn* __restrict__ neat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && raw[i].valid) neat[pos[i]] = raw[i];
+}
+// bias_arrange_op (device_thrust.cu:431-452) fused with the path copy
+__global__ void k_gather_paths(const spc_train_path* __restrict__ raw, int n, const int* __restrict__ ppos, const int* __restrict__ cpos,
+                               spc_train_path* __restrict__ neat_paths, spc_train_conn* __restrict__ neat_conns, int sample_bias, int node_bias) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !raw[i].valid) return;
+    spc_train_path s = raw[i];
+    const int id = ppos[i];
+    const int len = s.end_ind - s.begin_ind;
+    const int b = cpos[s.begin_ind];
+    s.begin_ind = node_bias + b;
+    s.end_ind = node_bias + b + len;
+    neat_paths[sample_bias + id] = s;
+    for (int k = 0; k < len; k++) neat_conns[node_bias + b + k].path_id = id + sample_bias;
+}
+
+template <typename T>
+static void grow_keep(DevBuf<T>& buf, size_t used, size_t need, cudaStream_t st) {
+    if (need <= buf.n && buf.p) return;
+    size_t cap = std::max<size_t>(need, buf.n * 2);
+    T* np = nullptr;
+    SPC_CUDA(cudaMalloc((void**)&np, cap * sizeof(T)));
+    if (used && buf.p) SPC_CUDA(cudaMemcpyAsync(np, buf.p, used * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    SPC_CUDA(cudaStreamSynchronize(st));
+    if (buf.p) cudaFree(buf.p);
+    buf.p = np;
+    buf.n = cap;
+}
+
+static void pinned(Context& c) {
+    if (!c.h_pinned) SPC_CUDA(cudaMallocHost((void**)&c.h_pinned, 64 * sizeof(int)));
+}
+
+int train_gather(Context& c, const spc_train_path* raw_paths, int max_paths, const spc_train_conn* raw_conns, int max_conns) {
+    TrainBuffers& t = c.train;
+    pinned(c);
+    cudaStream_t st = c.stream;
+    t.flag_p.alloc(max_paths); t.flag_c.alloc(max_conns); t.pos_p.alloc(max_paths); t.pos_c.alloc(max_conns); t.totals.alloc(8);
+    k_path_flags<<<(max_paths + 255) / 256, 256, 0, st>>>(raw_paths, max_paths, t.flag_p.p);
+    k_conn_flags<<<(max_conns + 255) / 256, 256, 0, st>>>(raw_conns, max_conns, t.flag_c.p);
+    c.launches += 2;
+    exclusive_scan(c, t.flag_p.p, t.pos_p.p, max_paths, t.scan_sums, t.totals.p);
+    exclusive_scan(c, t.flag_c.p, t.pos_c.p, max_conns, t.scan_sums2, t.totals.p + 1);
+    SPC_CUDA(cudaMemcpyAsync(c.h_pinned, t.totals.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SPC_CUDA(cudaStreamSynchronize(st));
+    const int sample_count = c.h_pinned[0], node_count = c.h_pinned[1];
+    grow_keep(t.paths, t.n_paths, t.n_paths + sample_count, st);
+    grow_keep(t.conns, t.n_conns, t.n_conns + node_count, st);
+    k_gather_conns<<<(max_conns + 255) / 256, 256, 0, st>>>(raw_conns, max_conns, t.pos_c.p, t.conns.p + t.n_conns);
+    k_gather_paths<<<(max_paths + 255) / 256, 256, 0, st>>>(raw_paths, max_paths, t.pos_p.p, t.pos_c.p, t.paths.p, t.conns.p, (int)t.n_paths, (int)t.n_conns);
+    c.launches += 2;
+    SPC_CUDA(cudaGetLastError());
+    t.n_paths += sample_count;
+    t.n_conns += node_count;
+    return sample_count;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sample_reweight: weight[block] = sum of contri/pdf over the paths of a 10x10-pixel block IN PATH ORDER
+// (grid stride hard-coded to 192 = 1920/10, table of 1920*1000/100*1.1 entries, as in the reference)
+// ---------------------------------------------------------------------------------------------
+constexpr int kReweightBins = (int)(1920 * 1000 / 100 * 1.1);
+__global__ void k_reweight_keys(const spc_train_path* __restrict__ p, int n, int* __restrict__ key, float* __restrict__ w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int n_id = p[i].pixel_x / 10 + p[i].pixel_y / 10 * 192;
+    const float ww = (p[i].contri.x + p[i].contri.y + p[i].contri.z) / p[i].sample_pdf;
+    const bool skip = isnan(ww) || isinf(ww) || n_id < 0 || n_id >= kReweightBins;
+    key[i] = skip ? -1 : n_id;
+    w[i] = skip ? 0.f : ww;
+}
+__global__ void k_reweight_apply(spc_train_path* __restrict__ p, int n, const spc_subspace* __restrict__ bins) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int n_id = p[i].pixel_x / 10 + p[i].pixel_y / 10 * 192;
+    const float sum = (n_id >= 0 && n_id < kReweightBins) ? bins[n_id].sum_pmf : 0.f;
+    const float w = (float)((double)(sum / 100) + 0.1);
+    const float3 c = f3(p[i].contri.x, p[i].contri.y, p[i].contri.z) / w;
+    p[i].contri = spc_float3{c.x, c.y, c.z};
+}
+void train_reweight(Context& c) {
+    TrainBuffers& t = c.train;
+    const int n = (int)t.n_paths;
+    if (n == 0) return;
+    LvcBuffers& b = c.bins_tmp;
+    b.key.alloc(n); b.weight.alloc(n); b.totals.alloc(kReweightBins + 8);
+    SPC_CUDA(cudaMemsetAsync(b.totals.p + kReweightBins, 0, 8 * sizeof(int), c.stream));
+    k_reweight_keys<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, n, b.key.p, b.weight.p);
+    bin_ordered(c, b, n, kReweightBins, b.totals.p + kReweightBins);
+    k_reweight_apply<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, n, b.subspace.p);
+    c.launches += 2;
+    SPC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// get_weighted_point_for_tree_building: connections of the first `limit` paths are the first paths[limit-1].end_ind
+// entries of the connection array (paths and their connections are both stored in path order)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tree_points(const spc_train_path* __restrict__ paths, const spc_train_conn* __restrict__ conns, int n_conn, int eye_side,
+                              spc_divide_weight* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_conn) return;
+    const spc_train_conn& s = conns[j];
+    spc_divide_weight t;
+    t.position = t.dir = t.normal = spc_float3{0.f, 0.f, 0.f};
+    t.weight = 0.f;   // the reference pushes an uninitialised record for emitter endpoints on the light side
+    const spc_train_path& p = paths[s.path_id];
+    float w = (p.contri.x + p.contri.y + p.contri.z) / p.sample_pdf;
+    // deviation: a NaN/Inf weight (sample_pdf underflowed to 0 on a long path) would poison every sum of the
+    // tree builder -- the reference then degenerates to a single subspace; such samples get weight 0 here
+    if (isnan(w) || isinf(w)) w = 0.f;
+    if (eye_side) {
+        t.dir = s.A_dir; t.normal = s.A_normal; t.position = s.A_position; t.weight = w;
+    } else if (!s.light_source) {
+        t.dir = s.B_dir; t.normal = s.B_normal; t.position = s.B_position; t.weight = w;
+    }
+    out[j] = t;
+}
+int train_tree_points(Context& c, int eye_side, int max_size, spc_divide_weight* out_host, int cap) {
+    TrainBuffers& t = c.train;
+    if (t.n_paths == 0) return 0;
+    pinned(c);
+    const size_t limit = max_size == 0 ? t.n_paths : std::min(t.n_paths, (size_t)max_size);
+    spc_train_path last;
+    SPC_CUDA(cudaMemcpyAsync(&last, t.paths.p + limit - 1, sizeof(last), cudaMemcpyDeviceToHost, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    const int n = last.end_ind;
+    if (n > cap || !out_host) return n;
+    t.tree_pts.alloc(n);
+    k_tree_points<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, t.conns.p, n, eye_side, t.tree_pts.p);
+    c.launches++;
+    SPC_CUDA(cudaMemcpyAsync(out_host, t.tree_pts.p, (size_t)n * sizeof(spc_divide_weight), cudaMemcpyDeviceToHost, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// node_label
+// ---------------------------------------------------------------------------------------------
+__global__ void k_node_label(spc_train_conn* __restrict__ conns, int n, const spc_tree_node* __restrict__ eye_tree, const spc_tree_node* __restrict__ light_tree) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    spc_train_conn& s = conns[i];
+    s.label_A = tree_label(eye_tree, f3(s.A_position.x, s.A_position.y, s.A_position.z), f3(s.A_normal.x, s.A_normal.y, s.A_normal.z));
+    if (!s.light_source) s.label_B = tree_label(light_tree, f3(s.B_position.x, s.B_position.y, s.B_position.z), f3(s.B_normal.x, s.B_normal.y, s.B_normal.z));
+}
+void train_node_label(Context& c, const spc_tree_node* eye_tree, const spc_tree_node* light_tree) {
+    TrainBuffers& t = c.train;
+    const int n = (int)t.n_conns;
+    if (!n) return;
+    k_node_label<<<(n + 255) / 256, 256, 0, c.stream>>>(t.conns.p, n, eye_tree, light_tree);
+    c.launches++;
+    SPC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// preprocess_getQ: Q = running mean (weighted by path counts) of  sum_{v in subspace} w_v / path_count
+// ---------------------------------------------------------------------------------------------
+__global__ void k_q_update(float* __restrict__ Q, const spc_subspace* __restrict__ sub, int K, int path_count, float t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const float tmp = sub[i].sum_pmf / (float)path_count;
+    Q[i] = Q[i] * (1 - t) + tmp * t;
+}
+__global__ void k_q_zero_handle(float* __restrict__ Q, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K && Q[i] == 0) Q[i] = FLT_MAX;
+}
+int train_get_Q(Context& c, const spc_vertex* lvc, const uint8_t* valid, int n, int reset) {
+    TrainBuffers& t = c.train;
+    pinned(c);
+    const int K = c.K;
+    if (reset || !t.has_Q) {
+        t.Q.alloc(K);
+        SPC_CUDA(cudaMemsetAsync(t.Q.p, 0, K * sizeof(float), c.stream));
+        t.acc_valid_path = 0;
+        t.has_Q = true;
+    }
+    int* counters = lvc_bin(c, c.bins_tmp, lvc, valid, n);
+    SPC_CUDA(cudaMemcpyAsync(c.h_pinned, counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    const int path_count = c.h_pinned[1];
+    t.acc_valid_path += path_count;
+    const float tt = (float)path_count / (float)t.acc_valid_path;
+    k_q_update<<<(K + 127) / 128, 128, 0, c.stream>>>(t.Q.p, c.bins_tmp.subspace.p, K, path_count, tt);
+    c.launches++;
+    SPC_CUDA(cudaGetLastError());
+    return t.acc_valid_path;
+}
+void train_Q_zero_handle(Context& c) {
+    TrainBuffers& t = c.train;
+    SPC_REQUIRE(t.has_Q, SPC_ERR_INVALID, "Q_zero_handle before preprocess_getQ");
+    k_q_zero_handle<<<(c.K + 127) / 128, 128, 0, c.stream>>>(t.Q.p, c.K);
+    c.launches++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// build_optimal_E_train_data
+// ---------------------------------------------------------------------------------------------
+#define SPC_LOSS_THRESHOLD 1000000.0f   // optimal_E_loss_threshold (device_thrust.cu:3097)
+__device__ __forceinline__ float outlier_value(const spc_train_path& s, const spc_train_conn* __restrict__ nodes, const float* __restrict__ Q) {
+    float outler_value = s.fix_pdf;
+    const float weight = s.contri.x + s.contri.y + s.contri.z;
+    float loss = weight * weight / s.sample_pdf;
+    if (loss > SPC_LOSS_THRESHOLD || isnan(loss)) loss = SPC_LOSS_THRESHOLD;
+    for (int i = s.begin_ind; i < s.end_ind; i++)
+        outler_value = (float)((double)outler_value + (double)(nodes[i].peak_pdf / Q[nodes[i].label_B]) / 1000.0);   // float += double
+    return loss / outler_value;
+}
+__global__ void k_outlier_values(const spc_train_path* __restrict__ paths, int n, const spc_train_conn* __restrict__ nodes, const float* __restrict__ Q, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = outlier_value(paths[i], nodes, Q);
+}
+__global__ void k_outlier_clean(spc_train_path* __restrict__ paths, int n, const spc_train_conn* __restrict__ nodes, const float* __restrict__ Q, float threshold) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (outlier_value(paths[i], nodes, Q) > threshold) {
+        paths[i].contri.x *= 0; paths[i].contri.y *= 0; paths[i].contri.z *= 0;
+    }
+}
+__global__ void k_td_samples(const spc_train_path* __restrict__ paths, int n, float* __restrict__ f_square, float* __restrict__ pdf0, int* __restrict__ P2N) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const spc_train_path& s = paths[id];
+    const float weight = s.contri.x + s.contri.y + s.contri.z;
+    float f = weight * weight / s.sample_pdf;
+    if (f > SPC_LOSS_THRESHOLD || isnan(f)) f = SPC_LOSS_THRESHOLD;
+    f_square[id] = f;
+    pdf0[id] = s.fix_pdf;
+    P2N[id] = s.begin_ind;
+}
+__global__ void k_td_nodes(const spc_train_conn* __restrict__ nodes, int m, const float* __restrict__ Q, int K, float* __restrict__ peak, int* __restrict__ label_E,
+                           int* __restrict__ label_P) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= m) return;
+    const spc_train_conn& s = nodes[id];
+    label_E[id] = s.label_A * K + s.label_B;
+    label_P[id] = s.path_id;
+    float p = (double)Q[s.label_B] > 0.0 ? s.peak_pdf / Q[s.label_B] : 0.0f;
+    if (isnan(p) || isinf(p)) p = 0;
+    peak[id] = p;
+}
+void train_build_data(Context& c, int n_samples) {
+    TrainBuffers& t = c.train;
+    SPC_REQUIRE(t.has_Q, SPC_ERR_INVALID, "build_optimal_E_train_data before preprocess_getQ");
+    SPC_REQUIRE(n_samples >= 1000 && (size_t)n_samples <= t.n_paths, SPC_ERR_INVALID, "build_optimal_E_train_data: N=%d but the set holds %zu paths (>= 1000 needed)", n_samples, t.n_paths);
+    pinned(c);
+    cudaStream_t st = c.stream;
+    spc_train_path last;
+    SPC_CUDA(cudaMemcpyAsync(&last, t.paths.p + n_samples - 1, sizeof(last), cudaMemcpyDeviceToHost, st));
+    t.outlier.alloc(1000);
+    k_outlier_values<<<4, 256, 0, st>>>(t.paths.p, 1000, t.conns.p, t.Q.p, t.outlier.p);
+    float h[1000];
+    SPC_CUDA(cudaMemcpyAsync(h, t.outlier.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SPC_CUDA(cudaStreamSynchronize(st));
+    std::sort(h, h + 1000);   // thrust::sort + [999] (device_thrust.cu:3282-3284); NaNs cannot occur past the loss clamp unless Q is NaN
+    t.outlier_threshold = h[999];
+    const int np = (int)t.n_paths;
+    k_outlier_clean<<<(np + 255) / 256, 256, 0, st>>>(t.paths.p, np, t.conns.p, t.Q.p, t.outlier_threshold);
+    t.N = n_samples;
+    t.M = last.end_ind;
+    t.f_square.alloc(t.N); t.pdf0.alloc(t.N); t.P2N.alloc(t.N); t.peak.alloc(t.M); t.label_E.alloc(t.M); t.label_P.alloc(t.M);
+    k_td_samples<<<(t.N + 255) / 256, 256, 0, st>>>(t.paths.p, t.N, t.f_square.p, t.pdf0.p, t.P2N.p);
+    k_td_nodes<<<(t.M + 255) / 256, 256, 0, st>>>(t.conns.p, t.M, t.Q.p, c.K, t.peak.p, t.label_E.p, t.label_P.p);
+    c.launches += 4;
+    SPC_CUDA(cudaGetLastError());
+    t.h_P2N.resize(t.N);
+    SPC_CUDA(cudaMemcpyAsync(t.h_P2N.data(), t.P2N.p, (size_t)t.N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    SPC_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---------------------------------------------------------------------------------------------
+// preprocess_getGamma
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gamma_hist(const spc_train_path* __restrict__ paths, const spc_train_conn* __restrict__ conns, int n_conns, int K, float* __restrict__ G) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_conns) return;
+    const spc_train_conn& s = conns[j];
+    const spc_train_path& p = paths[s.path_id];
+    const float weight = (p.contri.x + p.contri.y + p.contri.z) / p.sample_pdf;
+    const float weight2 = (float)fmin((double)weight, 10.0);
+    atomicAdd(G + (size_t)s.label_A * K + s.label_B, weight2);
+}
+__global__ void k_gamma_rownorm(float* __restrict__ G, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    float* row = G + (size_t)i * K;
+    float weightS = 0;
+    for (int j = 0; j < K; j++) weightS += row[j];
+    for (int j = 0; j < K; j++) {
+        row[j] /= weightS;
+        if (weightS <= 1e-10f) row[j] = (float)(1.0 / K);
+    }
+}
+float* train_get_gamma(Context& c) {
+    TrainBuffers& t = c.train;
+    const int K = c.K;
+    t.gamma.alloc((size_t)K * K);
+    SPC_CUDA(cudaMemsetAsync(t.gamma.p, 0, (size_t)K * K * sizeof(float), c.stream));
+    const int n = (int)t.n_conns;
+    if (n) k_gamma_hist<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, t.conns.p, n, K, t.gamma.p);
+    k_gamma_rownorm<<<(K + 63) / 64, 64, 0, c.stream>>>(t.gamma.p, K);
+    c.launches += 2;
+    SPC_CUDA(cudaGetLastError());
+    return t.gamma.p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// train_optimal_E: minimise sum_i f2_i / (pdf0_i + sum_{n in i} peak_n * E[label_n]) over theta,
+// E = (1-c) * sigmoid(theta) / rowsum + c / K, Adam(lr .01, .9, .999, 1e-8); 1 epoch of N/20000 batches
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_ref(float a) { return (float)(1.0 / (1.0 + (double)cm_expf(-a))); }   // sigmoid<float> (:705-712)
+
+// one block per row: E = sigmoid(theta); row sum; E = E / sum * (1-c) + c/K   (get_E, :1149-1172)
+__global__ void k_train_E(const float* __restrict__ theta, int K, float c_keep, float c_uniform, float* __restrict__ E, float* __restrict__ Esum, float* __restrict__ dE) {
+    __shared__ float s_red[32];
+    const int row = blockIdx.x;
+    float part = 0.f;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        const float s = sigmoidf_ref(theta[(size_t)row * K + j]);
+        E[(size_t)row * K + j] = s;
+        dE[(size_t)row * K + j] = 0.f;
+        part += s;
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) { s_red[0] = v; Esum[row] = v; }
+    }
+    __syncthreads();
+    const float sum = s_red[0];
+    for (int j = threadIdx.x; j < K; j += blockDim.x) E[(size_t)row * K + j] = E[(size_t)row * K + j] / sum * c_keep + c_uniform;
+}
+// one lane per path of the batch: forward pdf, d(loss)/d(pdf), scatter-add into dE (get_forward_pdfs .. get_dE, :981-1088)
+__global__ void k_train_paths(const float* __restrict__ E, const float* __restrict__ f_square, const float* __restrict__ pdf0, const float* __restrict__ peak,
+                              const int* __restrict__ label_E, const int* __restrict__ P2N, int bias_sample, int batch, int N, int M,
+                              float* __restrict__ dE, float* __restrict__ loss_acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float loss = 0.f;
+    if (i < batch) {
+        const int b = P2N[bias_sample + i];
+        // a path's nodes are [P2N[i], P2N[i+1]).  (The reference hands the last batch every remaining node, device_thrust.cu:1636,
+        // which only is well-defined when N is a multiple of the batch size -- its own use, 2 000 000 / 20 000.)
+        const int e = (bias_sample + i + 1 < N) ? P2N[bias_sample + i + 1] : M;
+        float pdf = 0.f;
+        for (int k = b; k < e; k++) pdf += peak[k] * E[label_E[k]];
+        pdf += pdf0[bias_sample + i];
+        const float f2 = f_square[bias_sample + i];
+        loss = f2 / pdf;
+        const float d = -f2 / pdf / pdf;   // inver_gradient (:832-840)
+        for (int k = b; k < e; k++) atomicAdd(dE + label_E[k], peak[k] * d);
+    }
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss_acc, loss);
+}
+// one block per row: dE_sum, d(loss)/d(theta) (gradient_E2theta, :1090-1147) and the Adam step (:1437-1470)
+__global__ void k_train_step(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ E, const float* __restrict__ Esum,
+                             const float* __restrict__ dE, int K, int t, float lr, float beta1, float beta2, float eps) {
+    __shared__ float s_red[32];
+    const int row = blockIdx.x;
+    const float den = Esum[row];
+    float part = 0.f;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        const float res = E[(size_t)row * K + j];
+        const float value = res * den;
+        part += (-value / den / den) * dE[(size_t)row * K + j];   // inver_gradient_res * dE
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float x = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (threadIdx.x == 0) s_red[0] = x;
+    }
+    __syncthreads();
+    const float dEsum = s_red[0];
+    const float bc1 = 1 - cm_powf(beta1, (float)t), bc2 = 1 - cm_powf(beta2, (float)t);
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        const size_t i = (size_t)row * K + j;
+        const float th = theta[i];
+        const float sig = sigmoidf_ref(th);
+        const float a = sig * (1 - sig) * dEsum;          // sigmoid_gradient_theta * dE_sum
+        const float sg = E[i] * den;                        // theta_gradient
+        const float b0 = sg * (1 - sg) / den * dE[i];
+        const float g = a + b0;
+        const float mi = beta1 * m[i] + (1 - beta1) * g;
+        const float vi = beta2 * v[i] + (1 - beta2) * (g * g);
+        m[i] = mi;
+        v[i] = vi;
+        const float step = (mi / bc1) / (sqrtf(vi / bc2) + eps);
+        if (!isnan(step)) theta[i] = th - lr * step;
+    }
+}
+__global__ void k_theta_init(const float* __restrict__ G, size_t n, float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    theta[i] = (float)(-log(1.0 / (double)G[i] - 1));   // inver_sigmoid (:714-721)
+    m[i] = 0.f;
+    v[i] = 0.f;
+}
+// matrix_parameter::toE (:1583-1599): sigmoid + row normalise, no conservative mixing
+__global__ void k_train_toE(const float* __restrict__ theta, int K, float* __restrict__ G) {
+    __shared__ float s_red[32];
+    const int row = blockIdx.x;
+    float part = 0.f;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        const float s = sigmoidf_ref(theta[(size_t)row * K + j]);
+        G[(size_t)row * K + j] = s;
+        part += s;
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float x = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (threadIdx.x == 0) s_red[0] = x;
+    }
+    __syncthreads();
+    const float sum = s_red[0];
+    for (int j = threadIdx.x; j < K; j += blockDim.x) G[(size_t)row * K + j] /= sum;
+}
+
+float* train_optimal_E(Context& c, int batch_size, int epochs, float lr, float* loss_out_host, int loss_cap, int* n_loss) {
+    TrainBuffers& t = c.train;
+    SPC_REQUIRE(t.N > 0 && t.gamma.p, SPC_ERR_INVALID, "train_optimal_E needs build_optimal_E_train_data and preprocess_getGamma first");
+    SPC_REQUIRE(batch_size > 0 && t.N >= batch_size, SPC_ERR_INVALID, "train_optimal_E: batch %d > %d training paths", batch_size, t.N);
+    const int K = c.K;
+    const size_t n = (size_t)K * K;
+    cudaStream_t st = c.stream;
+    t.theta.alloc(n); t.adam_m.alloc(n); t.adam_v.alloc(n); t.E.alloc(n); t.dE.alloc(n); t.Esum.alloc(K);
+    const int num_batches = t.N / batch_size;
+    t.loss.alloc((size_t)num_batches * epochs + 1);
+    SPC_CUDA(cudaMemsetAsync(t.loss.p, 0, ((size_t)num_batches * epochs + 1) * sizeof(float), st));
+    k_theta_init<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.gamma.p, n, t.theta.p, t.adam_m.p, t.adam_v.p);
+    c.launches++;
+    const float c_keep = (float)(1 - 0.2), c_uniform = (float)(0.2 / (double)(float)K);   // CONSERVATIVE_RATE (optixPathTracer.h:36)
+    int step = 0;
+    for (int ep = 0; ep < epochs; ep++)
+        for (int b = 0; b < num_batches; b++) {
+            const int bias_sample = b * batch_size;
+            step++;
+            k_train_E<<<K, 256, 0, st>>>(t.theta.p, K, c_keep, c_uniform, t.E.p, t.Esum.p, t.dE.p);
+            k_train_paths<<<(batch_size + 127) / 128, 128, 0, st>>>(t.E.p, t.f_square.p, t.pdf0.p, t.peak.p, t.label_E.p, t.P2N.p, bias_sample, batch_size,
+                                                                   t.N, t.M, t.dE.p, t.loss.p + (step - 1));
+            k_train_step<<<K, 256, 0, st>>>(t.theta.p, t.adam_m.p, t.adam_v.p, t.E.p, t.Esum.p, t.dE.p, K, step, lr, 0.9f, 0.999f, 1e-8f);
+            c.launches += 3;
+        }
+    k_train_toE<<<K, 256, 0, st>>>(t.theta.p, K, t.gamma.p);
+    c.launches++;
+    SPC_CUDA(cudaGetLastError());
+    if (n_loss) *n_loss = step;
+    if (loss_out_host && loss_cap > 0) {
+        const int m = std::min(loss_cap, step);
+        std::vector<float> h(m);
+        SPC_CUDA(cudaMemcpyAsync(h.data(), t.loss.p, m * sizeof(float), cudaMemcpyDeviceToHost, st));
+        SPC_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < m; i++) loss_out_host[i] = h[i] / (float)batch_size;
+    }
+    return t.gamma.p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gamma2CMFGamma: 0.8 * Gamma + 0.2 / K, sequential row prefix, last entry forced to 1
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gamma_to_cmf(const float* __restrict__ G, int K, float* __restrict__ cmf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const float t = 0.2f;   // CONSERVATIVE_RATE as a float (device_thrust.cu:3415)
+    float run = 0.f;
+    for (int j = 0; j < K; j++) {
+        const float p = (float)((double)(G[(size_t)i * K + j] * (1 - t)) + (1.0 / K) * (double)t);
+        run = j == 0 ? p : p + run;
+        cmf[(size_t)i * K + j] = run;
+    }
+    cmf[(size_t)(i + 1) * K - 1] = 1;
+}
+float* train_gamma_to_cmf(Context& c, const float* gamma_dev) {
+    TrainBuffers& t = c.train;
+    const int K = c.K;
+    t.cmf.alloc((size_t)K * K);
+    k_gamma_to_cmf<<<(K + 63) / 64, 64, 0, c.stream>>>(gamma_dev, K, t.cmf.p);
+    c.launches++;
+    SPC_CUDA(cudaGetLastError());
+    return t.cmf.p;
+}
+
+}  // namespace spc

@@ -144,6 +144,24 @@ def _box(center_xz, size_xz, height, angle_deg, m):
     return _merge(faces)
 
 
+def scaled(sc, k):
+    """uniformly scale a scene (geometry, lights, camera) by k"""
+    k = np.float32(k)
+    for m in sc.meshes:
+        m["positions"] = (m["positions"] * k).astype(np.float32)
+    lights = []
+    for i in range(sc.lights.shape[0]):
+        L = sc.lights[i]
+        lights.append(make_quad_light(int(L["id"]), L["corner"] * k, L["u"] * k, L["v"] * k, L["emission"], int(L["divLevel"]), int(L["ssBase"])))
+    sc.lights = np.concatenate(lights)
+    li = 0
+    for j, m in enumerate(sc.meshes):
+        if m["light_id"] >= 0:
+            sc.meshes[j] = light_mesh(sc.lights[m["light_id"]:m["light_id"] + 1], m["light_id"])
+    sc.camera = dict(sc.camera, eye=tuple(np.asarray(sc.camera["eye"], np.float32) * k), lookat=tuple(np.asarray(sc.camera["lookat"], np.float32) * k))
+    return sc
+
+
 def cornell_scene(wall_cells=48, box_cells=36, div_level=2, K=64):
     """Cornell-class fixture of config 1: 5 walls, 2 boxes, one quad light
     divLevel 2 with emission (17,12,4); Disney materials roughness .5 metallic 0; camera eye

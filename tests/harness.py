@@ -207,3 +207,49 @@ def float_bits_differ(x, y):
     x = np.ascontiguousarray(x, np.float32)
     y = np.ascontiguousarray(y, np.float32)
     return (x.view(np.uint32) != y.view(np.uint32)) & ~(np.isnan(x) & np.isnan(y))
+
+
+def setup_pretrace(frame, num_core, padding=10, iteration=1):
+    """allocate the pretrace output buffers of a HostFrame (preTracer_params_setup, optixPathTracer.cpp:479-488)"""
+    pkg = frame.pkg
+    frame.tp = np.zeros(num_core, pkg.TRAIN_PATH)
+    frame.tc = np.zeros(num_core * padding, pkg.TRAIN_CONN)
+    pt = frame.P["pre_tracer"]
+    pt["num_core"], pt["padding"], pt["iteration"] = num_core, padding, iteration
+    pt["paths"], pt["conns"] = frame.tp.ctypes.data, frame.tc.ctypes.data
+
+
+def compare_train(pkg, pa, ca, pb, cb, exact=True):
+    """pretrace outputs a vs b: valid flags, then every field of the valid paths / connections"""
+    bad = []
+    if not np.array_equal(pa["valid"], pb["valid"]):
+        return ["path valid flags differ on %d" % int((pa["valid"] != pb["valid"]).sum())]
+    if not np.array_equal(ca["valid"], cb["valid"]):
+        return ["conn valid flags differ on %d" % int((ca["valid"] != cb["valid"]).sum())]
+    v = pa["valid"] == 1
+    for k in ("contri", "sample_pdf", "fix_pdf", "begin_ind", "end_ind", "pixel_id"):
+        x, y = pa[k][v], pb[k][v]
+        ne = float_bits_differ(x, y) if x.dtype.kind == "f" else (x != y)
+        if ne.any():
+            bad.append("path.%s: %d of %d differ" % (k, int(ne.sum()), ne.size))
+    v = ca["valid"] == 1
+    for k in ("A_position", "B_position", "A_dir", "B_dir", "A_normal", "B_normal", "peak_pdf", "label_A", "label_B", "light_source"):
+        x, y = ca[k][v], cb[k][v]
+        ne = float_bits_differ(x, y) if x.dtype.kind == "f" else (x != y)
+        if ne.any():
+            bad.append("conn.%s: %d of %d differ" % (k, int(ne.sum()), ne.size))
+    return bad
+
+
+def setup_pretrace_device(df, num_core, padding=10, iteration=1):
+    """device twin of setup_pretrace for a DeviceFrame"""
+    torch, pkg = df.torch, df.pkg
+    df.tp = torch.zeros(num_core * pkg.TRAIN_PATH.itemsize, dtype=torch.uint8, device="cuda")
+    df.tc = torch.zeros(num_core * padding * pkg.TRAIN_CONN.itemsize, dtype=torch.uint8, device="cuda")
+    pt = df.P["pre_tracer"]
+    pt["num_core"], pt["padding"], pt["iteration"] = num_core, padding, iteration
+    pt["paths"], pt["conns"] = df.tp.data_ptr(), df.tc.data_ptr()
+
+
+def pretrace_host(df):
+    return df.tp.cpu().numpy().view(df.pkg.TRAIN_PATH).copy(), df.tc.cpu().numpy().view(df.pkg.TRAIN_CONN).copy()

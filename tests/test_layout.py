@@ -84,3 +84,17 @@ def test_product_does_not_reference_oracle():
                     txt = open(os.path.join(dp, f), errors="ignore").read()
                     m = bad.search(txt)
                     assert not m, "%s: %s" % (f, m.group(0))
+
+
+def test_tree_build_matches_reference_golden(pkg):
+    """spc_build_tree (host code, as in the reference) against the tree the reference's own
+    classTree::buildTreeBaseOnExistSample produced on the same 2000 samples (tests/golden/tree.npz)"""
+    g = np.load(os.path.join(GOLD, "tree.npz"))
+    tree, max_label = pkg.build_tree(g["samples"], 16, 0)
+    ref = g["tree"]
+    assert tree.shape[0] == ref.shape[0] and max_label == int(g["max_label"])
+    assert np.array_equal(tree["leaf"], ref["leaf"]) and np.array_equal(tree["label"], ref["label"])
+    inner = ref["leaf"] == 0     # mid / child / type of leaves are uninitialised memory in the reference
+    assert np.array_equal(tree["type"][inner], ref["type"][inner])
+    assert np.array_equal(tree["child"][inner], ref["child"][inner])
+    assert np.array_equal(tree["mid"][inner].view(np.uint32), ref["mid"][inner].view(np.uint32))
