@@ -374,7 +374,7 @@ void TrainSet::gamma_histogram(int K, std::vector<float>& G) const {
     for (size_t i = 0; i < paths.size(); i++) {
         const float weight = sum3(ld(paths[i].contri)) / paths[i].sample_pdf;
         for (int j = paths[i].begin_ind; j < paths[i].end_ind; j++) {
-            const float weight2 = (float)std::min((double)weight, 10.0);   // min(float, double literal)
+            const float weight2 = (float)std::fmin((double)weight, 10.0);   // CUDA host min(float,double) = fmin: NaN -> 10
             G[(size_t)conns[j].label_A * K + conns[j].label_B] += weight2;
         }
     }

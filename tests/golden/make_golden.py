@@ -9,6 +9,7 @@ Files:
   rng.json          tea<4>/tea<16> known answers + LCG streams (src/cuda/random.h)
   tree.npz          classTree::buildTreeBaseOnExistSample on 2000 seeded samples + tree_index labels
   bsdf.npz          Tracer::Eval / Pdf / Sample on 256 seeded inputs
+  train.npz         the reference's __raygen__TrainData (3000 launch indices, iteration 5) on the same fixture
   render.npz        the reference's raygen/closest-hit programs on a 682-triangle Cornell fixture:
                     LVC of a light-trace launch, accum buffers of three SPCBPT_eye subframes
                     (intersection = the contract of oracle/orc_scene.cpp, see ref_host.cpp header)
@@ -127,6 +128,16 @@ def main():
     np.savez_compressed(os.path.join(HERE, "render.npz"), eye_tree=eye_tree, light_tree=light_tree,
                         q_sha=hashlib.sha256(Q.tobytes()).hexdigest(), cmf_sha=hashlib.sha256(cmf.tobytes()).hexdigest(), lvc=lvc, valid=fr.valid,
                         sub=sub, cmfs=cmfs, jump=jump, vc=vc, pc=pc, accum=np.stack(accums), frame=np.stack(frames))
+    # ---- training tracer: the reference's __raygen__TrainData on the same fixture (jitter drawn right-to-left: g++ build)
+    from harness import setup_pretrace
+    setup_pretrace(fr, 3000, 10, iteration=5)
+    ref.launch(fr.P, ref.KIND_PRETRACE, 3000, 1, threads=4)
+    tp, tc = fr.tp.copy(), fr.tc.copy()
+    tp[tp["valid"] == 0] = np.zeros(1, pkg.TRAIN_PATH)      # undefined content of invalid records
+    tc[tc["valid"] == 0] = np.zeros(1, pkg.TRAIN_CONN)
+    tc["path_id"] = 0                                        # set later by valid_sample_gather
+    tp["choice_id"] = 0                                      # never written by the reference
+    np.savez_compressed(os.path.join(HERE, "train.npz"), paths=tp, conns=tc)
     ref.lib().ref_scene_destroy()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from harness import GOLDEN_CFG, HostFrame, compare_lvc, golden_scene, random_q_gamma
+from harness import GOLDEN_CFG, HostFrame, compare_lvc, compare_train, golden_scene, random_q_gamma, setup_pretrace
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -111,3 +111,99 @@ def test_eye_pass_accum(pkg, orc, golden_frame):
     finally:
         orc.set_jitter_rtl(0)
     assert fr.accum[:, :3].mean() > 0.01
+
+
+def test_pretrace_vs_reference_golden(pkg, orc, golden_frame):
+    """oracle __raygen__TrainData restatement == the reference's own program (tests/golden/train.npz)"""
+    g, sc, osc, fr, K = golden_frame
+    t = np.load(os.path.join(GOLD, "train.npz"))
+    setup_pretrace(fr, 3000, 10, iteration=5)
+    orc.set_jitter_rtl(1)
+    try:
+        orc.pretrace(osc, fr.P, K, threads=4)
+    finally:
+        orc.set_jitter_rtl(0)
+    bad = compare_train(pkg, fr.tp, fr.tc, t["paths"], t["conns"])
+    assert not bad, bad
+    assert t["paths"]["valid"].sum() > 1000
+
+
+def test_training_oracle_properties(pkg, orc, golden_frame):
+    """structure of the MyThrustOp restatement on the golden training paths: gather keeps order and fixes indices, the Gamma
+    histogram rows are normalised, the CDF is monotone and ends at 1, the trainer lowers its own loss"""
+    g, sc, osc, fr, K = golden_frame
+    t = np.load(os.path.join(GOLD, "train.npz"))
+    ts = orc.TrainSet(pkg)
+    n = ts.gather(t["paths"], t["conns"])
+    assert n == int(t["paths"]["valid"].sum())
+    p, c = ts.read()
+    assert (p["end_ind"] > p["begin_ind"]).all() and p["begin_ind"][0] == 0 and (p["begin_ind"][1:] == p["end_ind"][:-1]).all()
+    assert c.shape[0] == p["end_ind"][-1] and (c["path_id"] == np.repeat(np.arange(n), p["end_ind"] - p["begin_ind"])).all()
+    ts.reweight()
+    ts.label(g["eye_tree"], g["light_tree"])
+    p, c = ts.read()
+    assert c["label_A"].max() < K and c["label_B"].max() < K
+    Q = np.full(K, 0.5, np.float32)
+    td = ts.build_train_data(n, Q, K)
+    G = ts.gamma_histogram(K)
+    assert np.allclose(G.sum(1), 1, atol=1e-4)
+    E, loss = orc.train_gamma(td, K, G, 500, 3, 0.01)
+    # (this 556-unit fixture underflows sample_pdf on long paths, so a few losses are inf: only the bookkeeping is checked
+    #  here; the trainer's arithmetic is checked against numpy in test_trainer_matches_numpy and on the GPU chain)
+    assert loss.shape[0] == 3 * (n // 500)
+    ok = np.isfinite(E).all(1)
+    assert ok.mean() > 0.95 and np.allclose(E[ok].sum(1), 1, atol=1e-4)
+    C = orc.gamma_to_cmf(E, K)
+    assert (C[:, -1] == 1).all() and (np.diff(C[ok], axis=1) >= -1e-7).all()
+
+
+def test_trainer_matches_numpy(pkg, orc):
+    """train_optimal_E restatement (sigmoid/row-normalised E, 1/pdf loss, the reference's gradient formulas, Adam) against an
+    independent float64 numpy implementation on a synthetic training set"""
+    K, N, B = 8, 1200, 400
+    rng = np.random.default_rng(0)
+    paths = np.zeros(N, pkg.TRAIN_PATH)
+    conns = np.zeros(N * 10, pkg.TRAIN_CONN)
+    lens = rng.integers(1, 4, N)
+    for i in range(N):
+        paths[i]["valid"], paths[i]["begin_ind"], paths[i]["end_ind"] = 1, i * 10, i * 10 + lens[i]
+        paths[i]["contri"], paths[i]["sample_pdf"], paths[i]["fix_pdf"] = rng.uniform(0.1, 1, 3), rng.uniform(0.5, 2), rng.uniform(0.1, 0.5)
+        for k in range(lens[i]):
+            c = conns[i * 10 + k]
+            c["valid"], c["peak_pdf"], c["label_A"], c["label_B"] = 1, rng.uniform(0.1, 3), rng.integers(0, K), rng.integers(0, K)
+    ts = orc.TrainSet(pkg)
+    ts.gather(paths, conns)
+    td = ts.build_train_data(N, np.ones(K, np.float32), K)
+    G0 = ts.gamma_histogram(K)
+    E, loss = orc.train_gamma(td, K, G0, B, 1, 0.01)
+
+    def sig(x):
+        return 1 / (1 + np.exp(-x))
+    theta = -np.log(1 / G0.astype(np.float64) - 1)
+    m, v = np.zeros_like(theta), np.zeros_like(theta)
+    f2, pdf0, peak = (td[k].astype(np.float64) for k in ("f_square", "pdf0", "peak"))
+    P2N, lE, lP = td["P2N"], td["label_E"], td["label_P"]
+    ref_loss = []
+    for b in range(N // B):
+        bs, bn = b * B, P2N[b * B]
+        seg = (td["M"] if bs + B >= N else P2N[bs + B]) - bn
+        S = sig(theta)
+        Es = S.sum(1, keepdims=True)
+        Em = S / Es * 0.8 + 0.2 / K
+        pdf = np.zeros(B)
+        np.add.at(pdf, lP[bn:bn + seg] - bs, peak[bn:bn + seg] * Em.reshape(-1)[lE[bn:bn + seg]])
+        pdf += pdf0[bs:bs + B]
+        ref_loss.append((f2[bs:bs + B] / pdf).mean())
+        d = -f2[bs:bs + B] / pdf ** 2
+        dE = np.zeros(K * K)
+        np.add.at(dE, lE[bn:bn + seg], peak[bn:bn + seg] * d[lP[bn:bn + seg] - bs])
+        dE = dE.reshape(K, K)
+        dEsum = (-(Em * Es) / Es / Es * dE).sum(1, keepdims=True)
+        g = S * (1 - S) * dEsum + ((Em * Es) * (1 - (Em * Es)) / Es) * dE
+        t = b + 1
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        theta -= 0.01 * (m / (1 - 0.9 ** t)) / (np.sqrt(v / (1 - 0.999 ** t)) + 1e-8)
+    assert np.allclose(loss, ref_loss, rtol=1e-5)
+    S = sig(theta)
+    assert np.abs(S / S.sum(1, keepdims=True) - E).max() < 1e-5

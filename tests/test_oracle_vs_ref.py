@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from harness import HostFrame, compare_lvc, random_trees_and_gamma
+from harness import HostFrame, compare_lvc, compare_train, random_trees_and_gamma, setup_pretrace
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -112,3 +112,53 @@ def test_bsdf_random(pkg, orc, ref):
         b = orc.bsdf(osc, i, None, N, V, L, seed)
         assert np.array_equal(a[0].view(np.uint32), b[0].view(np.uint32)) and np.float32(a[1]).view(np.uint32) == np.float32(b[1]).view(np.uint32)
         assert np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32)) and a[3] == b[3]
+
+
+def test_pretrace_bit_exact(pkg, orc, ref):
+    """oracle TrainData restatement vs the reference's own __raygen__TrainData on the varied scene"""
+    sc = _varied_cornell(pkg)
+    K, KL = 1000, 200
+    osc = orc.Scene(pkg, sc)
+    ref.scene_create(pkg, sc)
+    P = np.concatenate([m["positions"][m["indices"].astype(np.int64)].mean(1) for m in sc.meshes]).astype(np.float32)
+    N = np.tile(np.array([[0, 1, 0]], np.float32), (P.shape[0], 1))
+    eye_tree, light_tree, Q, cmf = random_trees_and_gamma(pkg, P, N, K, KL, ref.tree_build, seed=3)
+    frames = []
+    orc.set_jitter_rtl(1)
+    try:
+        for kind in ("ref", "orc"):
+            fr = HostFrame(pkg, sc, 320, 200, K=K, num_core=8, core_padding=50, M_per_core=5)
+            fr.set_trees(eye_tree, light_tree)
+            setup_pretrace(fr, 8000, 10, iteration=2)
+            if kind == "ref":
+                ref.launch(fr.P, ref.KIND_PRETRACE, 8000, 1, threads=8)
+            else:
+                orc.pretrace(osc, fr.P, K, threads=8)
+            frames.append(fr)
+    finally:
+        orc.set_jitter_rtl(0)
+        ref.lib().ref_scene_destroy()
+    bad = compare_train(pkg, frames[1].tp, frames[1].tc, frames[0].tp, frames[0].tc)
+    assert not bad, bad
+    assert frames[0].tp["valid"].sum() > 3000
+
+
+def test_tree_builder_vs_reference_K1000(pkg, ref):
+    """spc_build_tree vs classTree::buildTreeBaseOnExistSample at the reference's K on 20 000 clustered samples"""
+    rng = np.random.default_rng(11)
+    n = 20000
+    s = np.zeros(n, pkg.DIVIDE_WEIGHT)
+    c = rng.uniform(-4, 4, (40, 3))
+    s["position"] = (c[rng.integers(0, 40, n)] + rng.normal(0, 0.3, (n, 3))).astype(np.float32)
+    nn = rng.normal(0, 1, (n, 3))
+    s["normal"] = (nn / np.linalg.norm(nn, axis=1, keepdims=True)).astype(np.float32)
+    s["dir"] = s["normal"]
+    s["weight"] = rng.uniform(0, 1, n).astype(np.float32) ** 3
+    for K, bias in ((1000, 0), (800, 0)):
+        a, ma = pkg.build_tree(s, K, bias)
+        b, mb = ref.tree_build(pkg, s, K, bias)
+        assert a.shape == b.shape and ma == mb
+        assert np.array_equal(a["leaf"], b["leaf"]) and np.array_equal(a["label"], b["label"])
+        inner = b["leaf"] == 0
+        assert np.array_equal(a["type"][inner], b["type"][inner]) and np.array_equal(a["child"][inner], b["child"][inner])
+        assert np.array_equal(a["mid"][inner].view(np.uint32), b["mid"][inner].view(np.uint32))
