@@ -55,3 +55,32 @@ REF_API void* ref_thrust_gamma_to_cmf() { return thrust::raw_pointer_cast(MyThru
 REF_API int ref_thrust_download(const void* dev, void* host, size_t bytes) {
     return (int)cudaMemcpy(host, dev, bytes, cudaMemcpyDeviceToHost);
 }
+
+// the reference's file-scope state (device_thrust.cu:428-429, 3098-3111), read back for comparison
+namespace MyThrustOp {
+extern thrust::device_vector<preTracePath> neat_paths;
+extern thrust::device_vector<preTraceConnection> neat_conns;
+extern thrust::device_vector<float> b_f_square, b_pdf0, b_pdf_peak;
+extern thrust::device_vector<int> b_label_E, b_label_P, b_P2N_ind_d;
+}
+REF_API void ref_thrust_set_sizes(int* n_paths, int* n_conns) {
+    *n_paths = (int)MyThrustOp::neat_paths.size();
+    *n_conns = (int)MyThrustOp::neat_conns.size();
+}
+REF_API void ref_thrust_set_read(void* paths_host, void* conns_host) {
+    cudaMemcpy(paths_host, thrust::raw_pointer_cast(MyThrustOp::neat_paths.data()), MyThrustOp::neat_paths.size() * sizeof(preTracePath), cudaMemcpyDeviceToHost);
+    cudaMemcpy(conns_host, thrust::raw_pointer_cast(MyThrustOp::neat_conns.data()), MyThrustOp::neat_conns.size() * sizeof(preTraceConnection), cudaMemcpyDeviceToHost);
+}
+REF_API void ref_thrust_train_data_sizes(int* N, int* M) {
+    *N = (int)MyThrustOp::b_f_square.size();
+    *M = (int)MyThrustOp::b_pdf_peak.size();
+}
+REF_API void ref_thrust_train_data_read(float* f_square, float* pdf0, int* P2N, float* peak, int* label_E, int* label_P) {
+    using namespace MyThrustOp;
+    cudaMemcpy(f_square, thrust::raw_pointer_cast(b_f_square.data()), b_f_square.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(pdf0, thrust::raw_pointer_cast(b_pdf0.data()), b_pdf0.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(P2N, thrust::raw_pointer_cast(b_P2N_ind_d.data()), b_P2N_ind_d.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(peak, thrust::raw_pointer_cast(b_pdf_peak.data()), b_pdf_peak.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(label_E, thrust::raw_pointer_cast(b_label_E.data()), b_label_E.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(label_P, thrust::raw_pointer_cast(b_label_P.data()), b_label_P.size() * 4, cudaMemcpyDeviceToHost);
+}
