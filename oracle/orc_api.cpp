@@ -158,6 +158,15 @@ ORC_API void orc_eye_pass(void* sc, const spc_params* p, int K, int connections,
     });
 }
 
+// optixLaunch of "pt" (the comparison integrator, raygen.cu:71-170)
+ORC_API void orc_pt_pass(void* sc, const spc_params* p, int K, int threads) {
+    const Frame fr = make_frame(sc, p, K, 3, 0);
+    const int W = (int)p->width, H = (int)p->height;
+    parallel_for((int64_t)W * H, threads, [&](int64_t b, int64_t e) {
+        for (int64_t i = b; i < e; i++) pt_pixel(fr, (int)(i % W), (int)(i / W));
+    });
+}
+
 // stage-wise entry points -----------------------------------------------------------------------
 ORC_API void orc_bsdf(void* sc, int material_id, const float* color3, const float* N, const float* V, const float* L, uint32_t* seed,
                       float* eval3, float* pdf1, float* sample3) {

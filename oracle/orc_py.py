@@ -150,6 +150,13 @@ def eye_pass(scene, params, K, connections=3, max_depth=0, threads=8, want_first
     return fp, fl
 
 
+def pt_pass(scene, params, K, threads=8):
+    L = lib()
+    L.orc_pt_pass.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    L.orc_pt_pass.restype = None
+    L.orc_pt_pass(scene.h, params.ctypes.data, K, threads)
+
+
 def bsdf(scene, material_id, color, N, V, Ldir, seed):
     L = lib(); _bind_render(L)
     N, V, Ldir = (np.ascontiguousarray(a, np.float32) for a in (N, V, Ldir))

@@ -801,3 +801,114 @@ void lvc_process(const spc_vertex* lvc, const uint8_t* valid, int n, int K, spc_
 }
 
 }  // namespace orc
+
+// ============================================================================================
+// "pt": the reference's comparison integrator (unidirectional path tracing + next-event estimation + MIS):
+// __raygen__pinhole (raygen.cu:71-170), __closesthit__radiance (hit_program.cu:439-552),
+// __closesthit__lightsource (:148-180), __miss__constant_radiance (raygen.cu:687-696)
+// ============================================================================================
+namespace orc {
+
+void pt_pixel(const Frame& fr, int px, int py) {
+    const spc_params& P = fr.p;
+    const unsigned W = P.width, H = P.height;
+    const int subframe_index = (int)P.subframe_index;
+    const unsigned image_index = (unsigned)py * W + (unsigned)px;
+    uint32_t seed = tea(4, image_index, (uint32_t)subframe_index);
+    float jx = 0.5f, jy = 0.5f;
+    if (subframe_index != 0) {
+        if (g_jitter_rtl) { jy = rnd(seed); jx = rnd(seed); }
+        else { jx = rnd(seed); jy = rnd(seed); }
+    }
+    const float dx = 2.0f * (((float)px + jx) / (float)W) - 1.0f;
+    const float dy = 2.0f * (((float)py + jy) / (float)H) - 1.0f;
+    f3 ray_direction = normalize(dx * ld(P.U) + dy * ld(P.V) + ld(P.W));
+    f3 ray_origin = ld(P.eye);
+    // PayloadRadiance (whitted.h:86-108)
+    f3 result = mk3(0.0f), throughput = mk3(1.0f), currentResult = mk3(0.0f), vis_A = mk3(0.0f), vis_B = mk3(0.0f);
+    float prd_pdf = 0.f;
+    int depth = 0;
+    bool done = false;
+    while (true) {
+        Hit h;
+        if (!fr.sc->closest(ray_origin, ray_direction, SCENE_EPS, 1e16f, true, h)) {
+            done = true;                       // __miss__constant_radiance (no sky)
+            currentResult = mk3(0.0f);
+        } else {
+            const Tri& tr = fr.sc->tris[h.prim];
+            const LocalGeom geom = local_geometry(tr, h.u, h.v);
+            if (tr.light >= 0) {               // __closesthit__lightsource
+                LightSample ls;
+                light_reverse_sample(fr, fr.sc->lights[tr.light], geom.uvx, geom.uvy, ls);
+                const f3 ln = ld(ls.light->normal);
+                if (dot(ray_direction, ln) <= 0) {
+                    float MIS_weight = 1;
+                    if (depth != 0) {
+                        const float pdf_hit = prd_pdf * absf(dot(ray_direction, ln)) / (h.t * h.t);
+                        const float pdf_area = ls.pdf;
+                        MIS_weight = pdf_hit / (pdf_area + pdf_hit);
+                    }
+                    result += throughput * ls.emission * MIS_weight;
+                }
+                done = true;
+            } else {                           // __closesthit__radiance
+                const Pbr pbr = shade_pbr(*fr.sc, tr.material, geom.uvx, geom.uvy);
+                f3 N = geom.Ng;
+                if (dot(N, ray_direction) > 0.f) N = -N;
+                const f3 in_dir = -ray_direction;
+                f3 res = mk3(0.0f);
+                const float rr_rate = std::fmax(0.3f, std::fmin(fmax3(pbr.base_color), 1.0f));   // clamp(fmaxf(color), MIN_RR_RATE, 1.0)
+                const int light_id = pick_light(fr, seed);
+                const spc_light& light = fr.sc->lights[light_id];
+                LightSample ls;
+                light_sample_pos(fr, light, seed, ls);
+                const float L_dist = length(ls.position - geom.P);
+                const f3 L = (ls.position - geom.P) / L_dist;
+                const f3 V = -normalize(ray_direction);
+                const f3 LN = ld(light.normal);
+                const float L_dot_LN = dot(-L, LN);
+                const float N_dot_L = dot(N, L);
+                const float N_dot_V = dot(N, V);
+                if (N_dot_L > 0.0f && N_dot_V > 0.0f && L_dot_LN > 0.0f) {
+                    vis_A = geom.P;
+                    vis_B = ls.position;
+                    const f3 eval = bsdf_eval(pbr, N, V, L);
+                    const float pdf_area = ls.pdf;
+                    const float pdf_hit = bsdf_pdf(pbr, N, V, L) * absf(L_dot_LN) / (L_dist * L_dist) * rr_rate;
+                    const float MIS_weight = pdf_area / (pdf_hit + pdf_area);
+                    res += throughput * ls.emission * 1.0f / ls.pdf * N_dot_L * L_dot_LN / L_dist / L_dist * eval * MIS_weight;
+                }
+                currentResult += res;
+                ray_origin = geom.P;
+                if (rnd(seed) > rr_rate) {
+                    done = true;
+                } else {
+                    ray_direction = bsdf_sample(pbr, N, in_dir, seed);
+                    const float pdf = bsdf_pdf(pbr, N, in_dir, ray_direction);
+                    if (pdf > 0.0f) {
+                        throughput *= bsdf_eval(pbr, N, in_dir, ray_direction) * absf(dot(ray_direction, N)) / pdf / rr_rate;
+                        prd_pdf = pdf * rr_rate;
+                    } else {
+                        done = true;
+                    }
+                }
+            }
+        }
+        if (sum3(currentResult) > 0.0) {
+            if (visibility_test(fr, vis_A, vis_B)) result += currentResult;
+            currentResult = mk3(0.0f);
+        }
+        if (done || depth > 30) break;
+        depth += 1;
+    }
+    f3 accum_color = result;
+    if (subframe_index > 0) {
+        const float a = 1.0f / (float)(subframe_index + 1);
+        const spc_float4& prev = P.accum_buffer[image_index];
+        accum_color = lerp3(f3{prev.x, prev.y, prev.z}, accum_color, a);
+    }
+    P.accum_buffer[image_index] = spc_float4{accum_color.x, accum_color.y, accum_color.z, 1.0f};
+    if (P.frame_buffer) P.frame_buffer[image_index] = tonemap_pack(accum_color);
+}
+
+}  // namespace orc

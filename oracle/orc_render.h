@@ -38,6 +38,7 @@ float connect_mis_and_eval(const Frame& fr, const spc_vertex& a, const spc_verte
 
 void light_trace_core(const Frame& fr, int core);
 void eye_pixel(const Frame& fr, int px, int py, int* first_prim, int* first_label);
+void pt_pixel(const Frame& fr, int px, int py);   // the "pt" comparison integrator
 void lvc_process(const spc_vertex* lvc, const uint8_t* valid, int n, int K, spc_subspace* subspace, float* cmfs, int* jump,
                  int* vertex_count, int* path_count);
 

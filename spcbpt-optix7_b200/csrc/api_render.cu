@@ -48,6 +48,9 @@ int spc_launch(spc_context* ctx, int kind, int width, int height) {
                         "spc_launch(pretrace): launch size must be (pre_tracer.num_core, 1)");
             spc::launch_pretrace(c);
             break;
+        case SPC_LAUNCH_PT:
+            spc::launch_pt(c, width, height);
+            break;
         case SPC_LAUNCH_SPCBPT_EYE:
             spc::launch_eye_pass(c, width, height);
             break;

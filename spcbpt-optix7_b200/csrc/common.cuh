@@ -183,6 +183,7 @@ void launch_trace_occlusion_q(Context& ctx, const spc_ray* rays, const int* n_de
 void launch_light_trace(Context& ctx);                       // "light trace" raygen
 void launch_eye_pass(Context& ctx, int width, int height);   // "SPCBPT_eye" raygen
 void launch_pretrace(Context& ctx);                          // "pretrace" raygen
+void launch_pt(Context& ctx, int width, int height);         // "pt" raygen
 void lvc_process(Context& ctx, const spc_vertex* lvc, const uint8_t* valid, int n, spc_subspace_sampler* out);
 void bin_ordered(Context& c, LvcBuffers& b, int n, int K, int* counters);
 int* lvc_bin(Context& c, LvcBuffers& b, const spc_vertex* lvc, const uint8_t* valid, int n);

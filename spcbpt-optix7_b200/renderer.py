@@ -1,0 +1,157 @@
+"""Host-side mirror of the reference application's schedule (src/OptiXPathTracer/optixPathTracer.cpp) on top of the C ABI:
+buffer setup (initLaunchParams :260-310, lt_params_setup :462-476, preTracer_params_setup :479-488), preprocessing()
+(:552-608) and the per-frame loop (launchLVCTrace :515-522, launchSubframe :609-635).  Python here is only the
+sequencer -- every step is a call into libspcbpt_b200.so; torch is used as the device allocator and for NCCL.
+
+The C++ twin of this file is host/spcbpt_main.cpp (same calls, no Python)."""
+import time
+
+import numpy as np
+
+from . import (LAUNCH_LIGHT_TRACE, LAUNCH_PRETRACE, LAUNCH_PT, LAUNCH_SPCBPT_EYE, PARAMS, TRAIN_CONN, TRAIN_PATH, VERTEX, Context, build_tree)
+
+
+class Renderer:
+    def __init__(self, scene, width, height, device=0, K=1000, K_light=0, connections=3, max_depth=0,
+                 lt_num_core=1000, lt_core_padding=800, lt_M_per_core=100, pretrace_num_core=10000, pretrace_padding=10, stream=None):
+        import torch
+        self.torch = torch
+        self.scene, self.w, self.h = scene, width, height
+        self.K = K
+        self.K_light = K_light if K_light else int(0.2 * K)
+        self.ctx = Context(device, K=K, K_light=self.K_light, connections=connections)
+        if stream is not None:
+            self.ctx.set_stream(stream)
+        self.ctx.upload_scene(scene)
+        dev = torch.device("cuda", device)
+        self.dev = dev
+        P = np.zeros(1, PARAMS)
+        self.P = P
+        eye, U, V, W = scene.camera_frame(width, height)
+        P["width"], P["height"], P["max_depth"] = width, height, max_depth
+        P["eye"], P["U"], P["V"], P["W"] = eye, U, V, W
+        self.accum = torch.zeros((width * height, 4), dtype=torch.float32, device=dev)
+        self.frame = torch.zeros(width * height, dtype=torch.int32, device=dev)
+        P["accum_buffer"], P["frame_buffer"] = self.accum.data_ptr(), self.frame.data_ptr()
+        n = lt_num_core * lt_core_padding
+        self.n_lvc = n
+        self.lvc = torch.zeros(n * VERTEX.itemsize, dtype=torch.uint8, device=dev)
+        self.valid = torch.zeros(n, dtype=torch.uint8, device=dev)
+        lt = P["lt"]
+        lt["num_core"], lt["core_padding"], lt["M_per_core"], lt["M"] = lt_num_core, lt_core_padding, lt_M_per_core, lt_num_core * lt_M_per_core
+        lt["ans"], lt["validState"] = self.lvc.data_ptr(), self.valid.data_ptr()
+        self.tp = torch.zeros(pretrace_num_core * TRAIN_PATH.itemsize, dtype=torch.uint8, device=dev)
+        self.tc = torch.zeros(pretrace_num_core * pretrace_padding * TRAIN_CONN.itemsize, dtype=torch.uint8, device=dev)
+        pt = P["pre_tracer"]
+        pt["num_core"], pt["padding"], pt["iteration"] = pretrace_num_core, pretrace_padding, 0
+        pt["paths"], pt["conns"] = self.tp.data_ptr(), self.tc.data_ptr()
+        P["subspace_info"]["subspaceNum"] = K
+        self.subframe = 0
+        self.stats = {}
+
+    # ---- launch helpers (optixPathTracer.cpp:491-549) ------------------------------------------
+    def launch_light_trace(self):
+        self.P["lt"]["launch_frame"] += 1
+        self.ctx.set_params(self.P)
+        self.ctx.launch(LAUNCH_LIGHT_TRACE, int(self.P["lt"]["num_core"][0]), 1)
+
+    def launch_lvc_trace(self):
+        self.launch_light_trace()
+        self.P["sampler"] = self.ctx.lvc_process(self.lvc, self.valid, self.n_lvc)[0]
+
+    def launch_pretrace(self):
+        pt = self.P["pre_tracer"]
+        pt["iteration"] += 1
+        self.ctx.set_params(self.P)
+        n = int(pt["num_core"][0])
+        self.ctx.launch(LAUNCH_PRETRACE, n, 1)
+        return self.ctx.valid_sample_gather(self.tp, n, self.tc, n * int(pt["padding"][0]))
+
+    def launch_subframe(self):
+        self.P["subframe_index"] = self.subframe
+        self.ctx.set_params(self.P)
+        self.ctx.launch(LAUNCH_SPCBPT_EYE, self.w, self.h)
+
+    # ---- preprocessing() (optixPathTracer.cpp:552-608) -----------------------------------------
+    def preprocessing(self, target_samples=2000000, target_Q_samples=2000000, tree_samples=100000, batch_size=20000, epochs=1, lr=0.01,
+                      allreduce=None, broadcast=None, verbose=False):
+        """the subspace-training schedule.  Multi-GPU (parallel.py): `allreduce(tensor)` averages a statistic across ranks in
+        place, `broadcast(None)` returns this rank and `broadcast(obj)` returns rank 0's object."""
+        ctx, K = self.ctx, self.K
+        t0 = time.perf_counter()
+        n = 0
+        while n < target_samples:
+            n += self.launch_pretrace()
+        t1 = time.perf_counter()
+        ctx.sample_reweight()
+        if broadcast is None or broadcast(None) == 0:    # the tree build stays on rank 0's host
+            eye_tree, _ = build_tree(ctx.get_tree_points(True, tree_samples), K, 0)
+            light_tree, _ = build_tree(ctx.get_tree_points(False, tree_samples), K - self.K_light, 0)
+        else:
+            eye_tree = light_tree = None
+        if broadcast is not None:
+            eye_tree, light_tree = broadcast((eye_tree, light_tree))
+        self.eye_tree, self.light_tree = eye_tree, light_tree
+        si = self.P["subspace_info"]
+        si["eye_tree"] = ctx.tree_to_device(True, eye_tree)
+        si["light_tree"] = ctx.tree_to_device(False, light_tree)
+        t2 = time.perf_counter()
+        acc, first, q_dev = 0, True, 0
+        while acc < target_Q_samples:
+            self.launch_light_trace()
+            q_dev, cum = ctx.preprocess_getQ(self.lvc, self.valid, self.n_lvc, reset=first)
+            first = False
+            acc += cum      # sic: the reference adds the CUMULATIVE count each time (optixPathTracer.cpp:590, device_thrust.cu:408)
+        if allreduce is not None:
+            allreduce(self._as_tensor(q_dev, K))
+        ctx.Q_zero_handle()
+        ctx.node_label(int(si["eye_tree"][0]), int(si["light_tree"][0]))
+        n_train = (min(n, target_samples) // batch_size) * batch_size
+        ctx.build_optimal_E_train_data(n_train)
+        g_dev = ctx.preprocess_getGamma()
+        if allreduce is not None:
+            allreduce(self._as_tensor(g_dev, K * K))
+        g_dev, loss = ctx.train_optimal_E(batch_size, epochs, lr)
+        if allreduce is not None:
+            allreduce(self._as_tensor(g_dev, K * K))
+        si["Q"] = q_dev
+        si["CMFGamma"] = ctx.Gamma2CMFGamma(g_dev)
+        ctx.synchronize()
+        t3 = time.perf_counter()
+        self.stats.update(train_paths=n, pretrace_s=t1 - t0, trees_s=t2 - t1, q_gamma_s=t3 - t2, loss_first=float(loss[0]) if len(loss) else None,
+                          loss_last=float(loss[-1]) if len(loss) else None, eye_tree_nodes=int(eye_tree.shape[0]), light_tree_nodes=int(light_tree.shape[0]))
+        if verbose:
+            print(self.stats)
+        return self.stats
+
+    def _as_tensor(self, dev_ptr, count):
+        """wrap a device pointer owned by the context as a float32 torch tensor (for torch.distributed collectives)"""
+        torch = self.torch
+        iface = {"shape": (count,), "typestr": "<f4", "data": (int(dev_ptr), False), "version": 2}
+        holder = type("DevArray", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=self.dev)
+
+    # ---- the per-frame loop (optixPathTracer.cpp:791-822 without the GL display) ------------------
+    def render_frame(self):
+        self.launch_lvc_trace()
+        self.launch_subframe()
+        self.subframe += 1
+
+    def render_frame_pt(self):
+        """one subframe of the "pt" comparison integrator (Space key in the reference UI, optixPathTracer.cpp:198-208)"""
+        self.P["subframe_index"] = self.subframe
+        self.ctx.set_params(self.P)
+        self.ctx.launch(LAUNCH_PT, self.w, self.h)
+        self.subframe += 1
+
+    def reset_accumulation(self):
+        self.subframe = 0
+
+    def image(self):
+        """(H, W, 3) float32 accumulated radiance"""
+        self.ctx.synchronize()
+        return self.accum.cpu().numpy()[:, :3].reshape(self.h, self.w, 3)
+
+    def frame_rgba8(self):
+        self.ctx.synchronize()
+        return self.frame.cpu().numpy().view(np.uint8).reshape(self.h, self.w, 4)

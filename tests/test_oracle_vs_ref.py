@@ -162,3 +162,30 @@ def test_tree_builder_vs_reference_K1000(pkg, ref):
         inner = b["leaf"] == 0
         assert np.array_equal(a["type"][inner], b["type"][inner]) and np.array_equal(a["child"][inner], b["child"][inner])
         assert np.array_equal(a["mid"][inner].view(np.uint32), b["mid"][inner].view(np.uint32))
+
+
+def test_pt_integrator_bit_exact(pkg, orc, ref):
+    """oracle "pt" restatement vs the reference's own __raygen__pinhole / __closesthit__radiance / __closesthit__lightsource"""
+    sc = _varied_cornell(pkg)
+    osc = orc.Scene(pkg, sc)
+    ref.scene_create(pkg, sc)
+    outs = {}
+    orc.set_jitter_rtl(1)
+    try:
+        for kind in ("ref", "orc"):
+            fr = HostFrame(pkg, sc, 64, 48, K=1000, num_core=8, core_padding=50, M_per_core=5)
+            res = []
+            for sf in (0, 1, 2, 7):
+                fr.P["subframe_index"] = sf
+                if kind == "ref":
+                    ref.launch(fr.P, ref.KIND_PT, 64, 48, threads=8)
+                else:
+                    orc.pt_pass(osc, fr.P, 1000, threads=8)
+                res.append((fr.accum.copy(), fr.frame.copy()))
+            outs[kind] = res
+    finally:
+        orc.set_jitter_rtl(0)
+        ref.lib().ref_scene_destroy()
+    for (a, fa), (b, fb) in zip(outs["ref"], outs["orc"]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(fa, fb)
+    assert outs["ref"][0][0][:, :3].mean() > 0.01

@@ -141,3 +141,23 @@ def test_full_frame_pipeline_vs_oracle(gpu_ctx, orc):
         bad = float_bits_differ(acc, hf.accum).any(1)
         assert bad.sum() <= 4, "subframe %d: %d of %d pixels differ" % (sf, bad.sum(), bad.size)
     assert vc > 20000
+
+
+def test_pt_integrator_vs_oracle(gold, orc):
+    """the "pt" comparison integrator (raygen.cu:71-170) against its oracle restatement (pinned to the reference's own program
+    in tests/test_oracle_vs_ref.py): four subframes, bit-exact accumulation"""
+    pkg, g, sc, ctx, df, K, Q, cmf = gold
+    c = GOLDEN_CFG
+    hf = HostFrame(pkg, sc, c["w"], c["h"], K=K, num_core=c["num_core"], core_padding=c["core_padding"], M_per_core=c["M_per_core"])
+    osc = orc.Scene(pkg, sc)
+    df.accum.zero_()
+    for sf in (0, 1, 2, 3):
+        df.P["subframe_index"] = sf
+        hf.P["subframe_index"] = sf
+        ctx.set_params(df.P)
+        ctx.launch("pt", c["w"], c["h"])
+        ctx.synchronize()
+        orc.pt_pass(osc, hf.P, K, threads=8)
+        bad = float_bits_differ(df.accum.cpu().numpy(), hf.accum).any(1)
+        assert bad.sum() <= MAX_BAD, "subframe %d: %d pixels differ" % (sf, bad.sum())
+    assert hf.accum[:, :3].mean() > 0.01
