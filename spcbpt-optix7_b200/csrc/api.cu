@@ -175,6 +175,7 @@ int spc_scene_upload(spc_context* ctx, const spc_mesh* meshes, int n_meshes, con
         SPC_CUDA(cudaMemcpyAsync(g.tex_desc.p, desc.data(), desc.size() * sizeof(int4), cudaMemcpyHostToDevice, c.stream));
     }
     SPC_CUDA(cudaStreamSynchronize(c.stream));  // host staging vectors die at scope exit
+    spc::build_material_tables(c);
     spc::build_bvh(c, g.tri_pos.p, n);
     c.has_scene = true;
     SPC_API_END

@@ -83,6 +83,7 @@ struct SceneGeom {
     DevBuf<float4>   tri_pos;     // 3 per prim: {P0, bits(material)}, {P1, bits(light_id)}, {P2, bits(mesh)}
     DevBuf<float2>   tri_uv;      // 3 per prim
     DevBuf<spc_pbr>  materials;
+    DevBuf<float>    mat_log_cc;  // per material: log of the squared clearcoat alpha (see shade.cuh GTR1)
     DevBuf<spc_light> lights;
     DevBuf<uint8_t>  tex_data;    // all textures, RGBA8, concatenated
     DevBuf<int4>     tex_desc;    // {offset_bytes, width, height, 0} per texture
@@ -157,6 +158,8 @@ struct Context {
     DevBuf<spc_hit> scratch_hits;
     DevBuf<uint8_t> scratch_vis;
     DevBuf<unsigned long long> counters;
+    DevBuf<unsigned long long> fetch_counters;   // ray-fetch counters of the persistent traversal kernels (one slot per launch)
+    unsigned      fetch_slot = 0;
     // render path
     spc_params    params = {};
     bool          has_params = false;
@@ -171,6 +174,7 @@ struct Context {
 };
 
 void build_bvh(Context& ctx, const float4* d_tri_pos /*3 per prim*/, uint32_t n_prims);
+void build_material_tables(Context& ctx);
 
 void launch_trace_closest(Context& ctx, const spc_ray* rays, int64_t n, int flags, spc_hit* hits,
                           unsigned long long* counters /*nullable*/);

@@ -129,31 +129,40 @@ __global__ void k_lvc_scatter(const int* __restrict__ key, const float* __restri
     }
 }
 
-// one warp per subspace: sequential running sum in slot order, then normalise
-__global__ void k_lvc_cmf(spc_subspace* __restrict__ sub, int K, const float* __restrict__ wsorted, float* __restrict__ cmfs) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// one warp per subspace: running fp32 sum in slot order, then normalise.  The summation order is the reference's
+// (sequential), so the only serial resource is the FADD dependency chain: the warp stages 256 weights at a time in
+// shared memory with coalesced loads, lane 0 runs the chain over shared memory (4-cycle adds, loads off the critical
+// path), and all lanes write the prefixes back coalesced.
+constexpr int kCmfTile = 256;
+__global__ void __launch_bounds__(128) k_lvc_cmf(spc_subspace* __restrict__ sub, int K, const float* __restrict__ wsorted, float* __restrict__ cmfs) {
+    __shared__ float s_buf[4][kCmfTile];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * 4 + wib;
     if (warp >= K) return;
+    float* buf = s_buf[wib];
     const int bias = sub[warp].jump_bias, size = sub[warp].size;
     float run = 0.f;
-    bool first = true;
-    for (int base = 0; base < size; base += 32) {
-        const int i = base + lane;
-        const float w = i < size ? wsorted[bias + i] : 0.f;
-        float mine = 0.f;
-        const int m = min(32, size - base);
-        for (int j = 0; j < m; j++) {
-            const float wj = __shfl_sync(0xffffffffu, w, j);
+    for (int base = 0; base < size; base += kCmfTile) {
+        const int m = min(kCmfTile, size - base);
+        for (int j = lane; j < m; j += 32) buf[j] = wsorted[bias + base + j];
+        __syncwarp();
+        if (lane == 0) {
             // the reference's first element is the weight itself, later ones `w + previous` (device_thrust.cu:281-286)
-            run = first ? wj : wj + run;
-            first = false;
-            if (j == lane) mine = run;
+            int j = 0;
+            if (base == 0) { run = buf[0]; j = 1; }
+#pragma unroll 8
+            for (; j < m; j++) {
+                run = buf[j] + run;
+                buf[j] = run;
+            }
         }
-        if (i < size) cmfs[bias + i] = mine;
+        __syncwarp();
+        for (int j = lane; j < m; j += 32) cmfs[bias + base + j] = buf[j];
+        __syncwarp();
     }
     // Q_subspace_vertex[s] += w accumulates the same sequence starting from 0: 0 + w0 = w0, so it equals the last running sum
-    const float total = size > 0 ? run : 0.f;
+    const float total = __shfl_sync(0xffffffffu, size > 0 ? run : 0.f, 0);
     if (lane == 0) sub[warp].sum_pmf = total;
-    __syncwarp();
     for (int i = lane; i < size; i += 32) cmfs[bias + i] = cmfs[bias + i] / total;
 }
 
@@ -181,7 +190,7 @@ void bin_ordered(Context& c, LvcBuffers& b, int n, int K, int* counters /* [0] <
     k_lvc_colscan<<<(K + 127) / 128, 128, 0, st>>>(b.hist.p, n_chunks, K, b.totals.p);
     k_lvc_bias<<<1, 1024, 0, st>>>(b.totals.p, K, b.subspace.p, counters);
     k_lvc_scatter<<<grid, wpb * 32, smem, st>>>(b.key.p, b.weight.p, n, K, n_chunks, b.hist.p, b.subspace.p, b.jump.p, b.wsorted.p);
-    k_lvc_cmf<<<(int)(((size_t)K * 32 + 127) / 128), 128, 0, st>>>(b.subspace.p, K, b.wsorted.p, b.cmfs.p);
+    k_lvc_cmf<<<(K + 3) / 4, 128, 0, st>>>(b.subspace.p, K, b.wsorted.p, b.cmfs.p);
     c.launches += 5;
     SPC_CUDA(cudaGetLastError());
 }

@@ -6,6 +6,7 @@
 // The eye pass is a wavefront: per bounce  trace -> shade+classify+sample connections -> shadow rays ->
 // connection eval + MIS -> ordered gather, with queue sizes kept on the device (no host round trip per stage).
 #include <algorithm>
+#include <cstdlib>
 #include "shade.cuh"
 #include "traverse.cuh"
 
@@ -21,6 +22,7 @@ DevFrame make_dev_frame(Context& c) {
     fr.sc.tex_desc = c.geom.tex_desc.p;
     fr.sc.nodes = c.bvh.nodes.p;
     fr.sc.tris = c.bvh.tris.p;
+    fr.sc.mat_log_cc = c.geom.mat_log_cc.p;
     fr.sc.n_lights = c.geom.n_lights;
     fr.sc.n_materials = c.geom.n_materials;
     fr.p = c.params;
@@ -28,6 +30,21 @@ DevFrame make_dev_frame(Context& c) {
     fr.connections = c.connections;
     fr.max_depth = c.params.max_depth > 0 ? c.params.max_depth : 50;
     return fr;
+}
+
+// per-material constants of the BSDF, computed once at scene upload by the same device functions the kernels would call
+__global__ void k_material_tables(const spc_pbr* __restrict__ mats, int n, float* __restrict__ log_cc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = lerpf(0.1f, 0.001f, mats[i].clearcoatGloss);
+    log_cc[i] = cm_logf(a * a);
+}
+void build_material_tables(Context& c) {
+    const int n = c.geom.n_materials;
+    c.geom.mat_log_cc.alloc(n);
+    if (n) k_material_tables<<<(n + 127) / 128, 128, 0, c.stream>>>(c.geom.materials.p, n, c.geom.mat_log_cc.p);
+    SPC_CUDA(cudaGetLastError());
+    c.launches++;
 }
 
 // =============================================================================================
@@ -40,12 +57,12 @@ DevFrame make_dev_frame(Context& c) {
 // =============================================================================================
 constexpr int kLtWarps = 4;
 
-__global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFrame fr) {
-    __shared__ uint2 s_stack[kSmStack * kLtWarps];
-    const int warp = threadIdx.x >> 5;
-    const int core = blockIdx.x * kLtWarps + warp;
+__global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFrame fr, int lanes) {
+    __shared__ uint2 s_stack[kSmStack * kLtWarps * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int core = (blockIdx.x * kLtWarps + warp) * lanes + lane;
     const spc_light_trace_params& lt = fr.p.lt;
-    if ((threadIdx.x & 31) != 0 || core >= lt.num_core) return;
+    if (lane >= lanes || core >= lt.num_core) return;
 
     uint32_t seed = tea<4>((uint32_t)core, (uint32_t)lt.launch_frame);
     uint32_t hit_seed = seed;   // payload.seed: a copy taken once (raygen.cu:628)
@@ -80,7 +97,7 @@ __global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFr
             TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
             TravHit h;
             bool pushed = false;
-            if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, s_stack + warp, kLtWarps, h, cn, ct)) {
+            if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, s_stack + threadIdx.x, kLtWarps * 32, h, cn, ct)) {
                 done = true;                                   // __miss__BDPTVertex, raygen.cu:699-704
             } else {
                 const LocalGeom g = hit_geometry(fr.sc, h.prim, h.u, h.v);
@@ -121,7 +138,13 @@ void launch_light_trace(Context& c) {
     SPC_REQUIRE(lt.num_core > 0 && lt.core_padding > 0 && lt.ans && lt.validState, SPC_ERR_INVALID, "spc_launch(light trace): MyParams::lt is not set up");
     SPC_REQUIRE(c.geom.n_lights > 0, SPC_ERR_NO_SCENE, "spc_launch(light trace): the scene has no lights");
     const DevFrame fr = make_dev_frame(c);
-    k_light_trace_cores<<<(lt.num_core + kLtWarps - 1) / kLtWarps, kLtWarps * 32, 0, c.stream>>>(fr);
+    static int lanes = 0;
+    if (!lanes) {
+        const char* e = getenv("SPC_LT_LANES");
+        lanes = e ? std::max(1, std::min(32, atoi(e))) : 1;
+    }
+    const int per_block = kLtWarps * lanes;
+    k_light_trace_cores<<<(lt.num_core + per_block - 1) / per_block, kLtWarps * 32, 0, c.stream>>>(fr, lanes);
     SPC_CUDA(cudaGetLastError());
     c.launches++;
 }

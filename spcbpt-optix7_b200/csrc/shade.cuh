@@ -38,6 +38,7 @@ struct DevScene {
     const int4*      tex_desc;
     const float4*    nodes;
     const float4*    tris;
+    const float*     mat_log_cc;   // per material: cm_logf(a^2), a = lerp(0.1, 0.001, clearcoatGloss) (GTR1's only transcendental)
     int              n_lights;
     int              n_materials;
 };
@@ -53,6 +54,7 @@ struct DevFrame {
 struct Pbr {   // the fields of MaterialData::Pbr the BSDF reads (src/cuda/MaterialData.h:78-97)
     float3 base_color;
     float  metallic, roughness, specular, specularTint, subsurface, sheen, sheenTint, clearcoat, clearcoatGloss;
+    float  log_cc;   // cm_logf(a^2) of the clearcoat lobe, precomputed per material by the same device function (bit-identical)
     bool   brdf;
 };
 
@@ -65,6 +67,7 @@ __device__ __forceinline__ Pbr load_pbr(const DevScene& sc, int id) {
     m.subsurface = c.x; /* anisotropic c.y unused */ m.sheen = c.z; m.sheenTint = c.w;
     const float2 d = __ldg(reinterpret_cast<const float2*>(q + 3));
     m.clearcoat = d.x; m.clearcoatGloss = d.y;
+    m.log_cc = __ldg(sc.mat_log_cc + id);
     m.brdf = sc.materials[id].brdf != 0;
     return m;
 }
@@ -150,11 +153,13 @@ __device__ __forceinline__ float SchlickFresnel(float u) {
     const float m2 = m * m;
     return m2 * m2 * m;
 }
-__device__ __forceinline__ float GTR1(float NDotH, float a) {
+// GTR1 (cuProg.h:693-699); log_a2 = cm_logf(a*a), taken from the per-material table (k_material_tables) instead of
+// being re-evaluated in fp64 ten times per connection
+__device__ __forceinline__ float GTR1(float NDotH, float a, float log_a2) {
     if (a >= 1.0f) return (1.0f / SPC_PI_F);
     const float a2 = a * a;
     const float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
-    return (a2 - 1.0f) / (SPC_PI_F * cm_logf(a2) * t);
+    return (a2 - 1.0f) / (SPC_PI_F * log_a2 * t);
 }
 __device__ __forceinline__ float GTR2(float NDotH, float a) {
     const float a2 = a * a;
@@ -192,7 +197,7 @@ static __device__ __noinline__ float3 bsdf_eval(const Pbr& mat, float3 N, float3
     const float roughg = sqr(mat.roughness * 0.5f + 0.5f);
     const float Gs = smithG_GGX(NDotL, roughg) * smithG_GGX(NDotV, roughg);
     const float3 Fsheen = FH * mat.sheen * Csheen;
-    const float Dr = GTR1(NDotH, lerpf(0.1f, 0.001f, mat.clearcoatGloss));
+    const float Dr = GTR1(NDotH, lerpf(0.1f, 0.001f, mat.clearcoatGloss), mat.log_cc);
     const float Fr = lerpf(0.04f, 1.0f, FH);
     const float Gr = smithG_GGX(NDotL, 0.25f) * smithG_GGX(NDotV, 0.25f);
     const float3 out = ((1.0f / SPC_PI_F) * lerpf(Fd, ss, mat.subsurface) * Cdlin + Fsheen) * (1.0f - mat.metallic) + Gs * Fs * Ds +
@@ -237,7 +242,7 @@ static __device__ __noinline__ float bsdf_pdf(const Pbr& mat, float3 n, float3 V
     const float3 half = normalize(L + V);
     const float cosTheta = fabsf(dot(half, n));
     const float pdfGTR2 = GTR2(cosTheta, specularAlpha) * cosTheta;
-    const float pdfGTR1 = GTR1(cosTheta, clearcoatAlpha) * cosTheta;
+    const float pdfGTR1 = GTR1(cosTheta, clearcoatAlpha, mat.log_cc) * cosTheta;
     const float ratio = 1.0f / (1.0f + mat.clearcoat);
     // `/ (4.0 * abs(...))`: the literal is a double, so this one division is fp64 in the reference (cuProg.h:892)
     const float pdfSpec = (float)((double)lerpf(pdfGTR1, pdfGTR2, ratio) / (4.0 * (double)fabsf(dot(L, half))));

@@ -2,6 +2,8 @@
 // Stand in for the optixTrace calls of the reference (cuProg.h:384-487); one lane per ray, rays
 // and hits are 128-bit coalesced loads/stores (32 B in, 16 B out), traversal stacks live in shared
 // memory (kSmStack entries per lane) with a local-memory tail.
+#include <algorithm>
+#include <cstdlib>
 #include "traverse.cuh"
 
 namespace spc {
@@ -65,6 +67,103 @@ k_trace_occlusion(const float4* __restrict__ nodes, const float4* __restrict__ t
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent warps with dynamic ray fetch.  A plain one-ray-per-lane launch leaves a warp running until its longest
+// ray ends (measured: 6.7 of 32 lanes active per issued instruction on incoherent rays, profiles/r1a_summary.md).
+// Here each warp keeps pulling rays from a global counter: whenever at least `fetch_threshold` lanes are idle the
+// idle lanes claim new rays with one warp-aggregated atomicAdd, so lanes stay busy until the batch is drained.
+// The grid is sized to the resident capacity of the GPU (SM count x blocks per SM), not to the ray count.
+// ---------------------------------------------------------------------------------------------
+template <bool ANYHIT>
+__global__ void __launch_bounds__(kTraceBlock)
+k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ rays,
+                const int* __restrict__ n_dev, int mult, int64_t n_host, int cull_back, int fetch_threshold,
+                float4* __restrict__ hits, uint8_t* __restrict__ visible, unsigned long long* __restrict__ counter) {
+    __shared__ uint2 s_stack[kSmStack * kTraceBlock];
+    uint2 lstack[kLocStack];
+    const int64_t n = n_dev ? (int64_t)__ldg(n_dev) * mult : n_host;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    Trav s;
+    int64_t ray = -1;
+    bool exhausted = false;
+    unsigned cn = 0, ct = 0;
+    while (true) {
+        unsigned idle = __ballot_sync(0xffffffffu, ray < 0);
+        if (idle) {
+            if (!exhausted && (idle == 0xffffffffu || __popc(idle) >= fetch_threshold)) {
+                const int cnt = __popc(idle);
+                const int leader = __ffs(idle) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(counter, (unsigned long long)cnt);
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (ray < 0) {
+                    const int64_t my = (int64_t)base + __popc(idle & lt_mask);
+                    if (my < n) {
+                        const float4 ro = __ldg(rays + 2 * my);
+                        const float4 rd = __ldg(rays + 2 * my + 1);
+                        if (ANYHIT && !(rd.w > ro.w)) {
+                            visible[my] = 1;   // empty interval: an unused connection slot
+                        } else {
+                            TravRay r{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w};
+                            trav_init(s, r);
+                            ray = my;
+                        }
+                    }
+                }
+                if ((int64_t)base + cnt >= n) exhausted = true;
+                idle = __ballot_sync(0xffffffffu, ray < 0);
+            }
+            if (exhausted && idle == 0xffffffffu) break;
+        }
+        if (ray >= 0) {
+            if (trav_step<ANYHIT, false>(nodes, tris, s, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, lstack, cn, ct)) {
+                if (ANYHIT) {
+                    visible[ray] = s.best_prim >= 0 ? 0 : 1;
+                } else {
+                    const bool hit = s.best_prim >= 0;
+                    hits[ray] = make_float4(hit ? s.tcur : 0.0f, s.best_u, s.best_v, __int_as_float(s.best_prim));
+                }
+                ray = -1;
+            }
+        }
+    }
+}
+
+static int trace_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <bool ANYHIT>
+static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits, uint8_t* visible) {
+    static int blocks_per_sm = 0, fetch_t = 0;
+    if (!blocks_per_sm) {
+        SPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_persist<ANYHIT>, kTraceBlock, 0));
+        blocks_per_sm = std::max(1, std::min(blocks_per_sm, trace_env("SPC_TRACE_BLOCKS_PER_SM", 16)));
+        fetch_t = trace_env("SPC_FETCH_THRESHOLD", 6);
+    }
+    if (ctx.fetch_counters.n < 256) {
+        ctx.fetch_counters.alloc(256);
+        ctx.fetch_slot = 0;
+    }
+    unsigned long long* counter = ctx.fetch_counters.p + (ctx.fetch_slot++ & 255);
+    SPC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx.stream));
+    int64_t blocks = (n_max + kTraceBlock - 1) / kTraceBlock;
+    const int64_t cap = (int64_t)ctx.sm_count * blocks_per_sm;
+    if (blocks > cap) blocks = cap;
+    k_trace_persist<ANYHIT><<<(unsigned)blocks, kTraceBlock, 0, ctx.stream>>>(ctx.bvh.nodes.p, ctx.bvh.tris.p, (const float4*)rays, n_dev, mult, n_max,
+                                                                           (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0, fetch_t, (float4*)hits, visible, counter);
+    SPC_CUDA(cudaGetLastError());
+    ctx.launches++;
+}
+
+static bool use_persist() {
+    static int mode = -1;
+    if (mode < 0) mode = trace_env("SPC_TRACE_PERSISTENT", 1);
+    return mode != 0;
+}
+
 // Queue variants for the wavefront render passes: the number of rays is a device-side counter written by
 // the previous stage (times `mult` rays per queue entry), the grid is fixed (a multiple of the SM count) and
 // strides over the queue, so no host round trip is needed between bounces.
@@ -106,6 +205,10 @@ k_trace_occlusion_q(const float4* __restrict__ nodes, const float4* __restrict__
 
 void launch_trace_closest_q(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits) {
     if (n_max <= 0) return;
+    if (use_persist()) {
+        launch_persist<false>(ctx, rays, n_dev, mult, n_max, flags, hits, nullptr);
+        return;
+    }
     int64_t blocks = (n_max + kTraceBlock - 1) / kTraceBlock;
     const int64_t cap = (int64_t)ctx.sm_count * 16;
     if (blocks > cap) blocks = cap;
@@ -117,6 +220,10 @@ void launch_trace_closest_q(Context& ctx, const spc_ray* rays, const int* n_dev,
 
 void launch_trace_occlusion_q(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, uint8_t* visible) {
     if (n_max <= 0) return;
+    if (use_persist()) {
+        launch_persist<true>(ctx, rays, n_dev, mult, n_max, 0, nullptr, visible);
+        return;
+    }
     int64_t blocks = (n_max + kTraceBlock - 1) / kTraceBlock;
     const int64_t cap = (int64_t)ctx.sm_count * 16;
     if (blocks > cap) blocks = cap;
@@ -131,6 +238,10 @@ void launch_trace_closest(Context& ctx, const spc_ray* rays, int64_t n, int flag
     const int64_t blocks = (n + kTraceBlock - 1) / kTraceBlock;
     SPC_REQUIRE(blocks < 0x7fffffffLL, SPC_ERR_INVALID, "ray batch too large: %lld", (long long)n);
     const int cull = (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0;
+    if (!counters && use_persist()) {
+        launch_persist<false>(ctx, rays, nullptr, 1, n, flags, hits, nullptr);
+        return;
+    }
     if (counters)
         k_trace_closest<true><<<(unsigned)blocks, kTraceBlock, 0, ctx.stream>>>(
             ctx.bvh.nodes.p, ctx.bvh.tris.p, (const float4*)rays, n, cull, (float4*)hits, counters);
@@ -146,6 +257,10 @@ void launch_trace_occlusion(Context& ctx, const spc_ray* rays, int64_t n, uint8_
     if (n <= 0) return;
     const int64_t blocks = (n + kTraceBlock - 1) / kTraceBlock;
     SPC_REQUIRE(blocks < 0x7fffffffLL, SPC_ERR_INVALID, "ray batch too large: %lld", (long long)n);
+    if (!counters && use_persist()) {
+        launch_persist<true>(ctx, rays, nullptr, 1, n, 0, nullptr, visible);
+        return;
+    }
     if (counters)
         k_trace_occlusion<true><<<(unsigned)blocks, kTraceBlock, 0, ctx.stream>>>(
             ctx.bvh.nodes.p, ctx.bvh.tris.p, (const float4*)rays, n, visible, counters);

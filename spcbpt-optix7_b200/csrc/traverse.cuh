@@ -52,8 +52,36 @@ struct TravHit {
     int   prim;
 };
 
+// Traversal state of one ray.  The loop body is exposed as trav_step() so that the persistent wavefront kernels
+// (trace.cu) can interleave ray fetches with traversal steps; traverse_bvh8() runs it to completion for the
+// megakernel-style passes (light trace, training tracer, pt).
+struct Trav {
+    float ox, oy, oz, dx, dy, dz, tmin, tmax;
+    float idx, idy, idz;
+    uint32_t oct_inv;
+    float tcur, best_u, best_v;
+    int   best_prim;
+    uint2 ngroup;
+    int   sp;
+};
+
+__device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
+    const float eps = 1.0e-24f;
+    s.ox = r.ox; s.oy = r.oy; s.oz = r.oz; s.dx = r.dx; s.dy = r.dy; s.dz = r.dz; s.tmin = r.tmin; s.tmax = r.tmax;
+    s.idx = 1.0f / (fabsf(r.dx) > eps ? r.dx : copysignf(eps, r.dx));
+    s.idy = 1.0f / (fabsf(r.dy) > eps ? r.dy : copysignf(eps, r.dy));
+    s.idz = 1.0f / (fabsf(r.dz) > eps ? r.dz : copysignf(eps, r.dz));
+    const uint32_t oct = (r.dx < 0.f ? 1u : 0u) | (r.dy < 0.f ? 2u : 0u) | (r.dz < 0.f ? 4u : 0u);
+    s.oct_inv = 7u ^ oct;
+    s.tcur = r.tmax;
+    s.best_prim = -1;
+    s.best_u = s.best_v = 0.f;
+    s.ngroup = make_uint2(0u, 0x80000000u);
+    s.sp = 0;
+}
+
 // one child quad (4 of the 8 slots) of a node
-#define SPC_CHILD_TEST(J)                                                                         \
+#define SPC_CHILD_TEST2(J)                                                                        \
     {                                                                                             \
         float lx = __fmaf_rn(byte_to_float<J>(slox), adjx, orgx);                                 \
         float ly = __fmaf_rn(byte_to_float<J>(sloy), adjy, orgy);                                 \
@@ -61,147 +89,147 @@ struct TravHit {
         float hx = __fmaf_rn(byte_to_float<J>(shix), adjx, orgx);                                 \
         float hy = __fmaf_rn(byte_to_float<J>(shiy), adjy, orgy);                                 \
         float hz = __fmaf_rn(byte_to_float<J>(shiz), adjz, orgz);                                 \
-        float cmin = fmaxf(fmaxf(lx, ly), fmaxf(lz, r.tmin));                                     \
-        float cmax = fminf(fminf(hx, hy), fminf(hz, tcur));                                       \
+        float cmin = fmaxf(fmaxf(lx, ly), fmaxf(lz, s.tmin));                                     \
+        float cmax = fminf(fminf(hx, hy), fminf(hz, s.tcur));                                     \
         if (cmin <= cmax) hitmask |= byte_of(child_bits4, J) << byte_of(bit_index4, J);           \
     }
+
+// One iteration: take the nearest pending child of the current node group (or fall back to its triangles), test
+// its 8 children, intersect the triangles of the hit leaves, pop when the group is exhausted.
+// Returns true when the ray is finished (stack empty, or first hit for ANYHIT -- then s.best_prim >= 0).
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
+                                          uint2* sstack, int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris) {
+    const uint32_t oct_inv = s.oct_inv;
+    const uint32_t oct = 7u ^ oct_inv;
+    uint2 tgroup;
+    if (s.ngroup.y > 0x00ffffffu) {
+        const uint32_t hits  = s.ngroup.y;
+        const uint32_t imask = s.ngroup.y & 0xffu;
+        const uint32_t bit   = 31u - __clz(hits);
+        s.ngroup.y &= ~(1u << bit);
+        if (s.ngroup.y > 0x00ffffffu) {
+            if (s.sp < kSmStack) sstack[s.sp * sstride] = s.ngroup;
+            else lstack[s.sp - kSmStack] = s.ngroup;
+            s.sp++;
+        }
+        const uint32_t slot = (bit - 24u) ^ oct_inv;
+        const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
+        const float4*  np   = nodes + (size_t)(s.ngroup.x + rel) * 5;
+        const float4 n0 = __ldg(np + 0);
+        const float4 n1 = __ldg(np + 1);
+        const float4 n2 = __ldg(np + 2);
+        const float4 n3 = __ldg(np + 3);
+        const float4 n4 = __ldg(np + 4);
+        if (COUNT) cnt_nodes++;
+
+        const uint32_t e_im = __float_as_uint(n0.w);
+        const float adjx = __uint_as_float((e_im & 0xffu) << 23) * s.idx;
+        const float adjy = __uint_as_float(((e_im >> 8) & 0xffu) << 23) * s.idy;
+        const float adjz = __uint_as_float(((e_im >> 16) & 0xffu) << 23) * s.idz;
+        const float orgx = (n0.x - s.ox) * s.idx;
+        const float orgy = (n0.y - s.oy) * s.idy;
+        const float orgz = (n0.z - s.oz) * s.idz;
+        const uint32_t oct_inv4 = oct_inv * 0x01010101u;
+
+        uint32_t hitmask = 0;
+        {
+            const uint32_t meta4       = __float_as_uint(n1.z);
+            const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+            const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t qlox = __float_as_uint(n2.x), qloy = __float_as_uint(n2.z), qloz = __float_as_uint(n3.x);
+            const uint32_t qhix = __float_as_uint(n3.z), qhiy = __float_as_uint(n4.x), qhiz = __float_as_uint(n4.z);
+            const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
+            const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
+            const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
+            SPC_CHILD_TEST2(0) SPC_CHILD_TEST2(1) SPC_CHILD_TEST2(2) SPC_CHILD_TEST2(3)
+        }
+        {
+            const uint32_t meta4       = __float_as_uint(n1.w);
+            const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+            const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t qlox = __float_as_uint(n2.y), qloy = __float_as_uint(n2.w), qloz = __float_as_uint(n3.y);
+            const uint32_t qhix = __float_as_uint(n3.w), qhiy = __float_as_uint(n4.y), qhiz = __float_as_uint(n4.w);
+            const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
+            const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
+            const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
+            SPC_CHILD_TEST2(0) SPC_CHILD_TEST2(1) SPC_CHILD_TEST2(2) SPC_CHILD_TEST2(3)
+        }
+        s.ngroup.x = __float_as_uint(n1.x);
+        s.ngroup.y = (hitmask & 0xff000000u) | (e_im >> 24);
+        tgroup.x = __float_as_uint(n1.y);
+        tgroup.y = hitmask & 0x00ffffffu;
+    } else {
+        tgroup = s.ngroup;
+        s.ngroup = make_uint2(0u, 0u);
+    }
+
+    while (tgroup.y != 0u) {
+        const uint32_t ti = 31u - __clz(tgroup.y);
+        tgroup.y &= ~(1u << ti);
+        const float4* tp = tris + (size_t)(tgroup.x + ti) * 3;
+        const float4 a = __ldg(tp + 0);
+        const float4 b = __ldg(tp + 1);
+        const float4 c = __ldg(tp + 2);
+        if (COUNT) cnt_tris++;
+        float px, py, pz;
+        c_cross(s.dx, s.dy, s.dz, c.x, c.y, c.z, px, py, pz);
+        const float det = c_dot(b.x, b.y, b.z, px, py, pz);
+        const bool  single = cull_back && (__float_as_uint(b.w) & TRI_FLAG_SINGLE_SIDED);
+        if (single ? !(det > 0.0f) : !(det != 0.0f)) continue;
+        const float inv = __fdiv_rn(1.0f, det);
+        const float tx = __fsub_rn(s.ox, a.x), ty = __fsub_rn(s.oy, a.y), tz = __fsub_rn(s.oz, a.z);
+        const float u = __fmul_rn(c_dot(tx, ty, tz, px, py, pz), inv);
+        if (!(u >= 0.0f && u <= 1.0f)) continue;
+        float qx, qy, qz;
+        c_cross(tx, ty, tz, b.x, b.y, b.z, qx, qy, qz);
+        const float v = __fmul_rn(c_dot(s.dx, s.dy, s.dz, qx, qy, qz), inv);
+        if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) continue;
+        const float t = __fmul_rn(c_dot(c.x, c.y, c.z, qx, qy, qz), inv);
+        if (!(t > s.tmin)) continue;
+        const int prim = (int)__float_as_uint(a.w);
+        if (ANYHIT) {
+            if (t < s.tmax) {
+                s.best_prim = prim;
+                return true;
+            }
+        } else {
+            if (t < s.tcur || (t == s.tcur && prim < s.best_prim)) {
+                s.tcur = t;
+                s.best_prim = prim;
+                s.best_u = u;
+                s.best_v = v;
+            }
+        }
+    }
+
+    if (s.ngroup.y <= 0x00ffffffu) {
+        if (s.sp == 0) return true;
+        s.sp--;
+        s.ngroup = (s.sp < kSmStack) ? sstack[s.sp * sstride] : lstack[s.sp - kSmStack];
+    }
+    return false;
+}
 
 template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ bool traverse_bvh8(const float4* __restrict__ nodes,
                                               const float4* __restrict__ tris, const TravRay& r,
                                               bool cull_back, uint2* sstack, int sstride,
                                               TravHit& hit, unsigned& cnt_nodes, unsigned& cnt_tris) {
-    const float eps = 1.0e-24f;
-    const float idx = 1.0f / (fabsf(r.dx) > eps ? r.dx : copysignf(eps, r.dx));
-    const float idy = 1.0f / (fabsf(r.dy) > eps ? r.dy : copysignf(eps, r.dy));
-    const float idz = 1.0f / (fabsf(r.dz) > eps ? r.dz : copysignf(eps, r.dz));
-    const uint32_t oct      = (r.dx < 0.f ? 1u : 0u) | (r.dy < 0.f ? 2u : 0u) | (r.dz < 0.f ? 4u : 0u);
-    const uint32_t oct_inv  = 7u ^ oct;
-    const uint32_t oct_inv4 = oct_inv * 0x01010101u;
-
-    float tcur      = r.tmax;
-    int   best_prim = -1;
-    float best_u = 0.f, best_v = 0.f;
-
+    Trav s;
+    trav_init(s, r);
     uint2 lstack[kLocStack];
-    int   sp = 0;
-
-    uint2 ngroup = make_uint2(0u, 0x80000000u);
-    uint2 tgroup = make_uint2(0u, 0u);
-
-    while (true) {
-        if (ngroup.y > 0x00ffffffu) {
-            const uint32_t hits  = ngroup.y;
-            const uint32_t imask = ngroup.y & 0xffu;
-            const uint32_t bit   = 31u - __clz(hits);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00ffffffu) {
-                if (sp < kSmStack) sstack[sp * sstride] = ngroup;
-                else lstack[sp - kSmStack] = ngroup;
-                sp++;
-            }
-            const uint32_t slot = (bit - 24u) ^ oct_inv;
-            const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
-            const float4*  np   = nodes + (size_t)(ngroup.x + rel) * 5;
-            const float4 n0 = __ldg(np + 0);
-            const float4 n1 = __ldg(np + 1);
-            const float4 n2 = __ldg(np + 2);
-            const float4 n3 = __ldg(np + 3);
-            const float4 n4 = __ldg(np + 4);
-            if (COUNT) cnt_nodes++;
-
-            const uint32_t e_im = __float_as_uint(n0.w);
-            const float adjx = __uint_as_float((e_im & 0xffu) << 23) * idx;
-            const float adjy = __uint_as_float(((e_im >> 8) & 0xffu) << 23) * idy;
-            const float adjz = __uint_as_float(((e_im >> 16) & 0xffu) << 23) * idz;
-            const float orgx = (n0.x - r.ox) * idx;
-            const float orgy = (n0.y - r.oy) * idy;
-            const float orgz = (n0.z - r.oz) * idz;
-
-            uint32_t hitmask = 0;
-            {
-                const uint32_t meta4       = __float_as_uint(n1.z);
-                const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-                const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlox = __float_as_uint(n2.x), qloy = __float_as_uint(n2.z), qloz = __float_as_uint(n3.x);
-                const uint32_t qhix = __float_as_uint(n3.z), qhiy = __float_as_uint(n4.x), qhiz = __float_as_uint(n4.z);
-                const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
-                const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
-                const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
-                SPC_CHILD_TEST(0) SPC_CHILD_TEST(1) SPC_CHILD_TEST(2) SPC_CHILD_TEST(3)
-            }
-            {
-                const uint32_t meta4       = __float_as_uint(n1.w);
-                const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-                const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlox = __float_as_uint(n2.y), qloy = __float_as_uint(n2.w), qloz = __float_as_uint(n3.y);
-                const uint32_t qhix = __float_as_uint(n3.w), qhiy = __float_as_uint(n4.y), qhiz = __float_as_uint(n4.w);
-                const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
-                const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
-                const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
-                SPC_CHILD_TEST(0) SPC_CHILD_TEST(1) SPC_CHILD_TEST(2) SPC_CHILD_TEST(3)
-            }
-            ngroup.x = __float_as_uint(n1.x);
-            ngroup.y = (hitmask & 0xff000000u) | (e_im >> 24);
-            tgroup.x = __float_as_uint(n1.y);
-            tgroup.y = hitmask & 0x00ffffffu;
-        } else {
-            tgroup = ngroup;
-            ngroup = make_uint2(0u, 0u);
-        }
-
-        while (tgroup.y != 0u) {
-            const uint32_t ti = 31u - __clz(tgroup.y);
-            tgroup.y &= ~(1u << ti);
-            const float4* tp = tris + (size_t)(tgroup.x + ti) * 3;
-            const float4 a = __ldg(tp + 0);
-            const float4 b = __ldg(tp + 1);
-            const float4 c = __ldg(tp + 2);
-            if (COUNT) cnt_tris++;
-            float px, py, pz;
-            c_cross(r.dx, r.dy, r.dz, c.x, c.y, c.z, px, py, pz);
-            const float det = c_dot(b.x, b.y, b.z, px, py, pz);
-            const bool  single = cull_back && (__float_as_uint(b.w) & TRI_FLAG_SINGLE_SIDED);
-            if (single ? !(det > 0.0f) : !(det != 0.0f)) continue;
-            const float inv = __fdiv_rn(1.0f, det);
-            const float tx = __fsub_rn(r.ox, a.x), ty = __fsub_rn(r.oy, a.y), tz = __fsub_rn(r.oz, a.z);
-            const float u = __fmul_rn(c_dot(tx, ty, tz, px, py, pz), inv);
-            if (!(u >= 0.0f && u <= 1.0f)) continue;
-            float qx, qy, qz;
-            c_cross(tx, ty, tz, b.x, b.y, b.z, qx, qy, qz);
-            const float v = __fmul_rn(c_dot(r.dx, r.dy, r.dz, qx, qy, qz), inv);
-            if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) continue;
-            const float t = __fmul_rn(c_dot(c.x, c.y, c.z, qx, qy, qz), inv);
-            if (!(t > r.tmin)) continue;
-            const int prim = (int)__float_as_uint(a.w);
-            if (ANYHIT) {
-                if (t < r.tmax) return true;
-            } else {
-                if (t < tcur || (t == tcur && prim < best_prim)) {
-                    tcur = t;
-                    best_prim = prim;
-                    best_u = u;
-                    best_v = v;
-                }
-            }
-        }
-
-        if (ngroup.y <= 0x00ffffffu) {
-            if (sp == 0) break;
-            sp--;
-            ngroup = (sp < kSmStack) ? sstack[sp * sstride] : lstack[sp - kSmStack];
-        }
-    }
-    if (ANYHIT) return false;
-    hit.t = best_prim >= 0 ? tcur : 0.0f;
-    hit.u = best_u;
-    hit.v = best_v;
-    hit.prim = best_prim;
-    return best_prim >= 0;
+    while (!trav_step<ANYHIT, COUNT>(nodes, tris, s, cull_back, sstack, sstride, lstack, cnt_nodes, cnt_tris)) {}
+    if (ANYHIT) return s.best_prim >= 0;
+    hit.t = s.best_prim >= 0 ? s.tcur : 0.0f;
+    hit.u = s.best_u;
+    hit.v = s.best_v;
+    hit.prim = s.best_prim;
+    return s.best_prim >= 0;
 }
 
 }  // namespace spc

@@ -48,6 +48,7 @@ class Renderer:
         P["subspace_info"]["subspaceNum"] = K
         self.subframe = 0
         self.stats = {}
+        self._pipe = None
 
     # ---- launch helpers (optixPathTracer.cpp:491-549) ------------------------------------------
     def launch_light_trace(self):
@@ -133,8 +134,48 @@ class Renderer:
 
     # ---- the per-frame loop (optixPathTracer.cpp:791-822 without the GL display) ------------------
     def render_frame(self):
+        if self._pipe is not None:
+            return self._render_frame_pipelined()
         self.launch_lvc_trace()
         self.launch_subframe()
+        self.subframe += 1
+
+    def enable_pipelining(self):
+        """Overlap the (latency-bound, 1000-lane) light trace of frame f+1 with the eye pass of frame f: the light trace runs on
+        a side stream into the other half of a double-buffered LVC.  Same launches, same seeds, same results as render_frame()."""
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            main = torch.cuda.Stream()
+            side = torch.cuda.Stream(priority=-1)
+            lvc2 = torch.zeros_like(self.lvc)
+            valid2 = torch.zeros_like(self.valid)
+            self._pipe = dict(main=main, side=side, lvc=[self.lvc, lvc2], valid=[self.valid, valid2], cur=0, primed=False,
+                              ev_lt=[torch.cuda.Event(), torch.cuda.Event()], ev_eye=[torch.cuda.Event(), torch.cuda.Event()])
+        main.wait_stream(torch.cuda.current_stream(self.dev))
+        self.ctx.set_stream(main.cuda_stream)
+
+    def _trace_into(self, k):
+        p = self._pipe
+        lt = self.P["lt"]
+        lt["ans"], lt["validState"] = p["lvc"][k].data_ptr(), p["valid"][k].data_ptr()
+        self.ctx.set_stream(p["side"].cuda_stream)
+        p["side"].wait_event(p["ev_eye"][k])      # the eye pass that sampled this half must be done
+        self.launch_light_trace()
+        p["ev_lt"][k].record(p["side"])
+        self.ctx.set_stream(p["main"].cuda_stream)
+
+    def _render_frame_pipelined(self):
+        p = self._pipe
+        cur = p["cur"]
+        if not p["primed"]:
+            self._trace_into(cur)
+            p["primed"] = True
+        p["main"].wait_event(p["ev_lt"][cur])
+        self._trace_into(1 - cur)                   # next frame's light paths, under this frame's eye pass
+        self.P["sampler"] = self.ctx.lvc_process(p["lvc"][cur], p["valid"][cur], self.n_lvc)[0]
+        self.launch_subframe()
+        p["ev_eye"][cur].record(p["main"])
+        p["cur"] = 1 - cur
         self.subframe += 1
 
     def render_frame_pt(self):

@@ -25,3 +25,19 @@ for _ in range(n):
     tl += ev[0].elapsed_time(ev[1]); tp += ev[1].elapsed_time(ev[2]); te += ev[2].elapsed_time(ev[3])
 print("per frame ms: light trace %.3f  lvc_process %.3f  eye pass %.3f  -> %.2f Msamples/s" % (tl / n, tp / n, te / n, w * h / ((tl + tp + te) / n) / 1e3))
 print("launches", r.ctx.launch_count(), "mean", r.image().mean())
+
+r.ctx.synchronize(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(20): r.render_frame()
+r.ctx.synchronize(); torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / 20
+print("sequential frame (wall) %.3f ms -> %.2f Msamples/s" % (dt * 1e3, w * h / dt / 1e6))
+# pipelined loop: whole-frame wall time with the light trace under the eye pass
+r.enable_pipelining()
+for _ in range(3): r.render_frame()
+r.ctx.synchronize(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(20): r.render_frame()
+r.ctx.synchronize(); torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / 20
+print("pipelined frame %.3f ms -> %.2f Msamples/s" % (dt * 1e3, w * h / dt / 1e6))

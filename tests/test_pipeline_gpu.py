@@ -48,3 +48,24 @@ def test_config1_cornell_spcbpt_vs_pt_ground_truth(gpu_ctx):
     assert e64 < 0.05 and e256 < 0.6 * e64, (e64, e256)
     fb = r.frame_rgba8()
     assert fb[..., 3].min() == 255 and fb[..., :3].max() > 100
+
+
+def test_pipelined_frames_equal_sequential_frames(gpu_ctx):
+    """double-buffered LVC + light trace on a side stream: bit-identical images to the sequential loop (same trained state)"""
+    pkg = gpu_ctx
+    from spcbpt_optix7_b200.renderer import Renderer
+    sc = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=12, box_cells=8), 0.01)
+    kw = dict(K=64, K_light=12, lt_num_core=100, lt_core_padding=300, lt_M_per_core=40, pretrace_num_core=20000)
+    r = Renderer(sc, 96, 64, **kw)
+    r.preprocessing(target_samples=40000, target_Q_samples=20000, tree_samples=20000, batch_size=20000)
+    frame0 = int(r.P["lt"]["launch_frame"][0])
+    for _ in range(6):
+        r.render_frame()
+    a = r.image().copy()
+    r.reset_accumulation()
+    r.P["lt"]["launch_frame"] = frame0
+    r.enable_pipelining()
+    for _ in range(6):
+        r.render_frame()
+    b = r.image().copy()
+    assert a.mean() > 0.01 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
