@@ -393,6 +393,10 @@ enum { SPC_LAUNCH_PT = 0, SPC_LAUNCH_SPCBPT_EYE = 1, SPC_LAUNCH_LIGHT_TRACE = 2,
 SPC_API int  spc_launch(spc_context* ctx, int kind, int width, int height);
 /* by-name form of the same call: "pt" | "SPCBPT_eye" | "light trace" | "pretrace" (optixPathTracer.cpp:88,502,534,612) */
 SPC_API int  spc_launch_named(spc_context* ctx, const char* raygen_name, int width, int height);
+/* Multi-GPU sample partition: the eye / pt seeds become tea<4>(pixel, subframe_index + offset) so that ranks rendering the
+ * same local subframe indices draw different samples; each rank accumulates its own running mean and the means are
+ * reduced over NCCL at read-out.  offset 0 (default) = the reference's streams. */
+SPC_API int  spc_set_seed_offset(spc_context* ctx, uint32_t offset);
 /* optional parity dumps of the eye pass: per pixel, the primitive id of the primary hit (-1 miss) and the
  * subspace id of the first eye vertex (-1 none).  Device int[W*H] each, or NULL to disable. */
 SPC_API int  spc_set_debug_outputs(spc_context* ctx, int32_t* first_prim_dev, int32_t* first_label_dev);

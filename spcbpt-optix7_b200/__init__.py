@@ -138,6 +138,7 @@ def _bind_optional(L):
         "spc_launch": [vp, i32, i32, i32],
         "spc_launch_named": [vp, ctypes.c_char_p, i32, i32],
         "spc_set_debug_outputs": [vp, vp, vp],
+        "spc_set_seed_offset": [vp, ctypes.c_uint32],
         "spc_lvc_process": [vp, vp, vp, i32, vp],
         "spc_build_tree": [vp, i32, i32, i32, vp, i32, vp],
         "spc_valid_sample_gather": [vp, vp, i32, vp, i32, vp],
@@ -291,6 +292,9 @@ class Context:
             self._ck(self._L.spc_launch_named(self.h, kind.encode(), width, height), "spc_launch_named")
         else:
             self._ck(self._L.spc_launch(self.h, kind, width, height), "spc_launch")
+
+    def set_seed_offset(self, offset):
+        self._ck(self._L.spc_set_seed_offset(self.h, offset), "spc_set_seed_offset")
 
     def set_debug_outputs(self, first_prim_dev, first_label_dev):
         self._ck(self._L.spc_set_debug_outputs(self.h, _ptr(first_prim_dev), _ptr(first_label_dev)), "spc_set_debug_outputs")

@@ -77,6 +77,12 @@ int spc_launch_named(spc_context* ctx, const char* name, int width, int height) 
     return spc_launch(ctx, kind, width, height);
 }
 
+int spc_set_seed_offset(spc_context* ctx, uint32_t offset) {
+    SPC_API_BEGIN
+    c.seed_offset = offset;
+    SPC_API_END
+}
+
 int spc_set_debug_outputs(spc_context* ctx, int32_t* first_prim_dev, int32_t* first_label_dev) {
     SPC_API_BEGIN
     c.dbg_first_prim = first_prim_dev;

@@ -161,6 +161,7 @@ struct Context {
     DevBuf<unsigned long long> fetch_counters;   // ray-fetch counters of the persistent traversal kernels (one slot per launch)
     unsigned      fetch_slot = 0;
     // render path
+    uint32_t      seed_offset = 0;             // see DevFrame::seed_offset
     spc_params    params = {};
     bool          has_params = false;
     EyeBuffers    eye;

@@ -30,9 +30,9 @@ __global__ void __launch_bounds__(kPtPixBlock) k_pt(const DevFrame fr, int n_pix
     unsigned cn = 0, ct = 0;
     const unsigned W = fr.p.width, H = fr.p.height;
     const unsigned x = (unsigned)i % W, y = (unsigned)i / W;
-    uint32_t seed = tea<4>((uint32_t)i, fr.p.subframe_index);
+    uint32_t seed = tea<4>((uint32_t)i, fr.p.subframe_index + fr.seed_offset);
     float jx = 0.5f, jy = 0.5f;
-    if (fr.p.subframe_index != 0) {
+    if (fr.p.subframe_index + fr.seed_offset != 0) {
         jx = rnd(seed);
         jy = rnd(seed);
     }

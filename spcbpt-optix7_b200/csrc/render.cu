@@ -29,6 +29,7 @@ DevFrame make_dev_frame(Context& c) {
     fr.K = c.K;
     fr.connections = c.connections;
     fr.max_depth = c.params.max_depth > 0 ? c.params.max_depth : 50;
+    fr.seed_offset = c.seed_offset;
     return fr;
 }
 
@@ -178,9 +179,9 @@ __global__ void k_eye_init(const DevFrame fr, const EyeArgs a, int n_pix) {
     if (i >= n_pix) return;
     const unsigned W = fr.p.width, H = fr.p.height;
     const unsigned x = (unsigned)i % W, y = (unsigned)i / W;
-    uint32_t seed = tea<4>((uint32_t)i, fr.p.subframe_index);
+    uint32_t seed = tea<4>((uint32_t)i, fr.p.subframe_index + fr.seed_offset);
     float jx = 0.5f, jy = 0.5f;
-    if (fr.p.subframe_index != 0) {   // make_float2(rnd(seed), rnd(seed)): nvcc evaluates left to right
+    if (fr.p.subframe_index + fr.seed_offset != 0) {   // make_float2(rnd(seed), rnd(seed)): nvcc evaluates left to right
         jx = rnd(seed);
         jy = rnd(seed);
     }

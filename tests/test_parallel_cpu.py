@@ -1,0 +1,74 @@
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic in spcbpt-optix7_b200/parallel.py: statistics are averaged
+in place, rank-0 trees reach every rank bit-for-bit, accumulation buffers reduce to the mean of the ranks."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import spcbpt_loader
+    pkg = spcbpt_loader.load()
+    from spcbpt_optix7_b200.parallel import DistEnv
+    env = DistEnv(dist)
+    ok = env.rank == rank and env.world == world and env.broadcast(None) == rank
+    # statistics: Q-like vector and a Gamma-like matrix
+    qv = torch.full((16,), float(rank + 1))
+    env.allreduce_mean(qv)
+    ok &= bool(torch.allclose(qv, torch.full((16,), (1 + world) / 2)))
+    # trees: built on rank 0 only
+    if rank == 0:
+        g = np.random.default_rng(1)
+        s = np.zeros(500, pkg.DIVIDE_WEIGHT)
+        s["position"] = g.uniform(-1, 1, (500, 3))
+        s["normal"] = (0, 1, 0)
+        s["weight"] = g.uniform(0.1, 1, 500)
+        eye, _ = pkg.build_tree(s, 8, 0)
+        light, _ = pkg.build_tree(s, 6, 0)
+        obj = (eye, light)
+    else:
+        obj = (np.zeros(0, pkg.TREE_NODE), np.zeros(0, pkg.TREE_NODE))
+    got = env.broadcast(obj)
+    trees = [np.frombuffer(x.tobytes(), dtype=pkg.TREE_NODE) for x in got]
+    digest = [int(t["label"].sum()) + int(t["child"].sum()) + t.shape[0] for t in trees]
+    # accumulation buffers: mean over ranks
+    acc = torch.full((32, 4), float(rank))
+    env.allreduce_mean(acc)
+    ok &= bool(torch.allclose(acc, torch.full((32, 4), (world - 1) / 2)))
+    env.barrier()
+    q.put((rank, ok, digest))
+    dist.destroy_process_group()
+
+
+def test_distenv_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    assert all(r[1] for r in res)
+    assert res[0][2] == res[1][2] and res[0][2][0] > 10     # identical trees on both ranks
