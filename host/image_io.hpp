@@ -1,0 +1,32 @@
+// image_io.hpp -- images in and out of the host driver.
+//
+// In:  textures named by `albedoTex` in a .scene file, decoded to RGBA8 exactly as the reference hands them to
+//      CUDA (scene_shift.cpp:36-56: stbi_load(name, &w, &h, &ch, STBI_rgb_alpha), 8 bit, 4 channels, first row = top).
+//      Formats: baseline JPEG and PNG (what the shipped scene uses), binary PPM/PGM, and this repo's own raw
+//      cache "<file>.rgba8" (magic "SPCRGBA8", int32 w, int32 h, w*h*4 bytes).
+// Out: what replaces the GL display of the reference (sutil::GLDisplay / CUDAOutputBuffer, optixPathTracer.cpp:638-651):
+//      the tone-mapped uchar4 frame buffer as a binary PPM and the float4 accumulation buffer as a PFM.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace spchost {
+
+struct ImageRGBA8 {
+    int width = 0, height = 0;
+    std::vector<uint8_t> rgba;   // row-major, top row first
+};
+
+bool load_image_rgba8(const std::string& path, ImageRGBA8& out, std::string& err);
+bool decode_jpeg_rgba8(const uint8_t* data, size_t size, ImageRGBA8& out, std::string& err);   // jpeg_decode.cpp
+bool decode_png_rgba8(const uint8_t* data, size_t size, ImageRGBA8& out, std::string& err);    // png_decode.cpp
+bool write_rgba8_cache(const std::string& path, const ImageRGBA8& img);
+
+// Pixel (x, y) of the render lives at index y*W + x with y = 0 the BOTTOM row (raygen.cu:335-344 maps launch index y
+// to d.y = 2(y+jitter)/H - 1 along +V, and the reference displays the buffer through GL, origin bottom-left).
+// PPM is written top row first (flipped), PFM bottom row first (its native order, negative scale = little endian).
+bool write_ppm_from_uchar4(const std::string& path, const uint32_t* frame, int width, int height);
+bool write_pfm_from_float4(const std::string& path, const float* accum4, int width, int height);
+
+}  // namespace spchost

@@ -1,0 +1,83 @@
+// scene_tool.cpp -- scene conversion and texture decoding without a GPU (no dependency on libspcbpt_b200.so):
+//   spc_scene_tool convert <file.scene> <out.spcscene> [--data-root dir] [--K-light n]   .scene + OBJ + textures -> cache
+//   spc_scene_tool decode  <image> <out.rgba8>                                          JPEG/PNG/PNM -> raw RGBA8 cache
+//   spc_scene_tool scene   <file.scene> <out.txt> [data-root]                          parsed .scene as text (LoadScene check)
+//   spc_scene_tool obj     <file.obj> <out.bin>      shapes as: u32 n_shapes; per shape u32 nv, nt, nuv; f32 pos[3nv]; u32 idx[3nt]; f32 uv[nuv]
+// Used by tests/test_host_loader.py to compare the loaders with the reference's own tinyobj / stb_image / LoadScene.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "host_scene.hpp"
+
+using namespace spchost;
+
+int main(int argc, char** argv) {
+    if (argc < 4) {
+        fprintf(stderr, "usage: %s convert <file.scene> <out.spcscene> [--data-root dir] [--K-light n] | decode <image> <out.rgba8> | obj <file.obj> <out.bin>\n", argv[0]);
+        return 2;
+    }
+    const std::string cmd = argv[1];
+    std::string err;
+    if (cmd == "convert") {
+        std::string root;
+        int k_light = 200;
+        for (int i = 4; i + 1 < argc; i += 2) {
+            if (!strcmp(argv[i], "--data-root")) root = argv[i + 1];
+            if (!strcmp(argv[i], "--K-light")) k_light = atoi(argv[i + 1]);
+        }
+        SceneFile sf;
+        HostScene hs;
+        if (!load_scene_file(argv[2], root, sf, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        build_host_scene(sf, k_light, hs);
+        for (const auto& w : hs.warnings) fprintf(stderr, "warning: %s\n", w.c_str());
+        if (!save_scene_cache(argv[3], hs)) { fprintf(stderr, "cannot write %s\n", argv[3]); return 1; }
+        printf("%zu meshes %zu triangles %zu materials %zu lights %zu textures\n", hs.meshes.size(), hs.n_triangles(), hs.materials.size(), hs.lights.size(), hs.textures.size());
+        return 0;
+    }
+    if (cmd == "decode") {
+        ImageRGBA8 img;
+        if (!load_image_rgba8(argv[2], img, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        if (!write_rgba8_cache(argv[3], img)) { fprintf(stderr, "cannot write %s\n", argv[3]); return 1; }
+        printf("%d %d\n", img.width, img.height);
+        return 0;
+    }
+    if (cmd == "obj") {
+        std::vector<ObjShape> shapes;
+        if (!load_obj(argv[2], shapes, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        FILE* f = fopen(argv[3], "wb");
+        if (!f) return 1;
+        const uint32_t n = (uint32_t)shapes.size();
+        fwrite(&n, 4, 1, f);
+        for (const auto& s : shapes) {
+            const uint32_t h[3] = {(uint32_t)(s.positions.size() / 3), (uint32_t)(s.indices.size() / 3), (uint32_t)s.texcoords.size()};
+            fwrite(h, 4, 3, f);
+            fwrite(s.positions.data(), 4, s.positions.size(), f);
+            fwrite(s.indices.data(), 4, s.indices.size(), f);
+            fwrite(s.texcoords.data(), 4, s.texcoords.size(), f);
+        }
+        fclose(f);
+        printf("%u shapes\n", n);
+        return 0;
+    }
+    if (cmd == "scene") {   // the parsed .scene in the text form oracle/ref_shim/ref_loader.cpp prints for the reference's LoadScene
+        SceneFile s;
+        if (!load_scene_file(argv[2], argc > 4 ? argv[4] : "", s, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        FILE* f = fopen(argv[3], "w");
+        if (!f) return 1;
+        fprintf(f, "camera %.9g %.9g %.9g  %.9g %.9g %.9g  %.9g %.9g %.9g  %.9g %d\n", s.eye[0], s.eye[1], s.eye[2], s.lookat[0], s.lookat[1], s.lookat[2], s.up[0], s.up[1], s.up[2],
+                s.fov, (int)s.use_geometry_normal);
+        for (const auto& m : s.mesh_names) fprintf(f, "mesh %s\n", m.c_str());
+        for (const auto& m : s.materials)
+            fprintf(f, "material %d %.9g %.9g %.9g %.9g %.9g %.9g %.9g %d\n", m.albedoID, m.color[0], m.color[1], m.color[2], m.metallic, m.roughness, m.specular, m.clearcoatGloss, m.brdf);
+        for (const auto& l : s.lights)
+            fprintf(f, "light %d %d %.9g %.9g %.9g  %.9g %.9g %.9g  %.9g %.9g %.9g  %.9g %.9g %.9g  %.9g %.9g %.9g %.9g\n", l.lightType, l.divLevel, l.position[0], l.position[1],
+                    l.position[2], l.u[0], l.u[1], l.u[2], l.v[0], l.v[1], l.v[2], l.emission[0], l.emission[1], l.emission[2], l.normal[0], l.normal[1], l.normal[2], l.area);
+        for (const auto& t : s.texture_map) fprintf(f, "texture %d %s\n", t.first, t.second.c_str());
+        fclose(f);
+        return 0;
+    }
+    fprintf(stderr, "unknown command %s\n", cmd.c_str());
+    return 2;
+}

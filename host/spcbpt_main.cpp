@@ -1,0 +1,439 @@
+// spcbpt_main.cpp -- the host driver: the reference application's schedule on top of the C ABI of libspcbpt_b200.so.
+//
+// Stands in for src/OptiXPathTracer/optixPathTracer.cpp without the GLFW/GL/ImGui front end: scene loading
+// (LoadScene + Scene_shift + LightSource_shift, :735-741), buffer set-up (initLaunchParams :260-310, lt_params_setup
+// :462-476, preTracer_params_setup :479-488), the subspace-training schedule (preprocessing :552-608) and the
+// per-frame loop (updateState :371-380, launchLVCTrace :515-522, launchSubframe :609-635, main :790-822), with the
+// reference's timing read-out (sutil::displayStats) replaced by a summary line.  Every GPU step is one call into the
+// library; this file only sequences them (the Python twin is spcbpt-optix7_b200/renderer.py, used by the tests).
+//
+// Display is replaced by files: <out>.ppm (tone-mapped frame buffer) and <out>.pfm (accumulation buffer).
+#include <cuda_runtime_api.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "host_scene.hpp"
+#include "spcbpt_b200.h"
+
+using spchost::HostScene;
+
+#define SPC_CHECK(call)                                                                                   \
+    do {                                                                                                  \
+        if ((call) != SPC_OK) throw std::runtime_error(std::string(#call) + ": " + spc_last_error());     \
+    } while (0)
+#define CUDA_CHECK(call)                                                                                  \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+struct Options {
+    std::string scene, cache, data_root, out = "spcbpt_out", save_cache, alg = "SPCBPT_eye";
+    int  width = 1920, height = 1000;   // optixPathTracer.cpp:700-701
+    int  frames = 16, device = 0;
+    int  K = 1000, K_light = 0, connections = 3, max_depth = 0;
+    int  train_samples = 2000000, q_samples = 2000000, tree_samples = 100000, batch = 20000, epochs = 1;
+    float lr = 0.01f;
+    int  lt_cores = 1000, lt_padding = 800, lt_per_core = 100;   // lt_params_setup
+    int  pre_cores = 10000, pre_padding = 10;                    // preTracer_params_setup
+    unsigned seed_offset = 0;
+    bool pipeline = true, render = true, quiet = false, write_images = true;
+};
+
+void usage(const char* argv0) {
+    fprintf(stderr,
+            "Usage  : %s --scene <file.scene> | --cache <file.spcscene> [options]\n"
+            "         --dim=<width>x<height>      image dimensions; defaults to 1920x1000\n"
+            "         --data-root <dir>           directory the .scene's file names are relative to\n"
+            "         --frames <n>                subframes to accumulate (default 16)\n"
+            "         --alg pt|SPCBPT_eye         integrator (the reference toggles these with Space)\n"
+            "         --K <n> --K-light <n> --connections <n> --max-depth <n>\n"
+            "         --train-samples <n> --q-samples <n> --tree-samples <n> --batch <n> --epochs <n> --lr <f>\n"
+            "         --lt-cores <n> --lt-padding <n> --lt-per-core <n> --pretrace-cores <n> --pretrace-padding <n>\n"
+            "         --device <i> --seed-offset <u> --no-pipeline --no-images --quiet\n"
+            "         --out <prefix>              writes <prefix>.ppm and <prefix>.pfm (default spcbpt_out)\n"
+            "         --save-cache <file>         write the parsed scene as a .spcscene cache\n"
+            "         --no-render                 stop after loading (with --save-cache: scene conversion only, no GPU)\n",
+            argv0);
+}
+
+// sutil::parseDimensions (sutil/sutil.cpp:768-793)
+bool parse_dimensions(const char* arg, int& w, int& h) {
+    const char* x = strchr(arg, 'x');
+    if (!x || x == arg || !x[1]) return false;
+    w = atoi(std::string(arg, x).c_str());
+    h = atoi(x + 1);
+    return w > 0 && h > 0;
+}
+
+bool parse_args(int argc, char** argv, Options& o) {
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto need = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) throw std::runtime_error(std::string("missing value for ") + name);
+            return argv[++i];
+        };
+        if (a == "--help" || a == "-h") return false;
+        else if (a.rfind("--dim=", 0) == 0) { if (!parse_dimensions(a.c_str() + 6, o.width, o.height)) throw std::runtime_error("Failed to parse width, height from string '" + a.substr(6) + "'"); }
+        else if (a == "--scene") o.scene = need("--scene");
+        else if (a == "--cache") o.cache = need("--cache");
+        else if (a == "--data-root") o.data_root = need("--data-root");
+        else if (a == "--out") o.out = need("--out");
+        else if (a == "--save-cache") o.save_cache = need("--save-cache");
+        else if (a == "--alg") o.alg = need("--alg");
+        else if (a == "--frames") o.frames = atoi(need("--frames"));
+        else if (a == "--device") o.device = atoi(need("--device"));
+        else if (a == "--K") o.K = atoi(need("--K"));
+        else if (a == "--K-light") o.K_light = atoi(need("--K-light"));
+        else if (a == "--connections") o.connections = atoi(need("--connections"));
+        else if (a == "--max-depth") o.max_depth = atoi(need("--max-depth"));
+        else if (a == "--train-samples") o.train_samples = atoi(need("--train-samples"));
+        else if (a == "--q-samples") o.q_samples = atoi(need("--q-samples"));
+        else if (a == "--tree-samples") o.tree_samples = atoi(need("--tree-samples"));
+        else if (a == "--batch") o.batch = atoi(need("--batch"));
+        else if (a == "--epochs") o.epochs = atoi(need("--epochs"));
+        else if (a == "--lr") o.lr = (float)atof(need("--lr"));
+        else if (a == "--lt-cores") o.lt_cores = atoi(need("--lt-cores"));
+        else if (a == "--lt-padding") o.lt_padding = atoi(need("--lt-padding"));
+        else if (a == "--lt-per-core") o.lt_per_core = atoi(need("--lt-per-core"));
+        else if (a == "--pretrace-cores") o.pre_cores = atoi(need("--pretrace-cores"));
+        else if (a == "--pretrace-padding") o.pre_padding = atoi(need("--pretrace-padding"));
+        else if (a == "--seed-offset") o.seed_offset = (unsigned)strtoul(need("--seed-offset"), nullptr, 10);
+        else if (a == "--no-pipeline") o.pipeline = false;
+        else if (a == "--no-render") o.render = false;
+        else if (a == "--no-images") o.write_images = false;
+        else if (a == "--quiet") o.quiet = true;
+        else throw std::runtime_error("Unknown option '" + a + "'");
+    }
+    if (o.K_light <= 0) o.K_light = (int)(0.2 * o.K);   // NUM_SUBSPACE_LIGHTSOURCE (optixPathTracer.h:32)
+    return !(o.scene.empty() && o.cache.empty());
+}
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// --------------------------------------------------------------------------------------------------------------
+// Application state: what the reference keeps in file-scope globals (optixPathTracer.cpp:66-90)
+// --------------------------------------------------------------------------------------------------------------
+struct App {
+    Options     opt;
+    HostScene   scene;
+    spc_context* ctx = nullptr;
+    spc_params  params;          // MyParams
+    int         n_lvc = 0;
+    std::vector<spc_tree_node> eye_tree, light_tree;
+    // frame pipelining: the light trace of frame f+1 runs on a side stream under the eye pass of frame f
+    cudaStream_t main_stream = nullptr, side_stream = nullptr;
+    spc_vertex*  lvc[2] = {nullptr, nullptr};
+    uint8_t*     valid[2] = {nullptr, nullptr};
+    cudaEvent_t  ev_lt[2] = {nullptr, nullptr}, ev_eye[2] = {nullptr, nullptr};
+    int          cur = 0;
+    bool         primed = false;
+    double       t_pretrace = 0, t_trees = 0, t_qgamma = 0;
+    int          train_paths = 0;
+    std::vector<float> loss;
+
+    template <class T> T* dalloc(size_t count) {
+        void* p = nullptr;
+        SPC_CHECK(spc_device_alloc(ctx, count * sizeof(T), &p));
+        return static_cast<T*>(p);
+    }
+
+    // initLaunchParams + lt_params_setup + preTracer_params_setup + handleCameraUpdate
+    void init_launch_params() {
+        memset(&params, 0, sizeof(params));
+        const size_t P = (size_t)opt.width * opt.height;
+        params.width = (uint32_t)opt.width;
+        params.height = (uint32_t)opt.height;
+        params.accum_buffer = dalloc<spc_float4>(P);
+        params.frame_buffer = dalloc<uint32_t>(P);
+        params.subframe_index = 0u;
+        params.max_depth = opt.max_depth;
+        params.miss_color = {0.1f, 0.1f, 0.1f};
+        params.subspace_info.subspaceNum = opt.K;
+
+        spc_light_trace_params& lt = params.lt;
+        lt.M_per_core = opt.lt_per_core;
+        lt.core_padding = opt.lt_padding;
+        lt.num_core = opt.lt_cores;
+        lt.M = lt.M_per_core * lt.num_core;
+        lt.launch_frame = 0;
+        n_lvc = lt.num_core * lt.core_padding;
+        lvc[0] = dalloc<spc_vertex>(n_lvc);
+        valid[0] = dalloc<uint8_t>(n_lvc);
+        lt.ans = lvc[0];
+        lt.validState = valid[0];
+
+        spc_pretrace_params& pr = params.pre_tracer;
+        pr.num_core = opt.pre_cores;
+        pr.padding = opt.pre_padding;
+        pr.iteration = 0;
+        pr.paths = dalloc<spc_train_path>(pr.num_core);
+        pr.conns = dalloc<spc_train_conn>((size_t)pr.num_core * pr.padding);
+
+        params.sky.valid = 0;   // env_params_setup with no environment file (:422-427)
+        handle_camera_update();
+    }
+
+    void handle_camera_update() {
+        float U[3], V[3], W[3];
+        scene.camera_frame(opt.width, opt.height, U, V, W);
+        params.eye = {scene.eye[0], scene.eye[1], scene.eye[2]};
+        params.U = {U[0], U[1], U[2]};
+        params.V = {V[0], V[1], V[2]};
+        params.W = {W[0], W[1], W[2]};
+    }
+
+    void launch_light_trace() {
+        params.lt.launch_frame += 1;
+        SPC_CHECK(spc_set_params(ctx, &params));
+        SPC_CHECK(spc_launch_named(ctx, "light trace", params.lt.num_core, 1));
+    }
+
+    void launch_lvc_trace() {
+        launch_light_trace();
+        SPC_CHECK(spc_lvc_process(ctx, params.lt.ans, params.lt.validState, n_lvc, &params.sampler));
+    }
+
+    int launch_pretrace() {
+        params.pre_tracer.iteration += 1;
+        SPC_CHECK(spc_set_params(ctx, &params));
+        SPC_CHECK(spc_launch_named(ctx, "pretrace", params.pre_tracer.num_core, 1));
+        int valid_samples = 0;
+        SPC_CHECK(spc_valid_sample_gather(ctx, static_cast<const spc_train_path*>(params.pre_tracer.paths), params.pre_tracer.num_core,
+                                          static_cast<const spc_train_conn*>(params.pre_tracer.conns),
+                                          params.pre_tracer.num_core * params.pre_tracer.padding, &valid_samples));
+        return valid_samples;
+    }
+
+    std::vector<spc_tree_node> build_tree(bool eye_side, int subspaces) {
+        int n = 0;
+        SPC_CHECK(spc_get_tree_points(ctx, eye_side ? 1 : 0, opt.tree_samples, nullptr, 0, &n));
+        std::vector<spc_divide_weight> pts((size_t)(n > 0 ? n : 1));
+        SPC_CHECK(spc_get_tree_points(ctx, eye_side ? 1 : 0, opt.tree_samples, pts.data(), (int)pts.size(), &n));
+        std::vector<spc_tree_node> nodes((size_t)1 << 16);
+        int max_label = 0;
+        for (;;) {
+            const int count = spc_build_tree(pts.data(), n, subspaces, 0, nodes.data(), (int)nodes.size(), &max_label);
+            if (count < 0) throw std::runtime_error(std::string("spc_build_tree: ") + spc_last_error());
+            if ((size_t)count <= nodes.size()) {
+                nodes.resize((size_t)count);
+                break;
+            }
+            nodes.resize((size_t)count);
+        }
+        if (!opt.quiet) printf("class tree building complete:size %zu and max-label %d\n", nodes.size(), max_label);
+        return nodes;
+    }
+
+    // preprocessing() (optixPathTracer.cpp:552-608)
+    void preprocessing() {
+        double t0 = now_s();
+        int current = 0;
+        while (current < opt.train_samples) {
+            const int got = launch_pretrace();
+            current += got;
+            if (got == 0 && params.pre_tracer.iteration > 64 && current == 0) throw std::runtime_error("pretrace finds no valid path: is any light visible from the camera's paths?");
+        }
+        train_paths = current;
+        SPC_CHECK(spc_synchronize(ctx));
+        double t1 = now_s();
+        t_pretrace = t1 - t0;
+
+        SPC_CHECK(spc_sample_reweight(ctx));
+        eye_tree = build_tree(true, opt.K);
+        light_tree = build_tree(false, opt.K - opt.K_light);
+        SPC_CHECK(spc_tree_to_device(ctx, 1, eye_tree.data(), (int)eye_tree.size(), &params.subspace_info.eye_tree));
+        SPC_CHECK(spc_tree_to_device(ctx, 0, light_tree.data(), (int)light_tree.size(), &params.subspace_info.light_tree));
+        double t2 = now_s();
+        t_trees = t2 - t1;
+
+        int acc = 0;
+        bool first = true;
+        float* Q = nullptr;
+        while (acc < opt.q_samples) {
+            launch_light_trace();
+            int cumulative = 0;
+            SPC_CHECK(spc_preprocess_getQ(ctx, params.lt.ans, params.lt.validState, n_lvc, first ? 1 : 0, &Q, &cumulative));
+            first = false;
+            acc += cumulative;   // sic: the reference adds the running total each time (:590, device_thrust.cu:408)
+            if (cumulative == 0) throw std::runtime_error("light trace produced no paths");
+        }
+        SPC_CHECK(spc_Q_zero_handle(ctx));
+        SPC_CHECK(spc_node_label(ctx, params.subspace_info.eye_tree, params.subspace_info.light_tree));
+
+        const int usable = current < opt.train_samples ? current : opt.train_samples;
+        const int n_train = (usable / opt.batch) * opt.batch;
+        SPC_CHECK(spc_build_optimal_E_train_data(ctx, n_train));
+        float* gamma = nullptr;
+        SPC_CHECK(spc_preprocess_getGamma(ctx, &gamma));
+        loss.assign(4096, 0.0f);
+        int n_batches = 0;
+        SPC_CHECK(spc_train_optimal_E(ctx, opt.batch, opt.epochs, opt.lr, &gamma, loss.data(), (int)loss.size(), &n_batches));
+        loss.resize((size_t)(n_batches < (int)loss.size() ? n_batches : (int)loss.size()));
+        params.subspace_info.Q = Q;
+        SPC_CHECK(spc_Gamma2CMFGamma(ctx, gamma, &params.subspace_info.CMFGamma));
+        SPC_CHECK(spc_synchronize(ctx));
+        t_qgamma = now_s() - t2;
+    }
+
+    // launchSubframe (:609-635)
+    void launch_subframe() {
+        SPC_CHECK(spc_set_params(ctx, &params));
+        SPC_CHECK(spc_launch_named(ctx, opt.alg.c_str(), opt.width, opt.height));
+    }
+
+    void enable_pipelining() {
+        int lo = 0, hi = 0;
+        CUDA_CHECK(cudaSetDevice(opt.device));
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&main_stream, cudaStreamNonBlocking, lo));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, hi));
+        lvc[1] = dalloc<spc_vertex>(n_lvc);
+        valid[1] = dalloc<uint8_t>(n_lvc);
+        for (int k = 0; k < 2; k++) {
+            CUDA_CHECK(cudaEventCreateWithFlags(&ev_lt[k], cudaEventDisableTiming));
+            CUDA_CHECK(cudaEventCreateWithFlags(&ev_eye[k], cudaEventDisableTiming));
+        }
+        SPC_CHECK(spc_synchronize(ctx));
+        SPC_CHECK(spc_set_stream(ctx, main_stream));
+    }
+
+    void trace_into(int k) {
+        params.lt.ans = lvc[k];
+        params.lt.validState = valid[k];
+        SPC_CHECK(spc_set_stream(ctx, side_stream));
+        CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_eye[k], 0));   // the eye pass that sampled this half is done
+        launch_light_trace();
+        CUDA_CHECK(cudaEventRecord(ev_lt[k], side_stream));
+        SPC_CHECK(spc_set_stream(ctx, main_stream));
+    }
+
+    // one iteration of the render loop (main :796-820): light trace + LVC_Process + eye pass, or one pt subframe
+    void render_frame() {
+        if (opt.alg != "SPCBPT_eye") {
+            launch_subframe();
+        } else if (!main_stream) {
+            launch_lvc_trace();
+            launch_subframe();
+        } else {
+            if (!primed) {
+                trace_into(cur);
+                primed = true;
+            }
+            CUDA_CHECK(cudaStreamWaitEvent(main_stream, ev_lt[cur], 0));
+            trace_into(1 - cur);   // next frame's light paths, under this frame's eye pass
+            SPC_CHECK(spc_lvc_process(ctx, lvc[cur], valid[cur], n_lvc, &params.sampler));
+            launch_subframe();
+            CUDA_CHECK(cudaEventRecord(ev_eye[cur], main_stream));
+            cur = 1 - cur;
+        }
+        ++params.subframe_index;
+    }
+};
+
+HostScene load_scene(const Options& opt) {
+    HostScene hs;
+    std::string err;
+    if (!opt.cache.empty()) {
+        if (!spchost::load_scene_cache(opt.cache, hs, err)) throw std::runtime_error(err);
+        return hs;
+    }
+    spchost::SceneFile sf;
+    if (!spchost::load_scene_file(opt.scene, opt.data_root, sf, err)) throw std::runtime_error(err);
+    if (!spchost::build_host_scene(sf, opt.K_light, hs)) throw std::runtime_error("scene conversion failed");
+    return hs;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    App app;
+    try {
+        if (!parse_args(argc, argv, app.opt)) {
+            usage(argv[0]);
+            return argc > 1 ? 0 : 1;
+        }
+        const Options& opt = app.opt;
+        double t0 = now_s();
+        app.scene = load_scene(opt);
+        const double t_load = now_s() - t0;
+        if (!opt.quiet) {
+            for (const auto& w : app.scene.warnings) fprintf(stderr, "warning: %s\n", w.c_str());
+            printf("scene: %zu meshes, %zu triangles, %zu materials, %zu lights, %zu textures (%.2f s)\n", app.scene.meshes.size(), app.scene.n_triangles(),
+                   app.scene.materials.size(), app.scene.lights.size(), app.scene.textures.size(), t_load);
+            printf("scene aabb is %f %f %f\n", 0.5f * (app.scene.aabb_min[0] + app.scene.aabb_max[0]), 0.5f * (app.scene.aabb_min[1] + app.scene.aabb_max[1]),
+                   0.5f * (app.scene.aabb_min[2] + app.scene.aabb_max[2]));
+        }
+        if (!opt.save_cache.empty() && !spchost::save_scene_cache(opt.save_cache, app.scene)) throw std::runtime_error("cannot write " + opt.save_cache);
+        if (!opt.render) return 0;
+        if (app.scene.lights.empty()) throw std::runtime_error("the scene has no quad light: the SPCBPT path needs at least one");
+
+        // ---- Scene::finalize(): context + upload + BVH ------------------------------------------------------------
+        SPC_CHECK(spc_create(opt.device, opt.K, opt.K_light, opt.connections, &app.ctx));
+        std::vector<spc_mesh> meshes;
+        std::vector<spc_texture> textures;
+        app.scene.abi_views(meshes, textures);
+        t0 = now_s();
+        SPC_CHECK(spc_scene_upload(app.ctx, meshes.data(), (int)meshes.size(), app.scene.materials.data(), (int)app.scene.materials.size(), app.scene.lights.data(),
+                                   (int)app.scene.lights.size(), textures.data(), (int)textures.size()));
+        SPC_CHECK(spc_synchronize(app.ctx));
+        const double t_upload = now_s() - t0;
+        spc_bvh_stats bs;
+        SPC_CHECK(spc_bvh_stats_get(app.ctx, &bs));
+        if (!opt.quiet) printf("bvh: %u triangles, %u 8-wide nodes, depth %u, SAH %.2f, device build %.2f ms (upload + build %.1f ms)\n", bs.n_triangles, bs.n_nodes, bs.max_depth,
+                               bs.sah_cost, bs.build_ms, t_upload * 1e3);
+        if (opt.seed_offset) SPC_CHECK(spc_set_seed_offset(app.ctx, opt.seed_offset));
+
+        app.init_launch_params();
+        if (opt.alg == "SPCBPT_eye") {
+            if (!opt.quiet) printf("BDPTVertex Size %zu\n", sizeof(spc_vertex));
+            app.preprocessing();
+            if (!opt.quiet)
+                printf("preprocessing: %d training paths in %.3f s, trees (%zu + %zu nodes) %.3f s, Q + Gamma training %.3f s, loss %.6f -> %.6f\n", app.train_paths, app.t_pretrace,
+                       app.eye_tree.size(), app.light_tree.size(), app.t_trees, app.t_qgamma, app.loss.empty() ? 0.f : app.loss.front(), app.loss.empty() ? 0.f : app.loss.back());
+            if (opt.pipeline) app.enable_pipelining();
+        } else if (opt.alg != "pt") {
+            throw std::runtime_error("unknown integrator '" + opt.alg + "' (pt | SPCBPT_eye)");
+        }
+
+        // ---- render loop ----------------------------------------------------------------------------------------------
+        SPC_CHECK(spc_synchronize(app.ctx));
+        const int64_t launches0 = spc_launch_count(app.ctx);
+        t0 = now_s();
+        for (int f = 0; f < opt.frames; f++) app.render_frame();
+        SPC_CHECK(spc_synchronize(app.ctx));
+        if (app.side_stream) CUDA_CHECK(cudaStreamSynchronize(app.side_stream));
+        const double t_render = now_s() - t0;
+        const int64_t launches = spc_launch_count(app.ctx) - launches0;
+
+        const size_t P = (size_t)opt.width * opt.height;
+        std::vector<float> accum(P * 4);
+        std::vector<uint32_t> frame(P);
+        SPC_CHECK(spc_download(app.ctx, accum.data(), app.params.accum_buffer, accum.size() * sizeof(float)));
+        SPC_CHECK(spc_download(app.ctx, frame.data(), app.params.frame_buffer, frame.size() * sizeof(uint32_t)));
+        double mean = 0;
+        for (size_t i = 0; i < P; i++) mean += accum[4 * i] + accum[4 * i + 1] + accum[4 * i + 2];
+        mean /= (double)(3 * P);
+        if (opt.write_images) {
+            if (!spchost::write_ppm_from_uchar4(opt.out + ".ppm", frame.data(), opt.width, opt.height)) throw std::runtime_error("cannot write " + opt.out + ".ppm");
+            if (!spchost::write_pfm_from_float4(opt.out + ".pfm", accum.data(), opt.width, opt.height)) throw std::runtime_error("cannot write " + opt.out + ".pfm");
+        }
+        printf("{\"alg\": \"%s\", \"width\": %d, \"height\": %d, \"frames\": %d, \"triangles\": %zu, \"K\": %d, \"pipelined\": %s, \"render_s\": %.6f, \"ms_per_frame\": %.4f, "
+               "\"samples_per_s\": %.1f, \"kernel_launches\": %lld, \"train_paths\": %d, \"pretrace_s\": %.4f, \"trees_s\": %.4f, \"q_gamma_s\": %.4f, \"image_mean\": %.9g}\n",
+               opt.alg.c_str(), opt.width, opt.height, opt.frames, app.scene.n_triangles(), opt.K, app.main_stream ? "true" : "false", t_render, t_render / opt.frames * 1e3,
+               (double)P * opt.frames / t_render, (long long)launches, app.train_paths, app.t_pretrace, app.t_trees, app.t_qgamma, mean);
+        spc_destroy(app.ctx);
+    } catch (std::exception& e) {
+        fprintf(stderr, "Caught exception: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -9,7 +9,21 @@ Meshes follow scene_shift.cpp: one mesh per OBJ shape, then one 2-triangle mesh 
 vertices (corner, u, v, u+v-corner), triangles (0,1,3),(0,3,2), uv (0,0),(1,0),(0,1),(1,1)
 (scene_shift.cpp:274-293); Light.u / Light.v are corner+u, corner+v (scene_shift.cpp:127-129).
 """
+import ctypes
+import ctypes.util
+
 import numpy as np
+
+
+def _tanf(x):
+    """C tanf (what sutil/Camera.cpp:39 and host/host_scene.cpp call); numpy's float32 tan may differ in the last bit"""
+    try:
+        libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        libm.tanf.restype = ctypes.c_float
+        libm.tanf.argtypes = [ctypes.c_float]
+        return np.float32(libm.tanf(float(x)))
+    except OSError:
+        return np.float32(np.tan(np.float32(x)))
 
 
 class SceneData:
@@ -37,7 +51,7 @@ class SceneData:
         U = U * (f(1) / f(np.sqrt(np.dot(U, U))))
         V = np.cross(U, W).astype(f)
         V = V * (f(1) / f(np.sqrt(np.dot(V, V))))
-        vlen = f(wlen * f(np.tan(f(0.5) * f(self.camera["fov"]) * f(np.pi) / f(180.0))))
+        vlen = f(wlen * _tanf(f(0.5) * f(self.camera["fov"]) * f(np.pi) / f(180.0)))
         V = (V * vlen).astype(f)
         ulen = f(vlen * f(width / height))
         U = (U * ulen).astype(f)
@@ -321,3 +335,103 @@ def random_rays(scene, n, seed=3, tmin=1e-3, tmax=1e16):
     r["tmin"] = tmin
     r["tmax"] = tmax
     return r
+
+
+# ------------------------------------------------------------------------------------------------------------
+# on-disk formats: the reference's `.scene` + OBJ (sceneLoader.cpp, tiny_obj_loader.h) and this repo's binary
+# `.spcscene` cache (host/host_scene.cpp).  The C++ host driver (host/spcbpt_main.cpp) reads both.
+# ------------------------------------------------------------------------------------------------------------
+def export_scene(scene, out_dir, name="scene"):
+    """Write `scene` as <out_dir>/<name>/<name>.scene + one OBJ per mesh (+ PPM textures) in the reference's
+    format, so that <out_dir> plays the role of SAMPLES_DIR/data.  Floats are printed with 9 significant digits,
+    which round-trips binary32 through tinyobj's decimal parser.  Returns the path of the .scene file."""
+    import os
+    from . import LIGHT_QUAD
+    d = os.path.join(out_dir, name)
+    os.makedirs(os.path.join(d, "geometry"), exist_ok=True)
+    os.makedirs(os.path.join(d, "textures"), exist_ok=True)
+    g = lambda x: "%.9g" % float(x)   # noqa: E731
+    lines = []
+    cam = scene.camera
+    lines += ["cameraSetting", "{", "    eye " + " ".join(g(v) for v in cam["eye"]), "    lookat " + " ".join(g(v) for v in cam["lookat"]),
+              "    up " + " ".join(g(v) for v in cam["up"]), "    fov " + g(cam["fov"]), "    geo_normal 1", "}", ""]
+    tex_files = []
+    for i, t in enumerate(scene.textures):
+        px = np.ascontiguousarray(t, np.uint8)
+        rel = "%s/textures/tex%d.ppm" % (name, i)
+        with open(os.path.join(out_dir, rel), "wb") as f:
+            f.write(b"P6\n%d %d\n255\n" % (px.shape[1], px.shape[0]))
+            f.write(px[:, :, :3].tobytes())
+        tex_files.append(rel)
+    for i in range(scene.materials.shape[0]):
+        m = scene.materials[i]
+        lines += ["material mat%d" % i, "{", "   color " + " ".join(g(v) for v in m["base_color"][:3]), "   roughness " + g(m["roughness"]),
+                  "   metallic " + g(m["metallic"]), "   specular " + g(m["specular"])]
+        tex = int(m["base_color_tex"]["tex"])
+        if tex > 0:
+            lines.append("   albedoTex " + tex_files[tex - 1])
+        if int(m["brdf"]):
+            lines.append("   brdf %d" % int(m["brdf"]))
+        lines += ["}", ""]
+    k = 0
+    for m in scene.meshes:
+        if m["light_id"] >= 0:
+            continue
+        rel = "%s/geometry/mesh%d.obj" % (name, k)
+        with open(os.path.join(out_dir, rel), "w") as f:
+            f.write("# exported by spcbpt-b200 scenes.export_scene\no mesh%d\n" % k)
+            pos = np.asarray(m["positions"], np.float32)
+            f.write("".join("v %.9g %.9g %.9g\n" % (p[0], p[1], p[2]) for p in pos.tolist()))
+            uv = m.get("texcoords")
+            if uv is not None:
+                f.write("".join("vt %.9g %.9g\n" % (t[0], t[1]) for t in np.asarray(uv, np.float32).tolist()))
+                f.write("".join("f %d/%d %d/%d %d/%d\n" % (a + 1, a + 1, b + 1, b + 1, c + 1, c + 1) for a, b, c in np.asarray(m["indices"]).tolist()))
+            else:
+                f.write("".join("f %d %d %d\n" % (a + 1, b + 1, c + 1) for a, b, c in np.asarray(m["indices"]).tolist()))
+        # the reference writes Windows separators in its .scene files; keep one such line to exercise the path fix-up
+        lines += ["mesh", "{", "    file " + (rel.replace("/", "\\") if k == 0 else rel), "    material mat%d" % int(m["material_id"]), "}", ""]
+        k += 1
+    for i in range(scene.lights.shape[0]):
+        L = scene.lights[i]
+        assert int(L["type"]) == LIGHT_QUAD
+        lines += ["light", "{", "    position " + " ".join(g(v) for v in L["corner"]), "    v1 " + " ".join(g(v) for v in L["u"]),
+                  "    v2 " + " ".join(g(v) for v in L["v"]), "    emission " + " ".join(g(v) for v in L["emission"]), "    type Quad",
+                  "    divLevel %d" % int(L["divLevel"]), "}", ""]
+    path = os.path.join(d, name + ".scene")
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+    return path
+
+
+def load_spcscene(path):
+    """read a `.spcscene` cache written by host/host_scene.cpp save_scene_cache() (layout documented there)"""
+    from . import LIGHT, PBR
+    buf = np.fromfile(path, np.uint8)
+    assert buf[:8].tobytes() == b"SPCSCN01", "not a .spcscene file"
+    off = 8
+
+    def take(dtype, count):
+        nonlocal off
+        dt = np.dtype(dtype)
+        a = buf[off:off + dt.itemsize * count].view(dt)
+        off += dt.itemsize * count
+        return a
+    nm, nmat, nl, nt = (int(v) for v in take("<u4", 4))
+    cam = take("<f4", 10)
+    sc = SceneData()
+    sc.name = path
+    sc.camera = dict(eye=tuple(cam[0:3]), lookat=tuple(cam[3:6]), up=tuple(cam[6:9]), fov=float(cam[9]))
+    for _ in range(nm):
+        nv, ntri = (int(v) for v in take("<u4", 2))
+        mid, lid = (int(v) for v in take("<i4", 2))
+        pos = take("<f4", 3 * nv).reshape(-1, 3).copy()
+        idx = take("<u4", 3 * ntri).reshape(-1, 3).copy()
+        uv = take("<f4", 2 * nv).reshape(-1, 2).copy()
+        sc.meshes.append(dict(positions=pos, indices=idx, texcoords=uv, material_id=mid, light_id=lid))
+    sc.materials = take(PBR, nmat).copy()
+    sc.lights = take(LIGHT, nl).copy()
+    for _ in range(nt):
+        w, h = (int(v) for v in take("<i4", 2))
+        sc.textures.append(take("u1", 4 * w * h).reshape(h, w, 4).copy())
+    assert off == buf.shape[0], "trailing bytes in .spcscene"
+    return sc

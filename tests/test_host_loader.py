@@ -1,0 +1,213 @@
+"""Host-side scene ingest (host/: .scene parser, OBJ loader, JPEG/PNG decoders, scene conversion, .spcscene cache)
+against the reference's own loaders.  Golden files under tests/golden/loader/ were produced by LoadScene, tinyobjloader
+and stb_image compiled from the reference tree (tests/golden/make_golden_loader.py, oracle/ref_shim/ref_loader.cpp).
+Everything here is byte-exact: primitive order, vertex bits and texel bytes are part of the render parity contract.
+CPU only."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "loader")
+TOOL = os.path.join(ROOT, "host", "_build", "spc_scene_tool")
+HOUSE = "/root/reference/src/data/house"
+
+
+@pytest.fixture(scope="module")
+def tool():
+    if not os.path.exists(TOOL):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "host"), "_build/spc_scene_tool"], check=True, capture_output=True)
+    return TOOL
+
+
+def run(tool, *args):
+    r = subprocess.run([tool] + list(args), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+def test_obj_corner_cases_equal_tinyobj(tool, tmp_path):
+    """relative indices, polygon fans, v//vn, v/vt, g/o/usemtl splits, per-shape vertex de-duplication, tinyobj's own
+    decimal parser (not strtod), CRLF, faces with < 3 corners: same bytes as tinyobj::LoadObj of the reference"""
+    out = tmp_path / "q.bin"
+    run(tool, "obj", os.path.join(GOLD, "quirks.obj"), str(out))
+    assert out.read_bytes() == open(os.path.join(GOLD, "quirks.bin"), "rb").read()
+
+
+def test_obj_float_parser_matches_tinyobj_not_strtod(tool, tmp_path):
+    """values whose tinyobj parse is not the correctly rounded one must still come out as tinyobj gives them; checked
+    through the golden of quirks.obj above and here against the documented algorithm on random decimals"""
+    import math
+    rng = np.random.default_rng(11)
+    lines, expect = [], []
+    for _ in range(400):
+        ip, fd = int(rng.integers(0, 2000)), int(rng.integers(1, 12))
+        frac = "".join(str(int(d)) for d in rng.integers(0, 10, fd))
+        sign = "-" if rng.random() < 0.5 else ""
+        ex = int(rng.integers(-6, 7)) if rng.random() < 0.3 else None
+        txt = "%s%d.%s%s" % (sign, ip, frac, "" if ex is None else "e%d" % ex)
+        m = float(ip)
+        for k, d in enumerate(frac):
+            m += int(d) * math.pow(10.0, -(k + 1))
+        v = math.ldexp(m * math.pow(5.0, ex or 0), ex or 0) * (-1 if sign else 1)
+        expect.append(np.float32(v))
+        lines.append("v %s 0 0" % txt)
+    n = len(lines)
+    lines += ["f %d %d %d" % (i + 1, (i + 1) % n + 1, (i + 2) % n + 1) for i in range(0, n, 3)]
+    p = tmp_path / "floats.obj"
+    p.write_text("\n".join(lines) + "\n")
+    out = tmp_path / "floats.bin"
+    run(tool, "obj", str(p), str(out))
+    raw = np.fromfile(out, np.uint8)
+    nv, nt = (int(x) for x in raw[4:12].view(np.uint32))
+    pos = raw[16:16 + 12 * nv].view(np.float32).reshape(-1, 3)
+    idx = raw[16 + 12 * nv:16 + 12 * nv + 12 * nt].view(np.uint32)
+    src = np.concatenate([[i, (i + 1) % n, (i + 2) % n] for i in range(0, n, 3)])
+    assert np.array_equal(pos[idx, 0].view(np.uint32), np.asarray(expect, np.float32)[src].view(np.uint32))
+
+
+def test_jpeg_and_png_decoders_equal_stb_image(tool, tmp_path):
+    gold = np.load(os.path.join(GOLD, "stb_decodes.npz"))
+    assert len(gold.files) >= 15
+    for name in gold.files:
+        out = tmp_path / (name + ".rgba8")
+        run(tool, "decode", os.path.join(GOLD, name), str(out))
+        mine = np.fromfile(out, np.uint8)
+        assert mine.shape == gold[name].shape and np.array_equal(mine, gold[name]), name
+
+
+def test_progressive_jpeg_is_rejected_loudly(tool, tmp_path):
+    from PIL import Image
+    p = tmp_path / "prog.jpg"
+    Image.fromarray(np.zeros((16, 16, 3), np.uint8)).save(p, "JPEG", progressive=True)
+    r = subprocess.run([tool, "decode", str(p), str(tmp_path / "o.rgba8")], capture_output=True, text=True)
+    assert r.returncode != 0 and "progressive" in r.stderr
+
+
+def test_export_convert_roundtrip(tool, pkg, tmp_path):
+    """scenes.export_scene -> .scene + OBJ + PPM textures -> C++ loader -> .spcscene -> scenes.load_spcscene: identical
+    triangles (positions and uv bits per corner), materials, lights and camera; mesh order = file order then light quads"""
+    sc = pkg.scenes.cornell_scene(wall_cells=6, box_cells=4)
+    tex = (np.arange(8 * 4 * 4, dtype=np.uint32).reshape(4, 8, 4) * 7 % 256).astype(np.uint8)
+    tex[..., 3] = 255
+    sc.textures = [tex]
+    sc.materials["base_color_tex"]["tex"][1] = 1
+    sc.materials["metallic"][2] = 0.75
+    sc.materials["roughness"][2] = 0.125
+    path = pkg.scenes.export_scene(sc, str(tmp_path), "cb")
+    out = tmp_path / "cb.spcscene"
+    r = run(tool, "convert", path, str(out))
+    assert "%d triangles" % sc.n_triangles in r.stdout
+    s2 = pkg.scenes.load_spcscene(str(out))
+    assert len(s2.meshes) == len(sc.meshes)
+    for a, b in zip(sc.meshes, s2.meshes):
+        ia, ib = a["indices"].reshape(-1), b["indices"].reshape(-1)
+        assert np.array_equal(a["positions"].astype(np.float32)[ia].view(np.uint32), b["positions"][ib].view(np.uint32))
+        assert np.array_equal(a["texcoords"].astype(np.float32)[ia].view(np.uint32), b["texcoords"][ib].view(np.uint32))
+        assert a["light_id"] == b["light_id"]
+        if a["light_id"] < 0:
+            ma, mb = sc.materials[a["material_id"]], s2.materials[b["material_id"]]
+            for k in ("base_color", "metallic", "roughness", "specular", "specularTint", "subsurface", "anisotropic", "sheen", "sheenTint",
+                      "clearcoat", "clearcoatGloss", "brdf"):
+                assert np.array_equal(ma[k], mb[k]), k
+            assert int(ma["base_color_tex"]["tex"]) == int(mb["base_color_tex"]["tex"])
+    assert sc.lights.tobytes() == s2.lights.tobytes()
+    assert len(s2.textures) == 1 and np.array_equal(s2.textures[0], tex)
+    for k in ("eye", "lookat", "up"):
+        assert np.array_equal(np.asarray(sc.camera[k], np.float32), np.asarray(s2.camera[k], np.float32))
+    assert np.float32(sc.camera["fov"]) == np.float32(s2.camera["fov"])
+
+
+def test_scene_file_quirks(tool, tmp_path):
+    """behaviour of LoadScene that a scene author relies on: '#' only comments in column 0, 'specular' does not eat
+    'specularTint', a texture shared by two materials gets one id, a missing material keeps mesh k <-> material k, a
+    missing OBJ or texture is skipped with a warning, any line containing 'light' opens a light block"""
+    d = tmp_path / "data" / "s"
+    d.mkdir(parents=True)
+    (d / "a.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    (d / "t.ppm").write_bytes(b"P6\n2 1\n255\n" + bytes([1, 2, 3, 4, 5, 6]))
+    (d / "s.scene").write_text("""cameraSetting
+{
+  eye 1 2 3
+  lookat 0 0 0
+  fov 50
+}
+#material Ghost
+#{
+#  color 0 0 0
+#}
+material A
+{
+  color 0.1 0.2 0.3
+  specularTint 0.9
+  specular 0.25
+  albedoTex s/t.ppm
+}
+material B
+{
+  albedoTex s/t.ppm
+  metallic 1
+}
+mesh
+{
+  file s\\a.obj
+  material A
+}
+mesh
+{
+  file s/missing.obj
+  material Nope
+}
+mesh
+{
+  file s/a.obj
+  material B
+}
+  my light here
+{
+  position 0 5 0
+  v1 1 5 0
+  v2 0 5 1
+  emission 3 2 1
+  type Quad
+  divLevel 3
+}
+""")
+    txt = tmp_path / "s.txt"
+    run(tool, "scene", str(d / "s.scene"), str(txt))
+    lines = txt.read_text().splitlines()
+    assert lines[0].startswith("camera 1 2 3  0 0 0  0 1 0  50 0")
+    mats = [ln.split() for ln in lines if ln.startswith("material")]
+    assert len(mats) == 3
+    assert mats[0][1] == "1" and abs(float(mats[0][7]) - 0.25) < 1e-7      # albedoID 1, specular 0.25
+    assert mats[1][1] == "0" and mats[1][2:5] == ["1", "1", "1"]           # default material for 'Nope'
+    assert mats[2][1] == "1" and mats[2][5] == "1"                         # shared texture id, metallic 1
+    lights = [ln.split() for ln in lines if ln.startswith("light")]
+    assert len(lights) == 1 and lights[0][1:3] == ["1", "3"] and abs(float(lights[0][-1]) - 1.0) < 1e-7
+    out = tmp_path / "s.spcscene"
+    r = run(tool, "convert", str(d / "s.scene"), str(out))
+    assert "mesh skipped" in r.stderr and "3 meshes 4 triangles 3 materials 1 lights 1 textures" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(HOUSE), reason="the shipped scene lives in /root/reference (authoring container only)")
+def test_shipped_house_scene_equals_reference_loaders(tool, tmp_path):
+    dig = json.load(open(os.path.join(GOLD, "house_digest.json")))
+    txt = tmp_path / "scene.txt"
+    run(tool, "scene", os.path.join(HOUSE, "house_uvrefine2.scene"), str(txt), "/root/reference/src/data")
+    assert hashlib.sha256(txt.read_bytes()).hexdigest() == dig["scene"]
+    for f, h in dig["obj"].items():
+        out = tmp_path / "o.bin"
+        run(tool, "obj", os.path.join(HOUSE, "geometry", f), str(out))
+        assert hashlib.sha256(out.read_bytes()).hexdigest() == h, f
+    used = ("1-1PR0120602213_290_290.jpg", "5cceae599e438.jpg", "Chocofur_shaders_free_04_bump.jpg", "QUARTERSAWNTEAK.jpg", "Wood.jpg", "chair_wood.jpg")
+    for f in used + ("Country-Kitchen-JayHardy.png", "apple_leaf.JPG"):
+        out = tmp_path / "t.rgba8"
+        run(tool, "decode", os.path.join(HOUSE, "textures", f), str(out))
+        assert hashlib.sha256(out.read_bytes()).hexdigest() == dig["tex"][f], f
+    out = tmp_path / "house.spcscene"
+    r = run(tool, "convert", os.path.join(HOUSE, "house_uvrefine2.scene"), str(out))
+    assert "28 meshes %d triangles 29 materials 2 lights 6 textures" % dig["triangles"] in r.stdout
