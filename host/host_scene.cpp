@@ -13,6 +13,19 @@ size_t HostScene::n_triangles() const {
     return n;
 }
 
+void HostScene::compute_aabb() {
+    bool first = true;
+    for (const auto& m : meshes)
+        for (size_t i = 0; i + 2 < m.positions.size(); i += 3) {
+            for (int c = 0; c < 3; c++) {
+                const float x = m.positions[i + c];
+                if (first || x < aabb_min[c]) aabb_min[c] = x;
+                if (first || x > aabb_max[c]) aabb_max[c] = x;
+            }
+            first = false;
+        }
+}
+
 void HostScene::abi_views(std::vector<spc_mesh>& mo, std::vector<spc_texture>& to) const {
     mo.clear();
     to.clear();
@@ -176,15 +189,7 @@ bool build_host_scene(const SceneFile& src, int K_light, HostScene& dst) {
         dst.meshes.push_back(std::move(m));
     }
 
-    bool first = true;
-    for (const auto& m : dst.meshes)
-        for (size_t i = 0; i + 2 < m.positions.size(); i += 3)
-            for (int c = 0; c < 3; c++) {
-                const float x = m.positions[i + c];
-                if (first || x < dst.aabb_min[c]) dst.aabb_min[c] = x;
-                if (first || x > dst.aabb_max[c]) dst.aabb_max[c] = x;
-                if (c == 2) first = false;
-            }
+    dst.compute_aabb();
     return true;
 }
 
@@ -289,6 +294,7 @@ bool load_scene_cache(const std::string& path, HostScene& s, std::string& err) {
         s.textures.push_back(std::move(t));
     }
     fclose(f);
+    s.compute_aabb();
     if (!r.ok) err = "truncated or corrupt .spcscene file: " + path;
     return r.ok;
 }

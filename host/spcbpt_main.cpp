@@ -20,6 +20,7 @@
 
 #include "host_scene.hpp"
 #include "spcbpt_b200.h"
+#include "train_state.hpp"
 
 using spchost::HostScene;
 
@@ -36,7 +37,7 @@ using spchost::HostScene;
 namespace {
 
 struct Options {
-    std::string scene, cache, data_root, out = "spcbpt_out", save_cache, alg = "SPCBPT_eye";
+    std::string scene, cache, data_root, out = "spcbpt_out", save_cache, alg = "SPCBPT_eye", save_state, load_state;
     int  width = 1920, height = 1000;   // optixPathTracer.cpp:700-701
     int  frames = 16, device = 0;
     int  K = 1000, K_light = 0, connections = 3, max_depth = 0;
@@ -61,6 +62,8 @@ void usage(const char* argv0) {
             "         --device <i> --seed-offset <u> --no-pipeline --no-images --quiet\n"
             "         --out <prefix>              writes <prefix>.ppm and <prefix>.pfm (default spcbpt_out)\n"
             "         --save-cache <file>         write the parsed scene as a .spcscene cache\n"
+            "         --save-state <prefix>       write trees, Q and Gamma as <prefix>tree_eye.txt, tree_light.txt, Q.txt, E.txt\n"
+            "         --load-state <prefix>       read them back instead of training (the reference's tree_load / load_Q_file / load_Gamma_file)\n"
             "         --no-render                 stop after loading (with --save-cache: scene conversion only, no GPU)\n",
             argv0);
 }
@@ -89,6 +92,8 @@ bool parse_args(int argc, char** argv, Options& o) {
         else if (a == "--out") o.out = need("--out");
         else if (a == "--save-cache") o.save_cache = need("--save-cache");
         else if (a == "--alg") o.alg = need("--alg");
+        else if (a == "--save-state") o.save_state = need("--save-state");
+        else if (a == "--load-state") o.load_state = need("--load-state");
         else if (a == "--frames") o.frames = atoi(need("--frames"));
         else if (a == "--device") o.device = atoi(need("--device"));
         else if (a == "--K") o.K = atoi(need("--K"));
@@ -139,6 +144,7 @@ struct App {
     double       t_pretrace = 0, t_trees = 0, t_qgamma = 0;
     int          train_paths = 0;
     std::vector<float> loss;
+    float*       gamma_dev = nullptr;   // trained Gamma (E), owned by the library unless loaded from a file
 
     template <class T> T* dalloc(size_t count) {
         void* p = nullptr;
@@ -279,9 +285,38 @@ struct App {
         SPC_CHECK(spc_train_optimal_E(ctx, opt.batch, opt.epochs, opt.lr, &gamma, loss.data(), (int)loss.size(), &n_batches));
         loss.resize((size_t)(n_batches < (int)loss.size() ? n_batches : (int)loss.size()));
         params.subspace_info.Q = Q;
+        gamma_dev = gamma;
         SPC_CHECK(spc_Gamma2CMFGamma(ctx, gamma, &params.subspace_info.CMFGamma));
         SPC_CHECK(spc_synchronize(ctx));
         t_qgamma = now_s() - t2;
+    }
+
+    // trained state to / from the reference's debug text files (host/train_state.hpp)
+    void save_state(const std::string& prefix) {
+        spchost::TrainState st;
+        st.eye_tree = eye_tree;
+        st.light_tree = light_tree;
+        st.Q.resize((size_t)opt.K);
+        st.gamma.resize((size_t)opt.K * opt.K);
+        SPC_CHECK(spc_download(ctx, st.Q.data(), params.subspace_info.Q, st.Q.size() * sizeof(float)));
+        SPC_CHECK(spc_download(ctx, st.gamma.data(), gamma_dev, st.gamma.size() * sizeof(float)));
+        if (!spchost::save_train_state(prefix, st)) throw std::runtime_error("cannot write training state " + prefix + "*.txt");
+    }
+
+    void load_state(const std::string& prefix) {
+        spchost::TrainState st;
+        std::string err;
+        if (!spchost::load_train_state(prefix, opt.K, st, err)) throw std::runtime_error(err);
+        eye_tree = st.eye_tree;
+        light_tree = st.light_tree;
+        SPC_CHECK(spc_tree_to_device(ctx, 1, eye_tree.data(), (int)eye_tree.size(), &params.subspace_info.eye_tree));
+        SPC_CHECK(spc_tree_to_device(ctx, 0, light_tree.data(), (int)light_tree.size(), &params.subspace_info.light_tree));
+        float* q = dalloc<float>(st.Q.size());
+        gamma_dev = dalloc<float>(st.gamma.size());
+        SPC_CHECK(spc_upload(ctx, q, st.Q.data(), st.Q.size() * sizeof(float)));
+        SPC_CHECK(spc_upload(ctx, gamma_dev, st.gamma.data(), st.gamma.size() * sizeof(float)));
+        params.subspace_info.Q = q;
+        SPC_CHECK(spc_Gamma2CMFGamma(ctx, gamma_dev, &params.subspace_info.CMFGamma));
     }
 
     // launchSubframe (:609-635)
@@ -395,8 +430,10 @@ int main(int argc, char** argv) {
         app.init_launch_params();
         if (opt.alg == "SPCBPT_eye") {
             if (!opt.quiet) printf("BDPTVertex Size %zu\n", sizeof(spc_vertex));
-            app.preprocessing();
-            if (!opt.quiet)
+            if (!opt.load_state.empty()) app.load_state(opt.load_state);
+            else app.preprocessing();
+            if (!opt.save_state.empty()) app.save_state(opt.save_state);
+            if (!opt.quiet && opt.load_state.empty())
                 printf("preprocessing: %d training paths in %.3f s, trees (%zu + %zu nodes) %.3f s, Q + Gamma training %.3f s, loss %.6f -> %.6f\n", app.train_paths, app.t_pretrace,
                        app.eye_tree.size(), app.light_tree.size(), app.t_trees, app.t_qgamma, app.loss.empty() ? 0.f : app.loss.front(), app.loss.empty() ? 0.f : app.loss.back());
             if (opt.pipeline) app.enable_pipelining();

@@ -116,6 +116,7 @@ class Renderer:
         if allreduce is not None:
             allreduce(self._as_tensor(g_dev, K * K))
         si["Q"] = q_dev
+        self.gamma_dev = g_dev
         si["CMFGamma"] = ctx.Gamma2CMFGamma(g_dev)
         ctx.synchronize()
         t3 = time.perf_counter()
@@ -124,6 +125,50 @@ class Renderer:
         if verbose:
             print(self.stats)
         return self.stats
+
+    # ---- trained state on disk: the reference's debug text files (classTree::tree_load, load_Q_file, load_Gamma_file;
+    # same files as host/train_state.cpp) ------------------------------------------------------------------------------
+    def save_state(self, prefix):
+        si = self.P["subspace_info"]
+        for name, tree in (("tree_eye.txt", self.eye_tree), ("tree_light.txt", self.light_tree)):
+            with open(prefix + name, "w") as f:
+                for n in tree:
+                    if n["leaf"]:
+                        f.write("1 %d\n" % n["label"])
+                    else:
+                        f.write("0 %d %d %.9g %.9g %.9g %s\n" % (n["label"], n["type"], n["mid"][0], n["mid"][1], n["mid"][2], " ".join(str(int(c)) for c in n["child"])))
+        np.savetxt(prefix + "Q.txt", self.ctx.download(int(si["Q"][0]), np.float32, self.K), fmt="%.9g")
+        np.savetxt(prefix + "E.txt", self.ctx.download(int(self.gamma_dev), np.float32, self.K * self.K).reshape(self.K, self.K), fmt="%.9g")
+
+    def load_state(self, prefix):
+        from . import TREE_NODE
+        torch = self.torch
+        trees = []
+        for name in ("tree_eye.txt", "tree_light.txt"):
+            tok = open(prefix + name).read().split()
+            nodes, i = [], 0
+            while i < len(tok):
+                n = np.zeros(1, TREE_NODE)[0]
+                n["leaf"], n["label"] = int(tok[i]), int(tok[i + 1])
+                i += 2
+                if not n["leaf"]:
+                    n["type"] = int(tok[i])
+                    n["mid"] = [np.float32(t) for t in tok[i + 1:i + 4]]
+                    n["child"] = [int(t) for t in tok[i + 4:i + 12]]
+                    i += 12
+                nodes.append(n)
+            trees.append(np.array(nodes, TREE_NODE))
+        self.eye_tree, self.light_tree = trees
+        si = self.P["subspace_info"]
+        si["eye_tree"] = self.ctx.tree_to_device(True, self.eye_tree)
+        si["light_tree"] = self.ctx.tree_to_device(False, self.light_tree)
+        self._q_t = torch.from_numpy(np.loadtxt(prefix + "Q.txt", dtype=np.float32)).to(self.dev)
+        self._g_t = torch.from_numpy(np.loadtxt(prefix + "E.txt", dtype=np.float32).reshape(-1)).to(self.dev)
+        assert self._q_t.numel() == self.K and self._g_t.numel() == self.K * self.K
+        torch.cuda.synchronize(self.dev)
+        si["Q"] = self._q_t.data_ptr()
+        self.gamma_dev = self._g_t.data_ptr()
+        si["CMFGamma"] = self.ctx.Gamma2CMFGamma(self.gamma_dev)
 
     def _as_tensor(self, dev_ptr, count):
         """wrap a device pointer owned by the context as a float32 torch tensor (for torch.distributed collectives)"""
