@@ -11,6 +11,9 @@
 #include <cuda_runtime_api.h>
 
 #include <chrono>
+#include <exception>
+#include <memory>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,13 +42,13 @@ namespace {
 struct Options {
     std::string scene, cache, data_root, out = "spcbpt_out", save_cache, alg = "SPCBPT_eye", save_state, load_state;
     int  width = 1920, height = 1000;   // optixPathTracer.cpp:700-701
-    int  frames = 16, device = 0;
+    int  frames = 16, device = 0, lanes = 1;
     int  K = 1000, K_light = 0, connections = 3, max_depth = 0;
     int  train_samples = 2000000, q_samples = 2000000, tree_samples = 100000, batch = 20000, epochs = 1;
     float lr = 0.01f;
     int  lt_cores = 1000, lt_padding = 800, lt_per_core = 100;   // lt_params_setup
     int  pre_cores = 10000, pre_padding = 10;                    // preTracer_params_setup
-    unsigned seed_offset = 0;
+    unsigned seed_offset = 0, seed_stride = 1;
     bool pipeline = true, render = true, quiet = false, write_images = true;
 };
 
@@ -59,7 +62,9 @@ void usage(const char* argv0) {
             "         --K <n> --K-light <n> --connections <n> --max-depth <n>\n"
             "         --train-samples <n> --q-samples <n> --tree-samples <n> --batch <n> --epochs <n> --lr <f>\n"
             "         --lt-cores <n> --lt-padding <n> --lt-per-core <n> --pretrace-cores <n> --pretrace-padding <n>\n"
-            "         --device <i> --seed-offset <u> --no-pipeline --no-images --quiet\n"
+            "         --lanes <n>                 frame lanes: n contexts on their own streams and host threads render alternate subframes\n"
+            "                                     concurrently (same samples as the sequential loop, running means merged at read-out)\n"
+            "         --device <i> --seed-offset <u> --seed-stride <u> --no-pipeline --no-images --quiet\n"
             "         --out <prefix>              writes <prefix>.ppm and <prefix>.pfm (default spcbpt_out)\n"
             "         --save-cache <file>         write the parsed scene as a .spcscene cache\n"
             "         --save-state <prefix>       write trees, Q and Gamma as <prefix>tree_eye.txt, tree_light.txt, Q.txt, E.txt\n"
@@ -96,6 +101,7 @@ bool parse_args(int argc, char** argv, Options& o) {
         else if (a == "--load-state") o.load_state = need("--load-state");
         else if (a == "--frames") o.frames = atoi(need("--frames"));
         else if (a == "--device") o.device = atoi(need("--device"));
+        else if (a == "--lanes") o.lanes = atoi(need("--lanes"));
         else if (a == "--K") o.K = atoi(need("--K"));
         else if (a == "--K-light") o.K_light = atoi(need("--K-light"));
         else if (a == "--connections") o.connections = atoi(need("--connections"));
@@ -112,12 +118,15 @@ bool parse_args(int argc, char** argv, Options& o) {
         else if (a == "--pretrace-cores") o.pre_cores = atoi(need("--pretrace-cores"));
         else if (a == "--pretrace-padding") o.pre_padding = atoi(need("--pretrace-padding"));
         else if (a == "--seed-offset") o.seed_offset = (unsigned)strtoul(need("--seed-offset"), nullptr, 10);
+        else if (a == "--seed-stride") o.seed_stride = (unsigned)strtoul(need("--seed-stride"), nullptr, 10);
         else if (a == "--no-pipeline") o.pipeline = false;
         else if (a == "--no-render") o.render = false;
         else if (a == "--no-images") o.write_images = false;
         else if (a == "--quiet") o.quiet = true;
         else throw std::runtime_error("Unknown option '" + a + "'");
     }
+    if (o.lanes < 1 || o.lanes > 16) throw std::runtime_error("--lanes must be in 1..16");
+    if (o.seed_stride < 1) throw std::runtime_error("--seed-stride must be >= 1");
     if (o.K_light <= 0) o.K_light = (int)(0.2 * o.K);   // NUM_SUBSPACE_LIGHTSOURCE (optixPathTracer.h:32)
     return !(o.scene.empty() && o.cache.empty());
 }
@@ -130,6 +139,7 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 struct App {
     Options     opt;
     HostScene   scene;
+    const HostScene* scene_ref = nullptr;   // lanes share the host copy of the scene
     spc_context* ctx = nullptr;
     spc_params  params;          // MyParams
     int         n_lvc = 0;
@@ -190,8 +200,8 @@ struct App {
 
     void handle_camera_update() {
         float U[3], V[3], W[3];
-        scene.camera_frame(opt.width, opt.height, U, V, W);
-        params.eye = {scene.eye[0], scene.eye[1], scene.eye[2]};
+        scene_ref->camera_frame(opt.width, opt.height, U, V, W);
+        params.eye = {scene_ref->eye[0], scene_ref->eye[1], scene_ref->eye[2]};
         params.U = {U[0], U[1], U[2]};
         params.V = {V[0], V[1], V[2]};
         params.W = {W[0], W[1], W[2]};
@@ -351,6 +361,43 @@ struct App {
         SPC_CHECK(spc_set_stream(ctx, main_stream));
     }
 
+    // ---- frame lanes: this context renders the global subframes lane, lane + n_lanes, ... on its own stream ----------------------
+    int          lane = 0, n_lanes = 1, lt_base = 0;
+    cudaStream_t lane_stream = nullptr;
+
+    void create_and_upload(double* upload_s) {
+        SPC_CHECK(spc_create(opt.device, opt.K, opt.K_light, opt.connections, &ctx));
+        std::vector<spc_mesh> meshes;
+        std::vector<spc_texture> textures;
+        scene_ref->abi_views(meshes, textures);
+        const double t0 = now_s();
+        SPC_CHECK(spc_scene_upload(ctx, meshes.data(), (int)meshes.size(), scene_ref->materials.data(), (int)scene_ref->materials.size(), scene_ref->lights.data(),
+                                   (int)scene_ref->lights.size(), textures.data(), (int)textures.size()));
+        SPC_CHECK(spc_synchronize(ctx));
+        if (upload_s) *upload_s = now_s() - t0;
+    }
+
+    void become_lane(int k, int n, const App& trained) {
+        lane = k;
+        n_lanes = n;
+        params.subspace_info = trained.params.subspace_info;   // trees, Q, CMFGamma live on the same device: shared read-only
+        lt_base = trained.params.lt.launch_frame;
+        CUDA_CHECK(cudaSetDevice(opt.device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&lane_stream, cudaStreamNonBlocking));
+        SPC_CHECK(spc_synchronize(ctx));
+        SPC_CHECK(spc_set_stream(ctx, lane_stream));
+        SPC_CHECK(spc_set_seed_mapping(ctx, (uint32_t)k * opt.seed_stride + opt.seed_offset, (uint32_t)n * opt.seed_stride));
+    }
+
+    void render_lane_frames(int n_frames) {
+        for (int f = lane; f < n_frames; f += n_lanes) {
+            params.lt.launch_frame = lt_base + f;            // launch_light_trace adds 1: the index the sequential loop uses for frame f
+            params.subframe_index = (uint32_t)(f / n_lanes);   // local count -> running-mean weight; the seed uses f (seed mapping)
+            render_frame();
+        }
+        SPC_CHECK(spc_synchronize(ctx));
+    }
+
     // one iteration of the render loop (main :796-820): light trace + LVC_Process + eye pass, or one pt subframe
     void render_frame() {
         if (opt.alg != "SPCBPT_eye") {
@@ -412,22 +459,17 @@ int main(int argc, char** argv) {
         if (app.scene.lights.empty()) throw std::runtime_error("the scene has no quad light: the SPCBPT path needs at least one");
 
         // ---- Scene::finalize(): context + upload + BVH ------------------------------------------------------------
-        SPC_CHECK(spc_create(opt.device, opt.K, opt.K_light, opt.connections, &app.ctx));
-        std::vector<spc_mesh> meshes;
-        std::vector<spc_texture> textures;
-        app.scene.abi_views(meshes, textures);
-        t0 = now_s();
-        SPC_CHECK(spc_scene_upload(app.ctx, meshes.data(), (int)meshes.size(), app.scene.materials.data(), (int)app.scene.materials.size(), app.scene.lights.data(),
-                                   (int)app.scene.lights.size(), textures.data(), (int)textures.size()));
-        SPC_CHECK(spc_synchronize(app.ctx));
-        const double t_upload = now_s() - t0;
+        app.scene_ref = &app.scene;
+        double t_upload = 0;
+        app.create_and_upload(&t_upload);
         spc_bvh_stats bs;
         SPC_CHECK(spc_bvh_stats_get(app.ctx, &bs));
         if (!opt.quiet) printf("bvh: %u triangles, %u 8-wide nodes, depth %u, SAH %.2f, device build %.2f ms (upload + build %.1f ms)\n", bs.n_triangles, bs.n_nodes, bs.max_depth,
                                bs.sah_cost, bs.build_ms, t_upload * 1e3);
-        if (opt.seed_offset) SPC_CHECK(spc_set_seed_offset(app.ctx, opt.seed_offset));
+        if (opt.seed_offset || opt.seed_stride != 1) SPC_CHECK(spc_set_seed_mapping(app.ctx, opt.seed_offset, opt.seed_stride));
 
         app.init_launch_params();
+        const bool lanes_on = opt.lanes > 1;
         if (opt.alg == "SPCBPT_eye") {
             if (!opt.quiet) printf("BDPTVertex Size %zu\n", sizeof(spc_vertex));
             if (!opt.load_state.empty()) app.load_state(opt.load_state);
@@ -436,20 +478,67 @@ int main(int argc, char** argv) {
             if (!opt.quiet && opt.load_state.empty())
                 printf("preprocessing: %d training paths in %.3f s, trees (%zu + %zu nodes) %.3f s, Q + Gamma training %.3f s, loss %.6f -> %.6f\n", app.train_paths, app.t_pretrace,
                        app.eye_tree.size(), app.light_tree.size(), app.t_trees, app.t_qgamma, app.loss.empty() ? 0.f : app.loss.front(), app.loss.empty() ? 0.f : app.loss.back());
-            if (opt.pipeline) app.enable_pipelining();
+            if (opt.pipeline && !lanes_on) app.enable_pipelining();
         } else if (opt.alg != "pt") {
             throw std::runtime_error("unknown integrator '" + opt.alg + "' (pt | SPCBPT_eye)");
         }
 
+        // ---- frame lanes: more contexts on the same device sharing the trained state ------------------------------------
+        std::vector<std::unique_ptr<App>> extra;
+        std::vector<App*> lanes{&app};
+        if (lanes_on) {
+            for (int k = 1; k < opt.lanes; k++) {
+                extra.emplace_back(new App());
+                App& l = *extra.back();
+                l.opt = opt;
+                l.scene_ref = &app.scene;
+                l.create_and_upload(nullptr);
+                l.init_launch_params();
+                lanes.push_back(&l);
+            }
+            for (int k = 0; k < opt.lanes; k++) lanes[k]->become_lane(k, opt.lanes, app);
+        }
+
         // ---- render loop ----------------------------------------------------------------------------------------------
         SPC_CHECK(spc_synchronize(app.ctx));
-        const int64_t launches0 = spc_launch_count(app.ctx);
+        int64_t launches = 0;
+        for (App* l : lanes) launches -= spc_launch_count(l->ctx);
         t0 = now_s();
-        for (int f = 0; f < opt.frames; f++) app.render_frame();
-        SPC_CHECK(spc_synchronize(app.ctx));
-        if (app.side_stream) CUDA_CHECK(cudaStreamSynchronize(app.side_stream));
+        if (!lanes_on) {
+            for (int f = 0; f < opt.frames; f++) app.render_frame();
+            SPC_CHECK(spc_synchronize(app.ctx));
+            if (app.side_stream) CUDA_CHECK(cudaStreamSynchronize(app.side_stream));
+        } else {
+            std::vector<std::thread> threads;
+            std::vector<std::exception_ptr> errors(lanes.size());
+            for (size_t k = 0; k < lanes.size(); k++)
+                threads.emplace_back([&, k] {
+                    try {
+                        lanes[k]->render_lane_frames(opt.frames);
+                    } catch (...) {
+                        errors[k] = std::current_exception();
+                    }
+                });
+            for (auto& t : threads) t.join();
+            for (auto& e : errors)
+                if (e) std::rethrow_exception(e);
+        }
         const double t_render = now_s() - t0;
-        const int64_t launches = spc_launch_count(app.ctx) - launches0;
+        for (App* l : lanes) launches += spc_launch_count(l->ctx);
+
+        if (lanes_on) {   // read-out: merge the running means, weights = share of the subframes each lane rendered
+            std::vector<const spc_float4*> bufs;
+            std::vector<float> weights;
+            for (int k = 0; k < opt.lanes; k++) {
+                const int n_k = (opt.frames - k + opt.lanes - 1) / opt.lanes;
+                if (n_k <= 0) continue;
+                bufs.push_back(lanes[k]->params.accum_buffer);
+                weights.push_back((float)n_k / (float)opt.frames);
+            }
+            spc_float4* merged = app.dalloc<spc_float4>((size_t)opt.width * opt.height);
+            SPC_CHECK(spc_merge_accum(app.ctx, bufs.data(), weights.data(), (int)bufs.size(), opt.width * opt.height, merged, app.params.frame_buffer));
+            app.params.accum_buffer = merged;
+        }
 
         const size_t P = (size_t)opt.width * opt.height;
         std::vector<float> accum(P * 4);
@@ -463,10 +552,11 @@ int main(int argc, char** argv) {
             if (!spchost::write_ppm_from_uchar4(opt.out + ".ppm", frame.data(), opt.width, opt.height)) throw std::runtime_error("cannot write " + opt.out + ".ppm");
             if (!spchost::write_pfm_from_float4(opt.out + ".pfm", accum.data(), opt.width, opt.height)) throw std::runtime_error("cannot write " + opt.out + ".pfm");
         }
-        printf("{\"alg\": \"%s\", \"width\": %d, \"height\": %d, \"frames\": %d, \"triangles\": %zu, \"K\": %d, \"pipelined\": %s, \"render_s\": %.6f, \"ms_per_frame\": %.4f, "
+        printf("{\"alg\": \"%s\", \"width\": %d, \"height\": %d, \"frames\": %d, \"triangles\": %zu, \"K\": %d, \"lanes\": %d, \"pipelined\": %s, \"render_s\": %.6f, \"ms_per_frame\": %.4f, "
                "\"samples_per_s\": %.1f, \"kernel_launches\": %lld, \"train_paths\": %d, \"pretrace_s\": %.4f, \"trees_s\": %.4f, \"q_gamma_s\": %.4f, \"image_mean\": %.9g}\n",
-               opt.alg.c_str(), opt.width, opt.height, opt.frames, app.scene.n_triangles(), opt.K, app.main_stream ? "true" : "false", t_render, t_render / opt.frames * 1e3,
+               opt.alg.c_str(), opt.width, opt.height, opt.frames, app.scene.n_triangles(), opt.K, opt.lanes, app.main_stream ? "true" : "false", t_render, t_render / opt.frames * 1e3,
                (double)P * opt.frames / t_render, (long long)launches, app.train_paths, app.t_pretrace, app.t_trees, app.t_qgamma, mean);
+        for (auto& l : extra) spc_destroy(l->ctx);
         spc_destroy(app.ctx);
     } catch (std::exception& e) {
         fprintf(stderr, "Caught exception: %s\n", e.what());

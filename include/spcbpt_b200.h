@@ -397,6 +397,16 @@ SPC_API int  spc_launch_named(spc_context* ctx, const char* raygen_name, int wid
  * same local subframe indices draw different samples; each rank accumulates its own running mean and the means are
  * reduced over NCCL at read-out.  offset 0 (default) = the reference's streams. */
 SPC_API int  spc_set_seed_offset(spc_context* ctx, uint32_t offset);
+/* General form: seed = tea<4>(pixel, subframe_index * stride + offset); (0, 1) = the reference.  With (lane, n_lanes) a context that
+ * numbers ITS subframes 0,1,2,... (so that its running mean weights stay 1/(n+1), raygen.cu:430-437) draws exactly the samples of the
+ * global subframes lane, lane + n_lanes, ...: this is how several contexts on one GPU render alternate subframes concurrently
+ * (host/spcbpt_main.cpp --lanes) and how ranks partition subframes across GPUs. */
+SPC_API int  spc_set_seed_mapping(spc_context* ctx, uint32_t offset, uint32_t stride);
+/* Read-out of a sample-partitioned render: out = sum_k weights[k] * accum_dev[k] (device float4[n_pixels] each, summed in the order
+ * given) and, when out_frame_dev is not NULL, the tone-mapped sRGB uchar4 image of it (ToneMap + make_color, raygen.cu:50-58,
+ * cuda/helpers.h:35-67 -- what the eye pass writes to MyParams::frame_buffer).  accum_dev / weights are HOST arrays of n entries. */
+SPC_API int  spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_dev, const float* weights, int n, int n_pixels,
+                             spc_float4* out_accum_dev, uint32_t* out_frame_dev);
 /* optional parity dumps of the eye pass: per pixel, the primitive id of the primary hit (-1 miss) and the
  * subspace id of the first eye vertex (-1 none).  Device int[W*H] each, or NULL to disable. */
 SPC_API int  spc_set_debug_outputs(spc_context* ctx, int32_t* first_prim_dev, int32_t* first_label_dev);

@@ -139,6 +139,8 @@ def _bind_optional(L):
         "spc_launch_named": [vp, ctypes.c_char_p, i32, i32],
         "spc_set_debug_outputs": [vp, vp, vp],
         "spc_set_seed_offset": [vp, ctypes.c_uint32],
+        "spc_set_seed_mapping": [vp, ctypes.c_uint32, ctypes.c_uint32],
+        "spc_merge_accum": [vp, vp, vp, i32, i32, vp, vp],
         "spc_lvc_process": [vp, vp, vp, i32, vp],
         "spc_build_tree": [vp, i32, i32, i32, vp, i32, vp],
         "spc_valid_sample_gather": [vp, vp, i32, vp, i32, vp],
@@ -295,6 +297,15 @@ class Context:
 
     def set_seed_offset(self, offset):
         self._ck(self._L.spc_set_seed_offset(self.h, offset), "spc_set_seed_offset")
+
+    def set_seed_mapping(self, offset, stride):
+        self._ck(self._L.spc_set_seed_mapping(self.h, offset, stride), "spc_set_seed_mapping")
+
+    def merge_accum(self, accum_devs, weights, n_pixels, out_accum_dev, out_frame_dev=None):
+        """out = sum_k weights[k] * accum_devs[k] (+ the tone-mapped frame buffer): the read-out of a sample-partitioned render"""
+        ptrs = np.array([int(_ptr(a)) for a in accum_devs], np.uint64)
+        w = np.ascontiguousarray(weights, np.float32)
+        self._ck(self._L.spc_merge_accum(self.h, ptrs.ctypes.data, w.ctypes.data, len(ptrs), n_pixels, _ptr(out_accum_dev), _ptr(out_frame_dev)), "spc_merge_accum")
 
     def set_debug_outputs(self, first_prim_dev, first_label_dev):
         self._ck(self._L.spc_set_debug_outputs(self.h, _ptr(first_prim_dev), _ptr(first_label_dev)), "spc_set_debug_outputs")

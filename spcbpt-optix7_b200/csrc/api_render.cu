@@ -83,6 +83,21 @@ int spc_set_seed_offset(spc_context* ctx, uint32_t offset) {
     SPC_API_END
 }
 
+int spc_set_seed_mapping(spc_context* ctx, uint32_t offset, uint32_t stride) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(stride >= 1, SPC_ERR_INVALID, "spc_set_seed_mapping: stride must be >= 1");
+    c.seed_offset = offset;
+    c.seed_stride = stride;
+    SPC_API_END
+}
+
+int spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_dev, const float* weights, int n, int n_pixels, spc_float4* out_accum_dev,
+                    uint32_t* out_frame_dev) {
+    SPC_API_BEGIN
+    spc::merge_accum(c, accum_dev, weights, n, n_pixels, out_accum_dev, out_frame_dev);
+    SPC_API_END
+}
+
 int spc_set_debug_outputs(spc_context* ctx, int32_t* first_prim_dev, int32_t* first_label_dev) {
     SPC_API_BEGIN
     c.dbg_first_prim = first_prim_dev;

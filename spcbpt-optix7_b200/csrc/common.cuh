@@ -158,10 +158,13 @@ struct Context {
     DevBuf<spc_hit> scratch_hits;
     DevBuf<uint8_t> scratch_vis;
     DevBuf<unsigned long long> counters;
+    DevBuf<void*> merge_ptrs;                    // spc_merge_accum argument staging
+    DevBuf<float> merge_w;
     DevBuf<unsigned long long> fetch_counters;   // ray-fetch counters of the persistent traversal kernels (one slot per launch)
     unsigned      fetch_slot = 0;
     // render path
-    uint32_t      seed_offset = 0;             // see DevFrame::seed_offset
+    uint32_t      seed_offset = 0;             // see DevFrame::seed_offset / seed_stride
+    uint32_t      seed_stride = 1;
     spc_params    params = {};
     bool          has_params = false;
     EyeBuffers    eye;
@@ -187,6 +190,7 @@ void launch_trace_occlusion_q(Context& ctx, const spc_ray* rays, const int* n_de
 
 void launch_light_trace(Context& ctx);                       // "light trace" raygen
 void launch_eye_pass(Context& ctx, int width, int height);   // "SPCBPT_eye" raygen
+void merge_accum(Context& ctx, const spc_float4* const* bufs_host, const float* weights_host, int n, int n_pix, spc_float4* out, uint32_t* frame);
 void launch_pretrace(Context& ctx);                          // "pretrace" raygen
 void launch_pt(Context& ctx, int width, int height);         // "pt" raygen
 void lvc_process(Context& ctx, const spc_vertex* lvc, const uint8_t* valid, int n, spc_subspace_sampler* out);

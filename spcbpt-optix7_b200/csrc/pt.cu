@@ -30,9 +30,10 @@ __global__ void __launch_bounds__(kPtPixBlock) k_pt(const DevFrame fr, int n_pix
     unsigned cn = 0, ct = 0;
     const unsigned W = fr.p.width, H = fr.p.height;
     const unsigned x = (unsigned)i % W, y = (unsigned)i / W;
-    uint32_t seed = tea<4>((uint32_t)i, fr.p.subframe_index + fr.seed_offset);
+    const uint32_t sample_index = fr.p.subframe_index * fr.seed_stride + fr.seed_offset;   // = subframe_index in the reference
+    uint32_t seed = tea<4>((uint32_t)i, sample_index);
     float jx = 0.5f, jy = 0.5f;
-    if (fr.p.subframe_index + fr.seed_offset != 0) {
+    if (sample_index != 0) {
         jx = rnd(seed);
         jy = rnd(seed);
     }

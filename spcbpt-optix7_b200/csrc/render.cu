@@ -30,6 +30,7 @@ DevFrame make_dev_frame(Context& c) {
     fr.connections = c.connections;
     fr.max_depth = c.params.max_depth > 0 ? c.params.max_depth : 50;
     fr.seed_offset = c.seed_offset;
+    fr.seed_stride = c.seed_stride;
     return fr;
 }
 
@@ -179,9 +180,10 @@ __global__ void k_eye_init(const DevFrame fr, const EyeArgs a, int n_pix) {
     if (i >= n_pix) return;
     const unsigned W = fr.p.width, H = fr.p.height;
     const unsigned x = (unsigned)i % W, y = (unsigned)i / W;
-    uint32_t seed = tea<4>((uint32_t)i, fr.p.subframe_index + fr.seed_offset);
+    const uint32_t sample_index = fr.p.subframe_index * fr.seed_stride + fr.seed_offset;   // = subframe_index in the reference
+    uint32_t seed = tea<4>((uint32_t)i, sample_index);
     float jx = 0.5f, jy = 0.5f;
-    if (fr.p.subframe_index + fr.seed_offset != 0) {   // make_float2(rnd(seed), rnd(seed)): nvcc evaluates left to right
+    if (sample_index != 0) {   // make_float2(rnd(seed), rnd(seed)): nvcc evaluates left to right
         jx = rnd(seed);
         jy = rnd(seed);
     }
@@ -370,6 +372,40 @@ __global__ void k_accumulate(const DevFrame fr, const float4* __restrict__ res, 
         const float3 v = f3(clampf(c.x * 1.0f * inv, 0.f, 1.f), clampf(c.y * 1.0f * inv, 0.f, 1.f), clampf(c.z * 1.0f * inv, 0.f, 1.f));
         fr.p.frame_buffer[i] = quantize8(to_srgb(v.x)) | (quantize8(to_srgb(v.y)) << 8) | (quantize8(to_srgb(v.z)) << 16) | (255u << 24);
     }
+}
+
+// Read-out of a sample-partitioned render: out = sum_k w_k * accum_k in the order given (fp32, one multiply-add chain per
+// channel, no contraction), then the display transform of k_accumulate.  Used for frame lanes on one GPU (host/spcbpt_main.cpp
+// --lanes) and after the NCCL gather of per-rank buffers.
+__global__ void k_merge_accum(const spc_float4* const* __restrict__ bufs, const float* __restrict__ w, int n, int n_pix,
+                              spc_float4* __restrict__ out, uint32_t* __restrict__ frame) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    float3 c = f3(0.f, 0.f, 0.f);
+    for (int k = 0; k < n; k++) {
+        const spc_float4 a = bufs[k][i];
+        const float wk = w[k];
+        c = f3(c.x + wk * a.x, c.y + wk * a.y, c.z + wk * a.z);
+    }
+    if (out) out[i] = spc_float4{c.x, c.y, c.z, 1.0f};
+    if (frame) {
+        const float lum = 0.3f * c.x + 0.6f * c.y + 0.1f * c.z;
+        const float inv = 1.0f / (1.0f + 1 * lum / 1.5f);
+        const float3 v = f3(clampf(c.x * 1.0f * inv, 0.f, 1.f), clampf(c.y * 1.0f * inv, 0.f, 1.f), clampf(c.z * 1.0f * inv, 0.f, 1.f));
+        frame[i] = quantize8(to_srgb(v.x)) | (quantize8(to_srgb(v.y)) << 8) | (quantize8(to_srgb(v.z)) << 16) | (255u << 24);
+    }
+}
+
+void merge_accum(Context& c, const spc_float4* const* bufs_host, const float* weights_host, int n, int n_pix, spc_float4* out, uint32_t* frame) {
+    SPC_REQUIRE(bufs_host && weights_host && n > 0 && n <= 64 && n_pix > 0 && (out || frame), SPC_ERR_INVALID, "spc_merge_accum: bad arguments");
+    c.merge_ptrs.alloc(64);
+    c.merge_w.alloc(64);
+    SPC_CUDA(cudaMemcpyAsync(c.merge_ptrs.p, bufs_host, n * sizeof(void*), cudaMemcpyHostToDevice, c.stream));
+    SPC_CUDA(cudaMemcpyAsync(c.merge_w.p, weights_host, n * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    k_merge_accum<<<(n_pix + 255) / 256, 256, 0, c.stream>>>((const spc_float4* const*)c.merge_ptrs.p, c.merge_w.p, n, n_pix, out, frame);
+    SPC_CUDA(cudaGetLastError());
+    SPC_CUDA(cudaStreamSynchronize(c.stream));   // the host arrays may go away after the call
+    c.launches++;
 }
 
 void launch_eye_pass(Context& c, int width, int height) {

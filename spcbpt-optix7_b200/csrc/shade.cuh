@@ -49,8 +49,9 @@ struct DevFrame {
     int        K;            // NUM_SUBSPACE (optixPathTracer.h:31), runtime here
     int        connections;  // CONNECTION_N (:37)
     int        max_depth;    // literal 50 in raygen.cu:361,668 unless MyParams::max_depth > 0
-    uint32_t   seed_offset;  // added to subframe_index in the eye/pt seeds: 0 = the reference's streams; rank-dependent when
-                             // subframes are partitioned across GPUs (each rank keeps its own running mean)
+    uint32_t   seed_offset;  // eye/pt seeds use tea<4>(pixel, subframe_index * seed_stride + seed_offset): (0, 1) = the reference's
+    uint32_t   seed_stride;  // streams; other values when subframes are partitioned across GPUs or frame lanes (each keeps its own
+                             // running mean over ITS subframes, numbered 0,1,2,... locally)
 };
 
 struct Pbr {   // the fields of MaterialData::Pbr the BSDF reads (src/cuda/MaterialData.h:78-97)

@@ -241,3 +241,91 @@ class Renderer:
     def frame_rgba8(self):
         self.ctx.synchronize()
         return self.frame.cpu().numpy().view(np.uint8).reshape(self.h, self.w, 4)
+
+
+class LaneRenderer:
+    """Frame lanes: `lanes` render contexts on one GPU, each on its own stream and driven by its own host thread, rendering
+    alternate subframes (lane k draws the samples of the global subframes k, k+lanes, ... through spc_set_seed_mapping and
+    keeps its own running mean).  The low-occupancy tail of one lane's eye pass (deep bounces with few live paths, each a
+    latency-bound kernel) and its light trace run under the full-width head of another lane's frame.  Read-out merges the
+    running means with weights n_k / n (spc_merge_accum): the same sample set as the sequential loop, summed in a different
+    fp32 order.  Training happens once, on lane 0; the other lanes share its trees, Q and CMFGamma (same device)."""
+
+    def __init__(self, scene, width, height, lanes=3, device=0, **kw):
+        import torch
+        self.torch = torch
+        self.w, self.h, self.n_lanes = width, height, lanes
+        self.lanes = [Renderer(scene, width, height, device=device, **kw) for _ in range(lanes)]
+        with torch.cuda.device(device):
+            self.streams = [torch.cuda.Stream() for _ in range(lanes)]
+        for k, (r, s) in enumerate(zip(self.lanes, self.streams)):
+            r.ctx.synchronize()
+            r.ctx.set_stream(s.cuda_stream)
+            r.ctx.set_seed_mapping(k, lanes)
+        self.ctx = self.lanes[0].ctx
+        self.frames = 0            # global subframes rendered so far
+        self.lt_base = 0
+        self.accum = torch.zeros((width * height, 4), dtype=torch.float32, device=self.lanes[0].dev)
+        self.frame = torch.zeros(width * height, dtype=torch.int32, device=self.lanes[0].dev)
+
+    def preprocessing(self, **kw):
+        r0 = self.lanes[0]
+        st = r0.preprocessing(**kw)
+        for r in self.lanes[1:]:
+            r.P["subspace_info"] = r0.P["subspace_info"]
+            r.eye_tree, r.light_tree = r0.eye_tree, r0.light_tree
+        self.lt_base = int(r0.P["lt"]["launch_frame"][0])
+        return st
+
+    def seed_mapping(self, offset, stride):
+        """compose with an outer partition (multi-GPU): global sample index = (local index) * stride + offset"""
+        for k, r in enumerate(self.lanes):
+            r.ctx.set_seed_mapping(k * stride + offset, self.n_lanes * stride)
+
+    def _worker(self, k, f0, f1, errors):
+        try:
+            r = self.lanes[k]
+            first = f0 + ((k - f0) % self.n_lanes)
+            for f in range(first, f1, self.n_lanes):
+                r.P["lt"]["launch_frame"] = self.lt_base + f     # render_frame adds 1: frame f uses light-trace index lt_base+f+1
+                r.subframe = f // self.n_lanes
+                r.render_frame()
+            r.ctx.synchronize()
+        except Exception as ex:   # surfaced by render()
+            errors.append(ex)
+
+    def render(self, n_frames):
+        """render the next n_frames global subframes (ctypes releases the GIL inside every library call)"""
+        import threading
+        errors = []
+        f0, f1 = self.frames, self.frames + n_frames
+        th = [threading.Thread(target=self._worker, args=(k, f0, f1, errors)) for k in range(self.n_lanes)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errors:
+            raise errors[0]
+        self.frames = f1
+
+    def lane_counts(self):
+        return [len(range(k, self.frames, self.n_lanes)) for k in range(self.n_lanes)]
+
+    def merge(self):
+        cnt = self.lane_counts()
+        used = [(r.accum, c / self.frames) for r, c in zip(self.lanes, cnt) if c > 0]
+        self.ctx.merge_accum([a for a, _ in used], [w for _, w in used], self.w * self.h, self.accum, self.frame)
+        return self.accum
+
+    def image(self):
+        self.merge()
+        self.ctx.synchronize()
+        return self.accum.cpu().numpy()[:, :3].reshape(self.h, self.w, 3)
+
+    def frame_rgba8(self):
+        self.merge()
+        self.ctx.synchronize()
+        return self.frame.cpu().numpy().view(np.uint8).reshape(self.h, self.w, 4)
+
+    def launch_count(self):
+        return sum(r.ctx.launch_count() for r in self.lanes)

@@ -84,6 +84,14 @@ def test_cpp_driver_equals_python_mirror(gpu_ctx, tmp_path):
     st2, _ = run_driver("--cache", cache, dim, "--frames", frames, "--out", tmp_path / "b", "--load-state", prefix, *SMALL)
     assert st2["pipelined"]
     assert np.array_equal(read_pfm(tmp_path / "b.pfm").view(np.uint32), img_cpp.view(np.uint32))
+    # frame lanes (3 contexts / streams / host threads rendering alternate subframes): the same samples, running means merged
+    # at read-out -> equal to the sequential image up to the fp32 summation order
+    st4, _ = run_driver("--cache", cache, dim, "--frames", 7, "--out", tmp_path / "l3", "--load-state", prefix, "--lanes", 3, *SMALL)
+    st5, _ = run_driver("--cache", cache, dim, "--frames", 7, "--out", tmp_path / "l1", "--load-state", prefix, "--no-pipeline", *SMALL)
+    assert st4["lanes"] == 3 and st5["lanes"] == 1
+    a3, a1 = read_pfm(tmp_path / "l3.pfm"), read_pfm(tmp_path / "l1.pfm")
+    assert np.allclose(a3, a1, rtol=2e-6, atol=1e-7) and not np.array_equal(a3, np.zeros_like(a3))
+    assert np.abs(read_ppm(tmp_path / "l3.ppm").astype(int) - read_ppm(tmp_path / "l1.ppm").astype(int)).max() <= 1
     # state files round-trip through the Python loader as well
     r2 = make_renderer(pkg, sc2, w, h)
     r2.load_state(prefix)
@@ -98,6 +106,32 @@ def test_cpp_driver_equals_python_mirror(gpu_ctx, tmp_path):
         r.render_frame()
     a, b = read_pfm(tmp_path / "d.pfm"), r.image()
     assert abs(a.mean() / b.mean() - 1) < 0.03, (a.mean(), b.mean())
+
+
+def test_python_lane_renderer_equals_sequential(gpu_ctx, tmp_path):
+    """LaneRenderer (bench.py's render loop): lanes render the sequential loop's subframes, one thread per lane"""
+    pkg = gpu_ctx
+    from spcbpt_optix7_b200.renderer import LaneRenderer
+    sc = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=12, box_cells=8), 0.01)
+    w, h = 80, 60
+    kw = dict(K=64, K_light=12, lt_num_core=100, lt_core_padding=300, lt_M_per_core=40, pretrace_num_core=20000)
+    lr = LaneRenderer(sc, w, h, lanes=3, **kw)
+    lr.preprocessing(target_samples=40000, target_Q_samples=20000, tree_samples=20000, batch_size=20000)
+    prefix = str(tmp_path / "st_")
+    lr.lanes[0].save_state(prefix)
+    lr.render(4)
+    lr.render(3)          # continues where the first call stopped
+    assert lr.frames == 7 and lr.lane_counts() == [3, 2, 2]
+    img = lr.image().copy()
+    seq = make_renderer(pkg, sc, w, h)
+    seq.load_state(prefix)
+    seq.P["lt"]["launch_frame"] = lr.lt_base
+    for _ in range(7):
+        seq.render_frame()
+    ref = seq.image()
+    assert ref.mean() > 0.01 and np.allclose(img, ref, rtol=2e-6, atol=1e-7)
+    # each lane's running mean is exactly the mean of its own subframes: lane 1 = sequential frames 1 and 4
+    assert np.abs(lr.frame_rgba8().astype(int) - seq.frame_rgba8().astype(int)).max() <= 1
 
 
 def test_cpp_driver_errors(gpu_ctx, tmp_path):
