@@ -80,7 +80,7 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
                 const int* __restrict__ n_dev, int mult, int64_t n_host, int cull_back, int fetch_threshold,
                 float4* __restrict__ hits, uint8_t* __restrict__ visible, unsigned long long* __restrict__ counter) {
     __shared__ uint2 s_stack[kSmStack * kTraceBlock];
-    uint2 lstack[kLocStack];
+    uint2 lstack[kLocStack + kMaxBvhDepth];   // triangle postponing parks at most one extra group per tree level
     const int64_t n = n_dev ? (int64_t)__ldg(n_dev) * mult : n_host;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -117,7 +117,7 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
             if (exhausted && idle == 0xffffffffu) break;
         }
         if (ray >= 0) {
-            if (trav_step<ANYHIT, false>(nodes, tris, s, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, lstack, cn, ct)) {
+            if (trav_step<ANYHIT, false, true>(nodes, tris, s, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, lstack, cn, ct)) {
                 if (ANYHIT) {
                     visible[ray] = s.best_prim >= 0 ? 0 : 1;
                 } else {

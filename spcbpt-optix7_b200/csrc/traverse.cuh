@@ -30,12 +30,13 @@ __device__ __forceinline__ void c_cross(float ax, float ay, float az, float bx, 
     cz = __fmaf_rn(ax, by, -__fmul_rn(ay, bx));
 }
 
-// byte j of w as an exact float, without I2F: splice the byte into the mantissa of 2^23.
+// byte j of w, biased: the float 2^23 + 256*byte, built by splicing the byte into mantissa bits 8..15 of 2^23 (one PRMT, no
+// I2F and no subtraction).  The bias is folded into the per-node plane origins (trav_step), so a child plane costs PRMT + FFMA.
 template <int J>
-__device__ __forceinline__ float byte_to_float(uint32_t w) {
+__device__ __forceinline__ float byte_to_biased_float(uint32_t w) {
     uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "n"(0x7650 + J));
-    return __uint_as_float(r) - 8388608.0f;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "n"(0x7604 + 16 * J));
+    return __uint_as_float(r);
 }
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     uint32_t r;
@@ -83,12 +84,12 @@ __device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
 // one child quad (4 of the 8 slots) of a node
 #define SPC_CHILD_TEST2(J)                                                                        \
     {                                                                                             \
-        float lx = __fmaf_rn(byte_to_float<J>(slox), adjx, orgx);                                 \
-        float ly = __fmaf_rn(byte_to_float<J>(sloy), adjy, orgy);                                 \
-        float lz = __fmaf_rn(byte_to_float<J>(sloz), adjz, orgz);                                 \
-        float hx = __fmaf_rn(byte_to_float<J>(shix), adjx, orgx);                                 \
-        float hy = __fmaf_rn(byte_to_float<J>(shiy), adjy, orgy);                                 \
-        float hz = __fmaf_rn(byte_to_float<J>(shiz), adjz, orgz);                                 \
+        float lx = __fmaf_rn(byte_to_biased_float<J>(slox), adjx, olx);                           \
+        float ly = __fmaf_rn(byte_to_biased_float<J>(sloy), adjy, oly);                           \
+        float lz = __fmaf_rn(byte_to_biased_float<J>(sloz), adjz, olz);                           \
+        float hx = __fmaf_rn(byte_to_biased_float<J>(shix), adjx, ohx);                           \
+        float hy = __fmaf_rn(byte_to_biased_float<J>(shiy), adjy, ohy);                           \
+        float hz = __fmaf_rn(byte_to_biased_float<J>(shiz), adjz, ohz);                           \
         float cmin = fmaxf(fmaxf(lx, ly), fmaxf(lz, s.tmin));                                     \
         float cmax = fminf(fminf(hx, hy), fminf(hz, s.tcur));                                     \
         if (cmin <= cmax) hitmask |= byte_of(child_bits4, J) << byte_of(bit_index4, J);           \
@@ -97,7 +98,10 @@ __device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
 // One iteration: take the nearest pending child of the current node group (or fall back to its triangles), test
 // its 8 children, intersect the triangles of the hit leaves, pop when the group is exhausted.
 // Returns true when the ray is finished (stack empty, or first hit for ANYHIT -- then s.best_prim >= 0).
-template <bool ANYHIT, bool COUNT>
+// POSTPONE (wavefront kernels): when fewer than 1/5 of the lanes that entered the triangle loop are still in it, the stragglers
+// push their remaining triangles back on the stack and rejoin the warp for the next node step (Ylitie et al. 2017, "triangle
+// postponing").  The result does not depend on the order triangles are tested in (intersection contract above).
+template <bool ANYHIT, bool COUNT, bool POSTPONE = false>
 __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
                                           uint2* sstack, int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris) {
     const uint32_t oct_inv = s.oct_inv;
@@ -124,12 +128,20 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
         if (COUNT) cnt_nodes++;
 
         const uint32_t e_im = __float_as_uint(n0.w);
-        const float adjx = __uint_as_float((e_im & 0xffu) << 23) * s.idx;
-        const float adjy = __uint_as_float(((e_im >> 8) & 0xffu) << 23) * s.idy;
-        const float adjz = __uint_as_float(((e_im >> 16) & 0xffu) << 23) * s.idz;
-        const float orgx = (n0.x - s.ox) * s.idx;
-        const float orgy = (n0.y - s.oy) * s.idy;
-        const float orgz = (n0.z - s.oz) * s.idz;
+        // Child plane q (a byte) lies at t = q*step*id + (origin - o)*id.  The byte arrives as B = 2^23 + 256 q, so with
+        // adj = step*id/256 the plane is t = B*adj + (org - 2^23*adj): one FFMA per plane.  Folding the bias costs at most
+        // |adj|/2 of rounding in the constant (1/512 of a quantisation step, when the node is near the ray origin); entry planes
+        // are moved one |adj| (1/256 step) earlier and exit planes one |adj| later, which more than covers it -- the box test
+        // stays conservative and the hit set (decided by the triangle contract alone) is unchanged.
+        const float adjx = __uint_as_float((e_im & 0xffu) << 23) * s.idx * 0.00390625f;
+        const float adjy = __uint_as_float(((e_im >> 8) & 0xffu) << 23) * s.idy * 0.00390625f;
+        const float adjz = __uint_as_float(((e_im >> 16) & 0xffu) << 23) * s.idz * 0.00390625f;
+        const float orgx = __fmaf_rn(-8388608.0f, adjx, (n0.x - s.ox) * s.idx);
+        const float orgy = __fmaf_rn(-8388608.0f, adjy, (n0.y - s.oy) * s.idy);
+        const float orgz = __fmaf_rn(-8388608.0f, adjz, (n0.z - s.oz) * s.idz);
+        const float olx = orgx - fabsf(adjx), ohx = orgx + fabsf(adjx);
+        const float oly = orgy - fabsf(adjy), ohy = orgy + fabsf(adjy);
+        const float olz = orgz - fabsf(adjz), ohz = orgz + fabsf(adjz);
         const uint32_t oct_inv4 = oct_inv * 0x01010101u;
 
         uint32_t hitmask = 0;
@@ -168,7 +180,15 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
         s.ngroup = make_uint2(0u, 0u);
     }
 
+    const int tri_lanes = POSTPONE ? __popc(__activemask()) : 0;
     while (tgroup.y != 0u) {
+        if (POSTPONE && __popc(__activemask()) * 5 < tri_lanes) {
+            // park the triangles; if no inner node is pending the pop below hands them straight back as the current group
+            if (s.sp < kSmStack) sstack[s.sp * sstride] = tgroup;
+            else lstack[s.sp - kSmStack] = tgroup;
+            s.sp++;
+            break;
+        }
         const uint32_t ti = 31u - __clz(tgroup.y);
         tgroup.y &= ~(1u << ti);
         const float4* tp = tris + (size_t)(tgroup.x + ti) * 3;

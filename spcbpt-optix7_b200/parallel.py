@@ -68,6 +68,9 @@ def preprocess_distributed(renderer, env, tree_dtype, **kw):
 
 
 def reduce_accum(renderer, env):
-    """average the per-rank running means (every rank rendered the same number of subframes): the read-out collective"""
+    """average the per-rank running means (every rank rendered the same number of subframes): the read-out collective.
+    `renderer` is a Renderer or a LaneRenderer (whose lanes are merged first)."""
+    if hasattr(renderer, "merge"):
+        renderer.merge()
     renderer.ctx.synchronize()
     return env.allreduce_mean(renderer.accum)

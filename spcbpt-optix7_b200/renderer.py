@@ -269,13 +269,17 @@ class LaneRenderer:
         self.frame = torch.zeros(width * height, dtype=torch.int32, device=self.lanes[0].dev)
 
     def preprocessing(self, **kw):
+        st = self.lanes[0].preprocessing(**kw)
+        self.share_trained_state()
+        return st
+
+    def share_trained_state(self):
+        """after lane 0 has been trained (Renderer.preprocessing / parallel.preprocess_distributed / load_state)"""
         r0 = self.lanes[0]
-        st = r0.preprocessing(**kw)
         for r in self.lanes[1:]:
             r.P["subspace_info"] = r0.P["subspace_info"]
             r.eye_tree, r.light_tree = r0.eye_tree, r0.light_tree
         self.lt_base = int(r0.P["lt"]["launch_frame"][0])
-        return st
 
     def seed_mapping(self, offset, stride):
         """compose with an outer partition (multi-GPU): global sample index = (local index) * stride + offset"""
