@@ -307,23 +307,49 @@ __global__ void __launch_bounds__(128) k_eye_shade(const DevFrame fr, const EyeA
     }
 }
 
-// connectVertex_SPCBPT (raygen.cu:253-303) for every visible connection; one lane per connection
+// connectVertex_SPCBPT (raygen.cu:253-303) for every visible connection; one lane per connection.
+// Only a fraction of the slots carries a visible connection (empty slots, occluded shadow rays), so each warp first compacts
+// the slots that need work into a small shared-memory queue and evaluates them 32 at a time: measured 10 of 32 lanes active per
+// issued instruction without the queue (profiles/r1d_summary.md).  Every slot's term is written to its own place, so the order
+// in which connections are evaluated does not affect the result (k_eye_gather sums in slot order).
+__device__ __forceinline__ void eye_connect_one(const DevFrame& fr, const EyeArgs& a, int64_t k, int C) {
+    const int lv = a.conn_lvc[k];
+    const int pix = a.queue_cur[k / C];
+    const Vtx eye = vtx_load(a.ev + pix);
+    const Vtx light = vtx_load(fr.p.sampler.LVC + lv);
+    const float3 c = connect_vertices(fr, eye, light, nullptr);
+    const float3 res = c / a.conn_pmf[k];
+    float3 term = f3(0.f);
+    if (!invalid3(res)) term = res / (float)C;
+    a.contrib[k] = make_float4(term.x, term.y, term.z, 0.f);
+}
+
 __global__ void __launch_bounds__(128) k_eye_connect(const DevFrame fr, const EyeArgs a) {
+    __shared__ int64_t s_queue[4][64];
     const int C = fr.connections;
     const int64_t n = (int64_t)a.counts[a.bounce] * C;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
-        float3 term = f3(0.f);
-        const int lv = a.conn_lvc[k];
-        if (lv >= 0 && a.visible[k]) {
-            const int pix = a.queue_cur[k / C];
-            const Vtx eye = vtx_load(a.ev + pix);
-            const Vtx light = vtx_load(fr.p.sampler.LVC + lv);
-            const float3 c = connect_vertices(fr, eye, light, nullptr);
-            const float3 res = c / a.conn_pmf[k];
-            if (!invalid3(res)) term = res / (float)C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t* q = s_queue[warp];
+    int pending = 0;   // warp-uniform
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = base + lane;
+        bool work = false;
+        if (k < n) {
+            work = a.conn_lvc[k] >= 0 && a.visible[k];
+            if (!work) a.contrib[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        a.contrib[k] = make_float4(term.x, term.y, term.z, 0.f);
+        const unsigned m = __ballot_sync(0xffffffffu, work);
+        if (work) q[pending + __popc(m & ((1u << lane) - 1u))] = k;
+        pending += __popc(m);
+        __syncwarp();
+        if (pending >= 32) {
+            const int64_t mine = q[pending - 32 + lane];   // newest 32 entries: the older remainder stays at the front
+            __syncwarp();
+            eye_connect_one(fr, a, mine, C);
+            pending -= 32;
+        }
     }
+    if (lane < pending) eye_connect_one(fr, a, q[lane], C);
 }
 
 // result += res / CONNECTION_N, in connection order (raygen.cu:415)

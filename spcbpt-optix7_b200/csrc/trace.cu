@@ -75,9 +75,9 @@ k_trace_occlusion(const float4* __restrict__ nodes, const float4* __restrict__ t
 // The grid is sized to the resident capacity of the GPU (SM count x blocks per SM), not to the ray count.
 // ---------------------------------------------------------------------------------------------
 template <bool ANYHIT>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, 9)
 k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ rays,
-                const int* __restrict__ n_dev, int mult, int64_t n_host, int cull_back, int fetch_threshold,
+                const int* __restrict__ n_dev, int mult, int64_t n_host, int cull_back, int fetch_threshold, int postpone_div,
                 float4* __restrict__ hits, uint8_t* __restrict__ visible, unsigned long long* __restrict__ counter) {
     __shared__ uint2 s_stack[kSmStack * kTraceBlock];
     uint2 lstack[kLocStack + kMaxBvhDepth];   // triangle postponing parks at most one extra group per tree level
@@ -117,7 +117,7 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
             if (exhausted && idle == 0xffffffffu) break;
         }
         if (ray >= 0) {
-            if (trav_step<ANYHIT, false, true>(nodes, tris, s, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, lstack, cn, ct)) {
+            if (trav_step<ANYHIT, false, true>(nodes, tris, s, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, lstack, cn, ct, postpone_div)) {
                 if (ANYHIT) {
                     visible[ray] = s.best_prim >= 0 ? 0 : 1;
                 } else {
@@ -137,11 +137,12 @@ static int trace_env(const char* name, int dflt) {
 
 template <bool ANYHIT>
 static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits, uint8_t* visible) {
-    static int blocks_per_sm = 0, fetch_t = 0;
+    static int blocks_per_sm = 0, fetch_t = 0, postpone_div = 5;
     if (!blocks_per_sm) {
         SPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_persist<ANYHIT>, kTraceBlock, 0));
         blocks_per_sm = std::max(1, std::min(blocks_per_sm, trace_env("SPC_TRACE_BLOCKS_PER_SM", 16)));
         fetch_t = trace_env("SPC_FETCH_THRESHOLD", 6);
+        postpone_div = trace_env("SPC_POSTPONE_DIV", 5);
     }
     if (ctx.fetch_counters.n < 256) {
         ctx.fetch_counters.alloc(256);
@@ -153,7 +154,7 @@ static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, 
     const int64_t cap = (int64_t)ctx.sm_count * blocks_per_sm;
     if (blocks > cap) blocks = cap;
     k_trace_persist<ANYHIT><<<(unsigned)blocks, kTraceBlock, 0, ctx.stream>>>(ctx.bvh.nodes.p, ctx.bvh.tris.p, (const float4*)rays, n_dev, mult, n_max,
-                                                                           (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0, fetch_t, (float4*)hits, visible, counter);
+                                                                           (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0, fetch_t, postpone_div, (float4*)hits, visible, counter);
     SPC_CUDA(cudaGetLastError());
     ctx.launches++;
 }

@@ -103,7 +103,7 @@ __device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
 // postponing").  The result does not depend on the order triangles are tested in (intersection contract above).
 template <bool ANYHIT, bool COUNT, bool POSTPONE = false>
 __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
-                                          uint2* sstack, int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris) {
+                                          uint2* sstack, int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris, int postpone_div = 5) {
     const uint32_t oct_inv = s.oct_inv;
     const uint32_t oct = 7u ^ oct_inv;
     uint2 tgroup;
@@ -182,7 +182,7 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
 
     const int tri_lanes = POSTPONE ? __popc(__activemask()) : 0;
     while (tgroup.y != 0u) {
-        if (POSTPONE && __popc(__activemask()) * 5 < tri_lanes) {
+        if (POSTPONE && __popc(__activemask()) * postpone_div < tri_lanes) {
             // park the triangles; if no inner node is pending the pop below hands them straight back as the current group
             if (s.sp < kSmStack) sstack[s.sp * sstride] = tgroup;
             else lstack[s.sp - kSmStack] = tgroup;
