@@ -64,7 +64,15 @@ def preprocess_distributed(renderer, env, tree_dtype, **kw):
         if obj is None:
             return r
         return tuple(np.frombuffer(x.tobytes(), dtype=tree_dtype).copy() for x in r) if env.world > 1 else obj
-    return renderer.preprocessing(allreduce=env.allreduce_mean if env.world > 1 else None, broadcast=bcast if env.world > 1 else None, **kw)
+
+    def allreduce(t):
+        # the statistic was produced on the context's stream and is consumed there again; the collective runs on torch's
+        # streams, so fence both sides (three times per training run: cost is irrelevant)
+        renderer.ctx.synchronize()
+        env.allreduce_mean(t)
+        if getattr(t, "is_cuda", False):
+            renderer.torch.cuda.synchronize(t.device)
+    return renderer.preprocessing(allreduce=allreduce if env.world > 1 else None, broadcast=bcast if env.world > 1 else None, **kw)
 
 
 def reduce_accum(renderer, env):
@@ -73,4 +81,7 @@ def reduce_accum(renderer, env):
     if hasattr(renderer, "merge"):
         renderer.merge()
     renderer.ctx.synchronize()
-    return env.allreduce_mean(renderer.accum)
+    out = env.allreduce_mean(renderer.accum)
+    if getattr(out, "is_cuda", False):
+        renderer.torch.cuda.synchronize(out.device)
+    return out

@@ -435,3 +435,60 @@ def load_spcscene(path):
         sc.textures.append(take("u1", 4 * w * h).reshape(h, w, 4).copy())
     assert off == buf.shape[0], "trailing bytes in .spcscene"
     return sc
+
+
+def large_scene(n=3160, emitters=16, seed=3):
+    """Config 5 of BASELINE.json: large synthetic glossy scene -- a rough-metal fractal terrain of n x n quads
+    (2 n^2 triangles: n = 3160 -> 19 971 200) with glossy ridges, inside a closed box, lit by emitters^2 small quad
+    lights (16 x 16 = 256, divLevel 1 each -> 256 emitter subspaces: use K >= 1280, K_light = 256)."""
+    sc = SceneData()
+    sc.name = "large%d" % n
+    r = _lcg_floats(seed, 32)
+    s = np.linspace(0.0, 1.0, n + 1, dtype=np.float32)
+    Xg, Zg = np.meshgrid(s, s, indexing="xy")
+    H = np.zeros_like(Xg, dtype=np.float32)
+    amp, freq = 0.10, 1.3
+    for o in range(8):
+        ph1, ph2, a1, a2 = (float(v) for v in r[4 * o:4 * o + 4])
+        ang1, ang2 = 2 * np.pi * a1, 2 * np.pi * a2
+        H += (amp * np.sin(2 * np.pi * freq * (np.cos(ang1) * Xg + np.sin(ang1) * Zg) + 2 * np.pi * ph1)
+              * np.cos(2 * np.pi * freq * 0.83 * (np.cos(ang2) * Xg + np.sin(ang2) * Zg) + 2 * np.pi * ph2)).astype(np.float32)
+        amp *= 0.55
+        freq *= 2.03
+    H = (0.3 + H).astype(np.float32)
+    pos = np.stack([Xg, H, Zg], -1).reshape(-1, 3).astype(np.float32)
+    uv = np.stack([Xg, Zg], -1).reshape(-1, 2).astype(np.float32)
+    del Xg, Zg, H
+    i = np.arange(n, dtype=np.int64)
+    I, J = np.meshgrid(i, i, indexing="xy")
+    a = (J * (n + 1) + I).reshape(-1)
+    idx = np.empty((2 * n * n, 3), np.uint32)
+    idx[:n * n, 0], idx[:n * n, 1], idx[:n * n, 2] = a, a + 1, a + n + 2
+    idx[n * n:, 0], idx[n * n:, 1], idx[n * n:, 2] = a, a + n + 2, a + n + 1
+    del a, I, J
+    mats = make_pbr(2)
+    mats["base_color"][0] = (0.9, 0.85, 0.8, 1)     # glossy metal terrain (caustic caster)
+    mats["metallic"][0] = 1.0
+    mats["roughness"][0] = 0.12
+    mats["base_color"][1] = (0.7, 0.7, 0.72, 1)     # diffuse box
+    sc.materials = mats
+    sc.meshes.append(dict(positions=pos, indices=idx, texcoords=uv, material_id=0, light_id=-1))
+    walls = _merge([
+        _grid_quad((0, 0, 0), (1, 0, 0), (0, 0, 1), 1), _grid_quad((0, 1, 0), (1, 0, 0), (0, 0, 1), 1),
+        _grid_quad((0, 0, 0), (1, 0, 0), (0, 1, 0), 1), _grid_quad((0, 0, 1), (1, 0, 0), (0, 1, 0), 1),
+        _grid_quad((0, 0, 0), (0, 0, 1), (0, 1, 0), 1), _grid_quad((1, 0, 0), (0, 0, 1), (0, 1, 0), 1),
+    ])
+    sc.meshes.append(dict(positions=walls[0], indices=walls[1], texcoords=walls[2], material_id=1, light_id=-1))
+    lights = []
+    e = emitters
+    for k in range(e * e):
+        cx, cz = (k % e + 0.5) / e, (k // e + 0.5) / e
+        hs = 0.15 / e
+        y = 0.97
+        # facing down: u x v must point to -y
+        lights.append(make_quad_light(k, (cx - hs, y, cz - hs), (cx + hs, y, cz - hs), (cx - hs, y, cz + hs), (40.0, 36.0, 30.0), 1, k))
+    sc.lights = np.concatenate(lights)
+    for k in range(e * e):
+        sc.meshes.append(light_mesh(sc.lights[k:k + 1], k))
+    sc.camera = dict(eye=(0.5, 0.9, 0.03), lookat=(0.5, 0.3, 0.6), up=(0.0, 1.0, 0.0), fov=60.0)
+    return sc
