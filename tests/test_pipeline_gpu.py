@@ -69,3 +69,43 @@ def test_pipelined_frames_equal_sequential_frames(gpu_ctx):
         r.render_frame()
     b = r.image().copy()
     assert a.mean() > 0.01 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_shipped_scene_spcbpt_beats_pt_at_equal_spp(gpu_ctx):
+    """BASELINE.json configs[2] in small: the shipped house scene (its .spcscene cache is written by __graft_entry__.build() from
+    the reference's data where that exists and travels with the tree; skipped otherwise).  Ground truth = the `pt` integrator at
+    2048 spp from disjoint samples; SPCBPT with the reference's full training schedule must be unbiased against it (t=1 strategy
+    is dropped by the reference, readme.md:27, which is invisible at this tolerance) and beat `pt` at equal spp."""
+    import os
+    pkg = gpu_ctx
+    cache = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "_ref", "house.spcscene")
+    if not os.path.exists(cache):
+        pytest.skip("data/_ref/house.spcscene not present (built only where /root/reference exists)")
+    from spcbpt_optix7_b200.renderer import LaneRenderer, Renderer
+    sc = pkg.scenes.load_spcscene(cache)
+    assert sc.n_triangles == 119140 and len(sc.textures) == 6 and sc.lights.shape[0] == 2
+    w, h = 480, 250
+    gt = Renderer(sc, w, h, K=1000)
+    acc, cnt = np.zeros((h, w, 3)), np.zeros((h, w, 1))
+    for c in range(8):                      # chunks: the reference's pt has no NaN guard, a poisoned pixel-chunk is dropped
+        gt.reset_accumulation()
+        gt.ctx.set_seed_offset(7777777 + 256 * c)
+        for _ in range(256):
+            gt.render_frame_pt()
+        img = gt.image()
+        ok = np.isfinite(img).all(-1, keepdims=True)
+        acc += np.where(ok, img, 0.0)
+        cnt += ok
+    ref = (acc / np.maximum(cnt, 1)).astype(np.float32)
+    lr = LaneRenderer(sc, w, h, lanes=3, K=1000)
+    st = lr.preprocessing()
+    assert st["train_paths"] >= 2000000 and np.isfinite(st["loss_last"])
+    lr.render(64)
+    img = lr.image()
+    pt = Renderer(sc, w, h, K=1000)
+    for _ in range(64):
+        pt.render_frame_pt()
+    e_spc, e_pt = relmse(img, ref), relmse(np.nan_to_num(pt.image()), ref)
+    print("house 480x250 vs pt@2048spp: relMSE SPCBPT 64spp %.4f, pt 64spp %.4f, means %.4f / %.4f" % (e_spc, e_pt, img.mean(), ref.mean()))
+    assert np.isfinite(img).all() and abs(img.mean() / ref.mean() - 1) < 0.02
+    assert e_spc < 0.5 * e_pt and e_spc < 0.2
