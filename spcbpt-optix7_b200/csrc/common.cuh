@@ -158,6 +158,8 @@ struct Context {
     DevBuf<spc_hit> scratch_hits;
     DevBuf<uint8_t> scratch_vis;
     DevBuf<unsigned long long> counters;
+    cudaStream_t  pipe_streams[3] = {nullptr, nullptr, nullptr};   // host-buffer batch pipeline (api.cu)
+    cudaEvent_t   pipe_event = nullptr;
     DevBuf<void*> merge_ptrs;                    // spc_merge_accum argument staging
     DevBuf<float> merge_w;
     DevBuf<unsigned long long> fetch_counters;   // ray-fetch counters of the persistent traversal kernels (one slot per launch)
