@@ -141,6 +141,11 @@ struct TrainBuffers {
     DevBuf<int>   P2N, label_E, label_P;
     std::vector<int> h_P2N;
     DevBuf<float> gamma, cmf, theta, adam_m, adam_v, E, dE, Esum, loss;
+    // deterministic scatter-adds (train.cu): elements sorted by target cell (stable), summed in order per cell
+    DevBuf<uint32_t> sort_keys, sort_keys2;
+    DevBuf<float>    sort_vals, sort_vals2, path_d, path_loss;
+    DevBuf<int>      sort_idx, sort_idx2, node_path;
+    DevBuf<uint8_t>  sort_tmp;
 };
 
 struct Context {

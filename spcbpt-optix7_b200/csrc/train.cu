@@ -15,6 +15,7 @@
 // Not a dense contraction anywhere: CUDA cores + fp32 atomics, no tensor cores.
 #include <algorithm>
 #include <cfloat>
+#include <cub/cub.cuh>
 #include "shade.cuh"
 
 namespace spc {
@@ -369,14 +370,43 @@ void train_build_data(Context& c, int n_samples) {
 // ---------------------------------------------------------------------------------------------
 // preprocess_getGamma
 // ---------------------------------------------------------------------------------------------
-__global__ void k_gamma_hist(const spc_train_path* __restrict__ paths, const spc_train_conn* __restrict__ conns, int n_conns, int K, float* __restrict__ G) {
+// The reference adds the clamped path weight of every split to h_Gamma[eye * K + light] in one serial host loop over the
+// connections in index order (device_thrust.cu:633-646).  To get the same fp32 sums on the device the (cell, weight) pairs are
+// sorted by cell with a stable radix sort and each cell is then summed in order by the thread that owns its first element:
+// bit-identical to the serial loop, and run-to-run reproducible (no floating-point atomics).
+__global__ void k_gamma_pairs(const spc_train_path* __restrict__ paths, const spc_train_conn* __restrict__ conns, int n_conns, int K,
+                              uint32_t* __restrict__ keys, float* __restrict__ vals) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_conns) return;
     const spc_train_conn& s = conns[j];
     const spc_train_path& p = paths[s.path_id];
     const float weight = (p.contri.x + p.contri.y + p.contri.z) / p.sample_pdf;
-    const float weight2 = (float)fmin((double)weight, 10.0);
-    atomicAdd(G + (size_t)s.label_A * K + s.label_B, weight2);
+    keys[j] = (uint32_t)s.label_A * (uint32_t)K + (uint32_t)s.label_B;
+    vals[j] = (float)fmin((double)weight, 10.0);
+}
+// out[key] = in-order sum of the values of the key's run (keys sorted); runs start where the key changes
+__global__ void k_segment_sum_ordered(const uint32_t* __restrict__ keys, const float* __restrict__ vals, int n, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t key = keys[j];
+    if (j > 0 && keys[j - 1] == key) return;
+    // end of the run by bisection, so that the summation loop has a known trip count (loads run ahead of the FADD chain: a
+    // hot cell holds 10^4..10^5 entries)
+    int lo = j, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] == key) lo = mid;
+        else hi = mid;
+    }
+    float sum = 0.f;
+#pragma unroll 8
+    for (int k = j; k < hi; k++) sum += vals[k];
+    out[key] = sum;
+}
+static int bits_for(size_t n) {
+    int b = 1;
+    while (((size_t)1 << b) < n && b < 32) b++;
+    return b;
 }
 __global__ void k_gamma_rownorm(float* __restrict__ G, int K) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,9 +425,19 @@ float* train_get_gamma(Context& c) {
     t.gamma.alloc((size_t)K * K);
     SPC_CUDA(cudaMemsetAsync(t.gamma.p, 0, (size_t)K * K * sizeof(float), c.stream));
     const int n = (int)t.n_conns;
-    if (n) k_gamma_hist<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, t.conns.p, n, K, t.gamma.p);
+    if (n) {
+        t.sort_keys.alloc(n); t.sort_keys2.alloc(n); t.sort_vals.alloc(n); t.sort_vals2.alloc(n);
+        k_gamma_pairs<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, t.conns.p, n, K, t.sort_keys.p, t.sort_vals.p);
+        size_t tmp_bytes = 0;
+        const int end_bit = bits_for((size_t)K * K);
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, t.sort_keys.p, t.sort_keys2.p, t.sort_vals.p, t.sort_vals2.p, n, 0, end_bit, c.stream);
+        t.sort_tmp.alloc(tmp_bytes);
+        SPC_CUDA(cub::DeviceRadixSort::SortPairs(t.sort_tmp.p, tmp_bytes, t.sort_keys.p, t.sort_keys2.p, t.sort_vals.p, t.sort_vals2.p, n, 0, end_bit, c.stream));
+        k_segment_sum_ordered<<<(n + 255) / 256, 256, 0, c.stream>>>(t.sort_keys2.p, t.sort_vals2.p, n, t.gamma.p);
+        c.launches += 3;
+    }
     k_gamma_rownorm<<<(K + 63) / 64, 64, 0, c.stream>>>(t.gamma.p, K);
-    c.launches += 2;
+    c.launches += 1;
     SPC_CUDA(cudaGetLastError());
     return t.gamma.p;
 }
@@ -434,9 +474,8 @@ __global__ void k_train_E(const float* __restrict__ theta, int K, float c_keep, 
 // one lane per path of the batch: forward pdf, d(loss)/d(pdf), scatter-add into dE (get_forward_pdfs .. get_dE, :981-1088)
 __global__ void k_train_paths(const float* __restrict__ E, const float* __restrict__ f_square, const float* __restrict__ pdf0, const float* __restrict__ peak,
                               const int* __restrict__ label_E, const int* __restrict__ P2N, int bias_sample, int batch, int N, int M,
-                              float* __restrict__ dE, float* __restrict__ loss_acc) {
+                              float* __restrict__ path_d, float* __restrict__ path_loss) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float loss = 0.f;
     if (i < batch) {
         const int b = P2N[bias_sample + i];
         // a path's nodes are [P2N[i], P2N[i+1]).  (The reference hands the last batch every remaining node, device_thrust.cu:1636,
@@ -446,12 +485,54 @@ __global__ void k_train_paths(const float* __restrict__ E, const float* __restri
         for (int k = b; k < e; k++) pdf += peak[k] * E[label_E[k]];
         pdf += pdf0[bias_sample + i];
         const float f2 = f_square[bias_sample + i];
-        loss = f2 / pdf;
-        const float d = -f2 / pdf / pdf;   // inver_gradient (:832-840)
-        for (int k = b; k < e; k++) atomicAdd(dE + label_E[k], peak[k] * d);
+        path_loss[i] = f2 / pdf;
+        path_d[bias_sample + i] = -f2 / pdf / pdf;   // inver_gradient (:832-840)
     }
-    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(loss_acc, loss);
+}
+// dE[cell] = sum over the batch's nodes of that cell of peak * d(path), summed in node order.  `order` lists the node indices
+// sorted by (batch, cell) (stable, built once per training run); [lo, hi) is this batch's slice.  The reference uses thrust
+// sort_by_key + reduce_by_key here (device_thrust.cu:1045-1088), whose summation order is unspecified; ours is fixed, so a
+// training run is bit-reproducible.
+__global__ void k_train_dE_ordered(const int* __restrict__ order, const uint32_t* __restrict__ sorted_keys, int lo, int hi, const float* __restrict__ peak,
+                                   const int* __restrict__ node_path, const float* __restrict__ path_d, const int* __restrict__ label_E, float* __restrict__ dE) {
+    const int j = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= hi) return;
+    const uint32_t key = sorted_keys[j];
+    if (j > lo && sorted_keys[j - 1] == key) return;
+    float sum = 0.f;
+    int cell = 0;
+    for (int k = j; k < hi && sorted_keys[k] == key; k++) {
+        const int node = order[k];
+        cell = label_E[node];
+        sum += peak[node] * path_d[node_path[node]];
+    }
+    dE[cell] = sum;
+}
+__global__ void k_node_keys(const int* __restrict__ P2N, int N, int M, int batch, int cells_bits, const int* __restrict__ label_E,
+                            uint32_t* __restrict__ keys, int* __restrict__ idx, int* __restrict__ node_path) {
+    // one thread per path: its nodes get key (batch index << cells_bits) | cell
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int b = P2N[i], e = (i + 1 < N) ? P2N[i + 1] : M;
+    const uint32_t hi = (uint32_t)(i / batch) << cells_bits;
+    for (int k = b; k < e; k++) {
+        keys[k] = hi | (uint32_t)label_E[k];
+        idx[k] = k;
+        node_path[k] = i;
+    }
+}
+// fixed-order sum of n values into *out (one block): strided serial partials, then a shared-memory tree
+__global__ void k_sum_fixed(const float* __restrict__ v, int n, float* __restrict__ out) {
+    __shared__ float s[256];
+    float p = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) p += v[i];
+    s[threadIdx.x] = p;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s[0];
 }
 // one block per row: dE_sum, d(loss)/d(theta) (gradient_E2theta, :1090-1147) and the Adam step (:1437-1470)
 __global__ void k_train_step(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ E, const float* __restrict__ Esum,
@@ -536,6 +617,20 @@ float* train_optimal_E(Context& c, int batch_size, int epochs, float lr, float* 
     k_theta_init<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.gamma.p, n, t.theta.p, t.adam_m.p, t.adam_v.p);
     c.launches++;
     const float c_keep = (float)(1 - 0.2), c_uniform = (float)(0.2 / (double)(float)K);   // CONSERVATIVE_RATE (optixPathTracer.h:36)
+    // nodes sorted by (batch, cell), stable: one sort for the whole run
+    const int cells_bits = bits_for(n);
+    const int batch_bits = bits_for((size_t)num_batches + 1);
+    SPC_REQUIRE(cells_bits + batch_bits <= 32, SPC_ERR_INVALID, "train_optimal_E: K^2 x batches does not fit the 32-bit sort key");
+    t.sort_keys.alloc(t.M); t.sort_keys2.alloc(t.M); t.sort_idx.alloc(t.M); t.sort_idx2.alloc(t.M); t.node_path.alloc(t.M);
+    t.path_d.alloc(t.N); t.path_loss.alloc(batch_size);
+    k_node_keys<<<(t.N + 255) / 256, 256, 0, st>>>(t.P2N.p, t.N, t.M, batch_size, cells_bits, t.label_E.p, t.sort_keys.p, t.sort_idx.p, t.node_path.p);
+    {
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, t.sort_keys.p, t.sort_keys2.p, t.sort_idx.p, t.sort_idx2.p, t.M, 0, cells_bits + batch_bits, st);
+        t.sort_tmp.alloc(tmp_bytes);
+        SPC_CUDA(cub::DeviceRadixSort::SortPairs(t.sort_tmp.p, tmp_bytes, t.sort_keys.p, t.sort_keys2.p, t.sort_idx.p, t.sort_idx2.p, t.M, 0, cells_bits + batch_bits, st));
+    }
+    c.launches += 2;
     int step = 0;
     for (int ep = 0; ep < epochs; ep++)
         for (int b = 0; b < num_batches; b++) {
@@ -543,9 +638,15 @@ float* train_optimal_E(Context& c, int batch_size, int epochs, float lr, float* 
             step++;
             k_train_E<<<K, 256, 0, st>>>(t.theta.p, K, c_keep, c_uniform, t.E.p, t.Esum.p, t.dE.p);
             k_train_paths<<<(batch_size + 127) / 128, 128, 0, st>>>(t.E.p, t.f_square.p, t.pdf0.p, t.peak.p, t.label_E.p, t.P2N.p, bias_sample, batch_size,
-                                                                   t.N, t.M, t.dE.p, t.loss.p + (step - 1));
+                                                                   t.N, t.M, t.path_d.p, t.path_loss.p);
+            // the batch's nodes are the contiguous range [P2N[bias], P2N[bias + batch]) and keep that range after the (batch, cell) sort
+            const int lo = t.h_P2N[bias_sample];
+            const int hi = bias_sample + batch_size < t.N ? t.h_P2N[bias_sample + batch_size] : t.M;
+            if (hi > lo)
+                k_train_dE_ordered<<<(hi - lo + 255) / 256, 256, 0, st>>>(t.sort_idx2.p, t.sort_keys2.p, lo, hi, t.peak.p, t.node_path.p, t.path_d.p, t.label_E.p, t.dE.p);
+            k_sum_fixed<<<1, 256, 0, st>>>(t.path_loss.p, batch_size, t.loss.p + (step - 1));
             k_train_step<<<K, 256, 0, st>>>(t.theta.p, t.adam_m.p, t.adam_v.p, t.E.p, t.Esum.p, t.dE.p, K, step, lr, 0.9f, 0.999f, 1e-8f);
-            c.launches += 3;
+            c.launches += 5;
         }
     k_train_toE<<<K, 256, 0, st>>>(t.theta.p, K, t.gamma.p);
     c.launches++;

@@ -72,7 +72,7 @@ def test_cpp_driver_equals_python_mirror(gpu_ctx, tmp_path):
     r.preprocessing(target_samples=40000, target_Q_samples=20000, tree_samples=20000, batch_size=20000)
     prefix = str(tmp_path / "st_")
     r.save_state(prefix)
-    r.P["lt"]["launch_frame"] = 0      # the driver starts its light-trace counter at 0 when it does not train
+    r.P["lt"]["launch_frame"] = 0      # the driver starts its light-trace counter at 0 when it loads the state instead of training
     for _ in range(frames):
         r.render_frame()
     img_py = r.image().copy()
@@ -99,13 +99,15 @@ def test_cpp_driver_equals_python_mirror(gpu_ctx, tmp_path):
         r2.render_frame()
     assert np.array_equal(r2.image().view(np.uint32), img_py.view(np.uint32))
 
-    # 3. the driver's own training (no shared state): statistically the same image
-    st3, _ = run_driver("--cache", cache, dim, "--frames", 48, "--out", tmp_path / "d", "--save-state", tmp_path / "own_", *SMALL)
+    # 3. the driver's own training, no shared state: training has no floating-point atomics (train.cu sums every scatter-add in a
+    #    fixed order), so the whole pipeline -- pretrace, trees, Q, Gamma, Adam, render -- is bit-reproducible across processes
+    st3, _ = run_driver("--cache", cache, dim, "--frames", frames, "--out", tmp_path / "d", "--save-state", tmp_path / "own_", "--no-pipeline", *SMALL)
     assert st3["train_paths"] >= 40000 and os.path.exists(tmp_path / "own_E.txt")
-    for _ in range(48 - frames):
-        r.render_frame()
-    a, b = read_pfm(tmp_path / "d.pfm"), r.image()
-    assert abs(a.mean() / b.mean() - 1) < 0.03, (a.mean(), b.mean())
+    r3 = make_renderer(pkg, sc2, w, h)
+    r3.preprocessing(target_samples=40000, target_Q_samples=20000, tree_samples=20000, batch_size=20000)
+    for _ in range(frames):
+        r3.render_frame()
+    assert np.array_equal(read_pfm(tmp_path / "d.pfm").view(np.uint32), r3.image().view(np.uint32)), "own training: C++ driver and Python mirror disagree"
 
 
 def test_python_lane_renderer_equals_sequential(gpu_ctx, tmp_path):
