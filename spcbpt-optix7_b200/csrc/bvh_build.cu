@@ -11,6 +11,8 @@
 //   5. top-down emission of 80-byte nodes + 48-byte triangles, one queue per level (k_emit)
 #include <cub/cub.cuh>
 #include <cfloat>
+#include <cstdlib>
+#include <cstring>
 #include "traverse.cuh"
 
 namespace spc {
@@ -125,6 +127,143 @@ __global__ void k_radix_tree(const uint64_t* __restrict__ keys, int n, int* __re
     first[i] = lo;
     last[i] = hi;
     if (i == 0) parent[0] = -1;
+}
+
+// 3b -----------------------------------------------------------------------------------------
+// Binary topology by parallel locally-ordered clustering (PLOC, Meister & Bittner 2018) instead of the Morton radix
+// tree: clusters stay in Morton order; every round each cluster looks kPlocRadius neighbours to either side for the one
+// whose merged box has the smallest area, mutual nearest neighbours merge, the array is compacted (order kept).
+// Deterministic: ties go to the lower index and node ids come from a prefix sum, not from an atomic counter.
+// The radix tree only groups by Morton prefix; merging by surface area gives a tree whose SAH cost is markedly lower
+// (fewer node visits per ray), and the hit results cannot change (intersection contract, traverse.cuh).
+// Output in the form steps 4-5 expect: internal ids 0..n-2 with root 0, leaf k -> n-1+k where k is the position
+// in a depth-first leaf order (so every subtree owns a contiguous [first,last] range of `sorted_prim`).
+constexpr int kPlocRadius = 16;
+
+__global__ void k_ploc_init(int n, const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ plo,
+                            const float4* __restrict__ phi, float pad, float4* nb_lo, float4* nb_hi, int* cid, int* cnt) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t p = sorted_prim[k];
+    float4 l = plo[p], h = phi[p];
+    l.x -= pad; l.y -= pad; l.z -= pad;
+    h.x += pad; h.y += pad; h.z += pad;
+    nb_lo[n - 1 + k] = l;
+    nb_hi[n - 1 + k] = h;
+    cid[k] = n - 1 + k;
+    cnt[n - 1 + k] = 1;
+}
+
+__global__ void k_ploc_nn(int m, const int* __restrict__ cid, const float4* __restrict__ nb_lo,
+                          const float4* __restrict__ nb_hi, int* __restrict__ nn) {
+    extern __shared__ float4 s_box[];   // [blockDim + 2R] lo, then hi
+    const int R = kPlocRadius;
+    const int W = blockDim.x + 2 * R;
+    float4* s_lo = s_box;
+    float4* s_hi = s_box + W;
+    const int base = blockIdx.x * blockDim.x - R;
+    for (int t = threadIdx.x; t < W; t += blockDim.x) {
+        const int g = base + t;
+        if (g >= 0 && g < m) {
+            const int id = cid[g];
+            s_lo[t] = nb_lo[id];
+            s_hi[t] = nb_hi[id];
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int li = threadIdx.x + R;
+    const float4 a_lo = s_lo[li], a_hi = s_hi[li];
+    float best = FLT_MAX;
+    int bj = -1;
+    for (int d = -R; d <= R; d++) {
+        const int j = i + d;
+        if (d == 0 || j < 0 || j >= m) continue;
+        const float4 b_lo = s_lo[li + d], b_hi = s_hi[li + d];
+        const float dx = fmaxf(a_hi.x, b_hi.x) - fminf(a_lo.x, b_lo.x);
+        const float dy = fmaxf(a_hi.y, b_hi.y) - fminf(a_lo.y, b_lo.y);
+        const float dz = fmaxf(a_hi.z, b_hi.z) - fminf(a_lo.z, b_lo.z);
+        const float area = dx * dy + dy * dz + dz * dx;
+        if (area < best) { best = area; bj = j; }   // ascending j: ties keep the lower index
+    }
+    nn[i] = bj;
+}
+
+// flag word: low 32 bits = 1 when position i survives the round, high 32 bits = 1 when i is the lower half of a merging pair
+__global__ void k_ploc_flags(int m, const int* __restrict__ nn, unsigned long long* __restrict__ fl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int j = nn[i];
+    const bool mutual = j >= 0 && nn[j] == i;
+    unsigned long long f = 1ull;
+    if (mutual) f = (i < j) ? (1ull | (1ull << 32)) : 0ull;
+    fl[i] = f;
+}
+
+__global__ void k_ploc_apply(int m, int n, int merged_before, const int* __restrict__ cid, const int* __restrict__ nn,
+                             const unsigned long long* __restrict__ fl, const unsigned long long* __restrict__ sc,
+                             int* __restrict__ cid_out, int* left, int* right, int* parent, int* cnt, float4* nb_lo, float4* nb_hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const unsigned long long f = fl[i];
+    if (!(f & 1ull)) return;
+    const unsigned long long s = sc[i];
+    const int pos = (int)(s & 0xffffffffull);
+    int id = cid[i];
+    if (f >> 32) {
+        const int rank = (int)(s >> 32);
+        const int a = id, b = cid[nn[i]];
+        id = n - 2 - (merged_before + rank);
+        left[id] = a;
+        right[id] = b;
+        parent[a] = id;
+        parent[b] = id;
+        cnt[id] = cnt[a] + cnt[b];
+        const float4 al = nb_lo[a], ah = nb_hi[a], bl = nb_lo[b], bh = nb_hi[b];
+        nb_lo[id] = make_float4(fminf(al.x, bl.x), fminf(al.y, bl.y), fminf(al.z, bl.z), 0.f);
+        nb_hi[id] = make_float4(fmaxf(ah.x, bh.x), fmaxf(ah.y, bh.y), fmaxf(ah.z, bh.z), 0.f);
+    }
+    cid_out[pos] = id;
+}
+
+// depth-first position of every node's first leaf: sum of the left siblings' leaf counts on the way to the root
+__global__ void k_ploc_order(int n, const int* __restrict__ left, const int* __restrict__ parent, const int* __restrict__ cnt,
+                             const uint32_t* __restrict__ sorted_prim, uint32_t* __restrict__ sorted_prim_out,
+                             int* __restrict__ first, int* __restrict__ last, int* __restrict__ leaf_pos) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * n - 1) return;
+    int pos = 0;
+    int c = id;
+    int p = parent[c];
+    while (p >= 0) {
+        const int l = left[p];
+        if (l != c) pos += cnt[l];
+        c = p;
+        p = parent[c];
+    }
+    if (id >= n - 1) {
+        leaf_pos[id - (n - 1)] = pos;
+        sorted_prim_out[pos] = sorted_prim[id - (n - 1)];
+    } else {
+        first[id] = pos;
+        last[id] = pos + cnt[id] - 1;
+    }
+}
+
+// renumber the leaves by their depth-first position
+__global__ void k_ploc_relink(int n, const int* __restrict__ leaf_pos, int* left, int* right, const int* __restrict__ parent,
+                              int* __restrict__ parent_out) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * n - 1) return;
+    if (id >= n - 1) {
+        parent_out[n - 1 + leaf_pos[id - (n - 1)]] = parent[id];
+    } else {
+        parent_out[id] = parent[id];
+        const int l = left[id], r = right[id];
+        if (l >= n - 1) left[id] = n - 1 + leaf_pos[l - (n - 1)];
+        if (r >= n - 1) right[id] = n - 1 + leaf_pos[r - (n - 1)];
+    }
 }
 
 // 4 ------------------------------------------------------------------------------------------
@@ -456,11 +595,63 @@ void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
     cost.alloc((size_t)n_int * 7);
     dec.alloc((size_t)n_int * 8);
     SPC_CUDA(cudaMemsetAsync(flags.p, 0, flags.bytes(), st));
-    if (n_int) {
+    // binary topology: PLOC by default, SPC_BVH_BUILDER=lbvh selects the Morton radix tree (kept for A/B measurements)
+    static const bool use_ploc = []() { const char* e = getenv("SPC_BVH_BUILDER"); return !(e && strcmp(e, "lbvh") == 0); }();
+    DevBuf<int> parent2;
+    DevBuf<uint32_t> sprim2;
+    const int* parent_p = parent.p;
+    int ploc_rounds = 0;
+    if (n_int && use_ploc) {
+        DevBuf<int> cidA, cidB, nn, cnt, leaf_pos;
+        DevBuf<unsigned long long> fl, sc;
+        cidA.alloc(n); cidB.alloc(n); nn.alloc(n); cnt.alloc(2 * (size_t)n); leaf_pos.alloc(n);
+        fl.alloc(n); sc.alloc(n);
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, fl.p, sc.p, (int)n, st);
+        DevBuf<uint8_t> scan_tmp;
+        scan_tmp.alloc(scan_bytes);
+        k_ploc_init<<<gN, B, 0, st>>>((int)n, sprim, plo.p, phi.p, pad, nb_lo.p, nb_hi.p, cidA.p, cnt.p);
+        ctx.launches++;
+        int m = (int)n, merged = 0;
+        int* ca = cidA.p;
+        int* cb = cidB.p;
+        const size_t nn_smem = (size_t)(B + 2 * kPlocRadius) * 2 * sizeof(float4);
+        while (m > 1) {
+            const unsigned g = (m + B - 1) / B;
+            k_ploc_nn<<<g, B, nn_smem, st>>>(m, ca, nb_lo.p, nb_hi.p, nn.p);
+            k_ploc_flags<<<g, B, 0, st>>>(m, nn.p, fl.p);
+            SPC_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, fl.p, sc.p, m, st));
+            k_ploc_apply<<<g, B, 0, st>>>(m, (int)n, merged, ca, nn.p, fl.p, sc.p, cb, left.p, right.p, parent.p, cnt.p, nb_lo.p, nb_hi.p);
+            ctx.launches += 4;
+            unsigned long long tail[2];
+            SPC_CUDA(cudaMemcpyAsync(&tail[0], sc.p + (m - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            SPC_CUDA(cudaMemcpyAsync(&tail[1], fl.p + (m - 1), sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            SPC_CUDA(cudaStreamSynchronize(st));
+            const unsigned long long tot = tail[0] + tail[1];
+            const int kept = (int)(tot & 0xffffffffull), pairs = (int)(tot >> 32);
+            SPC_REQUIRE(pairs > 0 && kept == m - pairs, SPC_ERR_CUDA, "PLOC round made no progress (%d clusters, %d pairs, %d kept)", m, pairs, kept);
+            merged += pairs;
+            m = kept;
+            int* t = ca; ca = cb; cb = t;
+            ploc_rounds++;
+        }
+        SPC_REQUIRE(merged == (int)n_int, SPC_ERR_CUDA, "PLOC built %d of %u internal nodes", merged, n_int);
+        const int root_parent = -1;
+        SPC_CUDA(cudaMemcpyAsync(parent.p, &root_parent, sizeof(int), cudaMemcpyHostToDevice, st));
+        parent2.alloc(2 * (size_t)n);
+        sprim2.alloc(n);
+        const unsigned g2 = (2 * n - 1 + B - 1) / B;
+        k_ploc_order<<<g2, B, 0, st>>>((int)n, left.p, parent.p, cnt.p, sprim, sprim2.p, first.p, last.p, leaf_pos.p);
+        k_ploc_relink<<<g2, B, 0, st>>>((int)n, leaf_pos.p, left.p, right.p, parent.p, parent2.p);
+        ctx.launches += 2;
+        SPC_CUDA(cudaStreamSynchronize(st));   // the round buffers go out of scope here
+        sprim = sprim2.p;
+        parent_p = parent2.p;
+    } else if (n_int) {
         k_radix_tree<<<(n_int + B - 1) / B, B, 0, st>>>(skeys, (int)n, left.p, right.p, parent.p, first.p, last.p);
         ctx.launches++;
     }
-    k_fit_dp<<<gN, B, 0, st>>>((int)n, sprim, plo.p, phi.p, pad, left.p, right.p, parent.p, first.p, last.p,
+    k_fit_dp<<<gN, B, 0, st>>>((int)n, sprim, plo.p, phi.p, pad, left.p, right.p, parent_p, first.p, last.p,
                               nb_lo.p, nb_hi.p, cost.p, dec.p, flags.p);
     ctx.launches++;
     SPC_CUDA(cudaGetLastError());

@@ -85,6 +85,7 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     Trav s;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_stack + threadIdx.x);
     int64_t ray = -1;
     bool exhausted = false;
     unsigned cn = 0, ct = 0;
@@ -107,6 +108,7 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
                         } else {
                             TravRay r{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w};
                             trav_init(s, r);
+                            s.sbase = sbase;
                             ray = my;
                         }
                     }
@@ -117,7 +119,7 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
             if (exhausted && idle == 0xffffffffu) break;
         }
         if (ray >= 0) {
-            if (trav_step<ANYHIT, false, true>(nodes, tris, s, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, lstack, cn, ct, postpone_div)) {
+            if (trav_step<ANYHIT, false, true>(nodes, tris, s, cull_back != 0, kTraceBlock, lstack, cn, ct, postpone_div)) {
                 if (ANYHIT) {
                     visible[ray] = s.best_prim >= 0 ? 0 : 1;
                 } else {

@@ -32,11 +32,24 @@ __device__ __forceinline__ void c_cross(float ax, float ay, float az, float bx, 
 
 // byte j of w, biased: the float 2^23 + 256*byte, built by splicing the byte into mantissa bits 8..15 of 2^23 (one PRMT, no
 // I2F and no subtraction).  The bias is folded into the per-node plane origins (trav_step), so a child plane costs PRMT + FFMA.
+// The bias word travels in a register (trav_bias()): PRMT takes one immediate, and with the selector as the immediate
+// ptxas no longer re-materialises the four selectors in front of every PRMT (48 moves per node in the r1d SASS).
 template <int J>
-__device__ __forceinline__ float byte_to_biased_float(uint32_t w) {
+__device__ __forceinline__ float byte_to_biased_float(uint32_t w, uint32_t bias) {
     uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "n"(0x7604 + 16 * J));
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(bias), "n"(0x7604 + 16 * J));
     return __uint_as_float(r);
+}
+// 0x4B000000 (the float 2^23) as a value ptxas cannot fold into an immediate: gridDim.z is 1 for every launch of this library.
+__device__ __forceinline__ uint32_t trav_bias() { return 0x4A000000u + (gridDim.z << 24); }
+// per-thread traversal stack in shared memory, addressed by 32-bit shared-window offsets
+__device__ __forceinline__ void sm_push(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 sm_pop(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
     uint32_t r;
@@ -64,6 +77,8 @@ struct Trav {
     int   best_prim;
     uint2 ngroup;
     int   sp;
+    uint32_t bias;    // trav_bias()
+    uint32_t sbase;   // shared-window address of this lane's stack slot 0
 };
 
 __device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
@@ -79,17 +94,18 @@ __device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
     s.best_u = s.best_v = 0.f;
     s.ngroup = make_uint2(0u, 0x80000000u);
     s.sp = 0;
+    s.bias = trav_bias();
 }
 
 // one child quad (4 of the 8 slots) of a node
 #define SPC_CHILD_TEST2(J)                                                                        \
     {                                                                                             \
-        float lx = __fmaf_rn(byte_to_biased_float<J>(slox), adjx, olx);                           \
-        float ly = __fmaf_rn(byte_to_biased_float<J>(sloy), adjy, oly);                           \
-        float lz = __fmaf_rn(byte_to_biased_float<J>(sloz), adjz, olz);                           \
-        float hx = __fmaf_rn(byte_to_biased_float<J>(shix), adjx, ohx);                           \
-        float hy = __fmaf_rn(byte_to_biased_float<J>(shiy), adjy, ohy);                           \
-        float hz = __fmaf_rn(byte_to_biased_float<J>(shiz), adjz, ohz);                           \
+        float lx = __fmaf_rn(byte_to_biased_float<J>(slox, bias), adjx, olx);                           \
+        float ly = __fmaf_rn(byte_to_biased_float<J>(sloy, bias), adjy, oly);                           \
+        float lz = __fmaf_rn(byte_to_biased_float<J>(sloz, bias), adjz, olz);                           \
+        float hx = __fmaf_rn(byte_to_biased_float<J>(shix, bias), adjx, ohx);                           \
+        float hy = __fmaf_rn(byte_to_biased_float<J>(shiy, bias), adjy, ohy);                           \
+        float hz = __fmaf_rn(byte_to_biased_float<J>(shiz, bias), adjz, ohz);                           \
         float cmin = fmaxf(fmaxf(lx, ly), fmaxf(lz, s.tmin));                                     \
         float cmax = fminf(fminf(hx, hy), fminf(hz, s.tcur));                                     \
         if (cmin <= cmax) hitmask |= byte_of(child_bits4, J) << byte_of(bit_index4, J);           \
@@ -103,9 +119,11 @@ __device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
 // postponing").  The result does not depend on the order triangles are tested in (intersection contract above).
 template <bool ANYHIT, bool COUNT, bool POSTPONE = false>
 __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
-                                          uint2* sstack, int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris, int postpone_div = 5) {
+                                          int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris, int postpone_div = 5) {
     const uint32_t oct_inv = s.oct_inv;
     const uint32_t oct = 7u ^ oct_inv;
+    const uint32_t bias = s.bias;
+    const uint32_t sstride_b = (uint32_t)sstride * 8u;
     uint2 tgroup;
     if (s.ngroup.y > 0x00ffffffu) {
         const uint32_t hits  = s.ngroup.y;
@@ -113,7 +131,7 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
         const uint32_t bit   = 31u - __clz(hits);
         s.ngroup.y &= ~(1u << bit);
         if (s.ngroup.y > 0x00ffffffu) {
-            if (s.sp < kSmStack) sstack[s.sp * sstride] = s.ngroup;
+            if (s.sp < kSmStack) sm_push(s.sbase + s.sp * sstride_b, s.ngroup);
             else lstack[s.sp - kSmStack] = s.ngroup;
             s.sp++;
         }
@@ -184,7 +202,7 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
     while (tgroup.y != 0u) {
         if (POSTPONE && __popc(__activemask()) * postpone_div < tri_lanes) {
             // park the triangles; if no inner node is pending the pop below hands them straight back as the current group
-            if (s.sp < kSmStack) sstack[s.sp * sstride] = tgroup;
+            if (s.sp < kSmStack) sm_push(s.sbase + s.sp * sstride_b, tgroup);
             else lstack[s.sp - kSmStack] = tgroup;
             s.sp++;
             break;
@@ -230,7 +248,7 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
     if (s.ngroup.y <= 0x00ffffffu) {
         if (s.sp == 0) return true;
         s.sp--;
-        s.ngroup = (s.sp < kSmStack) ? sstack[s.sp * sstride] : lstack[s.sp - kSmStack];
+        s.ngroup = (s.sp < kSmStack) ? sm_pop(s.sbase + s.sp * sstride_b) : lstack[s.sp - kSmStack];
     }
     return false;
 }
@@ -242,8 +260,9 @@ __device__ __forceinline__ bool traverse_bvh8(const float4* __restrict__ nodes,
                                               TravHit& hit, unsigned& cnt_nodes, unsigned& cnt_tris) {
     Trav s;
     trav_init(s, r);
+    s.sbase = (uint32_t)__cvta_generic_to_shared(sstack);
     uint2 lstack[kLocStack];
-    while (!trav_step<ANYHIT, COUNT>(nodes, tris, s, cull_back, sstack, sstride, lstack, cnt_nodes, cnt_tris)) {}
+    while (!trav_step<ANYHIT, COUNT>(nodes, tris, s, cull_back, sstride, lstack, cnt_nodes, cnt_tris)) {}
     if (ANYHIT) return s.best_prim >= 0;
     hit.t = s.best_prim >= 0 ? s.tcur : 0.0f;
     hit.u = s.best_u;
