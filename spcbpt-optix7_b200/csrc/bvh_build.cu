@@ -13,6 +13,8 @@
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <mutex>
 #include "traverse.cuh"
 
 namespace spc {
@@ -529,19 +531,64 @@ __global__ void k_emit(int n, const EmitItem* __restrict__ items, int n_items, E
 
 }  // namespace
 
+// Build scratch: one device allocation per build, carved up by a bump allocator (a dozen cudaMalloc/cudaFree pairs cost
+// more than all the build kernels together: 9 -> 90 ms at 1 M triangles when every buffer was its own allocation).
+struct BuildArena {
+    char*  base = nullptr;
+    size_t cap = 0, off = 0;
+    ~BuildArena() { if (base) cudaFree(base); }
+    void reserve(size_t bytes) {
+        SPC_CUDA(cudaMalloc((void**)&base, bytes));
+        cap = bytes;
+    }
+    void* take(size_t bytes) {
+        const size_t at = (off + 255) & ~(size_t)255;
+        SPC_REQUIRE(at + bytes <= cap, SPC_ERR_CAPACITY, "BVH build scratch exhausted (%zu + %zu of %zu bytes)", at, bytes, cap);
+        off = at + bytes;
+        return base + at;
+    }
+};
+static BuildArena* g_arena = nullptr;   // valid inside build_bvh only (builds are serialised per process by g_build_mutex)
+template <typename T>
+struct ScratchBuf {
+    T*     p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        if (count == 0) count = 1;
+        p = (T*)g_arena->take(count * sizeof(T));
+        n = count;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+static void stage_mark(cudaStream_t st, const char* what) {
+    static const bool on = getenv("SPC_BVH_VERBOSE") != nullptr;
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    fprintf(stderr, "[spc] build stage %-28s t=%.3f ms\n", what, (ts.tv_sec % 1000) * 1e3 + ts.tv_nsec * 1e-6);
+}
+
 void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
     SPC_REQUIRE(n >= 1, SPC_ERR_INVALID, "scene has no triangles");
     cudaStream_t st = ctx.stream;
+    static std::mutex g_build_mutex;
+    std::lock_guard<std::mutex> lock(g_build_mutex);
     cudaEvent_t ev0, ev1;
     SPC_CUDA(cudaEventCreate(&ev0));
     SPC_CUDA(cudaEventCreate(&ev1));
     SPC_CUDA(cudaEventRecord(ev0, st));
+    BuildArena arena;   // inside the timed region: build_ms includes the scratch allocation
+    g_arena = &arena;
+    arena.reserve((size_t)n * 420 + (64u << 20));
+    stage_mark(st, "start");
 
     const int B = 256;
     const unsigned gN = (n + B - 1) / B;
-    DevBuf<float4> plo, phi;
+    ScratchBuf<float4> plo, phi;
     plo.alloc(n); phi.alloc(n);
-    DevBuf<uint32_t> scene;
+    ScratchBuf<uint32_t> scene;
     scene.alloc(6);
     {
         uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
@@ -565,8 +612,8 @@ void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
     // triangle test (a few ulp of the coordinate magnitude); 2^-18 of the largest coordinate.
     const float pad = fmaxf(maxabs, 1e-20f) * (1.0f / 262144.0f);
 
-    DevBuf<uint64_t> keys, keys2;
-    DevBuf<uint32_t> vals, vals2;
+    ScratchBuf<uint64_t> keys, keys2;
+    ScratchBuf<uint32_t> vals, vals2;
     keys.alloc(n); keys2.alloc(n); vals.alloc(n); vals2.alloc(n);
     float3 fslo = make_float3(slo[0], slo[1], slo[2]);
     float3 sinv = make_float3(1.f / fmaxf(shi[0] - slo[0], 1e-30f), 1.f / fmaxf(shi[1] - slo[1], 1e-30f),
@@ -576,42 +623,45 @@ void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
     {
         size_t tmp_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys2.p, vals.p, vals2.p, (int)n, 0, 63, st);
-        DevBuf<uint8_t> tmp;
+        ScratchBuf<uint8_t> tmp;
         tmp.alloc(tmp_bytes);
         SPC_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys2.p, vals.p, vals2.p, (int)n, 0, 63, st));
         SPC_CUDA(cudaStreamSynchronize(st));
     }
+    stage_mark(st, "morton + sort");
     const uint64_t* skeys = keys2.p;
     const uint32_t* sprim = vals2.p;
 
     const uint32_t n_int = n > 1 ? n - 1 : 0;
-    DevBuf<int> left, right, parent, first, last, flags;
+    ScratchBuf<int> left, right, parent, first, last, flags;
     left.alloc(n_int); right.alloc(n_int); first.alloc(n_int); last.alloc(n_int); flags.alloc(n_int);
     parent.alloc(2 * (size_t)n);
-    DevBuf<float4> nb_lo, nb_hi;
+    ScratchBuf<float4> nb_lo, nb_hi;
     nb_lo.alloc(2 * (size_t)n); nb_hi.alloc(2 * (size_t)n);
-    DevBuf<float> cost;
-    DevBuf<uint8_t> dec;
+    ScratchBuf<float> cost;
+    ScratchBuf<uint8_t> dec;
     cost.alloc((size_t)n_int * 7);
     dec.alloc((size_t)n_int * 8);
     SPC_CUDA(cudaMemsetAsync(flags.p, 0, flags.bytes(), st));
     // binary topology: PLOC by default, SPC_BVH_BUILDER=lbvh selects the Morton radix tree (kept for A/B measurements)
     static const bool use_ploc = []() { const char* e = getenv("SPC_BVH_BUILDER"); return !(e && strcmp(e, "lbvh") == 0); }();
-    DevBuf<int> parent2;
-    DevBuf<uint32_t> sprim2;
+    ScratchBuf<int> parent2;
+    ScratchBuf<uint32_t> sprim2;
     const int* parent_p = parent.p;
     int ploc_rounds = 0;
     if (n_int && use_ploc) {
-        DevBuf<int> cidA, cidB, nn, cnt, leaf_pos;
-        DevBuf<unsigned long long> fl, sc;
+        ScratchBuf<int> cidA, cidB, nn, cnt, leaf_pos;
+        ScratchBuf<unsigned long long> fl, sc;
         cidA.alloc(n); cidB.alloc(n); nn.alloc(n); cnt.alloc(2 * (size_t)n); leaf_pos.alloc(n);
         fl.alloc(n); sc.alloc(n);
         size_t scan_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, fl.p, sc.p, (int)n, st);
-        DevBuf<uint8_t> scan_tmp;
+        ScratchBuf<uint8_t> scan_tmp;
         scan_tmp.alloc(scan_bytes);
+        stage_mark(st, "ploc allocs");
         k_ploc_init<<<gN, B, 0, st>>>((int)n, sprim, plo.p, phi.p, pad, nb_lo.p, nb_hi.p, cidA.p, cnt.p);
         ctx.launches++;
+        stage_mark(st, "ploc init");
         int m = (int)n, merged = 0;
         int* ca = cidA.p;
         int* cb = cidB.p;
@@ -630,12 +680,23 @@ void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
             const unsigned long long tot = tail[0] + tail[1];
             const int kept = (int)(tot & 0xffffffffull), pairs = (int)(tot >> 32);
             SPC_REQUIRE(pairs > 0 && kept == m - pairs, SPC_ERR_CUDA, "PLOC round made no progress (%d clusters, %d pairs, %d kept)", m, pairs, kept);
+            if (getenv("SPC_BVH_VERBOSE") && (ploc_rounds % 8 == 0 || m < 30)) {
+                timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+                fprintf(stderr, "[spc] PLOC round %d: %d clusters, %d pairs  t=%.3f ms\n", ploc_rounds, m, pairs, ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6);
+            }
             merged += pairs;
             m = kept;
             int* t = ca; ca = cb; cb = t;
             ploc_rounds++;
         }
         SPC_REQUIRE(merged == (int)n_int, SPC_ERR_CUDA, "PLOC built %d of %u internal nodes", merged, n_int);
+        if (getenv("SPC_BVH_VERBOSE")) {
+            SPC_CUDA(cudaEventRecord(ev1, st));
+            SPC_CUDA(cudaStreamSynchronize(st));
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev0, ev1);
+            fprintf(stderr, "[spc] PLOC: %d rounds for %u triangles, %.2f ms since build start\n", ploc_rounds, n, t);
+        }
         const int root_parent = -1;
         SPC_CUDA(cudaMemcpyAsync(parent.p, &root_parent, sizeof(int), cudaMemcpyHostToDevice, st));
         parent2.alloc(2 * (size_t)n);
@@ -645,6 +706,7 @@ void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
         k_ploc_relink<<<g2, B, 0, st>>>((int)n, leaf_pos.p, left.p, right.p, parent.p, parent2.p);
         ctx.launches += 2;
         SPC_CUDA(cudaStreamSynchronize(st));   // the round buffers go out of scope here
+        stage_mark(st, "ploc order + relink");
         sprim = sprim2.p;
         parent_p = parent2.p;
     } else if (n_int) {
@@ -656,14 +718,15 @@ void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
     ctx.launches++;
     SPC_CUDA(cudaGetLastError());
 
+    stage_mark(st, "fit + collapse DP");
     // emission, level by level
     const size_t max_wide = (size_t)(n_int ? n_int : 1);
-    DevBuf<float4> tmp_nodes;
+    ScratchBuf<float4> tmp_nodes;
     tmp_nodes.alloc(max_wide * 5);
     ctx.bvh.tris.alloc((size_t)n * 3);
-    DevBuf<EmitItem> qa, qb;
+    ScratchBuf<EmitItem> qa, qb;
     qa.alloc(max_wide); qb.alloc(max_wide);
-    DevBuf<EmitCounters> ctr;
+    ScratchBuf<EmitCounters> ctr;
     ctr.alloc(1);
     EmitCounters hc = {1u, 0u, 0u, 0u, 0.f};
     SPC_CUDA(cudaMemcpyAsync(ctr.p, &hc, sizeof(hc), cudaMemcpyHostToDevice, st));
@@ -684,6 +747,7 @@ void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
         SPC_CUDA(cudaMemcpyAsync(&ctr.p->n_next, &hc.n_next, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         EmitItem* t = cur; cur = nxt; nxt = t;
     }
+    stage_mark(st, "emit");
     SPC_REQUIRE(hc.n_tris == n, SPC_ERR_CUDA, "BVH emission lost triangles: %u of %u", hc.n_tris, n);
     SPC_REQUIRE((int)hc.max_depth <= kMaxBvhDepth, SPC_ERR_CAPACITY, "BVH depth %u exceeds traversal stack %d",
                 hc.max_depth, kMaxBvhDepth);
