@@ -106,6 +106,8 @@ struct EyeBuffers {
     DevBuf<float>      conn_pmf;  // path_count * pmf_1 * pmf_2
     DevBuf<float4>     contrib;   // per connection: contribution / pmf / CONNECTION_N (0 when rejected)
     DevBuf<int>        counts;    // counts[b] = live paths entering bounce b
+    DevBuf<short>      xlab;      // per pixel: light-tree label of the current eye vertex
+    DevBuf<short>      lvc_xlabel;   // per LVC slot: eye-tree label (valid slots only)
     size_t             pixels = 0;
     int                conns = 0;
 };

@@ -28,6 +28,7 @@ DevFrame make_dev_frame(Context& c) {
     fr.p = c.params;
     fr.K = c.K;
     fr.connections = c.connections;
+    fr.lvc_xlabel = nullptr;
     fr.max_depth = c.params.max_depth > 0 ? c.params.max_depth : 50;
     fr.seed_offset = c.seed_offset;
     fr.seed_stride = c.seed_stride;
@@ -171,6 +172,7 @@ struct EyeArgs {
     int*        counts;     // counts[bounce] in, counts[bounce+1] out
     int*        first_prim;
     int*        first_label;
+    short*      xlab;       // per pixel: light-tree label of the current eye vertex (cross label, shade.cuh)
     int         bounce;
 };
 
@@ -236,13 +238,14 @@ __global__ void __launch_bounds__(128) k_eye_shade(const DevFrame fr, const EyeA
                 const float3 ray_direction = f3(rd4.x, rd4.y, rd4.z);
                 const Vtx last = vtx_load(a.ev + pix);
                 const float4 pre = a.pre[pix];
+                const int last_x = a.bounce > 0 ? (int)a.xlab[pix] : -1;   // written by k_eye_sample of the previous bounce
                 float4 res = a.res[pix];
                 uint32_t seed = __float_as_uint(res.w);
                 const LocalGeom g = hit_geometry(fr.sc, prim, hit.y, hit.z);
                 Vtx mid;
                 if (g.light >= 0) {
                     // __closesthit__eyeSubpath_LightSource + lightStraghtHit (raygen.cu:305-317, :383-388)
-                    if (eye_hits_light(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, hit.x, ray_direction, mid)) {
+                    if (eye_hits_light(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, hit.x, ray_direction, mid, last_x)) {
                         if (a.bounce == 0 && a.first_label) a.first_label[pix] = mid.subspaceId;
                         const float3 ans = mid.flux / mid.pdf / mid.RMIS_pointer;
                         if (!invalid3(ans)) {
@@ -252,35 +255,12 @@ __global__ void __launch_bounds__(128) k_eye_shade(const DevFrame fr, const EyeA
                     }
                 } else {
                     SurfaceOut so;
-                    surface_hit(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, hit.x, ray_direction, false, seed, mid, so);
+                    surface_hit(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, hit.x, ray_direction, false, seed, mid, so, last_x);
                     if (a.bounce == 0 && a.first_label) a.first_label[pix] = mid.subspaceId;
                     vtx_store(a.ev + pix, mid);
                     a.pre[pix] = make_float4(so.next_flux.x, so.next_flux.y, so.next_flux.z, so.next_singlePdf);
-                    // CONNECTION_N probabilistic connections (raygen.cu:390-419): stage 1 picks a light subspace from
-                    // row eye-subspace of the Gamma CDF, stage 2 a vertex of that subspace from its cmf
-                    const spc_subspace_sampler& S = fr.p.sampler;
-                    for (int j = 0; j < C; j++) {
-                        int light_id = 0;
-                        float pmf1 = 1;
-                        if (fr.p.subspace_info.light_tree)
-                            light_id = binary_sample(fr.p.subspace_info.CMFGamma + (size_t)mid.subspaceId * fr.K, fr.K, seed, pmf1);
-                        const spc_subspace sub = S.subspace[light_id];
-                        if (sub.size != 0) {
-                            float pmf2;
-                            const int index = binary_sample(S.cmfs + sub.jump_bias, sub.size, seed, pmf2) + sub.jump_bias;
-                            const int lv = S.jump_buffer[index];
-                            const spc_vertex* L = S.LVC + lv;
-                            const float3 lp = f3(L->position.x, L->position.y, L->position.z);
-                            // visibilityTest (cuProg.h:489-502 -> :463-487)
-                            const float3 bias_pos = lp - mid.position;
-                            const float len = length(bias_pos);
-                            const float3 dir = bias_pos / len;
-                            a.shadow[2 * ((size_t)i * C + j)] = make_float4(mid.position.x, mid.position.y, mid.position.z, SPC_SCENE_EPS);
-                            a.shadow[2 * ((size_t)i * C + j) + 1] = make_float4(dir.x, dir.y, dir.z, len - SPC_SCENE_EPS);
-                            a.conn_lvc[(size_t)i * C + j] = lv;
-                            a.conn_pmf[(size_t)i * C + j] = (float)S.path_count * pmf2 * pmf1;
-                        }
-                    }
+                    // the CONNECTION_N probabilistic connections of this vertex are drawn by k_eye_sample (marker -2 in slot 0)
+                    a.conn_lvc[(size_t)i * C] = -2;
                     res.w = __uint_as_float(seed);
                     a.res[pix] = res;
                     // loop head of the next iteration (raygen.cu:361): payload.done || payload.depth > 50
@@ -307,6 +287,163 @@ __global__ void __launch_bounds__(128) k_eye_shade(const DevFrame fr, const EyeA
     }
 }
 
+// CONNECTION_N probabilistic connections per eye vertex (raygen.cu:390-419): stage 1 picks a light subspace from row
+// eye-subspace of the Gamma CDF, stage 2 a vertex of that subspace from its cmf; both with the reference's own bisect
+// (binary_sample, cuProg.h:245-264).  Split from k_eye_shade: that kernel needs ~100 registers (4 blocks per SM) and its
+// run time was the latency of this chain of ~60 dependent 4-byte probes per lane (ncu: issue slots 22 % busy, long-scoreboard
+// stalls dominant, profiles/r1e_summary.md).  Here one lane per path needs few registers (full occupancy), and for C <= 4
+// the C bisects of a stage run in lockstep, so their probes overlap.  The draws of connection j are numbers 2j and 2j+1
+// of the path's stream only while no earlier connection met an empty subspace (which draws one number, raygen.cu:400-403):
+// the lockstep path assumes that and falls back to the serial loop in the rare case it does not hold -- same draws, same
+// results as the serial loop in every case.
+struct ConnPick {
+    int   lv;      // LVC index, -1: no connection
+    float pmf;     // path_count * pmf2 * pmf1
+};
+
+__device__ __forceinline__ void eye_sample_serial(const DevFrame& fr, int eye_subspace, int C, uint32_t& seed, ConnPick* out) {
+    const spc_subspace_sampler& S = fr.p.sampler;
+    for (int j = 0; j < C; j++) {
+        out[j].lv = -1;
+        out[j].pmf = 0.f;
+        int light_id = 0;
+        float pmf1 = 1;
+        if (fr.p.subspace_info.light_tree)
+            light_id = binary_sample(fr.p.subspace_info.CMFGamma + (size_t)eye_subspace * fr.K, fr.K, seed, pmf1);
+        const spc_subspace sub = S.subspace[light_id];
+        if (sub.size != 0) {
+            float pmf2;
+            const int index = binary_sample(S.cmfs + sub.jump_bias, sub.size, seed, pmf2) + sub.jump_bias;
+            out[j].lv = S.jump_buffer[index];
+            out[j].pmf = (float)S.path_count * pmf2 * pmf1;
+        }
+    }
+}
+
+// CT bisects of equal size over the same table, in lockstep (the trip count of the reference's loop depends on the size only
+// through r-l, which differs between lanes of the group by at most the rounding of the halving: each keeps its own l, r)
+template <int CT>
+__device__ __forceinline__ void bisect_lockstep(const float* const* cmf, const int* size, const float* u, int* l_out, float* pmf_out) {
+    int l[CT], r[CT], mid[CT];
+#pragma unroll
+    for (int j = 0; j < CT; j++) { l[j] = 0; r[j] = size[j]; mid[j] = size[j] / 2 - 1; }
+    bool any = true;
+    while (any) {
+        any = false;
+        float v[CT];
+#pragma unroll
+        for (int j = 0; j < CT; j++) v[j] = (r[j] - l[j] > 1) ? __ldg(cmf[j] + mid[j]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < CT; j++) {
+            if (r[j] - l[j] > 1) {
+                if (u[j] < v[j]) r[j] = mid[j] + 1;
+                else l[j] = mid[j] + 1;
+                mid[j] = (l[j] + r[j]) / 2 - 1;
+                any |= (r[j] - l[j] > 1);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CT; j++) {
+        const float hi = __ldg(cmf[j] + l[j]);
+        const float lo = l[j] == 0 ? 0.f : __ldg(cmf[j] + l[j] - 1);
+        pmf_out[j] = l[j] == 0 ? hi : hi - lo;
+        l_out[j] = l[j];
+    }
+}
+
+template <int CT>
+__device__ __forceinline__ bool eye_sample_lockstep(const DevFrame& fr, int eye_subspace, uint32_t& seed, ConnPick* out) {
+    const spc_subspace_sampler& S = fr.p.sampler;
+    uint32_t s = seed;
+    float u1[CT], u2[CT];
+#pragma unroll
+    for (int j = 0; j < CT; j++) {
+        u1[j] = fr.p.subspace_info.light_tree ? rnd(s) * 1.0f : 0.f;
+        u2[j] = rnd(s) * 1.0f;
+    }
+    int light_id[CT];
+    float pmf1[CT];
+    if (fr.p.subspace_info.light_tree) {
+        const float* row = fr.p.subspace_info.CMFGamma + (size_t)eye_subspace * fr.K;
+        const float* cm[CT];
+        int sz[CT];
+#pragma unroll
+        for (int j = 0; j < CT; j++) { cm[j] = row; sz[j] = fr.K; }
+        bisect_lockstep<CT>(cm, sz, u1, light_id, pmf1);
+    } else {
+#pragma unroll
+        for (int j = 0; j < CT; j++) { light_id[j] = 0; pmf1[j] = 1; }
+    }
+    spc_subspace sub[CT];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < CT; j++) {
+        sub[j] = S.subspace[light_id[j]];
+        ok &= sub[j].size != 0;
+    }
+    if (!ok) return false;   // an empty subspace shifts the later draws: the caller takes the serial loop
+    const float* cm[CT];
+    int sz[CT], idx[CT];
+    float pmf2[CT];
+#pragma unroll
+    for (int j = 0; j < CT; j++) { cm[j] = S.cmfs + sub[j].jump_bias; sz[j] = sub[j].size; }
+    bisect_lockstep<CT>(cm, sz, u2, idx, pmf2);
+#pragma unroll
+    for (int j = 0; j < CT; j++) {
+        out[j].lv = S.jump_buffer[idx[j] + sub[j].jump_bias];
+        out[j].pmf = (float)S.path_count * pmf2[j] * pmf1[j];
+    }
+    seed = s;
+    return true;
+}
+
+template <int CT>
+__global__ void __launch_bounds__(128, 8) k_eye_sample(const DevFrame fr, const EyeArgs a) {
+    const int n = a.counts[a.bounce];
+    const int C = CT > 0 ? CT : fr.connections;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (a.conn_lvc[(size_t)i * C] != -2) continue;   // miss, emitter hit or no surface vertex: slots stay empty
+        const int pix = a.queue_cur[i];
+        const spc_vertex* ev = a.ev + pix;
+        const float3 pos = f3(ev->position.x, ev->position.y, ev->position.z);
+        const int eye_subspace = ev->subspaceId;
+        a.xlab[pix] = (short)tree_label(fr.p.subspace_info.light_tree, pos, f3(ev->normal.x, ev->normal.y, ev->normal.z));
+        uint32_t seed = __float_as_uint(a.res[pix].w);
+        ConnPick pick[CT > 0 ? CT : 16];
+        bool done = false;
+        if (CT > 0) done = eye_sample_lockstep<(CT > 0 ? CT : 1)>(fr, eye_subspace, seed, pick);
+        if (!done) eye_sample_serial(fr, eye_subspace, C, seed, pick);
+        reinterpret_cast<uint32_t*>(a.res + pix)[3] = seed;
+#pragma unroll
+        for (int j = 0; j < (CT > 0 ? CT : 16); j++) {
+            if (j >= C) break;
+            const int lv = pick[j].lv;
+            a.conn_lvc[(size_t)i * C + j] = lv;
+            if (lv < 0) continue;
+            const spc_vertex* L = fr.p.sampler.LVC + lv;
+            const float3 lp = f3(L->position.x, L->position.y, L->position.z);
+            // visibilityTest (cuProg.h:489-502 -> :463-487)
+            const float3 bias_pos = lp - pos;
+            const float len = length(bias_pos);
+            const float3 dir = bias_pos / len;
+            a.shadow[2 * ((size_t)i * C + j)] = make_float4(pos.x, pos.y, pos.z, SPC_SCENE_EPS);
+            a.shadow[2 * ((size_t)i * C + j) + 1] = make_float4(dir.x, dir.y, dir.z, len - SPC_SCENE_EPS);
+            a.conn_pmf[(size_t)i * C + j] = pick[j].pmf;
+        }
+    }
+}
+
+// eye-tree label of every valid LVC vertex (the `jump_buffer` lists them), once per frame: tracing_weight_light would
+// otherwise walk the eye tree for the light vertex of every single connection (shade.cuh, "cross labels")
+__global__ void k_lvc_xlabel(const DevFrame fr, int n_valid, short* __restrict__ xlabel) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_valid) return;
+    const int lv = fr.p.sampler.jump_buffer[j];
+    const spc_vertex* L = fr.p.sampler.LVC + lv;
+    xlabel[lv] = (short)tree_label(fr.p.subspace_info.eye_tree, f3(L->position.x, L->position.y, L->position.z), f3(L->normal.x, L->normal.y, L->normal.z));
+}
+
 // connectVertex_SPCBPT (raygen.cu:253-303) for every visible connection; one lane per connection.
 // Only a fraction of the slots carries a visible connection (empty slots, occluded shadow rays), so each warp first compacts
 // the slots that need work into a small shared-memory queue and evaluates them 32 at a time: measured 10 of 32 lanes active per
@@ -317,7 +454,7 @@ __device__ __forceinline__ void eye_connect_one(const DevFrame& fr, const EyeArg
     const int pix = a.queue_cur[k / C];
     const Vtx eye = vtx_load(a.ev + pix);
     const Vtx light = vtx_load(fr.p.sampler.LVC + lv);
-    const float3 c = connect_vertices(fr, eye, light, nullptr);
+    const float3 c = connect_vertices(fr, eye, light, nullptr, (int)a.xlab[pix], fr.lvc_xlabel ? (int)__ldg(fr.lvc_xlabel + lv) : -1);
     const float3 res = c / a.conn_pmf[k];
     float3 term = f3(0.f);
     if (!invalid3(res)) term = res / (float)C;
@@ -445,11 +582,11 @@ void launch_eye_pass(Context& c, int width, int height) {
                 "spc_launch(SPCBPT_eye): light_tree without CMFGamma");
     const size_t P = (size_t)width * height;
     SPC_REQUIRE(P < 0x7fffffffull / 16, SPC_ERR_INVALID, "spc_launch: image too large");
-    const DevFrame fr = make_dev_frame(c);
+    DevFrame fr = make_dev_frame(c);
     const int C = c.connections;
     EyeBuffers& e = c.eye;
     if (e.pixels < P || e.conns != C) {
-        e.ev.alloc(P); e.pre.alloc(P); e.res.alloc(P);
+        e.ev.alloc(P); e.pre.alloc(P); e.res.alloc(P); e.xlab.alloc(P);
         for (int k = 0; k < 2; k++) { e.rays[k].alloc(P); e.queue[k].alloc(P); }
         e.hits.alloc(P);
         e.shadow.alloc(P * C); e.visible.alloc(P * C); e.conn_lvc.alloc(P * C); e.conn_pmf.alloc(P * C); e.contrib.alloc(P * C);
@@ -466,6 +603,16 @@ void launch_eye_pass(Context& c, int width, int height) {
     a.hits = (const float4*)e.hits.p; a.shadow = (float4*)e.shadow.p; a.visible = e.visible.p;
     a.conn_lvc = e.conn_lvc.p; a.conn_pmf = e.conn_pmf.p; a.contrib = e.contrib.p; a.counts = e.counts.p;
     a.first_prim = c.dbg_first_prim; a.first_label = c.dbg_first_label;
+    a.xlab = e.xlab.p;
+    // cross labels of the light vertices: only when the sampler is the one spc_lvc_process built (then jump_buffer indexes
+    // c.lvc.n slots); a caller-made sampler keeps the in-kernel tree walk
+    fr.lvc_xlabel = nullptr;
+    if (S.jump_buffer == c.lvc.jump.p && c.lvc.n > 0 && S.vertex_count > 0 && S.vertex_count <= c.lvc.n) {
+        e.lvc_xlabel.alloc((size_t)c.lvc.n);
+        k_lvc_xlabel<<<(S.vertex_count + 255) / 256, 256, 0, st>>>(fr, S.vertex_count, e.lvc_xlabel.p);
+        c.launches++;
+        fr.lvc_xlabel = e.lvc_xlabel.p;
+    }
     a.bounce = 0;
     a.rays_cur = (float4*)e.rays[0].p; a.rays_next = (float4*)e.rays[1].p;
     a.queue_cur = e.queue[0].p; a.queue_next = e.queue[1].p;
@@ -483,11 +630,18 @@ void launch_eye_pass(Context& c, int width, int height) {
         launch_trace_closest_q(c, (const spc_ray*)a.rays_cur, e.counts.p + b, 1, n_max, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);
         const int g1 = (int)std::min<int64_t>((n_max + 127) / 128, grid_cap);
         k_eye_shade<<<g1, 128, 0, st>>>(fr, a);
+        switch (C) {
+            case 1: k_eye_sample<1><<<g1, 128, 0, st>>>(fr, a); break;
+            case 2: k_eye_sample<2><<<g1, 128, 0, st>>>(fr, a); break;
+            case 3: k_eye_sample<3><<<g1, 128, 0, st>>>(fr, a); break;
+            case 4: k_eye_sample<4><<<g1, 128, 0, st>>>(fr, a); break;
+            default: k_eye_sample<0><<<g1, 128, 0, st>>>(fr, a); break;
+        }
         launch_trace_occlusion_q(c, (const spc_ray*)a.shadow, e.counts.p + b, C, n_max * C, e.visible.p);
         const int g2 = (int)std::min<int64_t>((n_max * C + 127) / 128, grid_cap);
         k_eye_connect<<<g2, 128, 0, st>>>(fr, a);
         k_eye_gather<<<g1, 128, 0, st>>>(fr, a);
-        c.launches += 3;
+        c.launches += 4;
         SPC_CUDA(cudaGetLastError());
         // every 4th bounce: read the next queue size back to shrink the grids / stop early
         if ((b & 3) == 3 && b < fr.max_depth) {

@@ -50,6 +50,7 @@ struct DevFrame {
     int        connections;  // CONNECTION_N (:37)
     int        max_depth;    // literal 50 in raygen.cu:361,668 unless MyParams::max_depth > 0
     uint32_t   seed_offset;  // eye/pt seeds use tea<4>(pixel, subframe_index * seed_stride + seed_offset): (0, 1) = the reference's
+    const short* lvc_xlabel; // eye-tree label of every LVC slot (k_lvc_xlabel), or null: walk the tree where it is needed
     uint32_t   seed_stride;  // streams; other values when subframes are partitioned across GPUs or frame lanes (each keeps its own
                              // running mean over ITS subframes, numbered 0,1,2,... locally)
 };
@@ -437,9 +438,14 @@ __device__ __forceinline__ float getLL_pdf(const DevFrame& fr, const Vtx& Mid, c
     const float3 in_dir = normalize(Mid.position - Last.position);
     return getLast_pdf(fr, Last, in_dir);
 }
-__device__ __forceinline__ float tracing_weight_light(const DevFrame& fr, const Vtx& Mid, const Vtx& Last) {   // rmis.h:58-79
+// Cross labels.  The recursive MIS classifies a light vertex with the EYE tree (tracing_weight_light) and an eye vertex with the
+// LIGHT tree (tracing_weight_eye).  Both depend on the vertex alone, yet the reference walks the tree at every use: once per
+// connection and again when the path is extended.  The wavefront passes compute each label once per vertex (k_eye_sample,
+// k_lvc_xlabel) and hand it in through `xlabel`; a negative value means "not cached, walk the tree" -- the same function on the
+// same arguments, so the result is identical either way.
+__device__ __forceinline__ float tracing_weight_light(const DevFrame& fr, const Vtx& Mid, const Vtx& Last, int xlabel = -1) {   // rmis.h:58-79
     if (Last.lastBrdf || Last.isBrdf) return 0.0f;
-    const int eye_label = tree_label(fr.p.subspace_info.eye_tree, Last.position, Last.normal);
+    const int eye_label = xlabel >= 0 ? xlabel : tree_label(fr.p.subspace_info.eye_tree, Last.position, Last.normal);
     const int light_label = Last.lastZoneId;
     const float lum_sum = Last.last_lum;
     return connectRate_SOL(fr, eye_label, light_label, lum_sum);
@@ -462,11 +468,11 @@ __device__ __forceinline__ float3 getFluxMultiplier(const DevFrame& fr, const Vt
     const float3 out_vec = v.lastPosition - v.position;
     return getFluxMultiplier(fr, v, in_dir, normalize(out_vec));
 }
-__device__ __forceinline__ float3 tracing_weight_eye(const DevFrame& fr, const Vtx& Last) {   // rmis.h:131-151
+__device__ __forceinline__ float3 tracing_weight_eye(const DevFrame& fr, const Vtx& Last, int xlabel = -1) {   // rmis.h:131-151
     if (Last.lastBrdf || Last.isBrdf) return f3(0.0f);
     if (Last.depth == 1) return f3(0.0f);   // t=1 strategy disabled (readme.md:27)
     const int eye_label = Last.lastZoneId;
-    const int light_label = tree_label(fr.p.subspace_info.light_tree, Last.position, Last.normal);
+    const int light_label = xlabel >= 0 ? xlabel : tree_label(fr.p.subspace_info.light_tree, Last.position, Last.normal);
     return connectRate_SOL3(fr, eye_label, light_label, f3(1.0f));
 }
 __device__ __forceinline__ float getPdf(const DevFrame& fr, const Vtx& begin, const Vtx& end, float3 in_dir) {   // rmis.h:153-172
@@ -484,21 +490,21 @@ __device__ __forceinline__ float getPdf_from_light_source(const Vtx& light, cons
     const float angle2a = fabsf(dot(end.normal, conn_dir)) / (dot(conn_vec, conn_vec));
     return pdf_angle * angle2a;
 }
-__device__ __forceinline__ void tracing_update_eye(const DevFrame& fr, Vtx& Mid, const Vtx& Last) {   // rmis.h:189-203
+__device__ __forceinline__ void tracing_update_eye(const DevFrame& fr, Vtx& Mid, const Vtx& Last, int last_xlabel = -1) {   // rmis.h:189-203
     const float LL_pdf = getLL_pdf(fr, Mid, Last);
-    const float3 weight = tracing_weight_eye(fr, Last);
+    const float3 weight = tracing_weight_eye(fr, Last, last_xlabel);
     const float last_single_pdf = Last.singlePdf;
     const float3 flux_multiplier = getFluxMultiplier(fr, Last, normalize(Mid.position - Last.position));
     Mid.RMIS_pointer_3 = ((Last.RMIS_pointer_3 * LL_pdf * flux_multiplier) + weight) / last_single_pdf;
 }
-__device__ __forceinline__ float general_connection(const DevFrame& fr, const Vtx& eye, const Vtx& light) {   // rmis.h:212-247
+__device__ __forceinline__ float general_connection(const DevFrame& fr, const Vtx& eye, const Vtx& light, int eye_xlabel = -1, int light_xlabel = -1) {   // rmis.h:212-247
     if (eye.isBrdf || light.isBrdf) return 0.0f;
     const float3 connect_vec = eye.position - light.position;
     const float3 connect_dir = normalize(connect_vec);
     const float3 flux = light.flux / light.pdf;
     const float LL_pdf_A = getLL_pdf(fr, light, eye);
     const float3 flux_multiplier_0 = getFluxMultiplier(fr, eye, -connect_dir);
-    const float3 weight_A = tracing_weight_eye(fr, eye);
+    const float3 weight_A = tracing_weight_eye(fr, eye, eye_xlabel);
     const float3 D_A_0 = ((eye.RMIS_pointer_3 * LL_pdf_A * flux_multiplier_0) + weight_A);
     const float3 LA = normalize(light.lastPosition - light.position);
     const float pdf_A = getPdf(fr, light, eye, LA);
@@ -506,21 +512,21 @@ __device__ __forceinline__ float general_connection(const DevFrame& fr, const Vt
     const float D_A = sum3(D_A_0 * pdf_A * flux_multiplier_1 * flux / eye.singlePdf);
     const float weight = sum3(connectRate_SOL3(fr, eye.subspaceId, light.subspaceId, flux));
     const float LL_pdf_B = getLL_pdf(fr, eye, light);
-    const float weight_B = tracing_weight_light(fr, eye, light);
+    const float weight_B = tracing_weight_light(fr, eye, light, light_xlabel);
     const float D_B_0 = (light.RMIS_pointer * LL_pdf_B) + weight_B;
     const float3 LB = normalize(eye.lastPosition - eye.position);
     const float pdf_B = getPdf(fr, eye, light, LB);
     const float D_B = D_B_0 * pdf_B / light.singlePdf;
     return weight / (weight + D_A + D_B);
 }
-__device__ __forceinline__ float connection_lightSource(const DevFrame& fr, const Vtx& eye, const Vtx& light) {   // rmis.h:281-313
+__device__ __forceinline__ float connection_lightSource(const DevFrame& fr, const Vtx& eye, const Vtx& light, int eye_xlabel = -1) {   // rmis.h:281-313
     if (eye.isBrdf || light.isBrdf) return 0.0f;
     const float3 connect_vec = eye.position - light.position;
     const float3 connect_dir = normalize(connect_vec);
     const float3 flux = light.flux / light.pdf;
     const float LL_pdf_A = getLL_pdf(fr, light, eye);
     const float3 flux_multiplier_0 = getFluxMultiplier(fr, eye, -connect_dir);
-    const float3 weight_A = tracing_weight_eye(fr, eye);
+    const float3 weight_A = tracing_weight_eye(fr, eye, eye_xlabel);
     const float3 D_A_0 = ((eye.RMIS_pointer_3 * LL_pdf_A * flux_multiplier_0) + weight_A);
     const float pdf_A = getPdf_from_light_source(light, eye);
     const float flux_multiplier_1 = SPC_PI_F;
@@ -532,13 +538,13 @@ __device__ __forceinline__ float connection_lightSource(const DevFrame& fr, cons
     const float D_B = D_B_0 * pdf_B / light.singlePdf;
     return weight / (weight + D_A + D_B);
 }
-__device__ __forceinline__ float light_hit(const DevFrame& fr, const Vtx& eye, const Vtx& light) {   // rmis.h:359-389
+__device__ __forceinline__ float light_hit(const DevFrame& fr, const Vtx& eye, const Vtx& light, int eye_xlabel = -1) {   // rmis.h:359-389
     const float3 connect_vec = eye.position - light.position;
     const float3 connect_dir = normalize(connect_vec);
     const float3 flux = light.flux / light.pdf;
     const float LL_pdf_A = getLL_pdf(fr, light, eye);
     const float3 flux_multiplier_0 = getFluxMultiplier(fr, eye, -connect_dir);
-    const float3 weight_A = tracing_weight_eye(fr, eye);
+    const float3 weight_A = tracing_weight_eye(fr, eye, eye_xlabel);
     const float3 D_A_0 = ((eye.RMIS_pointer_3 * LL_pdf_A * flux_multiplier_0) + weight_A);
     const float pdf_A = getPdf_from_light_source(light, eye);
     const float flux_multiplier_1 = SPC_PI_F;
@@ -556,7 +562,7 @@ __device__ __forceinline__ bool invalid3(float3 a) {   // ISINVALIDVALUE, raygen
 }
 
 // connectVertex_SPCBPT (raygen.cu:253-303): contribution * MIS weight of joining eye vertex a to light vertex b
-__device__ __forceinline__ float3 connect_vertices(const DevFrame& fr, const Vtx& a, const Vtx& b, float* w_out) {
+__device__ __forceinline__ float3 connect_vertices(const DevFrame& fr, const Vtx& a, const Vtx& b, float* w_out, int a_xlabel = -1, int b_xlabel = -1) {
     const float3 connectVec = a.position - b.position;
     const float3 connectDir = normalize(connectVec);
     const float G = fabsf(dot(a.normal, connectDir)) * fabsf(dot(b.normal, connectDir)) / dot(connectVec, connectVec);
@@ -574,7 +580,7 @@ __device__ __forceinline__ float3 connect_vertices(const DevFrame& fr, const Vtx
     }
     const float3 contri = a.flux * b.flux * fa * fb * G;
     const float pdf = a.pdf * b.pdf;
-    const float w = (b.depth == 0 ? connection_lightSource(fr, a, b) : general_connection(fr, a, b));
+    const float w = (b.depth == 0 ? connection_lightSource(fr, a, b, a_xlabel) : general_connection(fr, a, b, a_xlabel, b_xlabel));
     if (w_out) *w_out = w;
     const float3 ans = contri / pdf * w;
     return invalid3(ans) ? f3(0.0f) : ans;
@@ -606,7 +612,8 @@ struct SurfaceOut {
     bool   done;
 };
 __device__ __forceinline__ void surface_hit(const DevFrame& fr, const Vtx& Last, float3 pre_flux, float pre_singlePdf, const LocalGeom& geom,
-                                            float t_hit, float3 ray_direction, bool light_side, uint32_t& seed, Vtx& Mid, SurfaceOut& out) {
+                                            float t_hit, float3 ray_direction, bool light_side, uint32_t& seed, Vtx& Mid, SurfaceOut& out,
+                                            int last_xlabel = -1) {
     const float3 inver_ray_direction = -ray_direction;
     const Pbr currentPbr = shade_pbr(fr.sc, geom.material, geom.uv);
     float3 N = geom.Ng;
@@ -644,7 +651,7 @@ __device__ __forceinline__ void surface_hit(const DevFrame& fr, const Vtx& Last,
         else tracing_update_light(fr, Mid, Last);
     } else {
         if (Mid.depth == 1) Mid.RMIS_pointer_3 = f3(0.0f);                          // rmis::tracing_init_eye, rmis.h:204-207
-        else tracing_update_eye(fr, Mid, Last);
+        else tracing_update_eye(fr, Mid, Last, last_xlabel);
     }
     const float r = rnd(seed);
     float rr_rate = fmax3(Mid.color);
@@ -656,7 +663,7 @@ __device__ __forceinline__ void surface_hit(const DevFrame& fr, const Vtx& Last,
 // __closesthit__eyeSubpath_LightSource (hit_program.cu:62-147).  Returns false when the emitter is seen
 // from behind (no vertex is added).
 __device__ __forceinline__ bool eye_hits_light(const DevFrame& fr, const Vtx& Last, float3 pre_flux, float pre_singlePdf, const LocalGeom& geom,
-                                               float t_hit, float3 ray_direction, Vtx& Mid) {
+                                               float t_hit, float3 ray_direction, Vtx& Mid, int last_xlabel = -1) {
     const spc_light& light = fr.sc.lights[geom.light];
     const float3 ln = ld3(light.normal);
     if (dot(ray_direction, ln) > 0) return false;
@@ -694,7 +701,7 @@ __device__ __forceinline__ bool eye_hits_light(const DevFrame& fr, const Vtx& La
     virtual_light.flux = ls.emission;
     virtual_light.subspaceId = Mid.subspaceId;
     virtual_light.isBrdf = 0;
-    Mid.RMIS_pointer = (float)(1.0 / (double)light_hit(fr, Last, virtual_light));
+    Mid.RMIS_pointer = (float)(1.0 / (double)light_hit(fr, Last, virtual_light, last_xlabel));
     return true;
 }
 
