@@ -461,32 +461,47 @@ __device__ __forceinline__ void eye_connect_one(const DevFrame& fr, const EyeArg
     a.contrib[k] = make_float4(term.x, term.y, term.z, 0.f);
 }
 
+// Two queues per warp: connections to emitter points (light-path depth 0: one-sided emission, connection_lightSource) and to
+// surface light vertices (second BSDF, general_connection) take different branches throughout connect_vertices; evaluated from one
+// mixed queue a warp ran both sides for most batches (ncu: 18 of 32 lanes active per instruction, profiles/r1e_summary.md).
 __global__ void __launch_bounds__(128) k_eye_connect(const DevFrame fr, const EyeArgs a) {
-    __shared__ int64_t s_queue[4][64];
+    __shared__ int64_t s_queue[4][2][64];
     const int C = fr.connections;
     const int64_t n = (int64_t)a.counts[a.bounce] * C;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t* q = s_queue[warp];
-    int pending = 0;   // warp-uniform
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32; base < n; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k = base + lane;
-        bool work = false;
-        if (k < n) {
-            work = a.conn_lvc[k] >= 0 && a.visible[k];
-            if (!work) a.contrib[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, work);
-        if (work) q[pending + __popc(m & ((1u << lane) - 1u))] = k;
-        pending += __popc(m);
-        __syncwarp();
-        if (pending >= 32) {
-            const int64_t mine = q[pending - 32 + lane];   // newest 32 entries: the older remainder stays at the front
+    int pending[2] = {0, 0};   // warp-uniform
+    bool last = false;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32;; base += (int64_t)gridDim.x * blockDim.x) {
+        if (base >= n) last = true;   // one extra round that drains what is left
+        if (!last) {
+            const int64_t k = base + lane;
+            int kind = -1;
+            if (k < n) {
+                const int lv = a.conn_lvc[k];
+                if (lv >= 0 && a.visible[k]) kind = fr.p.sampler.LVC[lv].depth == 0 ? 0 : 1;
+                else a.contrib[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const unsigned m = __ballot_sync(0xffffffffu, kind == t);
+                if (kind == t) s_queue[warp][t][pending[t] + __popc(m & ((1u << lane) - 1u))] = k;
+                pending[t] += __popc(m);
+            }
             __syncwarp();
-            eye_connect_one(fr, a, mine, C);
-            pending -= 32;
         }
+        const int threshold = last ? 1 : 32;
+#pragma unroll 1
+        for (;;) {
+            const int t = pending[1] >= threshold ? 1 : (pending[0] >= threshold ? 0 : -1);
+            if (t < 0) break;
+            const int cnt = min(32, pending[t]);
+            // newest `cnt` entries: the older remainder stays at the front of the queue
+            if (lane < cnt) eye_connect_one(fr, a, s_queue[warp][t][pending[t] - cnt + lane], C);
+            __syncwarp();
+            pending[t] -= cnt;
+        }
+        if (last) break;
     }
-    if (lane < pending) eye_connect_one(fr, a, q[lane], C);
 }
 
 // result += res / CONNECTION_N, in connection order (raygen.cu:415)
