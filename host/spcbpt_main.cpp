@@ -387,6 +387,7 @@ struct App {
         SPC_CHECK(spc_synchronize(ctx));
         SPC_CHECK(spc_set_stream(ctx, lane_stream));
         SPC_CHECK(spc_set_seed_mapping(ctx, (uint32_t)k * opt.seed_stride + opt.seed_offset, (uint32_t)n * opt.seed_stride));
+        if (n > 1) SPC_CHECK(spc_set_trace_blocks(ctx, 7));   // leave room for the other lanes' small kernels (renderer.py LANE_TRACE_BLOCKS)
     }
 
     void render_lane_frames(int n_frames) {

@@ -402,6 +402,11 @@ SPC_API int  spc_set_seed_offset(spc_context* ctx, uint32_t offset);
  * global subframes lane, lane + n_lanes, ...: this is how several contexts on one GPU render alternate subframes concurrently
  * (host/spcbpt_main.cpp --lanes) and how ranks partition subframes across GPUs. */
 SPC_API int  spc_set_seed_mapping(spc_context* ctx, uint32_t offset, uint32_t stride);
+/* Resident thread blocks per SM of the persistent traversal kernels launched by this context (0 = default: as many as fit, 9).
+ * No counterpart in the reference (OptiX schedules its own launches).  A context that shares the GPU with other contexts (frame
+ * lanes) leaves room for their small latency-bound kernels by asking for fewer: 7 measured best on the shipped scene with 4 lanes
+ * (profiles/r1e_summary.md).  Results do not depend on it. */
+SPC_API int  spc_set_trace_blocks(spc_context* ctx, int blocks_per_sm);
 /* Read-out of a sample-partitioned render: out = sum_k weights[k] * accum_dev[k] (device float4[n_pixels] each, summed in the order
  * given) and, when out_frame_dev is not NULL, the tone-mapped sRGB uchar4 image of it (ToneMap + make_color, raygen.cu:50-58,
  * cuda/helpers.h:35-67 -- what the eye pass writes to MyParams::frame_buffer).  accum_dev / weights are HOST arrays of n entries. */

@@ -140,6 +140,7 @@ def _bind_optional(L):
         "spc_set_debug_outputs": [vp, vp, vp],
         "spc_set_seed_offset": [vp, ctypes.c_uint32],
         "spc_set_seed_mapping": [vp, ctypes.c_uint32, ctypes.c_uint32],
+        "spc_set_trace_blocks": [vp, i32],
         "spc_merge_accum": [vp, vp, vp, i32, i32, vp, vp],
         "spc_lvc_process": [vp, vp, vp, i32, vp],
         "spc_build_tree": [vp, i32, i32, i32, vp, i32, vp],
@@ -300,6 +301,9 @@ class Context:
 
     def set_seed_mapping(self, offset, stride):
         self._ck(self._L.spc_set_seed_mapping(self.h, offset, stride), "spc_set_seed_mapping")
+
+    def set_trace_blocks(self, blocks_per_sm):
+        self._ck(self._L.spc_set_trace_blocks(self.h, blocks_per_sm), "spc_set_trace_blocks")
 
     def merge_accum(self, accum_devs, weights, n_pixels, out_accum_dev, out_frame_dev=None):
         """out = sum_k weights[k] * accum_devs[k] (+ the tone-mapped frame buffer): the read-out of a sample-partitioned render"""

@@ -91,6 +91,13 @@ int spc_set_seed_mapping(spc_context* ctx, uint32_t offset, uint32_t stride) {
     SPC_API_END
 }
 
+int spc_set_trace_blocks(spc_context* ctx, int blocks_per_sm) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(blocks_per_sm >= 0 && blocks_per_sm <= 32, SPC_ERR_INVALID, "spc_set_trace_blocks: %d is outside 0..32", blocks_per_sm);
+    c.trace_blocks_per_sm = blocks_per_sm;
+    SPC_API_END
+}
+
 int spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_dev, const float* weights, int n, int n_pixels, spc_float4* out_accum_dev,
                     uint32_t* out_frame_dev) {
     SPC_API_BEGIN

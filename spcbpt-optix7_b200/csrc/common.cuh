@@ -171,6 +171,7 @@ struct Context {
     DevBuf<float> merge_w;
     DevBuf<unsigned long long> fetch_counters;   // ray-fetch counters of the persistent traversal kernels (one slot per launch)
     unsigned      fetch_slot = 0;
+    int           trace_blocks_per_sm = 0;   // spc_set_trace_blocks: 0 = as many as fit
     // render path
     uint32_t      seed_offset = 0;             // see DevFrame::seed_offset / seed_stride
     uint32_t      seed_stride = 1;

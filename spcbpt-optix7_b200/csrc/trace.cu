@@ -153,7 +153,8 @@ static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, 
     unsigned long long* counter = ctx.fetch_counters.p + (ctx.fetch_slot++ & 255);
     SPC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx.stream));
     int64_t blocks = (n_max + kTraceBlock - 1) / kTraceBlock;
-    const int64_t cap = (int64_t)ctx.sm_count * blocks_per_sm;
+    const int bps = ctx.trace_blocks_per_sm > 0 ? std::min(ctx.trace_blocks_per_sm, blocks_per_sm) : blocks_per_sm;
+    const int64_t cap = (int64_t)ctx.sm_count * bps;
     if (blocks > cap) blocks = cap;
     k_trace_persist<ANYHIT><<<(unsigned)blocks, kTraceBlock, 0, ctx.stream>>>(ctx.bvh.nodes.p, ctx.bvh.tris.p, (const float4*)rays, n_dev, mult, n_max,
                                                                            (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0, fetch_t, postpone_div, (float4*)hits, visible, counter);

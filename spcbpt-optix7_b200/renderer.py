@@ -243,6 +243,9 @@ class Renderer:
         return self.frame.cpu().numpy().view(np.uint8).reshape(self.h, self.w, 4)
 
 
+LANE_TRACE_BLOCKS = 7   # resident blocks per SM of the persistent trace kernels when several lanes share a GPU (host/spcbpt_main.cpp uses the same)
+
+
 class LaneRenderer:
     """Frame lanes: `lanes` render contexts on one GPU, each on its own stream and driven by its own host thread, rendering
     alternate subframes (lane k draws the samples of the global subframes k, k+lanes, ... through spc_set_seed_mapping and
@@ -262,6 +265,8 @@ class LaneRenderer:
             r.ctx.synchronize()
             r.ctx.set_stream(s.cuda_stream)
             r.ctx.set_seed_mapping(k, lanes)
+            if lanes > 1:
+                r.ctx.set_trace_blocks(LANE_TRACE_BLOCKS)   # leave room for the other lanes' small kernels
         self.ctx = self.lanes[0].ctx
         self.frames = 0            # global subframes rendered so far
         self.lt_base = 0
