@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspcbpt_b200.so")
+# SPCBPT_LIB: development only (A/B of two builds, tests/quick_ab_*.sh); the product path is the in-tree build
+LIB_PATH = os.environ.get("SPCBPT_LIB") or os.path.join(_HERE, "libspcbpt_b200.so")
 
 # --------------------------------------------------------------------------------------------
 # numpy dtypes of the POD structs (byte-identical to include/spcbpt_b200.h)

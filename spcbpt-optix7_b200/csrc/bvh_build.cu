@@ -475,14 +475,13 @@ __global__ void k_emit(int n, const EmitItem* __restrict__ items, int n_items, E
     const uint32_t next_base = n_inner ? atomicAdd(&ctr->n_next, (uint32_t)n_inner) : 0u;
     atomicMax(&ctr->max_depth, (uint32_t)it.depth);
 
-    uint32_t imask = 0;
-    uint8_t meta[8], qlo[3][8], qhi[3][8];
+    uint32_t imask = 0, tword = 0;   // tword: bits 3s..3s+cnt-1 set for a leaf with cnt triangles in slot s (traverse.cuh)
+    uint8_t qlo[3][8], qhi[3][8];
     int inner_rank = 0, tri_off = 0;
     float sah = 0.f;
     for (int s = 0; s < 8; s++) {
         const int c = child_in_slot[s];
-        meta[s] = 0;
-        for (int a = 0; a < 3; a++) { qlo[a][s] = 0; qhi[a][s] = 0; }
+        for (int a = 0; a < 3; a++) { qlo[a][s] = 255; qhi[a][s] = 0; }   // empty slot: an inverted box, never entered
         if (c < 0) continue;
         for (int a = 0; a < 3; a++) {
             float ql = floorf((clo[c][a] - lo[a]) / scale[a]);
@@ -497,13 +496,12 @@ __global__ void k_emit(int n, const EmitItem* __restrict__ items, int n_items, E
         const float4 l4 = make_float4(clo[c][0], clo[c][1], clo[c][2], 0.f), h4 = make_float4(chi[c][0], chi[c][1], chi[c][2], 0.f);
         if (c_inner[c]) {
             imask |= 1u << s;
-            meta[s] = (uint8_t)(0x20 | (24 + s));
             next[next_base + inner_rank] = EmitItem{c_node[c], (int)(child_base + inner_rank), it.depth + 1};
             inner_rank++;
             sah += half_area(l4, h4) * kCostNode;
         } else {
             const int cnt = c_cnt[c];
-            meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | (uint32_t)tri_off);
+            tword |= ((1u << cnt) - 1u) << (3 * s);   // its triangles follow those of the lower slots: index = tri_base + rank in tword
             for (int t = 0; t < cnt; t++) {
                 const uint32_t prim = sorted_prim[c_first[c] + t];
                 const float4 a = tri_pos[3 * (size_t)prim], b = tri_pos[3 * (size_t)prim + 1], cc = tri_pos[3 * (size_t)prim + 2];
@@ -523,7 +521,7 @@ __global__ void k_emit(int n, const EmitItem* __restrict__ items, int n_items, E
     float4* o = out_nodes + 5 * (size_t)it.wide;
     o[0] = make_float4(lo[0], lo[1], lo[2],
                        __uint_as_float((uint32_t)ebias[0] | ((uint32_t)ebias[1] << 8) | ((uint32_t)ebias[2] << 16) | (imask << 24)));
-    o[1] = make_float4(__uint_as_float(child_base), __uint_as_float(tri_base), __uint_as_float(pack4(meta)), __uint_as_float(pack4(meta + 4)));
+    o[1] = make_float4(__uint_as_float(child_base), __uint_as_float(tri_base), __uint_as_float(tword), 0.f);
     o[2] = make_float4(__uint_as_float(pack4(qlo[0])), __uint_as_float(pack4(qlo[0] + 4)), __uint_as_float(pack4(qlo[1])), __uint_as_float(pack4(qlo[1] + 4)));
     o[3] = make_float4(__uint_as_float(pack4(qlo[2])), __uint_as_float(pack4(qlo[2] + 4)), __uint_as_float(pack4(qhi[0])), __uint_as_float(pack4(qhi[0] + 4)));
     o[4] = make_float4(__uint_as_float(pack4(qhi[1])), __uint_as_float(pack4(qhi[1] + 4)), __uint_as_float(pack4(qhi[2])), __uint_as_float(pack4(qhi[2] + 4)));

@@ -62,11 +62,13 @@ struct DevBuf {
 // ---------------------------------------------------------------------------------------------
 // Node = 5 x float4 (all loads are 128-bit):
 //   n0 = { p.x, p.y, p.z, bits(ex | ey<<8 | ez<<16 | imask<<24) }     box origin, biased exponents
-//   n1 = { bits(child_base), bits(tri_base), bits(meta[0..3]), bits(meta[4..7]) }
+//   n1 = { bits(child_base), bits(tri_base), bits(tword), 0 }
 //   n2 = { qlox[0..3], qlox[4..7], qloy[0..3], qloy[4..7] }           8-bit quantised child boxes
 //   n3 = { qloz[0..3], qloz[4..7], qhix[0..3], qhix[4..7] }
 //   n4 = { qhiy[0..3], qhiy[4..7], qhiz[0..3], qhiz[4..7] }
-// meta[slot]: 0 = empty; internal child = 0x20 | (24+slot); leaf = (unary tri count << 5) | tri offset.
+// tword: bits 3s..3s+cnt-1 set for a leaf with cnt (<= 3) triangles in slot s; the triangles of a node are stored in slot order, so
+// a triangle's index is tri_base + its rank among the set bits of tword.  Inner children: imask bit s; child index = child_base +
+// rank of s in imask.  Empty slots carry an inverted box (qlo 255, qhi 0).
 // Triangle = 3 x float4: { v0.xyz, bits(prim) }, { e1.xyz, bits(flags) }, { e2.xyz, 0 } with
 // e1 = v1-v0, e2 = v2-v0 (one IEEE subtraction each, as the intersection contract prescribes).
 struct Bvh8 {

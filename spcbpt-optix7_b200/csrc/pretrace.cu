@@ -142,6 +142,8 @@ constexpr int kPtBlock = 64;
 
 __global__ void __launch_bounds__(kPtBlock) k_pretrace(const DevFrame fr, spc_vertex* __restrict__ scratch) {
     __shared__ uint2 s_stack[kSmStack * kPtBlock];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);   // before any thread leaves
     const spc_pretrace_params& pt = fr.p.pre_tracer;
     const int launch_index = blockIdx.x * kPtBlock + threadIdx.x;
     if (launch_index >= pt.num_core) return;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kPtBlock) k_pretrace(const DevFrame fr, spc_ve
     while (true) {
         TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
         TravHit h;
-        if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, stack, kPtBlock, h, cn, ct)) break;   // miss: no vertex
+        if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, stack, kPtBlock, h, cn, ct, s_lut)) break;   // miss: no vertex
         const LocalGeom g = hit_geometry(fr.sc, h.prim, h.u, h.v);
         Vtx mid;
         if (g.light >= 0) {
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kPtBlock) k_pretrace(const DevFrame fr, spc_ve
             const float3 dir = vis_vec / len;
             TravRay sr{cur.position.x, cur.position.y, cur.position.z, dir.x, dir.y, dir.z, SPC_SCENE_EPS, len - SPC_SCENE_EPS};
             TravHit sh;
-            visible = !traverse_bvh8<true, false>(fr.sc.nodes, fr.sc.tris, sr, false, stack, kPtBlock, sh, cn, ct);
+            visible = !traverse_bvh8<true, false>(fr.sc.nodes, fr.sc.tris, sr, false, stack, kPtBlock, sh, cn, ct, s_lut);
         }
         if (visible && rr_acc_accept(resample_number, seed)) {
             if (dot(vis_vec, ls.normal) < 0) {

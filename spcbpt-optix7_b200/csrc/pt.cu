@@ -24,6 +24,8 @@ constexpr int kPtPixBlock = 64;
 
 __global__ void __launch_bounds__(kPtPixBlock) k_pt(const DevFrame fr, int n_pix) {
     __shared__ uint2 s_stack[kSmStack * kPtPixBlock];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);   // before any thread leaves
     const int i = blockIdx.x * kPtPixBlock + threadIdx.x;
     if (i >= n_pix) return;
     uint2* stack = s_stack + threadIdx.x;
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(kPtPixBlock) k_pt(const DevFrame fr, int n_pix
     while (true) {
         TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
         TravHit h;
-        if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, stack, kPtPixBlock, h, cn, ct)) {
+        if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, stack, kPtPixBlock, h, cn, ct, s_lut)) {
             done = true;   // __miss__constant_radiance (environment lighting is out of scope)
             currentResult = f3(0.0f);
         } else {
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(kPtPixBlock) k_pt(const DevFrame fr, int n_pix
             const float3 dir = bias_pos / len;
             TravRay sr{vis_A.x, vis_A.y, vis_A.z, dir.x, dir.y, dir.z, SPC_SCENE_EPS, len - SPC_SCENE_EPS};
             TravHit sh;
-            if (!traverse_bvh8<true, false>(fr.sc.nodes, fr.sc.tris, sr, false, stack, kPtPixBlock, sh, cn, ct)) result += currentResult;
+            if (!traverse_bvh8<true, false>(fr.sc.nodes, fr.sc.tris, sr, false, stack, kPtPixBlock, sh, cn, ct, s_lut)) result += currentResult;
             currentResult = f3(0.0f);
         }
         if (done || depth > 30) break;

@@ -62,6 +62,8 @@ constexpr int kLtWarps = 4;
 
 __global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFrame fr, int lanes) {
     __shared__ uint2 s_stack[kSmStack * kLtWarps * 32];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);   // before any thread leaves
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int core = (blockIdx.x * kLtWarps + warp) * lanes + lane;
     const spc_light_trace_params& lt = fr.p.lt;
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFr
             TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
             TravHit h;
             bool pushed = false;
-            if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, s_stack + threadIdx.x, kLtWarps * 32, h, cn, ct)) {
+            if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, s_stack + threadIdx.x, kLtWarps * 32, h, cn, ct, s_lut)) {
                 done = true;                                   // __miss__BDPTVertex, raygen.cu:699-704
             } else {
                 const LocalGeom g = hit_geometry(fr.sc, h.prim, h.u, h.v);

@@ -9,6 +9,9 @@
 namespace spc {
 
 constexpr int kTraceBlock = 128;
+#ifndef SPC_PERSIST_MIN_BLOCKS
+#define SPC_PERSIST_MIN_BLOCKS 8   // resident blocks per SM the persistent kernels are compiled for (register cap 65536 / (128 * n))
+#endif
 
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock)
@@ -16,6 +19,8 @@ k_trace_closest(const float4* __restrict__ nodes, const float4* __restrict__ tri
                 const float4* __restrict__ rays, int64_t n, int cull_back, float4* __restrict__ hits,
                 unsigned long long* __restrict__ counters) {
     __shared__ uint2 s_stack[kSmStack * kTraceBlock];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);
     const int64_t i = (int64_t)blockIdx.x * kTraceBlock + threadIdx.x;
     unsigned cn = 0, ct = 0;
     if (i < n) {
@@ -23,7 +28,7 @@ k_trace_closest(const float4* __restrict__ nodes, const float4* __restrict__ tri
         const float4 rd = __ldg(rays + 2 * i + 1);
         TravRay r{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w};
         TravHit h;
-        traverse_bvh8<false, COUNT>(nodes, tris, r, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, h, cn, ct);
+        traverse_bvh8<false, COUNT>(nodes, tris, r, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, h, cn, ct, s_lut);
         hits[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
     }
     if (COUNT) {
@@ -45,6 +50,8 @@ k_trace_occlusion(const float4* __restrict__ nodes, const float4* __restrict__ t
                   const float4* __restrict__ rays, int64_t n, uint8_t* __restrict__ visible,
                   unsigned long long* __restrict__ counters) {
     __shared__ uint2 s_stack[kSmStack * kTraceBlock];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);
     const int64_t i = (int64_t)blockIdx.x * kTraceBlock + threadIdx.x;
     unsigned cn = 0, ct = 0;
     if (i < n) {
@@ -52,7 +59,7 @@ k_trace_occlusion(const float4* __restrict__ nodes, const float4* __restrict__ t
         const float4 rd = __ldg(rays + 2 * i + 1);
         TravRay r{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w};
         TravHit h;
-        const bool blocked = traverse_bvh8<true, COUNT>(nodes, tris, r, false, s_stack + threadIdx.x, kTraceBlock, h, cn, ct);
+        const bool blocked = traverse_bvh8<true, COUNT>(nodes, tris, r, false, s_stack + threadIdx.x, kTraceBlock, h, cn, ct, s_lut);
         visible[i] = blocked ? 0 : 1;
     }
     if (COUNT) {
@@ -75,17 +82,20 @@ k_trace_occlusion(const float4* __restrict__ nodes, const float4* __restrict__ t
 // The grid is sized to the resident capacity of the GPU (SM count x blocks per SM), not to the ray count.
 // ---------------------------------------------------------------------------------------------
 template <bool ANYHIT>
-__global__ void __launch_bounds__(kTraceBlock, 9)
+__global__ void __launch_bounds__(kTraceBlock, SPC_PERSIST_MIN_BLOCKS)
 k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ rays,
                 const int* __restrict__ n_dev, int mult, int64_t n_host, int cull_back, int fetch_threshold, int postpone_div,
                 float4* __restrict__ hits, uint8_t* __restrict__ visible, unsigned long long* __restrict__ counter) {
     __shared__ uint2 s_stack[kSmStack * kTraceBlock];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);
     uint2 lstack[kLocStack + kMaxBvhDepth];   // triangle postponing parks at most one extra group per tree level
     const int64_t n = n_dev ? (int64_t)__ldg(n_dev) * mult : n_host;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     Trav s;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_stack + threadIdx.x);
+    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(&s_lut);
     int64_t ray = -1;
     bool exhausted = false;
     unsigned cn = 0, ct = 0;
@@ -119,7 +129,7 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
             if (exhausted && idle == 0xffffffffu) break;
         }
         if (ray >= 0) {
-            if (trav_step<ANYHIT, false, true>(nodes, tris, s, cull_back != 0, kTraceBlock, lstack, cn, ct, postpone_div)) {
+            if (trav_step<ANYHIT, false, true>(nodes, tris, s, cull_back != 0, kTraceBlock, lstack, cn, ct, lut, postpone_div)) {
                 if (ANYHIT) {
                     visible[ray] = s.best_prim >= 0 ? 0 : 1;
                 } else {
@@ -175,6 +185,8 @@ __global__ void __launch_bounds__(kTraceBlock)
 k_trace_closest_q(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ rays,
                   const int* __restrict__ n_dev, int mult, int cull_back, float4* __restrict__ hits) {
     __shared__ uint2 s_stack[kSmStack * kTraceBlock];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);
     const int64_t n = (int64_t)__ldg(n_dev) * mult;
     unsigned cn = 0, ct = 0;
     for (int64_t i = (int64_t)blockIdx.x * kTraceBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kTraceBlock) {
@@ -182,7 +194,7 @@ k_trace_closest_q(const float4* __restrict__ nodes, const float4* __restrict__ t
         const float4 rd = __ldg(rays + 2 * i + 1);
         TravRay r{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w};
         TravHit h;
-        traverse_bvh8<false, false>(nodes, tris, r, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, h, cn, ct);
+        traverse_bvh8<false, false>(nodes, tris, r, cull_back != 0, s_stack + threadIdx.x, kTraceBlock, h, cn, ct, s_lut);
         hits[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
     }
 }
@@ -191,6 +203,8 @@ __global__ void __launch_bounds__(kTraceBlock)
 k_trace_occlusion_q(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ rays,
                     const int* __restrict__ n_dev, int mult, uint8_t* __restrict__ visible) {
     __shared__ uint2 s_stack[kSmStack * kTraceBlock];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);
     const int64_t n = (int64_t)__ldg(n_dev) * mult;
     unsigned cn = 0, ct = 0;
     for (int64_t i = (int64_t)blockIdx.x * kTraceBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kTraceBlock) {
@@ -202,7 +216,7 @@ k_trace_occlusion_q(const float4* __restrict__ nodes, const float4* __restrict__
         }
         TravRay r{ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, ro.w, rd.w};
         TravHit h;
-        const bool blocked = traverse_bvh8<true, false>(nodes, tris, r, false, s_stack + threadIdx.x, kTraceBlock, h, cn, ct);
+        const bool blocked = traverse_bvh8<true, false>(nodes, tris, r, false, s_stack + threadIdx.x, kTraceBlock, h, cn, ct, s_lut);
         visible[i] = blocked ? 0 : 1;
     }
 }

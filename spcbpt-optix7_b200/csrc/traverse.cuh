@@ -58,6 +58,44 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
 }
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int j) { return (w >> (8 * j)) & 0xffu; }
 
+// Two small look-up tables in shared memory turn the 8-bit "which child boxes were hit" mask of a node into the two things the
+// traversal needs, instead of shifting a per-child meta byte into place for each of the 8 children (5 predicated ALU operations per
+// child in the r1d/r1e SASS; the kernel is bound by the half-rate ALU pipe):
+//   exp3[m]     bit j of m -> bits 3j..3j+2: ANDed with the node's triangle word T (bits 3j..3j+cnt-1 set for a leaf in slot j)
+//               it gives the triangles of the hit leaves; a triangle's index is tri_base + its rank among the set bits of T
+//   perm[o][x]  bit j of x -> bit j^o: the hit inner children in traversal priority order for ray octant o (Ylitie et al. 2017)
+struct TravLut {
+    uint32_t exp3[256];
+    uint8_t  perm[8 * 256];
+};
+// every kernel that traverses calls this once, before any thread leaves (it ends in __syncthreads)
+__device__ __forceinline__ void trav_lut_init(TravLut& L) {
+    for (int m = threadIdx.x; m < 256; m += blockDim.x) {
+        uint32_t e = 0;
+        for (int j = 0; j < 8; j++)
+            if (m & (1 << j)) e |= 7u << (3 * j);
+        L.exp3[m] = e;
+    }
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) {
+        const int o = i >> 8, x = i & 255;
+        uint32_t r = 0;
+        for (int j = 0; j < 8; j++)
+            if (x & (1 << j)) r |= 1u << (j ^ o);
+        L.perm[i] = (uint8_t)r;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 struct TravRay {
     float ox, oy, oz, dx, dy, dz, tmin, tmax;
 };
@@ -98,17 +136,17 @@ __device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
 }
 
 // one child quad (4 of the 8 slots) of a node
-#define SPC_CHILD_TEST2(J)                                                                        \
+#define SPC_CHILD_TEST2(J, SLOT)                                                                  \
     {                                                                                             \
-        float lx = __fmaf_rn(byte_to_biased_float<J>(slox, bias), adjx, olx);                           \
-        float ly = __fmaf_rn(byte_to_biased_float<J>(sloy, bias), adjy, oly);                           \
-        float lz = __fmaf_rn(byte_to_biased_float<J>(sloz, bias), adjz, olz);                           \
-        float hx = __fmaf_rn(byte_to_biased_float<J>(shix, bias), adjx, ohx);                           \
-        float hy = __fmaf_rn(byte_to_biased_float<J>(shiy, bias), adjy, ohy);                           \
-        float hz = __fmaf_rn(byte_to_biased_float<J>(shiz, bias), adjz, ohz);                           \
+        float lx = __fmaf_rn(byte_to_biased_float<J>(slox, bias), adjx, olx);                     \
+        float ly = __fmaf_rn(byte_to_biased_float<J>(sloy, bias), adjy, oly);                     \
+        float lz = __fmaf_rn(byte_to_biased_float<J>(sloz, bias), adjz, olz);                     \
+        float hx = __fmaf_rn(byte_to_biased_float<J>(shix, bias), adjx, ohx);                     \
+        float hy = __fmaf_rn(byte_to_biased_float<J>(shiy, bias), adjy, ohy);                     \
+        float hz = __fmaf_rn(byte_to_biased_float<J>(shiz, bias), adjz, ohz);                     \
         float cmin = fmaxf(fmaxf(lx, ly), fmaxf(lz, s.tmin));                                     \
         float cmax = fminf(fminf(hx, hy), fminf(hz, s.tcur));                                     \
-        if (cmin <= cmax) hitmask |= byte_of(child_bits4, J) << byte_of(bit_index4, J);           \
+        if (cmin <= cmax) hit8 |= 1u << (SLOT);                                                   \
     }
 
 // One iteration: take the nearest pending child of the current node group (or fall back to its triangles), test
@@ -119,12 +157,12 @@ __device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
 // postponing").  The result does not depend on the order triangles are tested in (intersection contract above).
 template <bool ANYHIT, bool COUNT, bool POSTPONE = false>
 __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
-                                          int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris, int postpone_div = 5) {
+                                          int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris, uint32_t lut, int postpone_div = 5) {
     const uint32_t oct_inv = s.oct_inv;
     const uint32_t oct = 7u ^ oct_inv;
     const uint32_t bias = s.bias;
     const uint32_t sstride_b = (uint32_t)sstride * 8u;
-    uint2 tgroup;
+    uint32_t tnode, tmask, tbase, tT;   // current triangle group: node index, hit triangles (bits of T), first triangle, triangle word
     if (s.ngroup.y > 0x00ffffffu) {
         const uint32_t hits  = s.ngroup.y;
         const uint32_t imask = s.ngroup.y & 0xffu;
@@ -137,7 +175,8 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
         }
         const uint32_t slot = (bit - 24u) ^ oct_inv;
         const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
-        const float4*  np   = nodes + (size_t)(s.ngroup.x + rel) * 5;
+        tnode = s.ngroup.x + rel;
+        const float4*  np   = nodes + (size_t)tnode * 5;
         const float4 n0 = __ldg(np + 0);
         const float4 n1 = __ldg(np + 1);
         const float4 n2 = __ldg(np + 2);
@@ -160,56 +199,55 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
         const float olx = orgx - fabsf(adjx), ohx = orgx + fabsf(adjx);
         const float oly = orgy - fabsf(adjy), ohy = orgy + fabsf(adjy);
         const float olz = orgz - fabsf(adjz), ohz = orgz + fabsf(adjz);
-        const uint32_t oct_inv4 = oct_inv * 0x01010101u;
 
-        uint32_t hitmask = 0;
+        uint32_t hit8 = 0;
         {
-            const uint32_t meta4       = __float_as_uint(n1.z);
-            const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
-            const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-            const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
             const uint32_t qlox = __float_as_uint(n2.x), qloy = __float_as_uint(n2.z), qloz = __float_as_uint(n3.x);
             const uint32_t qhix = __float_as_uint(n3.z), qhiy = __float_as_uint(n4.x), qhiz = __float_as_uint(n4.z);
             const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
             const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
             const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
-            SPC_CHILD_TEST2(0) SPC_CHILD_TEST2(1) SPC_CHILD_TEST2(2) SPC_CHILD_TEST2(3)
+            SPC_CHILD_TEST2(0, 0) SPC_CHILD_TEST2(1, 1) SPC_CHILD_TEST2(2, 2) SPC_CHILD_TEST2(3, 3)
         }
         {
-            const uint32_t meta4       = __float_as_uint(n1.w);
-            const uint32_t is_inner4   = (meta4 & (meta4 << 1)) & 0x10101010u;
-            const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-            const uint32_t bit_index4  = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
             const uint32_t qlox = __float_as_uint(n2.y), qloy = __float_as_uint(n2.w), qloz = __float_as_uint(n3.y);
             const uint32_t qhix = __float_as_uint(n3.w), qhiy = __float_as_uint(n4.y), qhiz = __float_as_uint(n4.w);
             const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
             const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
             const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
-            SPC_CHILD_TEST2(0) SPC_CHILD_TEST2(1) SPC_CHILD_TEST2(2) SPC_CHILD_TEST2(3)
+            SPC_CHILD_TEST2(0, 4) SPC_CHILD_TEST2(1, 5) SPC_CHILD_TEST2(2, 6) SPC_CHILD_TEST2(3, 7)
         }
+        const uint32_t imask_new = e_im >> 24;
+        tT = __float_as_uint(n1.z);
+        tmask = tT & lds_u32(lut + 4u * hit8);
+        tbase = __float_as_uint(n1.y);
+        const uint32_t ph = lds_u8(lut + 1024u + (oct_inv << 8) + (hit8 & imask_new));
         s.ngroup.x = __float_as_uint(n1.x);
-        s.ngroup.y = (hitmask & 0xff000000u) | (e_im >> 24);
-        tgroup.x = __float_as_uint(n1.y);
-        tgroup.y = hitmask & 0x00ffffffu;
+        s.ngroup.y = (ph << 24) | imask_new;
     } else {
-        tgroup = s.ngroup;
+        // a parked triangle group: {node index, triangle mask}; its base and triangle word are re-read from the node
+        tnode = s.ngroup.x;
+        tmask = s.ngroup.y;
+        const float4 n1 = __ldg(nodes + (size_t)tnode * 5 + 1);
+        tbase = __float_as_uint(n1.y);
+        tT = __float_as_uint(n1.z);
         s.ngroup = make_uint2(0u, 0u);
     }
 
     const int tri_lanes = POSTPONE ? __popc(__activemask()) : 0;
-    while (tgroup.y != 0u) {
+    while (tmask != 0u) {
         if (POSTPONE && __popc(__activemask()) * postpone_div < tri_lanes) {
             // park the triangles; if no inner node is pending the pop below hands them straight back as the current group
+            const uint2 tgroup = make_uint2(tnode, tmask);
             if (s.sp < kSmStack) sm_push(s.sbase + s.sp * sstride_b, tgroup);
             else lstack[s.sp - kSmStack] = tgroup;
             s.sp++;
             break;
         }
-        const uint32_t ti = 31u - __clz(tgroup.y);
-        tgroup.y &= ~(1u << ti);
-        const float4* tp = tris + (size_t)(tgroup.x + ti) * 3;
+        const uint32_t tb = 31u - __clz(tmask);
+        tmask &= ~(1u << tb);
+        const uint32_t ti = __popc(tT & ~(0xffffffffu << tb));   // rank of this triangle among the node's triangles
+        const float4* tp = tris + (size_t)(tbase + ti) * 3;
         const float4 a = __ldg(tp + 0);
         const float4 b = __ldg(tp + 1);
         const float4 c = __ldg(tp + 2);
@@ -257,12 +295,13 @@ template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ bool traverse_bvh8(const float4* __restrict__ nodes,
                                               const float4* __restrict__ tris, const TravRay& r,
                                               bool cull_back, uint2* sstack, int sstride,
-                                              TravHit& hit, unsigned& cnt_nodes, unsigned& cnt_tris) {
+                                              TravHit& hit, unsigned& cnt_nodes, unsigned& cnt_tris, const TravLut& lut) {
     Trav s;
     trav_init(s, r);
     s.sbase = (uint32_t)__cvta_generic_to_shared(sstack);
+    const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(&lut);
     uint2 lstack[kLocStack];
-    while (!trav_step<ANYHIT, COUNT>(nodes, tris, s, cull_back, sstride, lstack, cnt_nodes, cnt_tris)) {}
+    while (!trav_step<ANYHIT, COUNT>(nodes, tris, s, cull_back, sstride, lstack, cnt_nodes, cnt_tris, lut_addr)) {}
     if (ANYHIT) return s.best_prim >= 0;
     hit.t = s.best_prim >= 0 ? s.tcur : 0.0f;
     hit.u = s.best_u;
