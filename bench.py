@@ -96,6 +96,29 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Keep this rank's host threads and its pinned buffers on the NUMA node its GPU hangs off (the host-buffer `e2e` leg moves 72 GB/s
+    per rank through host memory; unbound ranks of a multi-GPU run land on one socket).  Best effort: returns a note for `config`."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bdf = out[-12:] if len(out) >= 12 else out          # nvidia-smi prints an 8-digit domain: keep dddd:bb:dd.f
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa: node %d has no usable cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "numa: bound to node %d (%d cpus)" % (node, len(cpus))
+    except Exception as ex:   # topology files absent (VM without NUMA information): leave the affinity alone
+        return "numa: not bound (%s)" % type(ex).__name__
+
+
 def cpu_trace_sample(pkg, orc, scene, sets, n_sample, threads):
     """oracle port on the host cores over the first n_sample rays of each set; returns (Mrays/s, seconds)"""
     osc = orc.Scene(pkg, scene)
@@ -245,12 +268,18 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     lr_.render(2 * lanes)
     torch.cuda.synchronize()
     env.barrier()
-    l0 = lr_.launch_count()
-    t0 = time.perf_counter()
-    lr_.render(args.render_frames)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    launches = lr_.launch_count() - l0
+    # three timed segments of `render_frames` frames each; the figure reported is the MEDIAN segment (the GPU boxes are VMs: an
+    # occasional host hiccup stretches one segment by tens of per cent, tests/quick_variance.sh), all three are listed
+    seg_s, launches = [], 0
+    for _ in range(3):
+        l0 = lr_.launch_count()
+        t0 = time.perf_counter()
+        lr_.render(args.render_frames)
+        torch.cuda.synchronize()
+        seg_s.append(time.perf_counter() - t0)
+        launches = lr_.launch_count() - l0
+        env.barrier()
+    dt = sorted(seg_s)[1]
     r = lr_
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -268,7 +297,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
                        "light trace 1000x100 paths per frame, %d frame lanes per GPU" % (K, K_light, scene_name, lanes),
            "samples_per_s": w * h * args.render_frames * world / dt_max, "ms_per_frame": dt_max / args.render_frames * 1e3, "frames": args.render_frames,
            "preprocess_s": pre_s, "train_paths": st["train_paths"], "loss_first": st["loss_first"], "loss_last": st["loss_last"],
-           "kernel_launches": int(launches), "accum_allreduce_ms": e0.elapsed_time(e1) if world > 1 else 0.0, "image_mean": mean}
+           "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_s], "kernel_launches": int(launches), "accum_allreduce_ms": e0.elapsed_time(e1) if world > 1 else 0.0, "image_mean": mean}
     if rank == 0:
         # CPU baseline of the same pass: the oracle eye pass on a 160x90 image with the same trained state, all host threads
         try:
@@ -330,6 +359,7 @@ def main():
     import spcbpt_loader
     pkg = spcbpt_loader.load()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU path"
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "numa: single rank, not bound"
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -454,7 +484,7 @@ def main():
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": 3 * n, "bvh_nodes": st["n_nodes"], "bvh_bytes": st["bytes_nodes"] + st["bytes_triangles"],
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": 3 * n, "host_affinity": numa_note, "bvh_nodes": st["n_nodes"], "bvh_bytes": st["bytes_nodes"] + st["bytes_triangles"],
                        "l2_policy": "ray inputs (3 x %d MiB per step) exceed L2; the %d MB BVH %s" % (
                            n * 32 >> 20, (st["bytes_nodes"] + st["bytes_triangles"]) // 1000000,
                            "is L2-resident by design (SURVEY.md section 7 hard parts)" if st["bytes_nodes"] + st["bytes_triangles"] < 100e6 else "does not fit the 126 MB L2"),

@@ -123,6 +123,8 @@ void spc_destroy(spc_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->c.device);
     if (ctx->c.h_pinned) cudaFreeHost(ctx->c.h_pinned);
+    for (cudaEvent_t ev : ctx->c.eye_events)
+        if (ev) cudaEventDestroy(ev);
     delete ctx;
 }
 

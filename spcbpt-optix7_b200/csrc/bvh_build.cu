@@ -21,7 +21,8 @@ namespace spc {
 
 namespace {
 
-constexpr float kCostPrim = 0.3f;
+__device__ float g_cost_prim = 0.3f;   // SAH cost of one triangle test relative to one node step (SPC_BVH_COST_PRIM overrides)
+#define kCostPrim g_cost_prim
 constexpr float kCostNode = 1.0f;
 constexpr int   kMaxLeafTris = 3;
 
@@ -577,6 +578,10 @@ void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
     SPC_CUDA(cudaEventCreate(&ev0));
     SPC_CUDA(cudaEventCreate(&ev1));
     SPC_CUDA(cudaEventRecord(ev0, st));
+    {
+        static const float cost_prim = []() { const char* e = getenv("SPC_BVH_COST_PRIM"); return e ? (float)atof(e) : 0.3f; }();
+        SPC_CUDA(cudaMemcpyToSymbolAsync(g_cost_prim, &cost_prim, sizeof(float), 0, cudaMemcpyHostToDevice, st));
+    }
     BuildArena arena;   // inside the timed region: build_ms includes the scratch allocation
     g_arena = &arena;
     arena.reserve((size_t)n * 420 + (64u << 20));

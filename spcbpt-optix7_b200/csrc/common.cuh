@@ -184,6 +184,7 @@ struct Context {
     int*          dbg_first_prim = nullptr;    // optional device outputs of the eye pass (parity dumps)
     int*          dbg_first_label = nullptr;
     int*          h_pinned = nullptr;          // small pinned staging block for counter read-backs
+    cudaEvent_t   eye_events[8] = {};          // lagged queue-size read-backs of the eye pass (render.cu)
     DevBuf<spc_vertex> pretrace_scratch;       // per-lane eye-vertex buffers of the training tracer
     TrainBuffers  train;
     LvcBuffers    bins_tmp;                    // ordered-binning scratch of getQ / sample_reweight

@@ -638,7 +638,15 @@ void launch_eye_pass(Context& c, int width, int height) {
     k_eye_init<<<(nP + 255) / 256, 256, 0, st>>>(fr, a, nP);
     c.launches++;
     const int grid_cap = c.sm_count * 16;
-    int64_t n_max = nP;   // host-side upper bound on the live paths (refreshed by the occasional read-back)
+    int64_t n_max = nP;   // host-side upper bound on the live paths (refreshed by the lagged read-backs)
+    // The size of every bounce's queue is copied to pinned memory behind the bounce, and the host looks at it kLag bounces later:
+    // it stops when a queue was empty and shrinks the grids, but it never drains the stream (a full synchronisation every 4th
+    // bounce left the GPU idle for a host round trip each time and made the frame time follow the host's scheduling noise).
+    constexpr int kLag = 3, kRing = 8;
+    if (!c.eye_events[0])
+        for (int k = 0; k < kRing; k++)
+            SPC_CUDA(cudaEventCreateWithFlags(&c.eye_events[k], cudaEventDisableTiming | (getenv("SPC_BLOCKING_SYNC") ? cudaEventBlockingSync : 0)));
+    int* h_ring = c.h_pinned + 16;
     // loop of raygen.cu:357-421: a path is traced while !done && depth <= max_depth, i.e. bounces 0..max_depth
     for (int b = 0; b <= fr.max_depth; b++) {
         a.bounce = b;
@@ -660,12 +668,15 @@ void launch_eye_pass(Context& c, int width, int height) {
         k_eye_gather<<<g1, 128, 0, st>>>(fr, a);
         c.launches += 4;
         SPC_CUDA(cudaGetLastError());
-        // every 4th bounce: read the next queue size back to shrink the grids / stop early
-        if ((b & 3) == 3 && b < fr.max_depth) {
-            SPC_CUDA(cudaMemcpyAsync(c.h_pinned, e.counts.p + b + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-            SPC_CUDA(cudaStreamSynchronize(st));
-            n_max = c.h_pinned[0];
-            if (n_max == 0) break;
+        if (b < fr.max_depth) {
+            SPC_CUDA(cudaMemcpyAsync(h_ring + (b % kRing), e.counts.p + b + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            SPC_CUDA(cudaEventRecord(c.eye_events[b % kRing], st));
+            if (b >= kLag) {
+                const int pb = b - kLag;   // live paths entering bounce pb + 1: an upper bound for every later bounce
+                SPC_CUDA(cudaEventSynchronize(c.eye_events[pb % kRing]));
+                n_max = h_ring[pb % kRing];
+                if (n_max == 0) break;
+            }
         }
     }
     k_accumulate<<<(nP + 255) / 256, 256, 0, st>>>(fr, e.res.p, nP);
