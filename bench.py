@@ -96,6 +96,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+ORIG_AFFINITY = None
+
+
+def restore_affinity():
+    """the CPU baseline legs use every host core"""
+    if ORIG_AFFINITY:
+        os.sched_setaffinity(0, ORIG_AFFINITY)
+
+
 def bind_to_gpu_numa_node(gpu_index):
     """Keep this rank's host threads and its pinned buffers on the NUMA node its GPU hangs off (the host-buffer `e2e` leg moves 72 GB/s
     per rank through host memory; unbound ranks of a multi-GPU run land on one socket).  Best effort: returns a note for `config`."""
@@ -110,7 +119,9 @@ def bind_to_gpu_numa_node(gpu_index):
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
+        global ORIG_AFFINITY
+        ORIG_AFFINITY = os.sched_getaffinity(0)
+        cpus &= ORIG_AFFINITY
         if not cpus:
             return "numa: node %d has no usable cpu" % node
         os.sched_setaffinity(0, cpus)
@@ -302,6 +313,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
         # CPU baseline of the same pass: the oracle eye pass on a 160x90 image with the same trained state, all host threads
         try:
             import spcbpt_loader
+            restore_affinity()
             orc = spcbpt_loader.load_oracle()
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             from harness import HostFrame
@@ -473,6 +485,7 @@ def main():
             except Exception:
                 traffic = None
         # cpu_baseline: oracle port on all host cores over a bounded sample of the same ray sets
+        restore_affinity()
         orc = spcbpt_loader.load_oracle()
         threads = os.cpu_count() or 1
         ns = min(args.cpu_sample, n)
