@@ -81,15 +81,16 @@ k_trace_occlusion(const float4* __restrict__ nodes, const float4* __restrict__ t
 // idle lanes claim new rays with one warp-aggregated atomicAdd, so lanes stay busy until the batch is drained.
 // The grid is sized to the resident capacity of the GPU (SM count x blocks per SM), not to the ray count.
 // ---------------------------------------------------------------------------------------------
-template <bool ANYHIT>
+template <bool ANYHIT, bool COUNT = false>
 __global__ void __launch_bounds__(kTraceBlock, SPC_PERSIST_MIN_BLOCKS)
 k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ rays,
                 const int* __restrict__ n_dev, int mult, int64_t n_host, int cull_back, int fetch_threshold, int postpone_div,
-                float4* __restrict__ hits, uint8_t* __restrict__ visible, unsigned long long* __restrict__ counter) {
+                float4* __restrict__ hits, uint8_t* __restrict__ visible, unsigned long long* __restrict__ counter,
+                unsigned long long* __restrict__ visit_counters = nullptr) {
     __shared__ uint2 s_stack[kSmStack * kTraceBlock];
     __shared__ TravLut s_lut;
     trav_lut_init(s_lut);
-    uint2 lstack[kLocStack + kMaxBvhDepth];   // triangle postponing parks at most one extra group per tree level
+    uint2 lstack[kLocStack + 2 * kMaxBvhDepth];   // per tree level: one node group, one parked and one postponed triangle group
     const int64_t n = n_dev ? (int64_t)__ldg(n_dev) * mult : n_host;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -129,7 +130,7 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
             if (exhausted && idle == 0xffffffffu) break;
         }
         if (ray >= 0) {
-            if (trav_step<ANYHIT, false, true>(nodes, tris, s, cull_back != 0, kTraceBlock, lstack, cn, ct, lut, postpone_div)) {
+            if (trav_step2<ANYHIT, COUNT>(nodes, tris, s, cull_back != 0, kTraceBlock, lstack, lut, postpone_div, cn, ct)) {
                 if (ANYHIT) {
                     visible[ray] = s.best_prim >= 0 ? 0 : 1;
                 } else {
@@ -140,6 +141,16 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
             }
         }
     }
+    if (COUNT) {   // the instrumented twin: nodes visited / triangles tested by exactly this traversal order
+        for (int o = 16; o > 0; o >>= 1) {
+            cn += __shfl_xor_sync(0xffffffffu, cn, o);
+            ct += __shfl_xor_sync(0xffffffffu, ct, o);
+        }
+        if (lane == 0) {
+            atomicAdd(visit_counters + 0, (unsigned long long)cn);
+            atomicAdd(visit_counters + 1, (unsigned long long)ct);
+        }
+    }
 }
 
 static int trace_env(const char* name, int dflt) {
@@ -148,7 +159,8 @@ static int trace_env(const char* name, int dflt) {
 }
 
 template <bool ANYHIT>
-static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits, uint8_t* visible) {
+static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits, uint8_t* visible,
+                           unsigned long long* visit_counters = nullptr) {
     static int blocks_per_sm = 0, fetch_t = 0, postpone_div = 5;
     if (!blocks_per_sm) {
         SPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_persist<ANYHIT>, kTraceBlock, 0));
@@ -166,8 +178,13 @@ static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, 
     const int bps = ctx.trace_blocks_per_sm > 0 ? std::min(ctx.trace_blocks_per_sm, blocks_per_sm) : blocks_per_sm;
     const int64_t cap = (int64_t)ctx.sm_count * bps;
     if (blocks > cap) blocks = cap;
-    k_trace_persist<ANYHIT><<<(unsigned)blocks, kTraceBlock, 0, ctx.stream>>>(ctx.bvh.nodes.p, ctx.bvh.tris.p, (const float4*)rays, n_dev, mult, n_max,
-                                                                           (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0, fetch_t, postpone_div, (float4*)hits, visible, counter);
+    const int cull = (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0;
+    if (visit_counters)
+        k_trace_persist<ANYHIT, true><<<(unsigned)blocks, kTraceBlock, 0, ctx.stream>>>(ctx.bvh.nodes.p, ctx.bvh.tris.p, (const float4*)rays, n_dev, mult, n_max, cull,
+                                                                                       fetch_t, postpone_div, (float4*)hits, visible, counter, visit_counters);
+    else
+        k_trace_persist<ANYHIT, false><<<(unsigned)blocks, kTraceBlock, 0, ctx.stream>>>(ctx.bvh.nodes.p, ctx.bvh.tris.p, (const float4*)rays, n_dev, mult, n_max, cull,
+                                                                                        fetch_t, postpone_div, (float4*)hits, visible, counter, nullptr);
     SPC_CUDA(cudaGetLastError());
     ctx.launches++;
 }
@@ -256,8 +273,8 @@ void launch_trace_closest(Context& ctx, const spc_ray* rays, int64_t n, int flag
     const int64_t blocks = (n + kTraceBlock - 1) / kTraceBlock;
     SPC_REQUIRE(blocks < 0x7fffffffLL, SPC_ERR_INVALID, "ray batch too large: %lld", (long long)n);
     const int cull = (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0;
-    if (!counters && use_persist()) {
-        launch_persist<false>(ctx, rays, nullptr, 1, n, flags, hits, nullptr);
+    if (use_persist()) {   // the counted variant is the same kernel with two visit counters (the instrumented twin of the roofline)
+        launch_persist<false>(ctx, rays, nullptr, 1, n, flags, hits, nullptr, counters);
         return;
     }
     if (counters)
@@ -275,8 +292,8 @@ void launch_trace_occlusion(Context& ctx, const spc_ray* rays, int64_t n, uint8_
     if (n <= 0) return;
     const int64_t blocks = (n + kTraceBlock - 1) / kTraceBlock;
     SPC_REQUIRE(blocks < 0x7fffffffLL, SPC_ERR_INVALID, "ray batch too large: %lld", (long long)n);
-    if (!counters && use_persist()) {
-        launch_persist<true>(ctx, rays, nullptr, 1, n, 0, nullptr, visible);
+    if (use_persist()) {
+        launch_persist<true>(ctx, rays, nullptr, 1, n, 0, nullptr, visible, counters);
         return;
     }
     if (counters)

@@ -155,99 +155,116 @@ __device__ __forceinline__ void trav_init(Trav& s, const TravRay& r) {
 // POSTPONE (wavefront kernels): when fewer than 1/5 of the lanes that entered the triangle loop are still in it, the stragglers
 // push their remaining triangles back on the stack and rejoin the warp for the next node step (Ylitie et al. 2017, "triangle
 // postponing").  The result does not depend on the order triangles are tested in (intersection contract above).
-template <bool ANYHIT, bool COUNT, bool POSTPONE = false>
-__device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
-                                          int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris, uint32_t lut, int postpone_div = 5) {
+// current triangle group: node index, hit triangles (bits of the node's triangle word), first triangle, triangle word
+struct TriGroup {
+    uint32_t node, mask, base, T;
+};
+
+__device__ __forceinline__ void trav_push(Trav& s, uint32_t sstride_b, uint2* lstack, uint2 v) {
+    if (s.sp < kSmStack) sm_push(s.sbase + s.sp * sstride_b, v);
+    else lstack[s.sp - kSmStack] = v;
+    s.sp++;
+}
+__device__ __forceinline__ uint2 trav_pop(Trav& s, uint32_t sstride_b, uint2* lstack) {
+    s.sp--;
+    return (s.sp < kSmStack) ? sm_pop(s.sbase + s.sp * sstride_b) : lstack[s.sp - kSmStack];
+}
+
+// Node step (requires s.ngroup.y > 0x00ffffff): take the nearest pending child of the current node group, test its 8 children;
+// s.ngroup becomes that node's hit inner children, g the triangles of its hit leaves.
+template <bool COUNT>
+__device__ __forceinline__ void trav_node(const float4* __restrict__ nodes, Trav& s, uint32_t sstride_b, uint2* lstack, uint32_t lut, TriGroup& g,
+                                          unsigned& cnt_nodes) {
     const uint32_t oct_inv = s.oct_inv;
     const uint32_t oct = 7u ^ oct_inv;
     const uint32_t bias = s.bias;
-    const uint32_t sstride_b = (uint32_t)sstride * 8u;
-    uint32_t tnode, tmask, tbase, tT;   // current triangle group: node index, hit triangles (bits of T), first triangle, triangle word
+    const uint32_t hits  = s.ngroup.y;
+    const uint32_t imask = s.ngroup.y & 0xffu;
+    const uint32_t bit   = 31u - __clz(hits);
+    s.ngroup.y &= ~(1u << bit);
     if (s.ngroup.y > 0x00ffffffu) {
-        const uint32_t hits  = s.ngroup.y;
-        const uint32_t imask = s.ngroup.y & 0xffu;
-        const uint32_t bit   = 31u - __clz(hits);
-        s.ngroup.y &= ~(1u << bit);
-        if (s.ngroup.y > 0x00ffffffu) {
-            if (s.sp < kSmStack) sm_push(s.sbase + s.sp * sstride_b, s.ngroup);
-            else lstack[s.sp - kSmStack] = s.ngroup;
-            s.sp++;
-        }
-        const uint32_t slot = (bit - 24u) ^ oct_inv;
-        const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
-        tnode = s.ngroup.x + rel;
-        const float4*  np   = nodes + (size_t)tnode * 5;
-        const float4 n0 = __ldg(np + 0);
-        const float4 n1 = __ldg(np + 1);
-        const float4 n2 = __ldg(np + 2);
-        const float4 n3 = __ldg(np + 3);
-        const float4 n4 = __ldg(np + 4);
-        if (COUNT) cnt_nodes++;
-
-        const uint32_t e_im = __float_as_uint(n0.w);
-        // Child plane q (a byte) lies at t = q*step*id + (origin - o)*id.  The byte arrives as B = 2^23 + 256 q, so with
-        // adj = step*id/256 the plane is t = B*adj + (org - 2^23*adj): one FFMA per plane.  Folding the bias costs at most
-        // |adj|/2 of rounding in the constant (1/512 of a quantisation step, when the node is near the ray origin); entry planes
-        // are moved one |adj| (1/256 step) earlier and exit planes one |adj| later, which more than covers it -- the box test
-        // stays conservative and the hit set (decided by the triangle contract alone) is unchanged.
-        const float adjx = __uint_as_float((e_im & 0xffu) << 23) * s.idx * 0.00390625f;
-        const float adjy = __uint_as_float(((e_im >> 8) & 0xffu) << 23) * s.idy * 0.00390625f;
-        const float adjz = __uint_as_float(((e_im >> 16) & 0xffu) << 23) * s.idz * 0.00390625f;
-        const float orgx = __fmaf_rn(-8388608.0f, adjx, (n0.x - s.ox) * s.idx);
-        const float orgy = __fmaf_rn(-8388608.0f, adjy, (n0.y - s.oy) * s.idy);
-        const float orgz = __fmaf_rn(-8388608.0f, adjz, (n0.z - s.oz) * s.idz);
-        const float olx = orgx - fabsf(adjx), ohx = orgx + fabsf(adjx);
-        const float oly = orgy - fabsf(adjy), ohy = orgy + fabsf(adjy);
-        const float olz = orgz - fabsf(adjz), ohz = orgz + fabsf(adjz);
-
-        uint32_t hit8 = 0;
-        {
-            const uint32_t qlox = __float_as_uint(n2.x), qloy = __float_as_uint(n2.z), qloz = __float_as_uint(n3.x);
-            const uint32_t qhix = __float_as_uint(n3.z), qhiy = __float_as_uint(n4.x), qhiz = __float_as_uint(n4.z);
-            const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
-            const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
-            const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
-            SPC_CHILD_TEST2(0, 0) SPC_CHILD_TEST2(1, 1) SPC_CHILD_TEST2(2, 2) SPC_CHILD_TEST2(3, 3)
-        }
-        {
-            const uint32_t qlox = __float_as_uint(n2.y), qloy = __float_as_uint(n2.w), qloz = __float_as_uint(n3.y);
-            const uint32_t qhix = __float_as_uint(n3.w), qhiy = __float_as_uint(n4.y), qhiz = __float_as_uint(n4.w);
-            const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
-            const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
-            const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
-            SPC_CHILD_TEST2(0, 4) SPC_CHILD_TEST2(1, 5) SPC_CHILD_TEST2(2, 6) SPC_CHILD_TEST2(3, 7)
-        }
-        const uint32_t imask_new = e_im >> 24;
-        tT = __float_as_uint(n1.z);
-        tmask = tT & lds_u32(lut + 4u * hit8);
-        tbase = __float_as_uint(n1.y);
-        const uint32_t ph = lds_u8(lut + 1024u + (oct_inv << 8) + (hit8 & imask_new));
-        s.ngroup.x = __float_as_uint(n1.x);
-        s.ngroup.y = (ph << 24) | imask_new;
-    } else {
-        // a parked triangle group: {node index, triangle mask}; its base and triangle word are re-read from the node
-        tnode = s.ngroup.x;
-        tmask = s.ngroup.y;
-        const float4 n1 = __ldg(nodes + (size_t)tnode * 5 + 1);
-        tbase = __float_as_uint(n1.y);
-        tT = __float_as_uint(n1.z);
-        s.ngroup = make_uint2(0u, 0u);
+        trav_push(s, sstride_b, lstack, s.ngroup);
     }
+    const uint32_t slot = (bit - 24u) ^ oct_inv;
+    const uint32_t rel  = __popc(imask & ~(0xffffffffu << slot));
+    g.node = s.ngroup.x + rel;
+    const float4*  np   = nodes + (size_t)g.node * 5;
+    const float4 n0 = __ldg(np + 0);
+    const float4 n1 = __ldg(np + 1);
+    const float4 n2 = __ldg(np + 2);
+    const float4 n3 = __ldg(np + 3);
+    const float4 n4 = __ldg(np + 4);
+    if (COUNT) cnt_nodes++;
 
+    const uint32_t e_im = __float_as_uint(n0.w);
+    // Child plane q (a byte) lies at t = q*step*id + (origin - o)*id.  The byte arrives as B = 2^23 + 256 q, so with
+    // adj = step*id/256 the plane is t = B*adj + (org - 2^23*adj): one FFMA per plane.  Folding the bias costs at most
+    // |adj|/2 of rounding in the constant (1/512 of a quantisation step, when the node is near the ray origin); entry planes
+    // are moved one |adj| (1/256 step) earlier and exit planes one |adj| later, which more than covers it -- the box test
+    // stays conservative and the hit set (decided by the triangle contract alone) is unchanged.
+    const float adjx = __uint_as_float((e_im & 0xffu) << 23) * s.idx * 0.00390625f;
+    const float adjy = __uint_as_float(((e_im >> 8) & 0xffu) << 23) * s.idy * 0.00390625f;
+    const float adjz = __uint_as_float(((e_im >> 16) & 0xffu) << 23) * s.idz * 0.00390625f;
+    const float orgx = __fmaf_rn(-8388608.0f, adjx, (n0.x - s.ox) * s.idx);
+    const float orgy = __fmaf_rn(-8388608.0f, adjy, (n0.y - s.oy) * s.idy);
+    const float orgz = __fmaf_rn(-8388608.0f, adjz, (n0.z - s.oz) * s.idz);
+    const float olx = orgx - fabsf(adjx), ohx = orgx + fabsf(adjx);
+    const float oly = orgy - fabsf(adjy), ohy = orgy + fabsf(adjy);
+    const float olz = orgz - fabsf(adjz), ohz = orgz + fabsf(adjz);
+
+    uint32_t hit8 = 0;
+    {
+        const uint32_t qlox = __float_as_uint(n2.x), qloy = __float_as_uint(n2.z), qloz = __float_as_uint(n3.x);
+        const uint32_t qhix = __float_as_uint(n3.z), qhiy = __float_as_uint(n4.x), qhiz = __float_as_uint(n4.z);
+        const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
+        const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
+        const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
+        SPC_CHILD_TEST2(0, 0) SPC_CHILD_TEST2(1, 1) SPC_CHILD_TEST2(2, 2) SPC_CHILD_TEST2(3, 3)
+    }
+    {
+        const uint32_t qlox = __float_as_uint(n2.y), qloy = __float_as_uint(n2.w), qloz = __float_as_uint(n3.y);
+        const uint32_t qhix = __float_as_uint(n3.w), qhiy = __float_as_uint(n4.y), qhiz = __float_as_uint(n4.w);
+        const uint32_t slox = (oct & 1u) ? qhix : qlox, shix = (oct & 1u) ? qlox : qhix;
+        const uint32_t sloy = (oct & 2u) ? qhiy : qloy, shiy = (oct & 2u) ? qloy : qhiy;
+        const uint32_t sloz = (oct & 4u) ? qhiz : qloz, shiz = (oct & 4u) ? qloz : qhiz;
+        SPC_CHILD_TEST2(0, 4) SPC_CHILD_TEST2(1, 5) SPC_CHILD_TEST2(2, 6) SPC_CHILD_TEST2(3, 7)
+    }
+    const uint32_t imask_new = e_im >> 24;
+    g.T = __float_as_uint(n1.z);
+    g.mask = g.T & lds_u32(lut + 4u * hit8);
+    g.base = __float_as_uint(n1.y);
+    const uint32_t ph = lds_u8(lut + 1024u + (oct_inv << 8) + (hit8 & imask_new));
+    s.ngroup.x = __float_as_uint(n1.x);
+    s.ngroup.y = (ph << 24) | imask_new;
+}
+
+// a parked triangle group {node index, triangle mask} sits in s.ngroup: its base and triangle word are re-read from the node
+__device__ __forceinline__ void trav_parked(const float4* __restrict__ nodes, Trav& s, TriGroup& g) {
+    g.node = s.ngroup.x;
+    g.mask = s.ngroup.y;
+    const float4 n1 = __ldg(nodes + (size_t)g.node * 5 + 1);
+    g.base = __float_as_uint(n1.y);
+    g.T = __float_as_uint(n1.z);
+    s.ngroup = make_uint2(0u, 0u);
+}
+
+// Triangles of g under the intersection contract.  Returns true when ANYHIT found an occluder (s.best_prim >= 0).
+// POSTPONE (wavefront kernels): when fewer than 1/postpone_div of the lanes that entered the loop are still in it, the stragglers
+// park their remaining triangles on the stack and rejoin the warp (Ylitie et al. 2017, "triangle postponing").  The result does not
+// depend on the order triangles are tested in.
+template <bool ANYHIT, bool COUNT, bool POSTPONE>
+__device__ __forceinline__ bool trav_tris(const float4* __restrict__ tris, Trav& s, TriGroup& g, bool cull_back, uint32_t sstride_b, uint2* lstack,
+                                          unsigned& cnt_tris, int postpone_div) {
     const int tri_lanes = POSTPONE ? __popc(__activemask()) : 0;
-    while (tmask != 0u) {
+    while (g.mask != 0u) {
         if (POSTPONE && __popc(__activemask()) * postpone_div < tri_lanes) {
-            // park the triangles; if no inner node is pending the pop below hands them straight back as the current group
-            const uint2 tgroup = make_uint2(tnode, tmask);
-            if (s.sp < kSmStack) sm_push(s.sbase + s.sp * sstride_b, tgroup);
-            else lstack[s.sp - kSmStack] = tgroup;
-            s.sp++;
+            trav_push(s, sstride_b, lstack, make_uint2(g.node, g.mask));
             break;
         }
-        const uint32_t tb = 31u - __clz(tmask);
-        tmask &= ~(1u << tb);
-        const uint32_t ti = __popc(tT & ~(0xffffffffu << tb));   // rank of this triangle among the node's triangles
-        const float4* tp = tris + (size_t)(tbase + ti) * 3;
+        const uint32_t tb = 31u - __clz(g.mask);
+        g.mask &= ~(1u << tb);
+        const uint32_t ti = __popc(g.T & ~(0xffffffffu << tb));   // rank of this triangle among the node's triangles
+        const float4* tp = tris + (size_t)(g.base + ti) * 3;
         const float4 a = __ldg(tp + 0);
         const float4 b = __ldg(tp + 1);
         const float4 c = __ldg(tp + 2);
@@ -282,13 +299,55 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
             }
         }
     }
+    return false;
+}
 
+// One iteration: node step (or a parked triangle group), the triangles of the hit leaves, pop when the group is exhausted.
+// Returns true when the ray is finished (stack empty, or first hit for ANYHIT -- then s.best_prim >= 0).
+template <bool ANYHIT, bool COUNT, bool POSTPONE = false>
+__device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
+                                          int sstride, uint2* lstack, unsigned& cnt_nodes, unsigned& cnt_tris, uint32_t lut, int postpone_div = 5) {
+    const uint32_t sstride_b = (uint32_t)sstride * 8u;
+    TriGroup g;
+    if (s.ngroup.y > 0x00ffffffu) trav_node<COUNT>(nodes, s, sstride_b, lstack, lut, g, cnt_nodes);
+    else trav_parked(nodes, s, g);
+    if (trav_tris<ANYHIT, COUNT, POSTPONE>(tris, s, g, cull_back, sstride_b, lstack, cnt_tris, postpone_div)) return true;
     if (s.ngroup.y <= 0x00ffffffu) {
         if (s.sp == 0) return true;
-        s.sp--;
-        s.ngroup = (s.sp < kSmStack) ? sm_pop(s.sbase + s.sp * sstride_b) : lstack[s.sp - kSmStack];
+        s.ngroup = trav_pop(s, sstride_b, lstack);
     }
     return false;
+}
+
+// Two node steps per triangle phase (persistent wavefront kernels).  The triangle loop is where the warp is emptiest (9 of 32 lanes:
+// only the lanes whose node had hit leaves take part, profiles/r1e_summary.md); collecting the leaves of two consecutive node steps
+// before intersecting roughly doubles its occupancy and halves the number of passes.  A lane that gets triangles from both steps
+// parks the older group on its stack.  Order of node visits and triangle tests changes, results do not (intersection contract).
+template <bool ANYHIT, bool COUNT>
+__device__ __forceinline__ bool trav_step2(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
+                                           int sstride, uint2* lstack, uint32_t lut, int postpone_div, unsigned& cn, unsigned& ct) {
+    const uint32_t sstride_b = (uint32_t)sstride * 8u;
+    // here s.ngroup.y == 0 means "no group" (a node group whose inner hits are used up keeps its imask in y: normalised below)
+    if (s.ngroup.y == 0u) s.ngroup = trav_pop(s, sstride_b, lstack);   // sp > 0: otherwise the previous call returned true
+    TriGroup p;
+    if (s.ngroup.y > 0x00ffffffu) {
+        trav_node<COUNT>(nodes, s, sstride_b, lstack, lut, p, cn);
+        if (s.ngroup.y <= 0x00ffffffu) s.ngroup.y = 0u;
+    } else {
+        trav_parked(nodes, s, p);
+    }
+    if (s.ngroup.y == 0u && s.sp > 0) s.ngroup = trav_pop(s, sstride_b, lstack);
+    if (s.ngroup.y > 0x00ffffffu) {   // (a parked triangle group popped here waits for the next call)
+        TriGroup q;
+        trav_node<COUNT>(nodes, s, sstride_b, lstack, lut, q, cn);
+        if (s.ngroup.y <= 0x00ffffffu) s.ngroup.y = 0u;
+        if (q.mask != 0u) {
+            if (p.mask != 0u) trav_push(s, sstride_b, lstack, make_uint2(p.node, p.mask));
+            p = q;
+        }
+    }
+    if (trav_tris<ANYHIT, COUNT, true>(tris, s, p, cull_back, sstride_b, lstack, ct, postpone_div)) return true;
+    return s.ngroup.y == 0u && s.sp == 0;
 }
 
 template <bool ANYHIT, bool COUNT>
