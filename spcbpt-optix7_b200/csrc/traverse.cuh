@@ -319,10 +319,13 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
     return false;
 }
 
-// Two node steps per triangle phase (persistent wavefront kernels).  The triangle loop is where the warp is emptiest (9 of 32 lanes:
+// SPC_NODE_STEPS node steps per triangle phase (persistent wavefront kernels).  The triangle loop is where the warp is emptiest (9 of 32 lanes:
 // only the lanes whose node had hit leaves take part, profiles/r1e_summary.md); collecting the leaves of two consecutive node steps
 // before intersecting roughly doubles its occupancy and halves the number of passes.  A lane that gets triangles from both steps
 // parks the older group on its stack.  Order of node visits and triangle tests changes, results do not (intersection contract).
+#ifndef SPC_NODE_STEPS
+#define SPC_NODE_STEPS 3   // node steps per triangle phase: 1 -> 2 -> 3 -> 4 gave 3776 / 4057 / 4150 / 4153 Mrays/s on bench.py (profiles/r1e_summary.md)
+#endif
 template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ bool trav_step2(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
                                            int sstride, uint2* lstack, uint32_t lut, int postpone_div, unsigned& cn, unsigned& ct) {
@@ -336,14 +339,17 @@ __device__ __forceinline__ bool trav_step2(const float4* __restrict__ nodes, con
     } else {
         trav_parked(nodes, s, p);
     }
-    if (s.ngroup.y == 0u && s.sp > 0) s.ngroup = trav_pop(s, sstride_b, lstack);
-    if (s.ngroup.y > 0x00ffffffu) {   // (a parked triangle group popped here waits for the next call)
-        TriGroup q;
-        trav_node<COUNT>(nodes, s, sstride_b, lstack, lut, q, cn);
-        if (s.ngroup.y <= 0x00ffffffu) s.ngroup.y = 0u;
-        if (q.mask != 0u) {
-            if (p.mask != 0u) trav_push(s, sstride_b, lstack, make_uint2(p.node, p.mask));
-            p = q;
+#pragma unroll
+    for (int k = 1; k < SPC_NODE_STEPS; k++) {
+        if (s.ngroup.y == 0u && s.sp > 0) s.ngroup = trav_pop(s, sstride_b, lstack);
+        if (s.ngroup.y > 0x00ffffffu) {   // (a parked triangle group popped here waits for the next call)
+            TriGroup q;
+            trav_node<COUNT>(nodes, s, sstride_b, lstack, lut, q, cn);
+            if (s.ngroup.y <= 0x00ffffffu) s.ngroup.y = 0u;
+            if (q.mask != 0u) {
+                if (p.mask != 0u) trav_push(s, sstride_b, lstack, make_uint2(p.node, p.mask));
+                p = q;
+            }
         }
     }
     if (trav_tris<ANYHIT, COUNT, true>(tris, s, p, cull_back, sstride_b, lstack, ct, postpone_div)) return true;
