@@ -257,8 +257,7 @@ __global__ void __launch_bounds__(128) k_eye_shade(const DevFrame fr, const EyeA
                     }
                 } else {
                     SurfaceOut so;
-                    surface_hit(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, hit.x, ray_direction, false, seed, mid, so, last_x);
-                    if (a.bounce == 0 && a.first_label) a.first_label[pix] = mid.subspaceId;
+                    surface_hit(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, hit.x, ray_direction, false, seed, mid, so, last_x, true);
                     vtx_store(a.ev + pix, mid);
                     a.pre[pix] = make_float4(so.next_flux.x, so.next_flux.y, so.next_flux.z, so.next_singlePdf);
                     // the CONNECTION_N probabilistic connections of this vertex are drawn by k_eye_sample (marker -2 in slot 0)
@@ -407,10 +406,14 @@ __global__ void __launch_bounds__(128, 8) k_eye_sample(const DevFrame fr, const 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (a.conn_lvc[(size_t)i * C] != -2) continue;   // miss, emitter hit or no surface vertex: slots stay empty
         const int pix = a.queue_cur[i];
-        const spc_vertex* ev = a.ev + pix;
+        spc_vertex* ev = a.ev + pix;
         const float3 pos = f3(ev->position.x, ev->position.y, ev->position.z);
-        const int eye_subspace = ev->subspaceId;
-        a.xlab[pix] = (short)tree_label(fr.p.subspace_info.light_tree, pos, f3(ev->normal.x, ev->normal.y, ev->normal.z));
+        // classification of the new vertex (labelUnit::getLabel in __closesthit__eyeSubpath, hit_program.cu:295) and its cross label
+        int eye_subspace, cross;
+        tree_label2(fr.p.subspace_info.eye_tree, fr.p.subspace_info.light_tree, pos, f3(ev->normal.x, ev->normal.y, ev->normal.z), eye_subspace, cross);
+        ev->subspaceId = (short)eye_subspace;
+        a.xlab[pix] = (short)cross;
+        if (a.bounce == 0 && a.first_label) a.first_label[pix] = eye_subspace;
         uint32_t seed = __float_as_uint(a.res[pix].w);
         ConnPick pick[CT > 0 ? CT : 16];
         bool done = false;

@@ -276,6 +276,45 @@ __device__ __forceinline__ int tree_label(const spc_tree_node* __restrict__ root
     }
 }
 
+// the same walk down two trees at once (eye-tree label and light-tree label of one vertex): two independent chains of dependent
+// loads in flight instead of one after the other
+__device__ __forceinline__ void tree_label2(const spc_tree_node* __restrict__ rootA, const spc_tree_node* __restrict__ rootB, float3 position,
+                                            float3 normal, int& labelA, int& labelB) {
+    int nodeA = 0, nodeB = 0;
+    bool doneA = rootA == nullptr, doneB = rootB == nullptr;
+    labelA = 0;
+    labelB = 0;
+    while (!(doneA && doneB)) {
+        const spc_tree_node* a = rootA + nodeA;
+        const spc_tree_node* b = rootB + nodeB;
+        int leafA = 1, leafB = 1, typeA = 0, typeB = 0;
+        if (!doneA) { leafA = __ldg(&a->leaf); typeA = __ldg(&a->type); }
+        if (!doneB) { leafB = __ldg(&b->leaf); typeB = __ldg(&b->type); }
+        if (!doneA) {
+            if (leafA) { labelA = __ldg(&a->label); doneA = true; }
+            else {
+                const float3 q = typeA == 0 ? position : (typeA == 1 ? normal : f3(0.0f));
+                int ind = 0;
+                ind += q.x > __ldg(&a->mid.x) ? 1 : 0;
+                ind += q.y > __ldg(&a->mid.y) ? 2 : 0;
+                ind += q.z > __ldg(&a->mid.z) ? 4 : 0;
+                nodeA = __ldg(&a->child[ind]);
+            }
+        }
+        if (!doneB) {
+            if (leafB) { labelB = __ldg(&b->label); doneB = true; }
+            else {
+                const float3 q = typeB == 0 ? position : (typeB == 1 ? normal : f3(0.0f));
+                int ind = 0;
+                ind += q.x > __ldg(&b->mid.x) ? 1 : 0;
+                ind += q.y > __ldg(&b->mid.y) ? 2 : 0;
+                ind += q.z > __ldg(&b->mid.z) ? 4 : 0;
+                nodeB = __ldg(&b->child[ind]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // emitter sampling: Tracer::lightSample (cuProg.h:554-666), QUAD lights
 // ---------------------------------------------------------------------------------------------
@@ -613,7 +652,7 @@ struct SurfaceOut {
 };
 __device__ __forceinline__ void surface_hit(const DevFrame& fr, const Vtx& Last, float3 pre_flux, float pre_singlePdf, const LocalGeom& geom,
                                             float t_hit, float3 ray_direction, bool light_side, uint32_t& seed, Vtx& Mid, SurfaceOut& out,
-                                            int last_xlabel = -1) {
+                                            int last_xlabel = -1, bool label_later = false) {
     const float3 inver_ray_direction = -ray_direction;
     const Pbr currentPbr = shade_pbr(fr.sc, geom.material, geom.uv);
     float3 N = geom.Ng;
@@ -635,7 +674,9 @@ __device__ __forceinline__ void surface_hit(const DevFrame& fr, const Vtx& Last,
     Mid.color = currentPbr.base_color;
     Mid.lastNormalProjection = fabsf(dot(Last.normal, ray_direction));
     Mid.materialId = (short)geom.material;
-    Mid.subspaceId = (short)tree_label(light_side ? fr.p.subspace_info.light_tree : fr.p.subspace_info.eye_tree, Mid.position, Mid.normal);
+    // label_later (wavefront eye pass): k_eye_sample classifies the vertex (both trees in one lockstep walk) and patches the field
+    Mid.subspaceId = label_later ? (short)-1
+                                 : (short)tree_label(light_side ? fr.p.subspace_info.light_tree : fr.p.subspace_info.eye_tree, Mid.position, Mid.normal);
     Mid.lastZoneId = Last.subspaceId;
     Mid.lastBrdf = Last.isBrdf;
     Mid.isOrigin = 0;
