@@ -1,6 +1,8 @@
 // api_train.cu -- extern "C" entry points of the subspace-training path (MyThrustOp seam, part 2) and the
 // plain memory helpers.
 #include <cstring>
+#include <cstring>
+#include <vector>
 #include "common.cuh"
 
 using spc::Context;
@@ -49,9 +51,43 @@ int spc_tree_to_device(spc_context* ctx, int eye_side, const spc_tree_node* node
     SPC_API_BEGIN
     SPC_REQUIRE(nodes_host && n > 0 && dev_out, SPC_ERR_INVALID, "spc_tree_to_device: bad arguments");
     spc::DevBuf<spc_tree_node>& b = eye_side ? c.train.eye_tree : c.train.light_tree;
+    spc::ctree_register(b.p, nullptr, &c);
     b.alloc(n);
     SPC_CUDA(cudaMemcpyAsync(b.p, nodes_host, (size_t)n * sizeof(spc_tree_node), cudaMemcpyHostToDevice, c.stream));
+    // compact copy for the device-side walks (shade.cuh "compact trees"): 48 B per node = {mid, type} + 8 children, a leaf child
+    // carries its label in the parent's entry (0x80000000 | label), a leaf root in the root's type word
+    bool compact_ok = true;
+    std::vector<float> ct((size_t)n * 12, 0.f);
+    for (int i = 0; i < n && compact_ok; i++) {
+        const spc_tree_node& nd = nodes_host[i];
+        uint32_t w[12] = {};
+        memcpy(&w[0], &nd.mid.x, 4); memcpy(&w[1], &nd.mid.y, 4); memcpy(&w[2], &nd.mid.z, 4);
+        if (nd.leaf) {
+            compact_ok = nd.label >= 0;
+            w[3] = 0x80000000u | (uint32_t)nd.label;
+        } else {
+            compact_ok = nd.type >= 0;
+            w[3] = (uint32_t)nd.type;
+            for (int k = 0; k < 8 && compact_ok; k++) {
+                const int ch = nd.child[k];
+                if (ch < 0 || ch >= n) { compact_ok = false; break; }
+                if (nodes_host[ch].leaf) {
+                    compact_ok = nodes_host[ch].label >= 0;
+                    w[4 + k] = 0x80000000u | (uint32_t)nodes_host[ch].label;
+                } else {
+                    w[4 + k] = (uint32_t)ch;
+                }
+            }
+        }
+        memcpy(&ct[(size_t)i * 12], w, sizeof(w));
+    }
+    spc::DevBuf<float4>& cb = eye_side ? c.train.eye_ctree : c.train.light_ctree;
+    if (compact_ok) {
+        cb.alloc((size_t)n * 3);
+        SPC_CUDA(cudaMemcpyAsync(cb.p, ct.data(), ct.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    }
     SPC_CUDA(cudaStreamSynchronize(c.stream));
+    if (compact_ok) spc::ctree_register(b.p, cb.p, &c);
     *dev_out = b.p;
     SPC_API_END
 }

@@ -124,6 +124,8 @@ struct LvcBuffers {
     DevBuf<float>        wsorted;
     DevBuf<int>          hist;        // [chunks][K]
     DevBuf<int>          totals;      // [K] + counters
+    DevBuf<int>          guide;       // guide tables of the cmfs (shade.cuh): table of subspace b at jump_bias + b, size + 1 entries
+    bool                 guide_valid = false;
     int                  n = 0;
 };
 
@@ -136,6 +138,7 @@ struct TrainBuffers {
     DevBuf<int> flag_p, flag_c, pos_p, pos_c, scan_sums, scan_sums2, totals;
     DevBuf<spc_divide_weight> tree_pts;
     DevBuf<spc_tree_node> eye_tree, light_tree;
+    DevBuf<float4>        eye_ctree, light_ctree;   // compact copies for the device-side walks (shade.cuh "compact trees")
     DevBuf<float> Q;
     int   acc_valid_path = 0;
     bool  has_Q = false;
@@ -145,6 +148,7 @@ struct TrainBuffers {
     DevBuf<int>   P2N, label_E, label_P;
     std::vector<int> h_P2N;
     DevBuf<float> gamma, cmf, theta, adam_m, adam_v, E, dE, Esum, loss;
+    DevBuf<int>   cmf_guide;   // guide tables of the CDF rows, [K][K+1] (train.cu)
     // deterministic scatter-adds (train.cu): elements sorted by target cell (stable), summed in order per cell
     DevBuf<uint32_t> sort_keys, sort_keys2;
     DevBuf<float>    sort_vals, sort_vals2, path_d, path_loss;
@@ -220,6 +224,11 @@ void   train_build_data(Context& c, int n_samples);
 float* train_get_gamma(Context& c);
 float* train_optimal_E(Context& c, int batch_size, int epochs, float lr, float* loss_out_host, int loss_cap, int* n_loss);
 float* train_gamma_to_cmf(Context& c, const float* gamma_dev);
+// compact copy of a classification tree uploaded by spc_tree_to_device, found by the reference-layout device pointer (or null)
+const float4* ctree_lookup(const spc_tree_node* tree_dev);
+void ctree_register(const spc_tree_node* tree_dev, const float4* ctree_dev, const void* owner);
+const int* gamma_guide_lookup(const float* cmf_gamma, int K);   // guide tables of a CDF built by train_gamma_to_cmf, or null
+void gamma_guide_forget(const void* owner);
 
 }  // namespace spc
 

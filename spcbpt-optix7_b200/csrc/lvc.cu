@@ -166,12 +166,21 @@ __global__ void __launch_bounds__(128) k_lvc_cmf(spc_subspace* __restrict__ sub,
     for (int i = lane; i < size; i += 32) cmfs[bias + i] = cmfs[bias + i] / total;
 }
 
+// guide tables of the per-subspace cmfs (shade.cuh, "guide tables"): one block per subspace
+__global__ void k_lvc_guide(const spc_subspace* __restrict__ sub, int K, const float* __restrict__ cmfs, int* __restrict__ guide) {
+    const int b = blockIdx.x;
+    if (b >= K) return;
+    const int n = sub[b].size, bias = sub[b].jump_bias;
+    if (n > 0) guide_build_table(cmfs + bias, n, guide + bias + b);
+}
+
 // Generic ordered binning: given per-element bin keys (-1 = skip) and weights, produce the stable bucket order
 // (jump), Subspace{jump_bias,id,size,sum_pmf} per bin with sum_pmf = the fp32 sum of the bin's weights IN ELEMENT
 // ORDER, and (optionally normalised) running sums.  Used by LVC_Process, preprocess_getQ and sample_reweight,
 // whose reference implementations are serial host loops with exactly this summation order.
 void bin_ordered(Context& c, LvcBuffers& b, int n, int K, int* counters /* [0] <- number of binned elements */) {
     const int n_chunks = (n + kChunk - 1) / kChunk;
+    b.guide_valid = false;   // the cmfs change: lvc_process rebuilds the guide tables
     b.subspace.alloc(K); b.cmfs.alloc(n); b.jump.alloc(n); b.wsorted.alloc(n);
     b.hist.alloc((size_t)n_chunks * K);
     cudaStream_t st = c.stream;
@@ -213,6 +222,10 @@ void lvc_process(Context& c, const spc_vertex* lvc, const uint8_t* valid, int n,
     LvcBuffers& b = c.lvc;
     if (!c.h_pinned) SPC_CUDA(cudaMallocHost((void**)&c.h_pinned, 64 * sizeof(int)));
     int* counters = lvc_bin(c, b, lvc, valid, n);
+    b.guide.alloc((size_t)n + c.K);
+    k_lvc_guide<<<c.K, 128, 0, c.stream>>>(b.subspace.p, c.K, b.cmfs.p, b.guide.p);
+    c.launches++;
+    b.guide_valid = true;
     SPC_CUDA(cudaMemcpyAsync(c.h_pinned, counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     SPC_CUDA(cudaStreamSynchronize(c.stream));
     out->LVC = lvc;

@@ -29,6 +29,10 @@ DevFrame make_dev_frame(Context& c) {
     fr.K = c.K;
     fr.connections = c.connections;
     fr.lvc_xlabel = nullptr;
+    fr.gamma_guide = nullptr;
+    fr.lvc_guide = nullptr;
+    fr.eye_ctree = c.has_params ? ctree_lookup(c.params.subspace_info.eye_tree) : nullptr;
+    fr.light_ctree = c.has_params ? ctree_lookup(c.params.subspace_info.light_tree) : nullptr;
     fr.max_depth = c.params.max_depth > 0 ? c.params.max_depth : 50;
     fr.seed_offset = c.seed_offset;
     fr.seed_stride = c.seed_stride;
@@ -353,6 +357,45 @@ __device__ __forceinline__ void bisect_lockstep(const float* const* cmf, const i
     }
 }
 
+// CT guided searches in lockstep (shade.cuh, "guide tables"): cell, two adjacent table reads, then a binary search over the bracket
+template <int CT>
+__device__ __forceinline__ void guided_lockstep(const float* const* cmf, const int* const* G, const int* size, const float* u, int* l_out, float* pmf_out) {
+    int lo[CT], hi[CT];
+#pragma unroll
+    for (int j = 0; j < CT; j++) {
+        const int cell = guide_cell(u[j], size[j]);
+        lo[j] = __ldg(G[j] + cell);
+        hi[j] = min(__ldg(G[j] + cell + 1), size[j] - 1);
+        lo[j] = min(lo[j], hi[j]);
+    }
+    bool any = true;
+    while (any) {   // first i in [lo, hi) with u < cmf[i], else hi
+        any = false;
+        float v[CT];
+        int mid[CT];
+#pragma unroll
+        for (int j = 0; j < CT; j++) {
+            mid[j] = (lo[j] + hi[j]) >> 1;
+            v[j] = lo[j] < hi[j] ? __ldg(cmf[j] + mid[j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < CT; j++) {
+            if (lo[j] < hi[j]) {
+                if (u[j] < v[j]) hi[j] = mid[j];
+                else lo[j] = mid[j] + 1;
+                any |= lo[j] < hi[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CT; j++) {
+        const float top = __ldg(cmf[j] + lo[j]);
+        const float below = lo[j] == 0 ? 0.f : __ldg(cmf[j] + lo[j] - 1);
+        pmf_out[j] = lo[j] == 0 ? top : top - below;
+        l_out[j] = lo[j];
+    }
+}
+
 template <int CT>
 __device__ __forceinline__ bool eye_sample_lockstep(const DevFrame& fr, int eye_subspace, uint32_t& seed, ConnPick* out) {
     const spc_subspace_sampler& S = fr.p.sampler;
@@ -371,7 +414,14 @@ __device__ __forceinline__ bool eye_sample_lockstep(const DevFrame& fr, int eye_
         int sz[CT];
 #pragma unroll
         for (int j = 0; j < CT; j++) { cm[j] = row; sz[j] = fr.K; }
-        bisect_lockstep<CT>(cm, sz, u1, light_id, pmf1);
+        if (fr.gamma_guide) {
+            const int* gt[CT];
+#pragma unroll
+            for (int j = 0; j < CT; j++) gt[j] = fr.gamma_guide + (size_t)eye_subspace * (fr.K + 1);
+            guided_lockstep<CT>(cm, gt, sz, u1, light_id, pmf1);
+        } else {
+            bisect_lockstep<CT>(cm, sz, u1, light_id, pmf1);
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < CT; j++) { light_id[j] = 0; pmf1[j] = 1; }
@@ -389,7 +439,14 @@ __device__ __forceinline__ bool eye_sample_lockstep(const DevFrame& fr, int eye_
     float pmf2[CT];
 #pragma unroll
     for (int j = 0; j < CT; j++) { cm[j] = S.cmfs + sub[j].jump_bias; sz[j] = sub[j].size; }
-    bisect_lockstep<CT>(cm, sz, u2, idx, pmf2);
+    if (fr.lvc_guide) {
+        const int* gt[CT];
+#pragma unroll
+        for (int j = 0; j < CT; j++) gt[j] = fr.lvc_guide + sub[j].jump_bias + light_id[j];
+        guided_lockstep<CT>(cm, gt, sz, u2, idx, pmf2);
+    } else {
+        bisect_lockstep<CT>(cm, sz, u2, idx, pmf2);
+    }
 #pragma unroll
     for (int j = 0; j < CT; j++) {
         out[j].lv = S.jump_buffer[idx[j] + sub[j].jump_bias];
@@ -410,7 +467,9 @@ __global__ void __launch_bounds__(128, 8) k_eye_sample(const DevFrame fr, const 
         const float3 pos = f3(ev->position.x, ev->position.y, ev->position.z);
         // classification of the new vertex (labelUnit::getLabel in __closesthit__eyeSubpath, hit_program.cu:295) and its cross label
         int eye_subspace, cross;
-        tree_label2(fr.p.subspace_info.eye_tree, fr.p.subspace_info.light_tree, pos, f3(ev->normal.x, ev->normal.y, ev->normal.z), eye_subspace, cross);
+        const float3 nrm = f3(ev->normal.x, ev->normal.y, ev->normal.z);
+        if (fr.eye_ctree && fr.light_ctree) ctree_label2(fr.eye_ctree, fr.light_ctree, pos, nrm, eye_subspace, cross);
+        else tree_label2(fr.p.subspace_info.eye_tree, fr.p.subspace_info.light_tree, pos, nrm, eye_subspace, cross);
         ev->subspaceId = (short)eye_subspace;
         a.xlab[pix] = (short)cross;
         if (a.bounce == 0 && a.first_label) a.first_label[pix] = eye_subspace;
@@ -446,7 +505,7 @@ __global__ void k_lvc_xlabel(const DevFrame fr, int n_valid, short* __restrict__
     if (j >= n_valid) return;
     const int lv = fr.p.sampler.jump_buffer[j];
     const spc_vertex* L = fr.p.sampler.LVC + lv;
-    xlabel[lv] = (short)tree_label(fr.p.subspace_info.eye_tree, f3(L->position.x, L->position.y, L->position.z), f3(L->normal.x, L->normal.y, L->normal.z));
+    xlabel[lv] = (short)eye_tree_label(fr, f3(L->position.x, L->position.y, L->position.z), f3(L->normal.x, L->normal.y, L->normal.z));
 }
 
 // connectVertex_SPCBPT (raygen.cu:253-303) for every visible connection; one lane per connection.
@@ -627,6 +686,8 @@ void launch_eye_pass(Context& c, int width, int height) {
     // cross labels of the light vertices: only when the sampler is the one spc_lvc_process built (then jump_buffer indexes
     // c.lvc.n slots); a caller-made sampler keeps the in-kernel tree walk
     fr.lvc_xlabel = nullptr;
+    fr.gamma_guide = c.params.subspace_info.light_tree ? gamma_guide_lookup(c.params.subspace_info.CMFGamma, c.K) : nullptr;
+    fr.lvc_guide = (S.cmfs == c.lvc.cmfs.p && S.subspace == c.lvc.subspace.p && c.lvc.guide_valid) ? c.lvc.guide.p : nullptr;
     if (S.jump_buffer == c.lvc.jump.p && c.lvc.n > 0 && S.vertex_count > 0 && S.vertex_count <= c.lvc.n) {
         e.lvc_xlabel.alloc((size_t)c.lvc.n);
         k_lvc_xlabel<<<(S.vertex_count + 255) / 256, 256, 0, st>>>(fr, S.vertex_count, e.lvc_xlabel.p);

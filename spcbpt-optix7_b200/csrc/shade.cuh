@@ -51,6 +51,10 @@ struct DevFrame {
     int        max_depth;    // literal 50 in raygen.cu:361,668 unless MyParams::max_depth > 0
     uint32_t   seed_offset;  // eye/pt seeds use tea<4>(pixel, subframe_index * seed_stride + seed_offset): (0, 1) = the reference's
     const short* lvc_xlabel; // eye-tree label of every LVC slot (k_lvc_xlabel), or null: walk the tree where it is needed
+    const float4* eye_ctree;   // compact copies of subspace_info.eye_tree / light_tree (spc_tree_to_device) or null: walk the
+    const float4* light_ctree; // reference-layout nodes
+    const int* gamma_guide;  // guide tables of the CMFGamma rows ([K][K+1], guide.cu) or null: the reference's bisect
+    const int* lvc_guide;    // guide tables of the per-subspace cmfs (table of subspace b at jump_bias + b, size + 1 entries) or null
     uint32_t   seed_stride;  // streams; other values when subframes are partitioned across GPUs or frame lanes (each keeps its own
                              // running mean over ITS subframes, numbered 0,1,2,... locally)
 };
@@ -276,6 +280,46 @@ __device__ __forceinline__ int tree_label(const spc_tree_node* __restrict__ root
     }
 }
 
+// Compact trees.  The reference-layout node (56 B: mid, 8 children, label, type, leaf) costs six scalar loads per level, each its own
+// L1 wavefront per lane once the lanes of a warp have diverged.  spc_tree_to_device keeps a second copy of 48 B = 3 x float4 per node:
+// {mid.xyz, type} and the 8 children, where a leaf child is stored in its parent as 0x80000000 | label: one 128-bit load plus one
+// 32-bit load per level, and no load at all for the leaf.  Same comparisons, same label.
+__device__ __forceinline__ int ctree_step(const float4* __restrict__ t, int node, float3 position, float3 normal) {
+    const float4 q = __ldg(t + (size_t)node * 3);
+    const uint32_t type = __float_as_uint(q.w);
+    const float3 p = type == 0 ? position : (type == 1 ? normal : f3(0.0f));
+    int ind = 0;
+    ind += p.x > q.x ? 1 : 0;
+    ind += p.y > q.y ? 2 : 0;
+    ind += p.z > q.z ? 4 : 0;
+    return __ldg(reinterpret_cast<const int*>(t + (size_t)node * 3 + 1) + ind);
+}
+__device__ __forceinline__ int ctree_label(const float4* __restrict__ t, float3 position, float3 normal) {
+    const uint32_t root = __float_as_uint(__ldg(t).w);
+    if (root & 0x80000000u) return (int)(root & 0x7fffffffu);
+    int node = 0;
+    while (node >= 0) node = ctree_step(t, node, position, normal);
+    return node & 0x7fffffff;
+}
+// both trees at once: two independent chains of dependent loads in flight
+__device__ __forceinline__ void ctree_label2(const float4* __restrict__ ta, const float4* __restrict__ tb, float3 position, float3 normal,
+                                             int& labelA, int& labelB) {
+    const uint32_t ra = __float_as_uint(__ldg(ta).w), rb = __float_as_uint(__ldg(tb).w);
+    int na = (ra & 0x80000000u) ? (int)ra : 0, nb = (rb & 0x80000000u) ? (int)rb : 0;
+    while (na >= 0 || nb >= 0) {
+        if (na >= 0) na = ctree_step(ta, na, position, normal);
+        if (nb >= 0) nb = ctree_step(tb, nb, position, normal);
+    }
+    labelA = na & 0x7fffffff;
+    labelB = nb & 0x7fffffff;
+}
+__device__ __forceinline__ int eye_tree_label(const DevFrame& fr, float3 position, float3 normal) {
+    return fr.eye_ctree ? ctree_label(fr.eye_ctree, position, normal) : tree_label(fr.p.subspace_info.eye_tree, position, normal);
+}
+__device__ __forceinline__ int light_tree_label(const DevFrame& fr, float3 position, float3 normal) {
+    return fr.light_ctree ? ctree_label(fr.light_ctree, position, normal) : tree_label(fr.p.subspace_info.light_tree, position, normal);
+}
+
 // the same walk down two trees at once (eye-tree label and light-tree label of one vertex): two independent chains of dependent
 // loads in flight instead of one after the other
 __device__ __forceinline__ void tree_label2(const spc_tree_node* __restrict__ rootA, const spc_tree_node* __restrict__ rootB, float3 position,
@@ -484,7 +528,7 @@ __device__ __forceinline__ float getLL_pdf(const DevFrame& fr, const Vtx& Mid, c
 // same arguments, so the result is identical either way.
 __device__ __forceinline__ float tracing_weight_light(const DevFrame& fr, const Vtx& Mid, const Vtx& Last, int xlabel = -1) {   // rmis.h:58-79
     if (Last.lastBrdf || Last.isBrdf) return 0.0f;
-    const int eye_label = xlabel >= 0 ? xlabel : tree_label(fr.p.subspace_info.eye_tree, Last.position, Last.normal);
+    const int eye_label = xlabel >= 0 ? xlabel : eye_tree_label(fr, Last.position, Last.normal);
     const int light_label = Last.lastZoneId;
     const float lum_sum = Last.last_lum;
     return connectRate_SOL(fr, eye_label, light_label, lum_sum);
@@ -511,7 +555,7 @@ __device__ __forceinline__ float3 tracing_weight_eye(const DevFrame& fr, const V
     if (Last.lastBrdf || Last.isBrdf) return f3(0.0f);
     if (Last.depth == 1) return f3(0.0f);   // t=1 strategy disabled (readme.md:27)
     const int eye_label = Last.lastZoneId;
-    const int light_label = xlabel >= 0 ? xlabel : tree_label(fr.p.subspace_info.light_tree, Last.position, Last.normal);
+    const int light_label = xlabel >= 0 ? xlabel : light_tree_label(fr, Last.position, Last.normal);
     return connectRate_SOL3(fr, eye_label, light_label, f3(1.0f));
 }
 __device__ __forceinline__ float getPdf(const DevFrame& fr, const Vtx& begin, const Vtx& end, float3 in_dir) {   // rmis.h:153-172
@@ -638,6 +682,37 @@ __device__ __forceinline__ int binary_sample(const float* __restrict__ cmf, int 
     return l;
 }
 
+// Guide tables (the "cutpoint method" for inverting a discrete CDF).  binary_sample returns, for a non-decreasing table, the first
+// index l with u < cmf[l] (n-1 when there is none): ~log2(n) dependent probes.  A guide table G over the same n entries,
+//     G[j] = first i with cmf[i] > j/n  (n when there is none),   j = 0..n,
+// brackets that index: with j/n <= u < (j+1)/n the answer lies in [G[j], G[j+1]], usually one or two entries wide, so a search costs two
+// adjacent table reads plus one or two probes.  The comparisons against cmf are the very same `u < cmf[i]`, hence the same index for
+// every u; tables are only built for arrays this library produced itself (monotone by construction: running fp32 sums of non-negative
+// weights divided by their total; CDF rows of positive entries), anything else keeps the reference's bisect.
+__device__ __forceinline__ float guide_cut(int j, float fn) { return __fdiv_rn((float)j, fn); }
+// the cell j with cut(j) <= u < cut(j+1), exact in fp32 (the product u*n may round across a cut)
+__device__ __forceinline__ int guide_cell(float u, int n) {
+    const float fn = (float)n;
+    int j = min((int)(u * fn), n - 1);
+    while (j > 0 && u < guide_cut(j, fn)) j--;
+    while (j < n - 1 && !(u < guide_cut(j + 1, fn))) j++;
+    return j;
+}
+// builder: one table, cooperatively by the calling block
+__device__ __forceinline__ void guide_build_table(const float* __restrict__ cmf, int n, int* __restrict__ G) {
+    const float fn = (float)n;
+    for (int j = threadIdx.x; j <= n; j += blockDim.x) {
+        const float c = guide_cut(j, fn);
+        int lo = 0, hi = n;   // first i in [0, n) with cmf[i] > c, else n
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cmf[mid] > c) hi = mid;
+            else lo = mid + 1;
+        }
+        G[j] = lo;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the two surface programs: __closesthit__eyeSubpath (hit_program.cu:246-340) and
 // __closesthit__lightSubpath (:341-438).  `Last` = path.currentVertex() before the hit, `pre_flux` /
@@ -676,7 +751,7 @@ __device__ __forceinline__ void surface_hit(const DevFrame& fr, const Vtx& Last,
     Mid.materialId = (short)geom.material;
     // label_later (wavefront eye pass): k_eye_sample classifies the vertex (both trees in one lockstep walk) and patches the field
     Mid.subspaceId = label_later ? (short)-1
-                                 : (short)tree_label(light_side ? fr.p.subspace_info.light_tree : fr.p.subspace_info.eye_tree, Mid.position, Mid.normal);
+                                 : (short)(light_side ? light_tree_label(fr, Mid.position, Mid.normal) : eye_tree_label(fr, Mid.position, Mid.normal));
     Mid.lastZoneId = Last.subspaceId;
     Mid.lastBrdf = Last.isBrdf;
     Mid.isOrigin = 0;

@@ -16,6 +16,9 @@
 #include <algorithm>
 #include <cfloat>
 #include <cub/cub.cuh>
+#include <iterator>
+#include <map>
+#include <mutex>
 #include "shade.cuh"
 
 namespace spc {
@@ -677,13 +680,66 @@ __global__ void k_gamma_to_cmf(const float* __restrict__ G, int K, float* __rest
     }
     cmf[(size_t)(i + 1) * K - 1] = 1;
 }
+// Guide tables of the CDF rows (shade.cuh, "guide tables").  The CDF travels to the eye pass as a bare pointer inside MyParams, possibly
+// through another context on the same device (frame lanes share the trained state by pointer), so the tables are found through a
+// process-wide registry keyed by that pointer; a CDF this library did not build has no entry and is sampled with the reference's bisect.
+__global__ void k_gamma_guide(const float* __restrict__ cmf, int K, int* __restrict__ guide) {
+    const int row = blockIdx.x;
+    if (row < K) guide_build_table(cmf + (size_t)row * K, K, guide + (size_t)row * (K + 1));
+}
+namespace {
+struct GammaGuide {
+    const int* guide;
+    int        K;
+    const void* owner;
+};
+std::mutex g_guide_mutex;
+std::map<const float*, GammaGuide> g_gamma_guides;
+struct CTreeEntry {
+    const float4* ctree;
+    const void*   owner;
+};
+std::map<const spc_tree_node*, CTreeEntry> g_ctrees;
+}  // namespace
+const float4* ctree_lookup(const spc_tree_node* tree_dev) {
+    if (!tree_dev) return nullptr;
+    std::lock_guard<std::mutex> lock(g_guide_mutex);
+    auto it = g_ctrees.find(tree_dev);
+    return it != g_ctrees.end() ? it->second.ctree : nullptr;
+}
+void ctree_register(const spc_tree_node* tree_dev, const float4* ctree_dev, const void* owner) {
+    std::lock_guard<std::mutex> lock(g_guide_mutex);
+    if (ctree_dev) g_ctrees[tree_dev] = CTreeEntry{ctree_dev, owner};
+    else g_ctrees.erase(tree_dev);
+}
+const int* gamma_guide_lookup(const float* cmf_gamma, int K) {
+    std::lock_guard<std::mutex> lock(g_guide_mutex);
+    auto it = g_gamma_guides.find(cmf_gamma);
+    return (it != g_gamma_guides.end() && it->second.K == K) ? it->second.guide : nullptr;
+}
+void gamma_guide_forget(const void* owner) {
+    std::lock_guard<std::mutex> lock(g_guide_mutex);
+    for (auto it = g_gamma_guides.begin(); it != g_gamma_guides.end();)
+        it = (it->second.owner == owner) ? g_gamma_guides.erase(it) : std::next(it);
+    for (auto it = g_ctrees.begin(); it != g_ctrees.end();)
+        it = (it->second.owner == owner) ? g_ctrees.erase(it) : std::next(it);
+}
 float* train_gamma_to_cmf(Context& c, const float* gamma_dev) {
     TrainBuffers& t = c.train;
     const int K = c.K;
+    gamma_guide_forget(&c);
     t.cmf.alloc((size_t)K * K);
+    t.cmf_guide.alloc((size_t)K * (K + 1));
     k_gamma_to_cmf<<<(K + 63) / 64, 64, 0, c.stream>>>(gamma_dev, K, t.cmf.p);
-    c.launches++;
+    k_gamma_guide<<<K, 128, 0, c.stream>>>(t.cmf.p, K, t.cmf_guide.p);
+    c.launches += 2;
     SPC_CUDA(cudaGetLastError());
+    {
+        // contexts on other streams may use the tables (frame lanes): make them complete before the pointer is handed out
+        SPC_CUDA(cudaStreamSynchronize(c.stream));
+        std::lock_guard<std::mutex> lock(g_guide_mutex);
+        g_gamma_guides[t.cmf.p] = GammaGuide{t.cmf_guide.p, K, &c};
+    }
     return t.cmf.p;
 }
 
