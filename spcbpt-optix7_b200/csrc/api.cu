@@ -125,7 +125,7 @@ void spc_destroy(spc_context* ctx) {
     if (ctx->c.h_pinned) cudaFreeHost(ctx->c.h_pinned);
     for (cudaEvent_t ev : ctx->c.eye_events)
         if (ev) cudaEventDestroy(ev);
-    spc::gamma_guide_forget(&ctx->c);
+    spc::gamma_guide_forget(&ctx->c, true);
     delete ctx;
 }
 

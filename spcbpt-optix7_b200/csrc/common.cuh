@@ -228,7 +228,7 @@ float* train_gamma_to_cmf(Context& c, const float* gamma_dev);
 const float4* ctree_lookup(const spc_tree_node* tree_dev);
 void ctree_register(const spc_tree_node* tree_dev, const float4* ctree_dev, const void* owner);
 const int* gamma_guide_lookup(const float* cmf_gamma, int K);   // guide tables of a CDF built by train_gamma_to_cmf, or null
-void gamma_guide_forget(const void* owner);
+void gamma_guide_forget(const void* owner, bool trees_too);   // context teardown: trees_too = true
 
 }  // namespace spc
 

@@ -313,12 +313,17 @@ __device__ __forceinline__ void eye_sample_serial(const DevFrame& fr, int eye_su
         out[j].pmf = 0.f;
         int light_id = 0;
         float pmf1 = 1;
-        if (fr.p.subspace_info.light_tree)
-            light_id = binary_sample(fr.p.subspace_info.CMFGamma + (size_t)eye_subspace * fr.K, fr.K, seed, pmf1);
+        if (fr.p.subspace_info.light_tree) {
+            const float* row = fr.p.subspace_info.CMFGamma + (size_t)eye_subspace * fr.K;
+            light_id = fr.gamma_guide ? guided_sample(row, fr.gamma_guide + (size_t)eye_subspace * (fr.K + 1), fr.K, seed, pmf1)
+                                      : binary_sample(row, fr.K, seed, pmf1);
+        }
         const spc_subspace sub = S.subspace[light_id];
         if (sub.size != 0) {
             float pmf2;
-            const int index = binary_sample(S.cmfs + sub.jump_bias, sub.size, seed, pmf2) + sub.jump_bias;
+            const float* cm = S.cmfs + sub.jump_bias;
+            const int index = (fr.lvc_guide ? guided_sample(cm, fr.lvc_guide + sub.jump_bias + light_id, sub.size, seed, pmf2)
+                                            : binary_sample(cm, sub.size, seed, pmf2)) + sub.jump_bias;
             out[j].lv = S.jump_buffer[index];
             out[j].pmf = (float)S.path_count * pmf2 * pmf1;
         }
@@ -363,10 +368,14 @@ __device__ __forceinline__ void guided_lockstep(const float* const* cmf, const i
     int lo[CT], hi[CT];
 #pragma unroll
     for (int j = 0; j < CT; j++) {
-        const int cell = guide_cell(u[j], size[j]);
-        lo[j] = __ldg(G[j] + cell);
-        hi[j] = min(__ldg(G[j] + cell + 1), size[j] - 1);
-        lo[j] = min(lo[j], hi[j]);
+        lo[j] = 0;
+        hi[j] = 0;
+        if (G[j]) {   // null: a dummy slot (no search, index 0)
+            const int cell = guide_cell(u[j], size[j]);
+            lo[j] = __ldg(G[j] + cell);
+            hi[j] = min(__ldg(G[j] + cell + 1), size[j] - 1);
+            lo[j] = min(lo[j], hi[j]);
+        }
     }
     bool any = true;
     while (any) {   // first i in [lo, hi) with u < cmf[i], else hi
@@ -396,63 +405,98 @@ __device__ __forceinline__ void guided_lockstep(const float* const* cmf, const i
     }
 }
 
+// All C connections of a vertex without a serial dependency.  Connection j draws its first-stage number at position s_j of the path's
+// stream, s_0 = 0, s_{j+1} = s_j + (1 if connection j met an empty subspace, else 2) (raygen.cu:390-408): s_j is one of j..2j.  The first
+// stage is therefore run for the 2C-1 candidate positions 0..2C-2 at once (lockstep searches, their probes overlap), the actual
+// positions are then resolved in registers, and the second stage runs in lockstep for the connections that have one.  Same draws,
+// same searches as the serial loop for every pattern of empty subspaces (in the shipped scene ~10 % of the vertices meet one: a
+// speculative version that fell back to the serial loop sent 3 lanes of almost every warp down that path, profiles/r1e_summary.md).
+// Requires a light tree (without one the first stage draws nothing: serial loop).
 template <int CT>
 __device__ __forceinline__ bool eye_sample_lockstep(const DevFrame& fr, int eye_subspace, uint32_t& seed, ConnPick* out) {
+    if (!fr.p.subspace_info.light_tree) return false;
+    constexpr int NC = 2 * CT - 1;   // candidate first-stage positions
     const spc_subspace_sampler& S = fr.p.sampler;
-    uint32_t s = seed;
-    float u1[CT], u2[CT];
+    uint32_t st[2 * CT + 1];         // st[k] = state after k draws
+    float d[2 * CT];
+    st[0] = seed;
 #pragma unroll
-    for (int j = 0; j < CT; j++) {
-        u1[j] = fr.p.subspace_info.light_tree ? rnd(s) * 1.0f : 0.f;
-        u2[j] = rnd(s) * 1.0f;
+    for (int k = 0; k < 2 * CT; k++) {
+        uint32_t t = st[k];
+        d[k] = rnd(t) * 1.0f;
+        st[k + 1] = t;
     }
-    int light_id[CT];
-    float pmf1[CT];
-    if (fr.p.subspace_info.light_tree) {
+    // first stage for every candidate position
+    int cand_id[NC];
+    float cand_pmf[NC];
+    {
         const float* row = fr.p.subspace_info.CMFGamma + (size_t)eye_subspace * fr.K;
-        const float* cm[CT];
-        int sz[CT];
+        const float* cm[NC];
+        int sz[NC];
+        float u[NC];
 #pragma unroll
-        for (int j = 0; j < CT; j++) { cm[j] = row; sz[j] = fr.K; }
+        for (int c = 0; c < NC; c++) { cm[c] = row; sz[c] = fr.K; u[c] = d[c]; }
         if (fr.gamma_guide) {
-            const int* gt[CT];
+            const int* gt[NC];
 #pragma unroll
-            for (int j = 0; j < CT; j++) gt[j] = fr.gamma_guide + (size_t)eye_subspace * (fr.K + 1);
-            guided_lockstep<CT>(cm, gt, sz, u1, light_id, pmf1);
+            for (int c = 0; c < NC; c++) gt[c] = fr.gamma_guide + (size_t)eye_subspace * (fr.K + 1);
+            guided_lockstep<NC>(cm, gt, sz, u, cand_id, cand_pmf);
         } else {
-            bisect_lockstep<CT>(cm, sz, u1, light_id, pmf1);
+            bisect_lockstep<NC>(cm, sz, u, cand_id, cand_pmf);
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < CT; j++) { light_id[j] = 0; pmf1[j] = 1; }
     }
-    spc_subspace sub[CT];
-    bool ok = true;
+    int cand_size[NC], cand_bias[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const spc_subspace sub = S.subspace[cand_id[c]];
+        cand_size[c] = sub.size;
+        cand_bias[c] = sub.jump_bias;
+    }
+    // resolve the positions (registers only)
+    int light_id[CT], size[CT], bias[CT];
+    float pmf1[CT], u2[CT];
+    int pos = 0;
 #pragma unroll
     for (int j = 0; j < CT; j++) {
-        sub[j] = S.subspace[light_id[j]];
-        ok &= sub[j].size != 0;
+        light_id[j] = 0; size[j] = 0; bias[j] = 0; pmf1[j] = 1.f; u2[j] = 0.f;
+#pragma unroll
+        for (int c = j; c <= 2 * j; c++) {
+            if (c == pos) {
+                light_id[j] = cand_id[c]; size[j] = cand_size[c]; bias[j] = cand_bias[c]; pmf1[j] = cand_pmf[c];
+                u2[j] = d[c + 1];
+            }
+        }
+        pos += size[j] != 0 ? 2 : 1;
     }
-    if (!ok) return false;   // an empty subspace shifts the later draws: the caller takes the serial loop
+    // second stage for the connections that have one (an empty subspace gets a one-entry dummy table and no connection)
     const float* cm[CT];
     int sz[CT], idx[CT];
     float pmf2[CT];
 #pragma unroll
-    for (int j = 0; j < CT; j++) { cm[j] = S.cmfs + sub[j].jump_bias; sz[j] = sub[j].size; }
+    for (int j = 0; j < CT; j++) { cm[j] = S.cmfs + bias[j]; sz[j] = max(size[j], 1); }
     if (fr.lvc_guide) {
         const int* gt[CT];
 #pragma unroll
-        for (int j = 0; j < CT; j++) gt[j] = fr.lvc_guide + sub[j].jump_bias + light_id[j];
+        for (int j = 0; j < CT; j++) gt[j] = size[j] != 0 ? fr.lvc_guide + bias[j] + light_id[j] : nullptr;
         guided_lockstep<CT>(cm, gt, sz, u2, idx, pmf2);
     } else {
         bisect_lockstep<CT>(cm, sz, u2, idx, pmf2);
     }
 #pragma unroll
     for (int j = 0; j < CT; j++) {
-        out[j].lv = S.jump_buffer[idx[j] + sub[j].jump_bias];
-        out[j].pmf = (float)S.path_count * pmf2[j] * pmf1[j];
+        out[j].lv = -1;
+        out[j].pmf = 0.f;
+        if (size[j] != 0) {
+            out[j].lv = S.jump_buffer[idx[j] + bias[j]];
+            out[j].pmf = (float)S.path_count * pmf2[j] * pmf1[j];
+        }
     }
-    seed = s;
+    // seed after the draws actually consumed: pos of them
+    uint32_t fin = st[CT];
+#pragma unroll
+    for (int k = CT; k <= 2 * CT; k++)
+        if (k == pos) fin = st[k];
+    seed = fin;
     return true;
 }
 

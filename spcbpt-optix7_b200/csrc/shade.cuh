@@ -698,6 +698,20 @@ __device__ __forceinline__ int guide_cell(float u, int n) {
     while (j < n - 1 && !(u < guide_cut(j + 1, fn))) j++;
     return j;
 }
+// binary_sample through a guide table: one draw, same index and pmf
+__device__ __forceinline__ int guided_sample(const float* __restrict__ cmf, const int* __restrict__ G, int size, uint32_t& seed, float& pmf) {
+    const float u = rnd(seed) * 1.0f;
+    const int cell = guide_cell(u, size);
+    int hi = min(__ldg(G + cell + 1), size - 1);
+    int lo = min(__ldg(G + cell), hi);
+    while (lo < hi) {   // first i in [lo, hi) with u < cmf[i], else hi
+        const int mid = (lo + hi) >> 1;
+        if (u < __ldg(cmf + mid)) hi = mid;
+        else lo = mid + 1;
+    }
+    pmf = lo == 0 ? __ldg(cmf + lo) : __ldg(cmf + lo) - __ldg(cmf + lo - 1);
+    return lo;
+}
 // builder: one table, cooperatively by the calling block
 __device__ __forceinline__ void guide_build_table(const float* __restrict__ cmf, int n, int* __restrict__ G) {
     const float fn = (float)n;

@@ -717,17 +717,18 @@ const int* gamma_guide_lookup(const float* cmf_gamma, int K) {
     auto it = g_gamma_guides.find(cmf_gamma);
     return (it != g_gamma_guides.end() && it->second.K == K) ? it->second.guide : nullptr;
 }
-void gamma_guide_forget(const void* owner) {
+void gamma_guide_forget(const void* owner, bool trees_too) {
     std::lock_guard<std::mutex> lock(g_guide_mutex);
     for (auto it = g_gamma_guides.begin(); it != g_gamma_guides.end();)
         it = (it->second.owner == owner) ? g_gamma_guides.erase(it) : std::next(it);
+    if (!trees_too) return;
     for (auto it = g_ctrees.begin(); it != g_ctrees.end();)
         it = (it->second.owner == owner) ? g_ctrees.erase(it) : std::next(it);
 }
 float* train_gamma_to_cmf(Context& c, const float* gamma_dev) {
     TrainBuffers& t = c.train;
     const int K = c.K;
-    gamma_guide_forget(&c);
+    gamma_guide_forget(&c, false);
     t.cmf.alloc((size_t)K * K);
     t.cmf_guide.alloc((size_t)K * (K + 1));
     k_gamma_to_cmf<<<(K + 63) / 64, 64, 0, c.stream>>>(gamma_dev, K, t.cmf.p);
