@@ -742,6 +742,15 @@ void launch_eye_pass(Context& c, int width, int height) {
     a.rays_cur = (float4*)e.rays[0].p; a.rays_next = (float4*)e.rays[1].p;
     a.queue_cur = e.queue[0].p; a.queue_next = e.queue[1].p;
 
+    if (getenv("SPC_EYE_REFERENCE_SEARCH")) {
+        // test switch (tests/test_render_gpu.py): the reference's bisect and the reference-layout tree walks instead of guide tables,
+        // compact trees and the cached light-vertex labels -- frames must come out bit-identical either way
+        fr.gamma_guide = nullptr;
+        fr.lvc_guide = nullptr;
+        fr.eye_ctree = nullptr;
+        fr.light_ctree = nullptr;
+        fr.lvc_xlabel = nullptr;
+    }
     const int nP = (int)P;
     k_eye_init<<<(nP + 255) / 256, 256, 0, st>>>(fr, a, nP);
     c.launches++;

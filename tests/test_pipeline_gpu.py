@@ -71,6 +71,34 @@ def test_pipelined_frames_equal_sequential_frames(gpu_ctx):
     assert a.mean() > 0.01 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_guide_tables_and_compact_trees_leave_frames_bit_identical(gpu_ctx):
+    """k_eye_sample's guide tables / compact trees / cached light-vertex labels against the reference's own bisect and tree walk
+    (SPC_EYE_REFERENCE_SEARCH switches them off at launch time): same trained state, same frames, every bit.  K = 64 with 12 emitter
+    subspaces on a small LVC leaves several light subspaces empty, so the empty-subspace draw shifts are exercised too."""
+    import os
+    pkg = gpu_ctx
+    from spcbpt_optix7_b200.renderer import Renderer
+    sc = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=12, box_cells=8), 0.01)
+    kw = dict(K=64, K_light=12, lt_num_core=100, lt_core_padding=300, lt_M_per_core=40, pretrace_num_core=20000)
+    r = Renderer(sc, 96, 64, **kw)
+    r.preprocessing(target_samples=40000, target_Q_samples=20000, tree_samples=20000, batch_size=20000)
+    frame0 = int(r.P["lt"]["launch_frame"][0])
+    assert "SPC_EYE_REFERENCE_SEARCH" not in os.environ
+    for _ in range(5):
+        r.render_frame()
+    a = r.image().copy()
+    r.reset_accumulation()
+    r.P["lt"]["launch_frame"] = frame0
+    os.environ["SPC_EYE_REFERENCE_SEARCH"] = "1"
+    try:
+        for _ in range(5):
+            r.render_frame()
+    finally:
+        del os.environ["SPC_EYE_REFERENCE_SEARCH"]
+    b = r.image().copy()
+    assert a.mean() > 0.01 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_shipped_scene_spcbpt_beats_pt_at_equal_spp(gpu_ctx):
     """BASELINE.json configs[2] in small: the shipped house scene (its .spcscene cache is written by __graft_entry__.build() from
     the reference's data where that exists and travels with the tree; skipped otherwise).  Ground truth = the `pt` integrator at
