@@ -326,6 +326,10 @@ __device__ __forceinline__ bool trav_step(const float4* __restrict__ nodes, cons
 #ifndef SPC_NODE_STEPS
 #define SPC_NODE_STEPS 3   // node steps per triangle phase: 1 -> 2 -> 3 -> 4 gave 3776 / 4057 / 4150 / 4153 Mrays/s on bench.py (profiles/r1e_summary.md)
 #endif
+#ifndef SPC_NODE_STEPS_ANYHIT
+#define SPC_NODE_STEPS_ANYHIT 3   // occlusion rays: steps before the triangles delay the early exit, yet 3 wins on the house scene too
+                                  // (shadow-ray kernel time of two frames: 5.47 / 4.95 / 4.85 ms for 1 / 2 / 3 steps, tests/quick_anyhit_steps.sh)
+#endif
 template <bool ANYHIT, bool COUNT>
 __device__ __forceinline__ bool trav_step2(const float4* __restrict__ nodes, const float4* __restrict__ tris, Trav& s, bool cull_back,
                                            int sstride, uint2* lstack, uint32_t lut, int postpone_div, unsigned& cn, unsigned& ct) {
@@ -339,8 +343,9 @@ __device__ __forceinline__ bool trav_step2(const float4* __restrict__ nodes, con
     } else {
         trav_parked(nodes, s, p);
     }
+    constexpr int kSteps = ANYHIT ? SPC_NODE_STEPS_ANYHIT : SPC_NODE_STEPS;
 #pragma unroll
-    for (int k = 1; k < SPC_NODE_STEPS; k++) {
+    for (int k = 1; k < kSteps; k++) {
         if (s.ngroup.y == 0u && s.sp > 0) s.ngroup = trav_pop(s, sstride_b, lstack);
         if (s.ngroup.y > 0x00ffffffu) {   // (a parked triangle group popped here waits for the next call)
             TriGroup q;
