@@ -188,12 +188,12 @@ void bin_ordered(Context& c, LvcBuffers& b, int n, int K, int* counters /* [0] <
     const int wpb = (int)std::min<size_t>(8, (160 * 1024) / ((size_t)K * 4));
     SPC_REQUIRE(wpb >= 1, SPC_ERR_CAPACITY, "ordered binning: %d bins do not fit the shared-memory histogram", K);
     const size_t smem = (size_t)wpb * K * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static const bool attr_set = []() {   // once per process, safe under concurrent first calls (frame lanes)
         SPC_CUDA(cudaFuncSetAttribute(k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SPC_CUDA(cudaFuncSetAttribute(k_lvc_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+        return true;
+    }();
+    (void)attr_set;
     const int grid = std::max(1, std::min((n_chunks + wpb - 1) / wpb, c.sm_count * 4));
     k_bin_hist<<<grid, wpb * 32, smem, st>>>(b.key.p, n, K, n_chunks, b.hist.p);
     k_lvc_colscan<<<(K + 127) / 128, 128, 0, st>>>(b.hist.p, n_chunks, K, b.totals.p);

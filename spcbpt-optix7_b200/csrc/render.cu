@@ -147,11 +147,10 @@ void launch_light_trace(Context& c) {
     SPC_REQUIRE(lt.num_core > 0 && lt.core_padding > 0 && lt.ans && lt.validState, SPC_ERR_INVALID, "spc_launch(light trace): MyParams::lt is not set up");
     SPC_REQUIRE(c.geom.n_lights > 0, SPC_ERR_NO_SCENE, "spc_launch(light trace): the scene has no lights");
     const DevFrame fr = make_dev_frame(c);
-    static int lanes = 0;
-    if (!lanes) {
+    static const int lanes = []() {
         const char* e = getenv("SPC_LT_LANES");
-        lanes = e ? std::max(1, std::min(32, atoi(e))) : 1;
-    }
+        return e ? std::max(1, std::min(32, atoi(e))) : 1;
+    }();
     const int per_block = kLtWarps * lanes;
     k_light_trace_cores<<<(lt.num_core + per_block - 1) / per_block, kLtWarps * 32, 0, c.stream>>>(fr, lanes);
     SPC_CUDA(cudaGetLastError());

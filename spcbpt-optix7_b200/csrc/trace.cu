@@ -161,13 +161,19 @@ static int trace_env(const char* name, int dflt) {
 template <bool ANYHIT>
 static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits, uint8_t* visible,
                            unsigned long long* visit_counters = nullptr) {
-    static int blocks_per_sm = 0, fetch_t = 0, postpone_div = 5;
-    if (!blocks_per_sm) {
-        SPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_persist<ANYHIT>, kTraceBlock, 0));
-        blocks_per_sm = std::max(1, std::min(blocks_per_sm, trace_env("SPC_TRACE_BLOCKS_PER_SM", 16)));
-        fetch_t = trace_env("SPC_FETCH_THRESHOLD", 6);
-        postpone_div = trace_env("SPC_POSTPONE_DIV", 5);
-    }
+    // launch configuration, computed once per process (frame lanes call this from several host threads: a C++11 magic static)
+    struct Cfg {
+        int blocks_per_sm, fetch_t, postpone_div;
+    };
+    static const Cfg cfg = []() {
+        Cfg k{0, 0, 5};
+        SPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k_trace_persist<ANYHIT>, kTraceBlock, 0));
+        k.blocks_per_sm = std::max(1, std::min(k.blocks_per_sm, trace_env("SPC_TRACE_BLOCKS_PER_SM", 16)));
+        k.fetch_t = trace_env("SPC_FETCH_THRESHOLD", 6);
+        k.postpone_div = trace_env("SPC_POSTPONE_DIV", 5);
+        return k;
+    }();
+    const int blocks_per_sm = cfg.blocks_per_sm, fetch_t = cfg.fetch_t, postpone_div = cfg.postpone_div;
     if (ctx.fetch_counters.n < 256) {
         ctx.fetch_counters.alloc(256);
         ctx.fetch_slot = 0;
@@ -190,8 +196,7 @@ static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, 
 }
 
 static bool use_persist() {
-    static int mode = -1;
-    if (mode < 0) mode = trace_env("SPC_TRACE_PERSISTENT", 1);
+    static const int mode = trace_env("SPC_TRACE_PERSISTENT", 1);
     return mode != 0;
 }
 
