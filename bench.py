@@ -265,7 +265,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     else:
         scene = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=72, box_cells=60), 0.01)
         scene_name = "cornell-class medium scene %d triangles" % scene.n_triangles
-    w, h = 1920, 1080
+    w, h = args.render_dim
     lanes = args.lanes
     lr_ = LaneRenderer(scene, w, h, lanes=lanes, device=local_rank, K=K, K_light=K_light, max_depth=max_depth)
     r = lr_.lanes[0]
@@ -304,8 +304,8 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     mean = float(r.image().mean())
     assert st["loss_last"] is not None and np.isfinite(st["loss_last"]) and np.isfinite(mean) and mean > 0, \
         "SPCBPT section: training or render produced no valid result (loss %r, image mean %r)" % (st["loss_last"], mean)
-    out = {"workload": "SPCBPT_eye 1920x1080, 1 spp per frame, K=%d (K_light %d), connections 3, %s, "
-                       "light trace 1000x100 paths per frame, %d frame lanes per GPU" % (K, K_light, scene_name, lanes),
+    out = {"workload": "SPCBPT_eye %dx%d, 1 spp per frame, K=%d (K_light %d), connections 3, %s, "
+                       "light trace 1000x100 paths per frame, %d frame lanes per GPU" % (w, h, K, K_light, scene_name, lanes),
            "samples_per_s": w * h * args.render_frames * world / dt_max, "ms_per_frame": dt_max / args.render_frames * 1e3, "frames": args.render_frames,
            "preprocess_s": pre_s, "train_paths": st["train_paths"], "loss_first": st["loss_first"], "loss_last": st["loss_last"],
            "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_s], "kernel_launches": int(launches), "accum_allreduce_ms": e0.elapsed_time(e1) if world > 1 else 0.0, "image_mean": mean}
@@ -354,6 +354,8 @@ def main():
     ap.add_argument("--render-frames", type=int, default=48)
     ap.add_argument("--workload", default="micro", choices=["micro", "large"],
                     help="micro = BASELINE.json configs[1] (default, the headline); large = configs[4] (20 M triangles, 256 emitters, depth 12)")
+    ap.add_argument("--render-dim", default="1920x1080", type=lambda v: tuple(int(x) for x in v.lower().split("x")),
+                    help="image size of the SPCBPT section; BASELINE.json configs[3] is --gpus 8 --render-dim 3840x2160")
     ap.add_argument("--lanes", type=int, default=4, help="frame lanes per GPU in the SPCBPT section (contexts rendering alternate subframes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
