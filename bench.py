@@ -131,19 +131,54 @@ def bind_to_gpu_numa_node(gpu_index):
 
 
 def cpu_trace_sample(pkg, orc, scene, sets, n_sample, threads):
-    """oracle port on the host cores over the first n_sample rays of each set; returns (Mrays/s, seconds)"""
+    """oracle port on the host cores over the first n_sample rays of each set; returns (Mrays/s, seconds, rays, results):
+    the results are kept -- they are the parity check of the GPU outputs on the very rays the bench times"""
     osc = orc.Scene(pkg, scene)
     t0 = time.perf_counter()
-    total = 0
+    total, results = 0, []
     for kind, rays in sets:
         r = rays[:n_sample]
         if kind == "occlusion":
-            osc.occlusion(r, threads=threads)
+            results.append(osc.occlusion(r, threads=threads))
         else:
-            osc.trace(r, threads=threads)
+            results.append(osc.trace(r, threads=threads))
         total += r.shape[0]
     dt = time.perf_counter() - t0
-    return total / dt / 1e6, dt, total
+    return total / dt / 1e6, dt, total, results
+
+
+def check_parity(pkg, gpu_hits, gpu_vis, oracle_results, ns):
+    """GPU results of the timed kernels against the oracle on the same rays: prim ids, t/u/v bits, visibility -- all exact"""
+    out = {"rays_checked": 0, "prim_mismatch": 0, "tuv_bit_mismatch": 0, "visibility_mismatch": 0}
+    for g, o in zip(gpu_hits, oracle_results[:2]):
+        g = g[:ns].cpu().numpy().view(pkg.HIT).reshape(-1)
+        out["rays_checked"] += int(o.shape[0])
+        out["prim_mismatch"] += int((g["prim"] != o["prim"]).sum())
+        for k in ("t", "u", "v"):
+            out["tuv_bit_mismatch"] += int((g[k].view(np.uint32) != o[k].view(np.uint32)).sum())
+    v = gpu_vis[:ns].cpu().numpy()
+    out["rays_checked"] += int(v.shape[0])
+    out["visibility_mismatch"] = int((v != oracle_results[2]).sum())
+    return out
+
+
+# compulsory lower bound of the algorithmic bytes per closest-hit ray (SURVEY.md section 8d): ray in + hit out + one root-to-leaf
+# descent of the 8-wide tree (ceil(log8(T/4)) nodes) + 4 triangles
+def compulsory_bytes_per_ray(n_triangles):
+    levels = 1
+    while 8 ** levels < n_triangles / 4.0:
+        levels += 1
+    return 32 + 16 + 80 * levels + 48 * 4
+
+
+def measured_traffic(workload_key):
+    """ncu counters of kernel B for this workload, captured under `ncu --set full` in an earlier run of the same command and
+    committed under profiles/ (DRAM bytes cannot be measured live without the profiler): keyed by workload, or None"""
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(prof)).get(workload_key, {}).get("B")
+    except Exception:
+        return None
 
 
 def make_ray_sets(pkg, ctx, scene, torch, side, subframe):
@@ -243,6 +278,11 @@ def host_bench_rays(pkg, scene, A, hA):
     return B, C
 
 
+def pkg_lane_blocks(lanes):
+    from spcbpt_optix7_b200.renderer import LANE_TRACE_BLOCKS
+    return LANE_TRACE_BLOCKS if lanes > 1 else 0
+
+
 def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=None):
     """BASELINE.json config 3 (and 4 at N>1): full SPCBPT at 1920x1080 with the reference's training schedule (2 M NEE paths,
     Q from light-trace launches, 100 Adam batches of 20 000), K = 1000, on a synthetic medium scene of the shipped scene's
@@ -310,6 +350,35 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
            "preprocess_s": pre_s, "train_paths": st["train_paths"], "loss_first": st["loss_first"], "loss_last": st["loss_last"],
            "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_s], "kernel_launches": int(launches), "accum_allreduce_ms": e0.elapsed_time(e1) if world > 1 else 0.0, "image_mean": mean}
     if rank == 0:
+        # in-frame work and stage times: lane 0 alone, sequential frames, every stage of every bounce bracketed by CUDA events
+        # (option "stage_timing"; slower than the production loop, used only to attribute the frame time and to state the
+        # in-frame Mrays/s of the two traversal kernels)
+        r0 = lr_.lanes[0]
+        r0.ctx.set_option("stage_timing", 1)
+        r0.ctx.set_trace_blocks(0)
+        agg, nfr = None, 4
+        for k in range(nfr + 1):
+            r0.render_frame()
+            es = r0.ctx.eye_stats()
+            if k == 0:
+                continue        # first frame after the lanes: warm-up
+            if agg is None:
+                agg = es
+            else:
+                for key in ("closest_rays", "shadow_slots", "shadow_rays", "visible_connections", "bounces"):
+                    agg[key] += es[key]
+                for key in es["stage_ms"]:
+                    agg["stage_ms"][key] += es["stage_ms"][key]
+        r0.ctx.set_option("stage_timing", 0)
+        r0.ctx.set_trace_blocks(pkg_lane_blocks(lanes))
+        sm = {k: v / nfr for k, v in agg["stage_ms"].items()}
+        out["in_frame"] = {
+            "how": "lane 0 alone, %d sequential frames, CUDA events around every stage of every bounce (spc_eye_stats_get)" % nfr,
+            "bounces_per_frame": agg["bounces"] / nfr, "stage_ms_per_frame": sm,
+            "closest_rays_per_frame": agg["closest_rays"] / nfr, "shadow_rays_per_frame": agg["shadow_rays"] / nfr,
+            "shadow_slots_per_frame": agg["shadow_slots"] / nfr, "visible_connections_per_frame": agg["visible_connections"] / nfr,
+            "closest_mrays_per_s": agg["closest_rays"] / nfr / (sm["trace"] * 1e-3) / 1e6 if sm["trace"] > 0 else None,
+            "shadow_mrays_per_s": agg["shadow_rays"] / nfr / (sm["shadow"] * 1e-3) / 1e6 if sm["shadow"] > 0 else None}
         # CPU baseline of the same pass: the oracle eye pass on a 160x90 image with the same trained state, all host threads
         try:
             import spcbpt_loader
@@ -349,7 +418,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=1 << 24, help="rays per set for the cpu_baseline leg (default: the whole sets, ~7 s on 16 cores)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="rays per set for the cpu_baseline + parity leg (default: the whole 2^24-ray sets "
+                    "of the micro workload, ~7 s on 16 cores; 2^20 per set for --workload large, whose oracle BVH takes ~20 s to build)")
     ap.add_argument("--no-render", action="store_true", help="skip the SPCBPT samples/s section (config 3)")
     ap.add_argument("--render-frames", type=int, default=48)
     ap.add_argument("--workload", default="micro", choices=["micro", "large"],
@@ -398,9 +468,14 @@ def main():
     A, B, C, hits = make_ray_sets(pkg, ctx, scene, torch, side, subframe=rank + 1)
     hitsB = torch.empty_like(hits)
     vis = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    # visit counts: (a) of the production kernel's own schedule, (b) of the strict front-to-back t-pruned traversal that SURVEY.md
+    # section 8d defines the algorithmic bytes by (option "count_canonical": independent of how the production kernel schedules)
     cntA = ctx.trace_counted(A, n, hits)
     cntB = ctx.trace_counted(B, n, hitsB)
     cntC = ctx.occlusion_counted(C, n, vis)
+    ctx.set_option("count_canonical", 1)
+    canB = ctx.trace_counted(B, n, hitsB)
+    ctx.set_option("count_canonical", 0)
 
     def step(evs=None):
         ctx.trace_device(A, n, hits)
@@ -476,24 +551,29 @@ def main():
 
     if rank == 0:
         peak, peak_src = hbm_peak()
-        nn, nt = cntB["nodes_visited"] / cntB["rays"], cntB["tris_tested"] / cntB["rays"]
+        nn, nt = canB["nodes_visited"] / canB["rays"], canB["tris_tested"] / canB["rays"]
+        nn_k, nt_k = cntB["nodes_visited"] / cntB["rays"], cntB["tris_tested"] / cntB["rays"]
         bytes_per_ray = 32 + 16 + 80 * nn + 48 * nt
         achieved = n * bytes_per_ray / (ms_B * 1e-3) / 1e9
-        traffic = None
-        prof = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(prof):
-            try:
-                traffic = json.load(open(prof)).get("k_trace_closest_incoherent_dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        comp_bytes = compulsory_bytes_per_ray(scene.n_triangles)
+        prof = measured_traffic("large" if large else "micro")
+        traffic = prof.get("dram_bytes_per_launch") if prof else None
+        if prof and prof.get("rays_per_launch") not in (None, n):
+            traffic = None      # the capture was taken on another launch size
         # cpu_baseline: oracle port on all host cores over a bounded sample of the same ray sets
         restore_affinity()
         orc = spcbpt_loader.load_oracle()
         threads = os.cpu_count() or 1
-        ns = min(args.cpu_sample, n)
+        ns = min(args.cpu_sample if args.cpu_sample > 0 else (1 << 20 if large else 1 << 24), n)
         sets = [("closest", A[:ns].cpu().numpy().view(pkg.RAY).reshape(-1)), ("closest", B[:ns].cpu().numpy().view(pkg.RAY).reshape(-1)),
                 ("occlusion", C[:ns].cpu().numpy().view(pkg.RAY).reshape(-1))]
-        cpu_val, cpu_s, cpu_n = cpu_trace_sample(pkg, orc, scene, sets, ns, threads)
+        cpu_val, cpu_s, cpu_n, cpu_res = cpu_trace_sample(pkg, orc, scene, sets, ns, threads)
+        # parity on the benchmarked configuration itself: the timed kernels' outputs against the oracle, ray by ray
+        ctx.trace_device(A, n, hits)
+        ctx.synchronize()
+        parity = check_parity(pkg, (hits, hitsB), vis, cpu_res, ns)
+        assert parity["prim_mismatch"] == 0 and parity["tuv_bit_mismatch"] == 0 and parity["visibility_mismatch"] == 0, \
+            "GPU traversal differs from the oracle on the benchmarked rays: %r" % parity
         st = ctx.bvh_stats()
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -508,10 +588,20 @@ def main():
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 3 * n * 32, "d2h_bytes_per_step": 2 * n * 16 + n, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            # achieved = algorithmic bytes (48 + 80 n_node + 48 n_tri per ray with the visit counts of the strict
+            # front-to-back traversal of the shipped BVH) / the production kernel's mean launch time.  Beside it: the same time
+            # against the compulsory bound (one root-to-leaf descent + 4 triangles: independent of any traversal), and the DRAM
+            # bytes ncu measured for this launch (what HBM really moves: the BVH of the micro workload is L2-resident).
             "roofline": {"bound": "hbm", "kernel": "k_trace_persist<false> (closest hit) on ray set B (incoherent)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nn, "tris_per_ray": nt, "kernel_ms": ms_B,
-                         "mrays_per_s": n / ms_B / 1e3},
+                         "mrays_per_s": n / ms_B / 1e3,
+                         "nodes_tris_per_ray_production_schedule": [nn_k, nt_k],
+                         "compulsory_bytes_per_ray": comp_bytes,
+                         "frac_compulsory": n * comp_bytes / (ms_B * 1e-3) / 1e9 / peak,
+                         "dram_frac": (traffic / (ms_B * 1e-3) / 1e9 / peak) if traffic else None,
+                         "ncu": prof},
+            "parity": parity,
             "cpu_baseline": {"value": cpu_val, "unit": "Mrays/s", "cores": threads, "kind": "port",
                              "sample": "first %d rays of each of the 3 sets (%d rays, %.1f s) on the oracle port" % (ns, cpu_n, cpu_s)},
         }

@@ -310,6 +310,10 @@ bool read_tables_and_frame(Decoder& z, int m) {
                 if (c.h > z.hmax) z.hmax = c.h;
                 if (c.v > z.vmax) z.vmax = c.v;
             }
+            // the resampler works with integer ratios hmax / h, vmax / v: a frame whose factors do not divide (e.g. 3 and 2)
+            // would make it read past the component rows (stb_image has the same weakness; textures are untrusted files)
+            for (int i = 0; i < z.ncomp; i++)
+                if (z.hmax % z.comp[i].h != 0 || z.vmax % z.comp[i].v != 0) return z.fail("unsupported sampling factors (not integer ratios)");
             z.mcu_w = z.hmax * 8;
             z.mcu_h = z.vmax * 8;
             z.mcus_x = (z.width + z.mcu_w - 1) / z.mcu_w;

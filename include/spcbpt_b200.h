@@ -412,6 +412,30 @@ SPC_API int  spc_set_trace_blocks(spc_context* ctx, int blocks_per_sm);
  * cuda/helpers.h:35-67 -- what the eye pass writes to MyParams::frame_buffer).  accum_dev / weights are HOST arrays of n entries. */
 SPC_API int  spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_dev, const float* weights, int n, int n_pixels,
                              spc_float4* out_accum_dev, uint32_t* out_frame_dev);
+/* Named integer switches of a context (no counterpart in the reference: its equivalents are compile-time #defines in
+ * optixPathTracer.h:31-41).  Unknown names fail with SPC_ERR_INVALID.  Results are bit-identical under every switch unless stated.
+ *   "reference_search"  1: the eye pass uses the reference's own bisect (binary_sample, cuProg.h:245-264) and walks the
+ *                          reference-layout trees instead of guide tables / compact trees / cached cross labels (test switch)
+ *   "blocking_sync"     1: the eye pass's lagged queue-size read-backs block the host thread instead of spinning
+ *   "count_canonical"   1: the *_counted entry points count the nodes / triangles of the strict front-to-back, t-pruned traversal
+ *                          (one ray per lane, one node per step: the traversal SURVEY.md section 8d defines the algorithmic bytes
+ *                          by) instead of the visits of the production kernel's own schedule
+ *   "stage_timing"      1: the eye pass brackets every stage of every bounce with CUDA events (slower: for spc_eye_stats_get) */
+SPC_API int  spc_set_option(spc_context* ctx, const char* name, int64_t value);
+SPC_API int  spc_get_option(spc_context* ctx, const char* name, int64_t* value);
+/* Work counters of the LAST eye pass of this context (no counterpart in the reference; bench.py's in-frame Mrays/s).  The call
+ * synchronises the context's stream.  stage_ms is filled (timed = 1) when the pass ran under option "stage_timing". */
+enum { SPC_STAGE_TRACE = 0, SPC_STAGE_SHADE, SPC_STAGE_SAMPLE, SPC_STAGE_SHADOW, SPC_STAGE_CONNECT, SPC_STAGE_GATHER, SPC_STAGE_OTHER, SPC_STAGE_TOTAL };
+typedef struct spc_eye_stats {
+    int32_t  bounces;              /* bounces launched                                                      */
+    int32_t  timed;
+    uint64_t closest_rays;         /* closest-hit rays traced (sum over bounces of the live paths)          */
+    uint64_t shadow_slots;         /* connection slots the occlusion kernel scanned (closest_rays * C)      */
+    uint64_t shadow_rays;          /* slots that carried a shadow ray (a light vertex was sampled)          */
+    uint64_t visible_connections;  /* shadow rays that found no occluder = connections evaluated            */
+    float    stage_ms[8];          /* indexed by SPC_STAGE_*: device time per stage summed over the bounces */
+} spc_eye_stats;
+SPC_API int  spc_eye_stats_get(spc_context* ctx, spc_eye_stats* out);
 /* optional parity dumps of the eye pass: per pixel, the primitive id of the primary hit (-1 miss) and the
  * subspace id of the first eye vertex (-1 none).  Device int[W*H] each, or NULL to disable. */
 SPC_API int  spc_set_debug_outputs(spc_context* ctx, int32_t* first_prim_dev, int32_t* first_label_dev);

@@ -48,6 +48,9 @@ SUBSPACE = np.dtype([("jump_bias", "i4"), ("id", "i4"), ("size", "i4"), ("sum_pm
 MESH = np.dtype([("positions", "u8"), ("indices", "u8"), ("texcoords", "u8"), ("n_vertices", "u4"),
                  ("n_triangles", "u4"), ("material_id", "i4"), ("light_id", "i4")])
 TEXTURE = np.dtype([("rgba", "u8"), ("width", "i4"), ("height", "i4")])
+EYE_STATS = np.dtype([("bounces", "i4"), ("timed", "i4"), ("closest_rays", "u8"), ("shadow_slots", "u8"), ("shadow_rays", "u8"),
+                      ("visible_connections", "u8"), ("stage_ms", "f4", 8)])
+STAGE_NAMES = ("trace", "shade", "sample", "shadow", "connect", "gather", "other", "total")
 BVH_STATS = np.dtype([("n_triangles", "u4"), ("n_nodes", "u4"), ("n_bvh2_nodes", "u4"), ("max_depth", "u4"),
                       ("sah_cost", "f4"), ("build_ms", "f4"), ("bytes_nodes", "u8"), ("bytes_triangles", "u8")])
 TRACE_COUNTERS = np.dtype([("rays", "u8"), ("nodes_visited", "u8"), ("tris_tested", "u8")])
@@ -70,7 +73,7 @@ PARAMS = np.dtype([("width", "u4"), ("height", "u4"), ("subframe_index", "u4"), 
                    ("subspace_info", SUBSPACE_INFO), ("sky", ENV_INFO)])
 
 EXPECTED_SIZES = {"RAY": 32, "HIT": 16, "TEXREF": 40, "PBR": 144, "LIGHT": 80, "VERTEX": 120, "TREE_NODE": 56,
-                  "DIVIDE_WEIGHT": 40, "SUBSPACE": 20, "TRAIN_PATH": 48, "TRAIN_CONN": 92, "MESH": 40, "TEXTURE": 16, "BUFFER_VIEW": 16,
+                  "DIVIDE_WEIGHT": 40, "SUBSPACE": 20, "EYE_STATS": 72, "TRAIN_PATH": 48, "TRAIN_CONN": 92, "MESH": 40, "TEXTURE": 16, "BUFFER_VIEW": 16,
                   "LT_PARAMS": 40, "PRETRACE_PARAMS": 32, "SAMPLER": 40, "SUBSPACE_INFO": 40, "ENV_INFO": 56,
                   "PARAMS": 352}
 
@@ -139,6 +142,9 @@ def _bind_optional(L):
         "spc_launch": [vp, i32, i32, i32],
         "spc_launch_named": [vp, ctypes.c_char_p, i32, i32],
         "spc_set_debug_outputs": [vp, vp, vp],
+        "spc_eye_stats_get": [vp, vp],
+        "spc_set_option": [vp, ctypes.c_char_p, i64],
+        "spc_get_option": [vp, ctypes.c_char_p, vp],
         "spc_set_seed_offset": [vp, ctypes.c_uint32],
         "spc_set_seed_mapping": [vp, ctypes.c_uint32, ctypes.c_uint32],
         "spc_set_trace_blocks": [vp, i32],
@@ -311,6 +317,22 @@ class Context:
         ptrs = np.array([int(_ptr(a)) for a in accum_devs], np.uint64)
         w = np.ascontiguousarray(weights, np.float32)
         self._ck(self._L.spc_merge_accum(self.h, ptrs.ctypes.data, w.ctypes.data, len(ptrs), n_pixels, _ptr(out_accum_dev), _ptr(out_frame_dev)), "spc_merge_accum")
+
+    def set_option(self, name, value):
+        self._ck(self._L.spc_set_option(self.h, name.encode(), int(value)), "spc_set_option(%s)" % name)
+
+    def get_option(self, name):
+        v = ctypes.c_int64(0)
+        self._ck(self._L.spc_get_option(self.h, name.encode(), ctypes.byref(v)), "spc_get_option(%s)" % name)
+        return v.value
+
+    def eye_stats(self):
+        """work counters (+ per-stage device ms under option stage_timing) of the last eye pass"""
+        s = np.zeros(1, EYE_STATS)
+        self._ck(self._L.spc_eye_stats_get(self.h, s.ctypes.data), "spc_eye_stats_get")
+        out = {k: int(s[0][k]) for k in EYE_STATS.names if k != "stage_ms"}
+        out["stage_ms"] = {n: float(v) for n, v in zip(STAGE_NAMES, s[0]["stage_ms"])}
+        return out
 
     def set_debug_outputs(self, first_prim_dev, first_label_dev):
         self._ck(self._L.spc_set_debug_outputs(self.h, _ptr(first_prim_dev), _ptr(first_label_dev)), "spc_set_debug_outputs")

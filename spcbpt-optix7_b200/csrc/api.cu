@@ -63,7 +63,9 @@ void pipelined_host_batch(Context& c, const spc_ray* rays_host, int64_t n, Launc
             copy_back(off, m, c.stream);
         }
     } catch (...) {
+        // copies to/from the caller's host buffers may still be in flight: drain them before the error reaches the caller
         c.stream = user;
+        for (int k = 0; k < kPipeStreams; k++) cudaStreamSynchronize(c.pipe_streams[k]);
         throw;
     }
     c.stream = user;
@@ -125,6 +127,10 @@ void spc_destroy(spc_context* ctx) {
     if (ctx->c.h_pinned) cudaFreeHost(ctx->c.h_pinned);
     for (cudaEvent_t ev : ctx->c.eye_events)
         if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->c.eye.stage_ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : ctx->c.pipe_streams)
+        if (st) cudaStreamDestroy(st);
+    if (ctx->c.pipe_event) cudaEventDestroy(ctx->c.pipe_event);
     spc::gamma_guide_forget(&ctx->c, true);
     delete ctx;
 }
@@ -160,6 +166,9 @@ int spc_scene_upload(spc_context* ctx, const spc_mesh* meshes, int n_meshes, con
         total += me.n_triangles;
     }
     SPC_REQUIRE(total >= 1 && total < 0x7fffffffull, SPC_ERR_INVALID, "spc_scene_upload: %llu triangles", (unsigned long long)total);
+    for (int i = 0; i < n_materials; i++)   // shade_pbr reads tex_desc[tex - 1]: a texture id above the table reads outside it
+        SPC_REQUIRE(materials[i].base_color_tex.tex <= (uint64_t)n_textures, SPC_ERR_INVALID,
+                    "spc_scene_upload: material %d names texture %llu of %d", i, (unsigned long long)materials[i].base_color_tex.tex, n_textures);
     const uint32_t n = (uint32_t)total;
     std::vector<float4> tri_pos((size_t)n * 3);
     std::vector<float2> tri_uv((size_t)n * 3);

@@ -105,6 +105,51 @@ int spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_dev, const 
     SPC_API_END
 }
 
+// name -> field table of the context switches
+static int64_t* option_slot(Context& c, const char* name, int64_t* lo, int64_t* hi) {
+    struct Opt { const char* name; int64_t* p; int64_t lo, hi; };
+    const Opt table[] = {
+        {"reference_search", &c.opt[spc::OPT_REFERENCE_SEARCH], 0, 1},
+        {"blocking_sync", &c.opt[spc::OPT_BLOCKING_SYNC], 0, 1},
+        {"count_canonical", &c.opt[spc::OPT_COUNT_CANONICAL], 0, 1},
+        {"stage_timing", &c.opt[spc::OPT_STAGE_TIMING], 0, 1},
+    };
+    for (const Opt& o : table)
+        if (!strcmp(o.name, name)) {
+            *lo = o.lo; *hi = o.hi;
+            return o.p;
+        }
+    return nullptr;
+}
+
+int spc_set_option(spc_context* ctx, const char* name, int64_t value) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(name, SPC_ERR_INVALID, "spc_set_option: null name");
+    int64_t lo, hi;
+    int64_t* p = option_slot(c, name, &lo, &hi);
+    SPC_REQUIRE(p, SPC_ERR_INVALID, "spc_set_option: unknown option '%s'", name);
+    SPC_REQUIRE(value >= lo && value <= hi, SPC_ERR_INVALID, "spc_set_option: %s = %lld outside [%lld, %lld]", name, (long long)value, (long long)lo, (long long)hi);
+    *p = value;
+    SPC_API_END
+}
+
+int spc_get_option(spc_context* ctx, const char* name, int64_t* value) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(name && value, SPC_ERR_INVALID, "spc_get_option: null argument");
+    int64_t lo, hi;
+    int64_t* p = option_slot(c, name, &lo, &hi);
+    SPC_REQUIRE(p, SPC_ERR_INVALID, "spc_get_option: unknown option '%s'", name);
+    *value = *p;
+    SPC_API_END
+}
+
+int spc_eye_stats_get(spc_context* ctx, spc_eye_stats* out) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(out, SPC_ERR_INVALID, "spc_eye_stats_get: out is null");
+    spc::eye_stats(c, out);
+    SPC_API_END
+}
+
 int spc_set_debug_outputs(spc_context* ctx, int32_t* first_prim_dev, int32_t* first_label_dev) {
     SPC_API_BEGIN
     c.dbg_first_prim = first_prim_dev;

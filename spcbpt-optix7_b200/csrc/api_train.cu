@@ -50,33 +50,46 @@ int spc_get_tree_points(spc_context* ctx, int eye_side, int max_size, spc_divide
 int spc_tree_to_device(spc_context* ctx, int eye_side, const spc_tree_node* nodes_host, int n, spc_tree_node** dev_out) {
     SPC_API_BEGIN
     SPC_REQUIRE(nodes_host && n > 0 && dev_out, SPC_ERR_INVALID, "spc_tree_to_device: bad arguments");
+    // A malformed tree (hand-edited tree_*.txt, a state trained with another K) would send the device walks out of bounds or into a
+    // cycle, and labels >= K index Q / the CMFGamma rows out of bounds: reject it here.  Well-formed = what the builder emits
+    // (classTree_host.h:103-284 appends the 8 children of a split behind their parent): root at 0, every child index in (parent, n)
+    // and referenced once, node types 0..2, leaf labels in [0, K).
+    {
+        std::vector<uint8_t> seen((size_t)n, 0);
+        for (int i = 0; i < n; i++) {
+            const spc_tree_node& nd = nodes_host[i];
+            if (nd.leaf) {
+                SPC_REQUIRE(nd.label >= 0 && nd.label < c.K, SPC_ERR_INVALID, "spc_tree_to_device: node %d: leaf label %d outside [0, %d)", i, nd.label, c.K);
+                continue;
+            }
+            SPC_REQUIRE(nd.type >= 0 && nd.type <= 2, SPC_ERR_INVALID, "spc_tree_to_device: node %d: type %d", i, nd.type);
+            for (int k = 0; k < 8; k++) {
+                const int ch = nd.child[k];
+                SPC_REQUIRE(ch > i && ch < n, SPC_ERR_INVALID, "spc_tree_to_device: node %d: child %d = %d outside (%d, %d)", i, k, ch, i, n);
+                SPC_REQUIRE(!seen[ch], SPC_ERR_INVALID, "spc_tree_to_device: node %d is the child of two nodes", ch);
+                seen[ch] = 1;
+            }
+        }
+    }
     spc::DevBuf<spc_tree_node>& b = eye_side ? c.train.eye_tree : c.train.light_tree;
     spc::ctree_register(b.p, nullptr, &c);
     b.alloc(n);
     SPC_CUDA(cudaMemcpyAsync(b.p, nodes_host, (size_t)n * sizeof(spc_tree_node), cudaMemcpyHostToDevice, c.stream));
     // compact copy for the device-side walks (shade.cuh "compact trees"): 48 B per node = {mid, type} + 8 children, a leaf child
     // carries its label in the parent's entry (0x80000000 | label), a leaf root in the root's type word
-    bool compact_ok = true;
+    const bool compact_ok = true;   // guaranteed by the validation above
     std::vector<float> ct((size_t)n * 12, 0.f);
-    for (int i = 0; i < n && compact_ok; i++) {
+    for (int i = 0; i < n; i++) {
         const spc_tree_node& nd = nodes_host[i];
         uint32_t w[12] = {};
         memcpy(&w[0], &nd.mid.x, 4); memcpy(&w[1], &nd.mid.y, 4); memcpy(&w[2], &nd.mid.z, 4);
         if (nd.leaf) {
-            compact_ok = nd.label >= 0;
             w[3] = 0x80000000u | (uint32_t)nd.label;
         } else {
-            compact_ok = nd.type >= 0;
             w[3] = (uint32_t)nd.type;
-            for (int k = 0; k < 8 && compact_ok; k++) {
+            for (int k = 0; k < 8; k++) {
                 const int ch = nd.child[k];
-                if (ch < 0 || ch >= n) { compact_ok = false; break; }
-                if (nodes_host[ch].leaf) {
-                    compact_ok = nodes_host[ch].label >= 0;
-                    w[4 + k] = 0x80000000u | (uint32_t)nodes_host[ch].label;
-                } else {
-                    w[4 + k] = (uint32_t)ch;
-                }
+                w[4 + k] = nodes_host[ch].leaf ? (0x80000000u | (uint32_t)nodes_host[ch].label) : (uint32_t)ch;
             }
         }
         memcpy(&ct[(size_t)i * 12], w, sizeof(w));

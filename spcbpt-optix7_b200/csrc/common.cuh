@@ -110,6 +110,10 @@ struct EyeBuffers {
     DevBuf<int>        counts;    // counts[b] = live paths entering bounce b
     DevBuf<short>      xlab;      // per pixel: light-tree label of the current eye vertex
     DevBuf<short>      lvc_xlabel;   // per LVC slot: eye-tree label (valid slots only)
+    DevBuf<unsigned long long> stat;   // work counters of the last pass (spc_eye_stats_get): shadow rays, visible connections, ...
+    int                last_bounces = 0;            // bounces launched by the last pass
+    std::vector<cudaEvent_t> stage_ev;              // option "stage_timing": 7 events per bounce + 2 around the pass
+    bool               last_timed = false;
     size_t             pixels = 0;
     int                conns = 0;
 };
@@ -156,6 +160,9 @@ struct TrainBuffers {
     DevBuf<uint8_t>  sort_tmp;
 };
 
+// spc_set_option switches (include/spcbpt_b200.h documents each)
+enum Option { OPT_REFERENCE_SEARCH = 0, OPT_BLOCKING_SYNC, OPT_COUNT_CANONICAL, OPT_STAGE_TIMING, OPT_COUNT };
+
 struct Context {
     int           device = 0;
     int           K = 1000, K_light = 200, connections = 3;
@@ -192,6 +199,10 @@ struct Context {
     DevBuf<spc_vertex> pretrace_scratch;       // per-lane eye-vertex buffers of the training tracer
     TrainBuffers  train;
     LvcBuffers    bins_tmp;                    // ordered-binning scratch of getQ / sample_reweight
+    // per-context one-time setup (function attributes and occupancy are per DEVICE, and spc_create accepts any device)
+    bool          lvc_attr_set = false;        // lvc.cu: dynamic shared-memory opt-in of the binning kernels
+    int           persist_blocks[2] = {0, 0};  // trace.cu: resident blocks per SM of k_trace_persist<ANYHIT> on this device (0 = not queried)
+    int64_t       opt[OPT_COUNT] = {};         // spc_set_option switches (api_render.cu), all 0 by default
 };
 
 void build_bvh(Context& ctx, const float4* d_tri_pos /*3 per prim*/, uint32_t n_prims);
@@ -207,6 +218,7 @@ void launch_trace_occlusion_q(Context& ctx, const spc_ray* rays, const int* n_de
 
 void launch_light_trace(Context& ctx);                       // "light trace" raygen
 void launch_eye_pass(Context& ctx, int width, int height);   // "SPCBPT_eye" raygen
+void eye_stats(Context& ctx, spc_eye_stats* out);
 void merge_accum(Context& ctx, const spc_float4* const* bufs_host, const float* weights_host, int n, int n_pix, spc_float4* out, uint32_t* frame);
 void launch_pretrace(Context& ctx);                          // "pretrace" raygen
 void launch_pt(Context& ctx, int width, int height);         // "pt" raygen

@@ -188,12 +188,11 @@ void bin_ordered(Context& c, LvcBuffers& b, int n, int K, int* counters /* [0] <
     const int wpb = (int)std::min<size_t>(8, (160 * 1024) / ((size_t)K * 4));
     SPC_REQUIRE(wpb >= 1, SPC_ERR_CAPACITY, "ordered binning: %d bins do not fit the shared-memory histogram", K);
     const size_t smem = (size_t)wpb * K * 4;
-    static const bool attr_set = []() {   // once per process, safe under concurrent first calls (frame lanes)
+    if (!c.lvc_attr_set) {   // function attributes are per device: once per context (a context is driven by one host thread at a time)
         SPC_CUDA(cudaFuncSetAttribute(k_bin_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SPC_CUDA(cudaFuncSetAttribute(k_lvc_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        return true;
-    }();
-    (void)attr_set;
+        c.lvc_attr_set = true;
+    }
     const int grid = std::max(1, std::min((n_chunks + wpb - 1) / wpb, c.sm_count * 4));
     k_bin_hist<<<grid, wpb * 32, smem, st>>>(b.key.p, n, K, n_chunks, b.hist.p);
     k_lvc_colscan<<<(K + 127) / 128, 128, 0, st>>>(b.hist.p, n_chunks, K, b.totals.p);

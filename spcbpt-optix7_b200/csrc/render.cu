@@ -178,6 +178,7 @@ struct EyeArgs {
     int*        first_prim;
     int*        first_label;
     short*      xlab;       // per pixel: light-tree label of the current eye vertex (cross label, shade.cuh)
+    unsigned long long* stat;   // work counters: [0] shadow rays, [1] visible connections (spc_eye_stats_get)
     int         bounce;
 };
 
@@ -503,6 +504,7 @@ template <int CT>
 __global__ void __launch_bounds__(128, 8) k_eye_sample(const DevFrame fr, const EyeArgs a) {
     const int n = a.counts[a.bounce];
     const int C = CT > 0 ? CT : fr.connections;
+    unsigned n_shadow = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (a.conn_lvc[(size_t)i * C] != -2) continue;   // miss, emitter hit or no surface vertex: slots stay empty
         const int pix = a.queue_cur[i];
@@ -537,8 +539,11 @@ __global__ void __launch_bounds__(128, 8) k_eye_sample(const DevFrame fr, const 
             a.shadow[2 * ((size_t)i * C + j)] = make_float4(pos.x, pos.y, pos.z, SPC_SCENE_EPS);
             a.shadow[2 * ((size_t)i * C + j) + 1] = make_float4(dir.x, dir.y, dir.z, len - SPC_SCENE_EPS);
             a.conn_pmf[(size_t)i * C + j] = pick[j].pmf;
+            n_shadow++;
         }
     }
+    n_shadow = __reduce_add_sync(0xffffffffu, n_shadow);   // every lane reaches this point
+    if ((threadIdx.x & 31) == 0 && n_shadow) atomicAdd(a.stat + 0, (unsigned long long)n_shadow);
 }
 
 // eye-tree label of every valid LVC vertex (the `jump_buffer` lists them), once per frame: tracing_weight_light would
@@ -577,6 +582,7 @@ __global__ void __launch_bounds__(128) k_eye_connect(const DevFrame fr, const Ey
     const int64_t n = (int64_t)a.counts[a.bounce] * C;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int pending[2] = {0, 0};   // warp-uniform
+    unsigned n_visible = 0;    // warp-uniform
     bool last = false;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32;; base += (int64_t)gridDim.x * blockDim.x) {
         if (base >= n) last = true;   // one extra round that drains what is left
@@ -593,6 +599,7 @@ __global__ void __launch_bounds__(128) k_eye_connect(const DevFrame fr, const Ey
                 const unsigned m = __ballot_sync(0xffffffffu, kind == t);
                 if (kind == t) s_queue[warp][t][pending[t] + __popc(m & ((1u << lane) - 1u))] = k;
                 pending[t] += __popc(m);
+                n_visible += __popc(m);
             }
             __syncwarp();
         }
@@ -609,6 +616,7 @@ __global__ void __launch_bounds__(128) k_eye_connect(const DevFrame fr, const Ey
         }
         if (last) break;
     }
+    if (lane == 0 && n_visible) atomicAdd(a.stat + 1, (unsigned long long)n_visible);
 }
 
 // result += res / CONNECTION_N, in connection order (raygen.cu:415)
@@ -716,9 +724,28 @@ void launch_eye_pass(Context& c, int width, int height) {
     }
     const int n_counts = fr.max_depth + 4;
     e.counts.alloc(n_counts);
+    e.stat.alloc(8);
     if (!c.h_pinned) SPC_CUDA(cudaMallocHost((void**)&c.h_pinned, 64 * sizeof(int)));
     cudaStream_t st = c.stream;
     SPC_CUDA(cudaMemsetAsync(e.counts.p, 0, n_counts * sizeof(int), st));
+    SPC_CUDA(cudaMemsetAsync(e.stat.p, 0, 8 * sizeof(unsigned long long), st));
+    // option "stage_timing": events around every stage of every bounce (spc_eye_stats_get sums them per stage)
+    const bool timed = c.opt[OPT_STAGE_TIMING] != 0;
+    constexpr int kEvPerBounce = 7;
+    if (timed) {
+        const size_t need = (size_t)(fr.max_depth + 1) * kEvPerBounce + 2;
+        while (e.stage_ev.size() < need) {
+            cudaEvent_t ev;
+            SPC_CUDA(cudaEventCreate(&ev));
+            e.stage_ev.push_back(ev);
+        }
+        SPC_CUDA(cudaEventRecord(e.stage_ev[0], st));
+    }
+    auto mark = [&](int b, int k) {
+        if (timed) SPC_CUDA(cudaEventRecord(e.stage_ev[2 + (size_t)b * kEvPerBounce + k], st));
+    };
+    e.last_timed = timed;
+    e.last_bounces = 0;
 
     EyeArgs a;
     a.ev = e.ev.p; a.pre = e.pre.p; a.res = e.res.p;
@@ -726,6 +753,7 @@ void launch_eye_pass(Context& c, int width, int height) {
     a.conn_lvc = e.conn_lvc.p; a.conn_pmf = e.conn_pmf.p; a.contrib = e.contrib.p; a.counts = e.counts.p;
     a.first_prim = c.dbg_first_prim; a.first_label = c.dbg_first_label;
     a.xlab = e.xlab.p;
+    a.stat = e.stat.p;
     // cross labels of the light vertices: only when the sampler is the one spc_lvc_process built (then jump_buffer indexes
     // c.lvc.n slots); a caller-made sampler keeps the in-kernel tree walk
     fr.lvc_xlabel = nullptr;
@@ -741,8 +769,8 @@ void launch_eye_pass(Context& c, int width, int height) {
     a.rays_cur = (float4*)e.rays[0].p; a.rays_next = (float4*)e.rays[1].p;
     a.queue_cur = e.queue[0].p; a.queue_next = e.queue[1].p;
 
-    if (getenv("SPC_EYE_REFERENCE_SEARCH")) {
-        // test switch (tests/test_render_gpu.py): the reference's bisect and the reference-layout tree walks instead of guide tables,
+    if (c.opt[OPT_REFERENCE_SEARCH]) {
+        // test switch (spc_set_option "reference_search", tests/test_pipeline_gpu.py): the reference's bisect and the reference-layout tree walks instead of guide tables,
         // compact trees and the cached light-vertex labels -- frames must come out bit-identical either way
         fr.gamma_guide = nullptr;
         fr.lvc_guide = nullptr;
@@ -761,16 +789,19 @@ void launch_eye_pass(Context& c, int width, int height) {
     constexpr int kLag = 3, kRing = 8;
     if (!c.eye_events[0])
         for (int k = 0; k < kRing; k++)
-            SPC_CUDA(cudaEventCreateWithFlags(&c.eye_events[k], cudaEventDisableTiming | (getenv("SPC_BLOCKING_SYNC") ? cudaEventBlockingSync : 0)));
+            SPC_CUDA(cudaEventCreateWithFlags(&c.eye_events[k], cudaEventDisableTiming | (c.opt[OPT_BLOCKING_SYNC] ? cudaEventBlockingSync : 0)));
     int* h_ring = c.h_pinned + 16;
     // loop of raygen.cu:357-421: a path is traced while !done && depth <= max_depth, i.e. bounces 0..max_depth
     for (int b = 0; b <= fr.max_depth; b++) {
         a.bounce = b;
         a.rays_cur = (float4*)e.rays[b & 1].p; a.rays_next = (float4*)e.rays[(b + 1) & 1].p;
         a.queue_cur = e.queue[b & 1].p; a.queue_next = e.queue[(b + 1) & 1].p;
+        mark(b, 0);
         launch_trace_closest_q(c, (const spc_ray*)a.rays_cur, e.counts.p + b, 1, n_max, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);
+        mark(b, 1);
         const int g1 = (int)std::min<int64_t>((n_max + 127) / 128, grid_cap);
         k_eye_shade<<<g1, 128, 0, st>>>(fr, a);
+        mark(b, 2);
         switch (C) {
             case 1: k_eye_sample<1><<<g1, 128, 0, st>>>(fr, a); break;
             case 2: k_eye_sample<2><<<g1, 128, 0, st>>>(fr, a); break;
@@ -778,10 +809,15 @@ void launch_eye_pass(Context& c, int width, int height) {
             case 4: k_eye_sample<4><<<g1, 128, 0, st>>>(fr, a); break;
             default: k_eye_sample<0><<<g1, 128, 0, st>>>(fr, a); break;
         }
+        mark(b, 3);
         launch_trace_occlusion_q(c, (const spc_ray*)a.shadow, e.counts.p + b, C, n_max * C, e.visible.p);
+        mark(b, 4);
         const int g2 = (int)std::min<int64_t>((n_max * C + 127) / 128, grid_cap);
         k_eye_connect<<<g2, 128, 0, st>>>(fr, a);
+        mark(b, 5);
         k_eye_gather<<<g1, 128, 0, st>>>(fr, a);
+        mark(b, 6);
+        e.last_bounces = b + 1;
         c.launches += 4;
         SPC_CUDA(cudaGetLastError());
         if (b < fr.max_depth) {
@@ -797,7 +833,42 @@ void launch_eye_pass(Context& c, int width, int height) {
     }
     k_accumulate<<<(nP + 255) / 256, 256, 0, st>>>(fr, e.res.p, nP);
     c.launches++;
+    if (timed) SPC_CUDA(cudaEventRecord(e.stage_ev[1], st));
     SPC_CUDA(cudaGetLastError());
+}
+
+// spc_eye_stats_get: counters (and, under option "stage_timing", per-stage device times) of the last eye pass
+void eye_stats(Context& c, spc_eye_stats* out) {
+    EyeBuffers& e = c.eye;
+    *out = spc_eye_stats{};
+    SPC_REQUIRE(e.last_bounces > 0 && e.stat.p && e.counts.p, SPC_ERR_INVALID, "spc_eye_stats_get: no eye pass has run on this context");
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    std::vector<int> counts((size_t)e.last_bounces);
+    unsigned long long stat[8];
+    SPC_CUDA(cudaMemcpy(counts.data(), e.counts.p, counts.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    SPC_CUDA(cudaMemcpy(stat, e.stat.p, sizeof(stat), cudaMemcpyDeviceToHost));
+    out->bounces = e.last_bounces;
+    for (int v : counts) out->closest_rays += (uint64_t)v;
+    out->shadow_slots = out->closest_rays * (uint64_t)c.connections;
+    out->shadow_rays = stat[0];
+    out->visible_connections = stat[1];
+    if (e.last_timed) {
+        constexpr int kEvPerBounce = 7;
+        static const int stage_of[6] = {SPC_STAGE_TRACE, SPC_STAGE_SHADE, SPC_STAGE_SAMPLE, SPC_STAGE_SHADOW, SPC_STAGE_CONNECT, SPC_STAGE_GATHER};
+        float sum = 0.f;
+        for (int b = 0; b < e.last_bounces; b++)
+            for (int k = 0; k < 6; k++) {
+                float ms = 0.f;
+                SPC_CUDA(cudaEventElapsedTime(&ms, e.stage_ev[2 + (size_t)b * kEvPerBounce + k], e.stage_ev[2 + (size_t)b * kEvPerBounce + k + 1]));
+                out->stage_ms[stage_of[k]] += ms;
+                sum += ms;
+            }
+        float total = 0.f;
+        SPC_CUDA(cudaEventElapsedTime(&total, e.stage_ev[0], e.stage_ev[1]));
+        out->stage_ms[SPC_STAGE_TOTAL] = total;
+        out->stage_ms[SPC_STAGE_OTHER] = total - sum;
+        out->timed = 1;
+    }
 }
 
 }  // namespace spc

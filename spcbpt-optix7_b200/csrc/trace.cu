@@ -161,19 +161,19 @@ static int trace_env(const char* name, int dflt) {
 template <bool ANYHIT>
 static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits, uint8_t* visible,
                            unsigned long long* visit_counters = nullptr) {
-    // launch configuration, computed once per process (frame lanes call this from several host threads: a C++11 magic static)
-    struct Cfg {
-        int blocks_per_sm, fetch_t, postpone_div;
+    // process-wide tuning knobs (environment, read once) and the per-device occupancy of this kernel (queried once per context:
+    // occupancy is a property of the device the context lives on)
+    struct Knobs {
+        int max_blocks, fetch_t, postpone_div;
     };
-    static const Cfg cfg = []() {
-        Cfg k{0, 0, 5};
-        SPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k.blocks_per_sm, k_trace_persist<ANYHIT>, kTraceBlock, 0));
-        k.blocks_per_sm = std::max(1, std::min(k.blocks_per_sm, trace_env("SPC_TRACE_BLOCKS_PER_SM", 16)));
-        k.fetch_t = trace_env("SPC_FETCH_THRESHOLD", 6);
-        k.postpone_div = trace_env("SPC_POSTPONE_DIV", 5);
-        return k;
-    }();
-    const int blocks_per_sm = cfg.blocks_per_sm, fetch_t = cfg.fetch_t, postpone_div = cfg.postpone_div;
+    static const Knobs knobs = {trace_env("SPC_TRACE_BLOCKS_PER_SM", 16), trace_env("SPC_FETCH_THRESHOLD", 6), trace_env("SPC_POSTPONE_DIV", 5)};
+    int& cached = ctx.persist_blocks[ANYHIT ? 1 : 0];
+    if (cached == 0) {
+        int b = 0;
+        SPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_persist<ANYHIT>, kTraceBlock, 0));
+        cached = std::max(1, std::min(b, knobs.max_blocks));
+    }
+    const int blocks_per_sm = cached, fetch_t = knobs.fetch_t, postpone_div = knobs.postpone_div;
     if (ctx.fetch_counters.n < 256) {
         ctx.fetch_counters.alloc(256);
         ctx.fetch_slot = 0;
@@ -278,7 +278,10 @@ void launch_trace_closest(Context& ctx, const spc_ray* rays, int64_t n, int flag
     const int64_t blocks = (n + kTraceBlock - 1) / kTraceBlock;
     SPC_REQUIRE(blocks < 0x7fffffffLL, SPC_ERR_INVALID, "ray batch too large: %lld", (long long)n);
     const int cull = (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0;
-    if (use_persist()) {   // the counted variant is the same kernel with two visit counters (the instrumented twin of the roofline)
+    // counted variants: the production kernel with two visit counters (what THIS kernel fetches), or -- option "count_canonical" --
+    // the plain one-ray-per-lane kernel: strict front-to-back, t-pruned order, the traversal SURVEY.md section 8d defines the
+    // algorithmic bytes by (independent of the production kernel's scheduling, so visiting more nodes cannot raise the roofline)
+    if (use_persist() && !(counters && ctx.opt[OPT_COUNT_CANONICAL])) {
         launch_persist<false>(ctx, rays, nullptr, 1, n, flags, hits, nullptr, counters);
         return;
     }
@@ -297,7 +300,7 @@ void launch_trace_occlusion(Context& ctx, const spc_ray* rays, int64_t n, uint8_
     if (n <= 0) return;
     const int64_t blocks = (n + kTraceBlock - 1) / kTraceBlock;
     SPC_REQUIRE(blocks < 0x7fffffffLL, SPC_ERR_INVALID, "ray batch too large: %lld", (long long)n);
-    if (use_persist()) {
+    if (use_persist() && !(counters && ctx.opt[OPT_COUNT_CANONICAL])) {
         launch_persist<true>(ctx, rays, nullptr, 1, n, 0, nullptr, visible, counters);
         return;
     }

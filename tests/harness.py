@@ -253,3 +253,24 @@ def setup_pretrace_device(df, num_core, padding=10, iteration=1):
 
 def pretrace_host(df):
     return df.tp.cpu().numpy().view(df.pkg.TRAIN_PATH).copy(), df.tc.cpu().numpy().view(df.pkg.TRAIN_CONN).copy()
+
+
+def varied_cornell(pkg):
+    """Cornell fixture with a metallic box, a textured box (random 24x16 RGBA texture) and a second quad light: the material /
+    texture / multi-light branches of the shading code (ColorTexSample hit_program.cu:182-198, LocalShading.h:37-53)"""
+    sc = pkg.scenes.cornell_scene(wall_cells=8, box_cells=5)
+    rng = np.random.default_rng(5)
+    mats = pkg.scenes.make_pbr(5)
+    mats[:3] = sc.materials
+    mats["base_color"][3] = (0.9, 0.8, 0.3, 1); mats["metallic"][3] = 1.0; mats["roughness"][3] = 0.15
+    mats["base_color"][4] = (1, 1, 1, 1); mats["roughness"][4] = 0.6
+    tex = rng.integers(0, 256, (16, 24, 4), dtype=np.uint8)
+    sc.textures = [tex]
+    mats["base_color_tex"]["tex"][4] = 1
+    sc.materials = mats
+    sc.meshes[3]["material_id"] = 3     # short box: metal
+    sc.meshes[4]["material_id"] = 4     # tall box: textured
+    L2 = pkg.scenes.make_quad_light(1, (20.0, 300.0, 100.0), (20.0, 300.0, 200.0), (20.0, 400.0, 100.0), (6.0, 8.0, 12.0), 3, 4)
+    sc.lights = np.concatenate([sc.lights, L2])
+    sc.meshes.append(pkg.scenes.light_mesh(L2, 1))
+    return sc

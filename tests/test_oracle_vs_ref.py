@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from harness import HostFrame, compare_lvc, compare_train, random_trees_and_gamma, setup_pretrace
+from harness import HostFrame, compare_lvc, compare_train, random_trees_and_gamma, setup_pretrace, varied_cornell as _varied_cornell
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -20,25 +20,6 @@ def ref():
     if not m.available():
         pytest.skip("reference tree absent and oracle/_ref not prebuilt")
     return m
-
-
-def _varied_cornell(pkg):
-    sc = pkg.scenes.cornell_scene(wall_cells=8, box_cells=5)
-    rng = np.random.default_rng(5)
-    mats = pkg.scenes.make_pbr(5)
-    mats[:3] = sc.materials
-    mats["base_color"][3] = (0.9, 0.8, 0.3, 1); mats["metallic"][3] = 1.0; mats["roughness"][3] = 0.15
-    mats["base_color"][4] = (1, 1, 1, 1); mats["roughness"][4] = 0.6
-    tex = rng.integers(0, 256, (16, 24, 4), dtype=np.uint8)
-    sc.textures = [tex]
-    mats["base_color_tex"]["tex"][4] = 1
-    sc.materials = mats
-    sc.meshes[3]["material_id"] = 3     # short box: metal
-    sc.meshes[4]["material_id"] = 4     # tall box: textured
-    L2 = pkg.scenes.make_quad_light(1, (20.0, 300.0, 100.0), (20.0, 300.0, 200.0), (20.0, 400.0, 100.0), (6.0, 8.0, 12.0), 3, 4)
-    sc.lights = np.concatenate([sc.lights, L2])
-    sc.meshes.append(pkg.scenes.light_mesh(L2, 1))
-    return sc
 
 
 def test_render_path_bit_exact(pkg, orc, ref):

@@ -73,9 +73,8 @@ def test_pipelined_frames_equal_sequential_frames(gpu_ctx):
 
 def test_guide_tables_and_compact_trees_leave_frames_bit_identical(gpu_ctx):
     """k_eye_sample's guide tables / compact trees / cached light-vertex labels against the reference's own bisect and tree walk
-    (SPC_EYE_REFERENCE_SEARCH switches them off at launch time): same trained state, same frames, every bit.  K = 64 with 12 emitter
+    (spc_set_option "reference_search" switches them off at launch time): same trained state, same frames, every bit.  K = 64 with 12 emitter
     subspaces on a small LVC leaves several light subspaces empty, so the empty-subspace draw shifts are exercised too."""
-    import os
     pkg = gpu_ctx
     from spcbpt_optix7_b200.renderer import Renderer
     sc = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=12, box_cells=8), 0.01)
@@ -83,18 +82,16 @@ def test_guide_tables_and_compact_trees_leave_frames_bit_identical(gpu_ctx):
     r = Renderer(sc, 96, 64, **kw)
     r.preprocessing(target_samples=40000, target_Q_samples=20000, tree_samples=20000, batch_size=20000)
     frame0 = int(r.P["lt"]["launch_frame"][0])
-    assert "SPC_EYE_REFERENCE_SEARCH" not in os.environ
+    assert r.ctx.get_option("reference_search") == 0
     for _ in range(5):
         r.render_frame()
     a = r.image().copy()
     r.reset_accumulation()
     r.P["lt"]["launch_frame"] = frame0
-    os.environ["SPC_EYE_REFERENCE_SEARCH"] = "1"
-    try:
-        for _ in range(5):
-            r.render_frame()
-    finally:
-        del os.environ["SPC_EYE_REFERENCE_SEARCH"]
+    r.ctx.set_option("reference_search", 1)
+    for _ in range(5):
+        r.render_frame()
+    r.ctx.set_option("reference_search", 0)
     b = r.image().copy()
     assert a.mean() > 0.01 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
