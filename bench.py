@@ -278,6 +278,124 @@ def host_bench_rays(pkg, scene, A, hA):
     return B, C
 
 
+def _load_oracle_module(name):
+    """oracle/<name>.py (reference-derived checkers: bench.py may execute oracle/ only in its baseline legs)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "oracle", name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def relmse(x, ref):
+    e = (x - ref) ** 2 / (ref ** 2 + 1e-2)      # SURVEY.md section 8d
+    return float(np.mean(e[np.isfinite(e)]))
+
+
+def time_lane_frames(lr_, frames, torch, env):
+    """three timed segments of `frames` frames; returns (median seconds, all seconds, launches of the last segment)"""
+    seg_s, launches = [], 0
+    for _ in range(3):
+        l0 = lr_.launch_count()
+        t0 = time.perf_counter()
+        lr_.render(frames)
+        torch.cuda.synchronize()
+        seg_s.append(time.perf_counter() - t0)
+        launches = lr_.launch_count() - l0
+        env.barrier()
+    return sorted(seg_s)[1], seg_s, launches
+
+
+def reference_gpu_rate(pkg, torch, r0, w, h, frames=8):
+    """GPU-side reference arm (north star: "the reference's own build on one B200"): the reference's OWN device programs compiled
+    unmodified with its own --use_fast_math (oracle/_ref/libref_device.so; optixTrace = this repository's traversal,
+    OptiX itself is absent) + its OWN MyThrustOp::LVC_Process (libref_thrust.so, T2) in the reference's frame loop, with the trained
+    state of `r0`.  Returns None when the prebuilt libraries are absent or K differs from the compiled-in NUM_SUBSPACE."""
+    rd, rt = _load_oracle_module("ref_device_py"), _load_oracle_module("ref_thrust_py")
+    if not (rd.available() and rt.available()) or r0.K != 1000:
+        return None
+    loop = rd.ReferenceLoop(pkg, r0, rt)
+    try:
+        loop.render_frame()
+        loop.stage_s = {k: 0.0 for k in loop.stage_s}
+        t0 = time.perf_counter()
+        for _ in range(frames):
+            loop.render_frame()
+        dt = time.perf_counter() - t0
+        mean = float(loop.image().mean())
+        return {"what": "reference programs (raygen.cu, hit_program.cu, cuProg.h, rmis.h unmodified, --use_fast_math) + reference LVC_Process on this GPU; "
+                        "optixTrace = this repository's traversal (OptiX SDK absent)", "kind": "reference",
+                "samples_per_s": w * h * frames / dt, "ms_per_frame": dt / frames * 1e3, "frames": frames,
+                "stage_ms_per_frame": {k: v / frames * 1e3 for k, v in loop.stage_s.items()}, "image_mean": mean}
+    finally:
+        loop.close()
+
+
+def equal_time_block(pkg, torch, scene, seconds, gt_spp, lanes):
+    """relMSE at equal render time (BASELINE.json metric) on the same scene at 960x540: `pt`, SPCBPT exact flavour, SPCBPT fast
+    flavour, and the reference programs on this GPU, each rendering for `seconds`; ground truth = `pt` at gt_spp from disjoint
+    samples (chunks with a non-finite pixel value are dropped for that pixel: the reference's pt has no NaN guard)."""
+    from spcbpt_optix7_b200.renderer import LaneRenderer, Renderer
+    w, h = 960, 540
+    gt = Renderer(scene, w, h, K=1000)
+    acc, cnt = np.zeros((h, w, 3)), np.zeros((h, w, 1))
+    chunk = 256
+    t0 = time.perf_counter()
+    for c in range(max(1, gt_spp // chunk)):
+        gt.reset_accumulation()
+        gt.ctx.set_seed_offset(7777777 + c * chunk)
+        for _ in range(chunk):
+            gt.render_frame_pt()
+        img = gt.image()
+        ok = np.isfinite(img).all(-1, keepdims=True)
+        acc += np.where(ok, img, 0.0)
+        cnt += ok
+    ref = (acc / np.maximum(cnt, 1)).astype(np.float32)
+    out = {"image": "%dx%d" % (w, h), "seconds_each": seconds, "ground_truth": "pt %d spp (%.1f s)" % (gt_spp, time.perf_counter() - t0), "rows": []}
+    gt.ctx.close()
+
+    def run(name, step, image, unit=1):
+        step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < seconds:
+            step()
+            n += unit
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        img = np.nan_to_num(image())
+        out["rows"].append({"alg": name, "spp": n, "seconds": dt, "relMSE": relmse(img, ref), "mean": float(img.mean())})
+
+    pt = Renderer(scene, w, h, K=1000)
+
+    def pt_step():
+        for _ in range(8):
+            pt.render_frame_pt()
+        pt.ctx.synchronize()
+    # (the warm-up step is part of the image for pt: reset afterwards is not needed, its samples are valid samples)
+    run("pt", pt_step, pt.image, 8)
+    out["rows"][-1]["spp"] += 8
+    pt.ctx.close()
+    trained = None
+    for fast in (False, True):
+        lr = LaneRenderer(scene, w, h, lanes=lanes, K=1000, fast=fast)
+        lr.preprocessing()
+        run("SPCBPT_eye %s flavour (%d lanes)" % ("fast" if fast else "exact", lanes), lambda: lr.render(lanes), lr.image, lanes)
+        out["rows"][-1]["spp"] += lanes
+        if not fast:
+            trained = lr
+    rd, rt = _load_oracle_module("ref_device_py"), _load_oracle_module("ref_thrust_py")
+    if rd.available() and rt.available():
+        loop = rd.ReferenceLoop(pkg, trained.lanes[0], rt)
+        try:
+            run("reference programs on this GPU (SPCBPT_eye loop)", loop.render_frame, loop.image, 1)
+            out["rows"][-1]["spp"] += 1
+        finally:
+            loop.close()
+    return out
+
+
 def pkg_lane_blocks(lanes):
     from spcbpt_optix7_b200.renderer import LANE_TRACE_BLOCKS
     return LANE_TRACE_BLOCKS if lanes > 1 else 0
@@ -321,16 +439,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     env.barrier()
     # three timed segments of `render_frames` frames each; the figure reported is the MEDIAN segment (the GPU boxes are VMs: an
     # occasional host hiccup stretches one segment by tens of per cent, tests/quick_variance.sh), all three are listed
-    seg_s, launches = [], 0
-    for _ in range(3):
-        l0 = lr_.launch_count()
-        t0 = time.perf_counter()
-        lr_.render(args.render_frames)
-        torch.cuda.synchronize()
-        seg_s.append(time.perf_counter() - t0)
-        launches = lr_.launch_count() - l0
-        env.barrier()
-    dt = sorted(seg_s)[1]
+    dt, seg_s, launches = time_lane_frames(lr_, args.render_frames, torch, env)
     r = lr_
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -349,6 +458,31 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
            "samples_per_s": w * h * args.render_frames * world / dt_max, "ms_per_frame": dt_max / args.render_frames * 1e3, "frames": args.render_frames,
            "preprocess_s": pre_s, "train_paths": st["train_paths"], "loss_first": st["loss_first"], "loss_last": st["loss_last"],
            "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_s], "kernel_launches": int(launches), "accum_allreduce_ms": e0.elapsed_time(e1) if world > 1 else 0.0, "image_mean": mean}
+    # the fast-arithmetic flavour of the same library (FMA contraction + hardware special functions in the shading kernels, as the
+    # reference's own --use_fast_math build; csrc/shade.cuh SPC_FAST_MATH, tests/test_fast_flavour_gpu.py): same schedule, own training
+    if not args.no_fast:
+        lf = LaneRenderer(scene, w, h, lanes=lanes, device=local_rank, K=K, K_light=K_light, max_depth=max_depth, fast=True)
+        lf.seed_mapping(rank, world)
+        t0 = time.perf_counter()
+        stf = preprocess_distributed(lf.lanes[0], env, pkg.TREE_NODE, target_samples=2000000, target_Q_samples=2000000, tree_samples=100000,
+                                     batch_size=20000, epochs=1, lr=0.01)
+        lf.share_trained_state()
+        torch.cuda.synchronize()
+        pre_f = time.perf_counter() - t0
+        lf.render(2 * lanes)
+        torch.cuda.synchronize()
+        env.barrier()
+        dtf, seg_f, _ = time_lane_frames(lf, args.render_frames, torch, env)
+        ttf = torch.tensor([dtf], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ttf, op=dist.ReduceOp.MAX)
+        dtf = float(ttf.item())
+        reduce_accum(lf, env)
+        out["fast_flavour"] = {"samples_per_s": w * h * args.render_frames * world / dtf, "ms_per_frame": dtf / args.render_frames * 1e3,
+                               "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_f], "preprocess_s": pre_f,
+                               "loss_last": stf["loss_last"], "image_mean": float(lf.image().mean()),
+                               "flags": "-fmad=true -prec-div=false -prec-sqrt=false -DSPC_FAST_MATH (render.cu, pt.cu, pretrace.cu); traversal / binning / training unchanged"}
+        del lf
     if rank == 0:
         # in-frame work and stage times: lane 0 alone, sequential frames, every stage of every bounce bracketed by CUDA events
         # (option "stage_timing"; slower than the production loop, used only to attribute the frame time and to state the
@@ -409,6 +543,18 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
                                    "sample": "oracle light trace (100k paths, %.1f s) + LVC_Process + eye pass on %dx%d (%.1f s), extrapolated to 1920x1080 by pixel count" % (t1 - t0, cw, ch, t2 - t1)}
         except Exception as ex:   # the CPU leg is informative only
             out["cpu_baseline"] = {"error": repr(ex)}
+        # GPU-side reference arm + relMSE at equal time (informative legs: a failure must not take the headline down)
+        try:
+            out["reference_gpu"] = reference_gpu_rate(pkg, torch, lr_.lanes[0], w, h)
+            if out["reference_gpu"]:
+                out["reference_gpu"]["ours_over_reference"] = out["samples_per_s"] / world / out["reference_gpu"]["samples_per_s"]
+        except Exception as ex:
+            out["reference_gpu"] = {"error": repr(ex)}
+        if world == 1 and large_scene is None and not args.no_equal_time:
+            try:
+                out["equal_time"] = equal_time_block(pkg, torch, scene, args.equal_time_seconds, args.gt_spp, lanes)
+            except Exception as ex:
+                out["equal_time"] = {"error": repr(ex)}
     return out
 
 
@@ -426,6 +572,10 @@ def main():
                     help="micro = BASELINE.json configs[1] (default, the headline); large = configs[4] (20 M triangles, 256 emitters, depth 12)")
     ap.add_argument("--render-dim", default="1920x1080", type=lambda v: tuple(int(x) for x in v.lower().split("x")),
                     help="image size of the SPCBPT section; BASELINE.json configs[3] is --gpus 8 --render-dim 3840x2160")
+    ap.add_argument("--no-fast", action="store_true", help="skip the fast-arithmetic flavour in the SPCBPT section")
+    ap.add_argument("--no-equal-time", action="store_true", help="skip the equal-time relMSE block of the SPCBPT section")
+    ap.add_argument("--equal-time-seconds", type=float, default=1.5)
+    ap.add_argument("--gt-spp", type=int, default=2048, help="ground-truth samples per pixel (pt) of the equal-time block")
     ap.add_argument("--lanes", type=int, default=4, help="frame lanes per GPU in the SPCBPT section (contexts rendering alternate subframes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

@@ -16,6 +16,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPCBPT_LIB: development only (A/B of two builds, tests/quick_ab_*.sh); the product path is the in-tree build
 LIB_PATH = os.environ.get("SPCBPT_LIB") or os.path.join(_HERE, "libspcbpt_b200.so")
+# the fast-arithmetic flavour of the same library (build.py NVCC_FLAGS_FAST, csrc/shade.cuh SPC_FAST_MATH): Context(fast=True)
+LIB_PATH_FAST = os.path.join(_HERE, "libspcbpt_b200_fast.so")
 
 # --------------------------------------------------------------------------------------------
 # numpy dtypes of the POD structs (byte-identical to include/spcbpt_b200.h)
@@ -91,6 +93,7 @@ class SpcError(RuntimeError):
 
 
 _lib = None
+_lib_fast = None
 
 
 def declared_symbols():
@@ -101,15 +104,23 @@ def declared_symbols():
     return sorted(set(re.findall(r"SPC_API\s+[\w\s\*]+?\b(spc_\w+)\s*\(", txt)))
 
 
-def lib():
-    """Load libspcbpt_b200.so (built in-tree by build.py); fail loudly if it is missing."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise SpcError("libspcbpt_b200.so is not built: run `python spcbpt-optix7_b200/build.py` "
-                       "(there is no Python or CPU fallback)")
-    L = ctypes.CDLL(LIB_PATH)
+def lib(fast=False):
+    """Load libspcbpt_b200.so (built in-tree by build.py), or its fast-arithmetic flavour; fail loudly if it is missing."""
+    global _lib, _lib_fast
+    if fast:
+        if _lib_fast is None:
+            _lib_fast = _load(LIB_PATH_FAST)
+        return _lib_fast
+    if _lib is None:
+        _lib = _load(LIB_PATH)
+    return _lib
+
+
+def _load(path):
+    if not os.path.exists(path):
+        raise SpcError("%s is not built: run `python spcbpt-optix7_b200/build.py` "
+                       "(there is no Python or CPU fallback)" % os.path.basename(path))
+    L = ctypes.CDLL(path)
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
     L.spc_last_error.restype = ctypes.c_char_p
     L.spc_version.restype = ctypes.c_char_p
@@ -129,7 +140,6 @@ def lib():
     L.spc_launch_count.argtypes = [vp]
     L.spc_launch_count.restype = i64
     _bind_optional(L)
-    _lib = L
     return L
 
 
@@ -238,8 +248,9 @@ class Context:
     """RAII wrapper of spc_context.  Mirrors the calls a reference host makes at its two seams
     (sutil::Scene launch seam and MyThrustOp post-processing seam, SURVEY.md section 8b)."""
 
-    def __init__(self, device=0, K=0, K_light=0, connections=0):
-        self._L = lib()
+    def __init__(self, device=0, K=0, K_light=0, connections=0, fast=False):
+        self._L = lib(fast)
+        self.fast = bool(fast)
         h = ctypes.c_void_p()
         rc = self._L.spc_create(device, K, K_light, connections, ctypes.byref(h))
         if rc != 0:

@@ -28,6 +28,20 @@ NVCC_FLAGS = [
 ]
 
 
+# The fast flavour (libspcbpt_b200_fast.so): the shading kernels as the reference's own build compiles its programs
+# (src/CMakeLists.txt:214-215 --use_fast_math): FMA contraction, approximate division / square root, hardware special-function
+# intrinsics (shade.cuh SPC_FAST_MATH).  -ftz stays off (explicit-intrinsic contract arithmetic of the traversal must not flush) and
+# only the three shading translation units change: traversal batches, primary rays, BVH build, LVC binning and training are the
+# exact objects in both libraries.  The exact library stays the default and the one all parity tests run.
+OUT_FAST = os.path.join(HERE, "libspcbpt_b200_fast.so")
+FAST_SOURCES = ("render.cu", "pt.cu", "pretrace.cu")
+FAST_SWAP = {"-prec-div=true": "-prec-div=false", "-prec-sqrt=true": "-prec-sqrt=false", "-fmad=false": "-fmad=true"}
+NVCC_FLAGS_FAST = [FAST_SWAP.get(f, f) for f in NVCC_FLAGS] + ["-DSPC_FAST_MATH=1"]
+
+
+LINK_LIBS = []
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -59,22 +73,31 @@ def build(force=False, verbose=False):
                     hdr.update(fh.read())
     hdr.update(" ".join(NVCC_FLAGS).encode())
     cflags = [f for f in NVCC_FLAGS if f != "--shared"]
-    jobs, objs, logs = [], [], {}
+    cflags_fast = [f for f in NVCC_FLAGS_FAST if f != "--shared"]
+    jobs, objs, objs_fast, logs = [], [], [], {}
     for src in sources():
-        h = hashlib.sha256(hdr.digest())
-        with open(src, "rb") as fh:
-            h.update(fh.read())
         base = os.path.splitext(os.path.basename(src))[0]
-        obj = os.path.join(objdir, base + ".o")
-        stamp = os.path.join(objdir, base + ".stamp")
-        log = os.path.join(objdir, base + ".log")
-        objs.append(obj)
-        if force or not (os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == h.hexdigest()):
-            jobs.append((src, obj, stamp, log, h.hexdigest()))
+        variants = [("", cflags)] + ([("_fast", cflags_fast)] if os.path.basename(src) in FAST_SOURCES else [])
+        for suffix, flags in variants:
+            h = hashlib.sha256(hdr.digest())
+            h.update(" ".join(flags).encode())
+            with open(src, "rb") as fh:
+                h.update(fh.read())
+            obj = os.path.join(objdir, base + suffix + ".o")
+            stamp = os.path.join(objdir, base + suffix + ".stamp")
+            log = os.path.join(objdir, base + suffix + ".log")
+            if suffix:
+                objs_fast.append(obj)
+            else:
+                objs.append(obj)
+                if os.path.basename(src) not in FAST_SOURCES:
+                    objs_fast.append(obj)
+            if force or not (os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == h.hexdigest()):
+                jobs.append((src, obj, stamp, log, h.hexdigest(), flags))
 
     def compile_one(job):
-        src, obj, stamp, log, dig = job
-        cmd = [nvcc] + cflags + ["-c", src, "-o", obj]
+        src, obj, stamp, log, dig, flags = job
+        cmd = [nvcc] + flags + ["-c", src, "-o", obj]
         if verbose:
             print(" ".join(cmd))
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -94,14 +117,15 @@ def build(force=False, verbose=False):
                 failed |= r.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libspcbpt_b200.so")
-    if jobs or not os.path.exists(OUT):
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler", "-fPIC"] + objs + ["-o", OUT, "-lcudart"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("link of libspcbpt_b200.so failed")
+    for out, olist in ((OUT, objs), (OUT_FAST, objs_fast)):
+        if jobs or not os.path.exists(out):
+            cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler", "-fPIC"] + olist + ["-o", out, "-lcudart"] + LINK_LIBS
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("link of %s failed" % os.path.basename(out))
     with open(os.path.join(HERE, "ptxas_info.txt"), "w") as fh:
-        for obj in objs:
+        for obj in sorted(set(objs + objs_fast)):
             fh.write(open(os.path.splitext(obj)[0] + ".log").read())
     return OUT
 

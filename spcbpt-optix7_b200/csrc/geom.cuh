@@ -30,6 +30,23 @@ __device__ __forceinline__ float3 lerp3(float3 a, float3 b, float t) { return a 
 __device__ __forceinline__ float3 ld3(const spc_float3& v) { return f3(v.x, v.y, v.z); }
 __device__ __forceinline__ void st3(spc_float3& d, float3 v) { d.x = v.x; d.y = v.y; d.z = v.z; }
 
+// ---- pinhole camera ray (raygen.cu:338-343): dir = normalize(d.x*U + d.y*V + W), d = 2*((idx+jitter)/dims) - 1.
+// Written with explicit IEEE operations in the source's evaluation order: the exact flavour (-fmad=false) gets the very bits the
+// plain expression gave, and the fast flavour (FMA contraction, approximate division: build.py) generates the SAME primary rays,
+// so primary-hit primitive ids are identical in both (tests/test_fast_flavour_gpu.py).
+__device__ __forceinline__ float3 pixel_dir_exact(float dx, float dy, float3 U, float3 V, float3 W) {
+    const float x = __fadd_rn(__fadd_rn(__fmul_rn(U.x, dx), __fmul_rn(V.x, dy)), W.x);
+    const float y = __fadd_rn(__fadd_rn(__fmul_rn(U.y, dx), __fmul_rn(V.y, dy)), W.y);
+    const float z = __fadd_rn(__fadd_rn(__fmul_rn(U.z, dx), __fmul_rn(V.z, dy)), W.z);
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))));
+    return f3(__fmul_rn(x, inv), __fmul_rn(y, inv), __fmul_rn(z, inv));
+}
+__device__ __forceinline__ float3 camera_dir_exact(float3 U, float3 V, float3 W, unsigned x, unsigned y, unsigned w, unsigned h, float jx, float jy) {
+    const float dx = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(__fadd_rn((float)x, jx), (float)w)), 1.0f);
+    const float dy = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(__fadd_rn((float)y, jy), (float)h)), 1.0f);
+    return pixel_dir_exact(dx, dy, U, V, W);
+}
+
 // ---- RNG: src/cuda/random.h:31-68 (TEA-N seed, LCG stream, 24-bit floats) ------------------------
 template <unsigned N>
 __host__ __device__ __forceinline__ uint32_t tea(uint32_t val0, uint32_t val1) {

@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(kPtBlock) k_pretrace(const DevFrame fr, spc_ve
     uint32_t seed = tea<4>((uint32_t)launch_index, (uint32_t)pt.iteration);
     const float jx = rnd(seed);   // make_float2(rnd(seed), rnd(seed)): nvcc evaluates left to right
     const float jy = rnd(seed);
-    const float dx = 2.0f * jx - 1.0f, dy = 2.0f * jy - 1.0f;
-    float3 ray_direction = normalize(dx * ld3(fr.p.U) + dy * ld3(fr.p.V) + ld3(fr.p.W));
+    const float dx = __fsub_rn(__fmul_rn(2.0f, jx), 1.0f), dy = __fsub_rn(__fmul_rn(2.0f, jy), 1.0f);
+    float3 ray_direction = pixel_dir_exact(dx, dy, ld3(fr.p.U), ld3(fr.p.V), ld3(fr.p.W));
     float3 ray_origin = ld3(fr.p.eye);
     spc_vertex* buffer = scratch + (size_t)launch_index * kMaxTrainVerts;   // BDPTVertex buffer[PRETRACE_CONN_PADDING]
     int buffer_size = 0;

@@ -39,9 +39,7 @@ __global__ void __launch_bounds__(kPtPixBlock) k_pt(const DevFrame fr, int n_pix
         jx = rnd(seed);
         jy = rnd(seed);
     }
-    const float dx = 2.0f * (((float)x + jx) / (float)W) - 1.0f;
-    const float dy = 2.0f * (((float)y + jy) / (float)H) - 1.0f;
-    float3 ray_direction = normalize(dx * ld3(fr.p.U) + dy * ld3(fr.p.V) + ld3(fr.p.W));
+    float3 ray_direction = camera_dir_exact(ld3(fr.p.U), ld3(fr.p.V), ld3(fr.p.W), x, y, W, H, jx, jy);
     float3 ray_origin = ld3(fr.p.eye);
     // PayloadRadiance (whitted.h:86-108)
     float3 result = f3(0.0f), throughput = f3(1.0f), currentResult = f3(0.0f), vis_A = f3(0.0f), vis_B = f3(0.0f);

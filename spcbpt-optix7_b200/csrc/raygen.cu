@@ -9,9 +9,7 @@ namespace spc {
 // jitter = (0.5,0.5) at subframe 0 else (rnd,rnd) drawn left to right       (raygen.cu:335-336)
 __device__ __forceinline__ float3 camera_dir(float3 U, float3 V, float3 W, unsigned x, unsigned y, unsigned w, unsigned h,
                                              float jx, float jy) {
-    const float dx = 2.0f * (((float)x + jx) / (float)w) - 1.0f;
-    const float dy = 2.0f * (((float)y + jy) / (float)h) - 1.0f;
-    return normalize(dx * U + dy * V + W);
+    return camera_dir_exact(U, V, W, x, y, w, h, jx, jy);
 }
 
 __global__ void k_camera_rays(float3 eye, float3 U, float3 V, float3 W, unsigned w, unsigned h, unsigned subframe,

@@ -195,10 +195,8 @@ __global__ void k_eye_init(const DevFrame fr, const EyeArgs a, int n_pix) {
         jx = rnd(seed);
         jy = rnd(seed);
     }
-    const float dx = 2.0f * (((float)x + jx) / (float)W) - 1.0f;
-    const float dy = 2.0f * (((float)y + jy) / (float)H) - 1.0f;
     const float3 eye = ld3(fr.p.eye);
-    const float3 d = normalize(dx * ld3(fr.p.U) + dy * ld3(fr.p.V) + ld3(fr.p.W));
+    const float3 d = camera_dir_exact(ld3(fr.p.U), ld3(fr.p.V), ld3(fr.p.W), x, y, W, H, jx, jy);
     Vtx v;
     vtx_zero(v);
     v.position = eye;

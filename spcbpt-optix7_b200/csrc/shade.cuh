@@ -13,11 +13,30 @@
 namespace spc {
 
 // ---- contract transcendental functions (see oracle/orc_math.h cm_*) ------------------------------------
+// Two flavours of the library (build.py):
+//   exact (libspcbpt_b200.so, the default and the one every parity test runs): fp64 libm rounded once to fp32, no contraction --
+//         frames compare bit-for-bit with the oracle;
+//   fast  (libspcbpt_b200_fast.so, -DSPC_FAST_MATH): what the reference's own build does (src/CMakeLists.txt:214-215
+//         --use_fast_math): the hardware's fp32 special-function intrinsics, FMA contraction and approximate division / square
+//         root in the shading code.  Traversal, primary rays and the training / binning code are identical in both flavours
+//         (explicit IEEE intrinsics; exact flags): hit primitive ids and t are bit-equal, shading agrees to ~1e-6 relative per
+//         operation (tests/test_fast_flavour_gpu.py states the tolerances).
+#ifdef SPC_FAST_MATH
+__device__ __forceinline__ float cm_sinf(float x) { return __sinf(x); }
+__device__ __forceinline__ float cm_cosf(float x) { return __cosf(x); }
+__device__ __forceinline__ float cm_logf(float x) { return __logf(x); }
+__device__ __forceinline__ float cm_expf(float x) { return __expf(x); }
+__device__ __forceinline__ float cm_powf(float x, float y) { return __powf(x, y); }
+// the few fp64 operations the reference's source spells with double literals (cuProg.h:892, rmis.h:183, ...)
+__device__ __forceinline__ float cm_div64(float a, float b) { return a / b; }
+#else
 __device__ __forceinline__ float cm_sinf(float x) { return (float)sin((double)x); }
 __device__ __forceinline__ float cm_cosf(float x) { return (float)cos((double)x); }
 __device__ __forceinline__ float cm_logf(float x) { return (float)log((double)x); }
 __device__ __forceinline__ float cm_expf(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float cm_powf(float x, float y) { return (float)pow((double)x, (double)y); }
+__device__ __forceinline__ float cm_div64(float a, float b) { return (float)((double)a / (double)b); }
+#endif
 
 #define SPC_PI_F 3.14159265358979323846f
 #define SPC_PI_D 3.14159265358979323846
@@ -139,13 +158,22 @@ __device__ __forceinline__ Pbr shade_pbr(const DevScene& sc, int id, float2 uv) 
 __device__ __forceinline__ LocalGeom hit_geometry(const DevScene& sc, int prim, float bu, float bv) {
     const float4 a = __ldg(sc.tri_pos + 3 * (size_t)prim), b = __ldg(sc.tri_pos + 3 * (size_t)prim + 1), c = __ldg(sc.tri_pos + 3 * (size_t)prim + 2);
     const float3 v0 = f3(a.x, a.y, a.z), v1 = f3(b.x, b.y, b.z), v2 = f3(c.x, c.y, c.z);
+    // explicit IEEE operations in the source's order (= what the plain expressions give without contraction): the vertex position and
+    // normal are the inputs of the subspace classification, so they are kept bit-identical in the exact and the fast flavour
     LocalGeom g;
-    const float w = 1.0f - bu - bv;
-    g.P = w * v0 + bu * v1 + bv * v2;
-    g.Ng = normalize(cross(v1 - v0, v2 - v0));
+    const float w = __fsub_rn(__fsub_rn(1.0f, bu), bv);
+    g.P.x = __fadd_rn(__fadd_rn(__fmul_rn(v0.x, w), __fmul_rn(v1.x, bu)), __fmul_rn(v2.x, bv));
+    g.P.y = __fadd_rn(__fadd_rn(__fmul_rn(v0.y, w), __fmul_rn(v1.y, bu)), __fmul_rn(v2.y, bv));
+    g.P.z = __fadd_rn(__fadd_rn(__fmul_rn(v0.z, w), __fmul_rn(v1.z, bu)), __fmul_rn(v2.z, bv));
+    const float3 e1 = f3(__fsub_rn(v1.x, v0.x), __fsub_rn(v1.y, v0.y), __fsub_rn(v1.z, v0.z));
+    const float3 e2 = f3(__fsub_rn(v2.x, v0.x), __fsub_rn(v2.y, v0.y), __fsub_rn(v2.z, v0.z));
+    const float3 n = f3(__fsub_rn(__fmul_rn(e1.y, e2.z), __fmul_rn(e1.z, e2.y)), __fsub_rn(__fmul_rn(e1.z, e2.x), __fmul_rn(e1.x, e2.z)),
+                        __fsub_rn(__fmul_rn(e1.x, e2.y), __fmul_rn(e1.y, e2.x)));
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(n.x, n.x), __fmul_rn(n.y, n.y)), __fmul_rn(n.z, n.z))));
+    g.Ng = f3(__fmul_rn(n.x, inv), __fmul_rn(n.y, inv), __fmul_rn(n.z, inv));
     const float2 t0 = __ldg(sc.tri_uv + 3 * (size_t)prim), t1 = __ldg(sc.tri_uv + 3 * (size_t)prim + 1), t2 = __ldg(sc.tri_uv + 3 * (size_t)prim + 2);
-    g.uv.x = w * t0.x + bu * t1.x + bv * t2.x;
-    g.uv.y = w * t0.y + bu * t1.y + bv * t2.y;
+    g.uv.x = __fadd_rn(__fadd_rn(__fmul_rn(w, t0.x), __fmul_rn(bu, t1.x)), __fmul_rn(bv, t2.x));
+    g.uv.y = __fadd_rn(__fadd_rn(__fmul_rn(w, t0.y), __fmul_rn(bu, t1.y)), __fmul_rn(bv, t2.y));
     g.material = __float_as_int(a.w);
     g.light = __float_as_int(b.w);
     g.mesh = __float_as_int(c.w);
@@ -253,7 +281,11 @@ static __device__ __noinline__ float bsdf_pdf(const Pbr& mat, float3 n, float3 V
     const float pdfGTR1 = GTR1(cosTheta, clearcoatAlpha, mat.log_cc) * cosTheta;
     const float ratio = 1.0f / (1.0f + mat.clearcoat);
     // `/ (4.0 * abs(...))`: the literal is a double, so this one division is fp64 in the reference (cuProg.h:892)
+#ifdef SPC_FAST_MATH
+    const float pdfSpec = lerpf(pdfGTR1, pdfGTR2, ratio) / (4.0f * fabsf(dot(L, half)));
+#else
     const float pdfSpec = (float)((double)lerpf(pdfGTR1, pdfGTR2, ratio) / (4.0 * (double)fabsf(dot(L, half))));
+#endif
     const float pdfDiff = fabsf(dot(L, n)) * (1.0f / SPC_PI_F);
     return diffuseRatio * pdfDiff + specularRatio * pdfSpec;
 }
@@ -373,7 +405,7 @@ __device__ __forceinline__ void light_reverse_sample(const DevFrame& fr, int li,
     s.position = ld3(L.u) * r1 + ld3(L.v) * r2 + ld3(L.corner) * r3;
     s.emission = ld3(L.emission);
     s.normal = ld3(L.normal);
-    s.pdf = (float)(1.0 / (double)L.area);
+    s.pdf = cm_div64(1.0f, L.area);
     s.pdf /= (float)(unsigned)fr.sc.n_lights;
     s.uvx = r1; s.uvy = r2;
     const int xb = max(0, min((int)floorf(s.uvx * L.divLevel), L.divLevel - 1));
@@ -569,7 +601,11 @@ __device__ __forceinline__ float getPdf(const DevFrame& fr, const Vtx& begin, co
 __device__ __forceinline__ float getPdf_from_light_source(const Vtx& light, const Vtx& end) {   // rmis.h:173-188
     const float3 conn_vec = end.position - light.position;
     const float3 conn_dir = normalize(conn_vec);
+#ifdef SPC_FAST_MATH
+    const float pdf_angle = fabsf(dot(light.normal, conn_dir)) * (1.0f / SPC_PI_F);
+#else
     const float pdf_angle = (float)((double)fabsf(dot(light.normal, conn_dir)) / SPC_PI_D);
+#endif
     const float angle2a = fabsf(dot(end.normal, conn_dir)) / (dot(conn_vec, conn_vec));
     return pdf_angle * angle2a;
 }
@@ -831,7 +867,7 @@ __device__ __forceinline__ bool eye_hits_light(const DevFrame& fr, const Vtx& La
     virtual_light.flux = ls.emission;
     virtual_light.subspaceId = Mid.subspaceId;
     virtual_light.isBrdf = 0;
-    Mid.RMIS_pointer = (float)(1.0 / (double)light_hit(fr, Last, virtual_light, last_xlabel));
+    Mid.RMIS_pointer = cm_div64(1.0f, light_hit(fr, Last, virtual_light, last_xlabel));
     return true;
 }
 

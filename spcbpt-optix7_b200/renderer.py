@@ -13,13 +13,13 @@ from . import (LAUNCH_LIGHT_TRACE, LAUNCH_PRETRACE, LAUNCH_PT, LAUNCH_SPCBPT_EYE
 
 class Renderer:
     def __init__(self, scene, width, height, device=0, K=1000, K_light=0, connections=3, max_depth=0,
-                 lt_num_core=1000, lt_core_padding=800, lt_M_per_core=100, pretrace_num_core=10000, pretrace_padding=10, stream=None):
+                 lt_num_core=1000, lt_core_padding=800, lt_M_per_core=100, pretrace_num_core=10000, pretrace_padding=10, stream=None, fast=False):
         import torch
         self.torch = torch
         self.scene, self.w, self.h = scene, width, height
         self.K = K
         self.K_light = K_light if K_light else int(0.2 * K)
-        self.ctx = Context(device, K=K, K_light=self.K_light, connections=connections)
+        self.ctx = Context(device, K=K, K_light=self.K_light, connections=connections, fast=fast)   # fast: the fast-arithmetic flavour
         if stream is not None:
             self.ctx.set_stream(stream)
         self.ctx.upload_scene(scene)

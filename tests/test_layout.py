@@ -53,9 +53,11 @@ def test_layout_matches_reference_headers(pkg):
         assert pkg.PBR.fields[k][1] == off, k
 
 
-def test_library_exports_every_declared_symbol(pkg):
-    assert os.path.exists(pkg.LIB_PATH), "build the extension first (python spcbpt-optix7_b200/build.py)"
-    L = ctypes.CDLL(pkg.LIB_PATH)
+@pytest.mark.parametrize("flavour", ["exact", "fast"])
+def test_library_exports_every_declared_symbol(pkg, flavour):
+    path = pkg.LIB_PATH if flavour == "exact" else pkg.LIB_PATH_FAST
+    assert os.path.exists(path), "build the extension first (python spcbpt-optix7_b200/build.py)"
+    L = ctypes.CDLL(path)
     syms = pkg.declared_symbols()
     assert len(syms) >= 15
     missing = [s for s in syms if not hasattr(L, s)]
