@@ -338,20 +338,25 @@ def equal_time_block(pkg, torch, scene, seconds, gt_spp, lanes):
     from spcbpt_optix7_b200.renderer import LaneRenderer, Renderer
     w, h = 960, 540
     gt = Renderer(scene, w, h, K=1000)
-    acc, cnt = np.zeros((h, w, 3)), np.zeros((h, w, 1))
+    acc, cnt = [np.zeros((h, w, 3)), np.zeros((h, w, 3))], [np.zeros((h, w, 1)), np.zeros((h, w, 1))]
     chunk = 256
     t0 = time.perf_counter()
-    for c in range(max(1, gt_spp // chunk)):
+    for c in range(max(2, gt_spp // chunk)):
         gt.reset_accumulation()
         gt.ctx.set_seed_offset(7777777 + c * chunk)
         for _ in range(chunk):
             gt.render_frame_pt()
         img = gt.image()
         ok = np.isfinite(img).all(-1, keepdims=True)
-        acc += np.where(ok, img, 0.0)
-        cnt += ok
-    ref = (acc / np.maximum(cnt, 1)).astype(np.float32)
-    out = {"image": "%dx%d" % (w, h), "seconds_each": seconds, "ground_truth": "pt %d spp (%.1f s)" % (gt_spp, time.perf_counter() - t0), "rows": []}
+        acc[c & 1] += np.where(ok, img, 0.0)       # even / odd chunks: two independent halves
+        cnt[c & 1] += ok
+    ref = ((acc[0] + acc[1]) / np.maximum(cnt[0] + cnt[1], 1)).astype(np.float32)
+    # The ground truth is itself a Monte-Carlo estimate: E[(I - G)^2] = Var(I) + Var(G) for independent unbiased I, G.  Var(G) is
+    # estimated from the two halves (E[(G1 - G2)^2] = 4 Var(G)) and subtracted: `relMSE_debiased` is the estimator's own error.
+    h1, h2 = acc[0] / np.maximum(cnt[0], 1), acc[1] / np.maximum(cnt[1], 1)
+    gt_noise = float(np.mean((h1 - h2) ** 2 / (ref.astype(np.float64) ** 2 + 1e-2))) / 4.0
+    out = {"image": "%dx%d" % (w, h), "seconds_each": seconds, "ground_truth": "pt %d spp (%.1f s)" % (gt_spp, time.perf_counter() - t0),
+           "ground_truth_noise_relMSE": gt_noise, "rows": []}
     gt.ctx.close()
 
     def run(name, step, image, unit=1):
@@ -365,7 +370,8 @@ def equal_time_block(pkg, torch, scene, seconds, gt_spp, lanes):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         img = np.nan_to_num(image())
-        out["rows"].append({"alg": name, "spp": n, "seconds": dt, "relMSE": relmse(img, ref), "mean": float(img.mean())})
+        e = relmse(img, ref)
+        out["rows"].append({"alg": name, "spp": n, "seconds": dt, "relMSE": e, "relMSE_debiased": e - gt_noise, "mean": float(img.mean())})
 
     pt = Renderer(scene, w, h, K=1000)
 
@@ -575,7 +581,7 @@ def main():
     ap.add_argument("--no-fast", action="store_true", help="skip the fast-arithmetic flavour in the SPCBPT section")
     ap.add_argument("--no-equal-time", action="store_true", help="skip the equal-time relMSE block of the SPCBPT section")
     ap.add_argument("--equal-time-seconds", type=float, default=1.5)
-    ap.add_argument("--gt-spp", type=int, default=2048, help="ground-truth samples per pixel (pt) of the equal-time block")
+    ap.add_argument("--gt-spp", type=int, default=4096, help="ground-truth samples per pixel (pt) of the equal-time block")
     ap.add_argument("--lanes", type=int, default=4, help="frame lanes per GPU in the SPCBPT section (contexts rendering alternate subframes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

@@ -13,6 +13,13 @@ size_t HostScene::n_triangles() const {
     return n;
 }
 
+size_t HostScene::upload_bytes() const {
+    size_t n = materials.size() * sizeof(spc_pbr) + lights.size() * sizeof(spc_light);
+    for (const auto& m : meshes) n += (m.positions.size() + m.texcoords.size()) * sizeof(float) + m.indices.size() * sizeof(uint32_t);
+    for (const auto& t : textures) n += (size_t)t.width * t.height * 4;
+    return n;
+}
+
 void HostScene::compute_aabb() {
     bool first = true;
     for (const auto& m : meshes)

@@ -33,6 +33,7 @@ struct HostScene {
     std::vector<std::string> warnings;
 
     size_t n_triangles() const;
+    size_t upload_bytes() const;   // host bytes spc_scene_upload reads: positions + indices + texcoords + materials + lights + textures
     void   compute_aabb();
     // views for spc_scene_upload; valid while *this is alive and unmodified
     void abi_views(std::vector<spc_mesh>& meshes_out, std::vector<spc_texture>& textures_out) const;

@@ -9,8 +9,11 @@
 //
 // Display is replaced by files: <out>.ppm (tone-mapped frame buffer) and <out>.pfm (accumulation buffer).
 #include <cuda_runtime_api.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include <chrono>
+#include <fstream>
 #include <exception>
 #include <memory>
 #include <thread>
@@ -50,6 +53,10 @@ struct Options {
     int  pre_cores = 10000, pre_padding = 10;                    // preTracer_params_setup
     unsigned seed_offset = 0, seed_stride = 1;
     bool pipeline = true, render = true, quiet = false, write_images = true;
+    // multi-GPU: one process per GPU.  `--ranks N` forks N ranks on devices 0..N-1 of this node; or start the ranks yourself
+    // with --rank r --world N --id-file <path> (rank 0 writes the NCCL unique id there, the others wait for it)
+    int  ranks = 1, rank = 0, world = 1;
+    std::string id_file;
 };
 
 void usage(const char* argv0) {
@@ -57,7 +64,10 @@ void usage(const char* argv0) {
             "Usage  : %s --scene <file.scene> | --cache <file.spcscene> [options]\n"
             "         --dim=<width>x<height>      image dimensions; defaults to 1920x1000\n"
             "         --data-root <dir>           directory the .scene's file names are relative to\n"
-            "         --frames <n>                subframes to accumulate (default 16)\n"
+            "         --frames <n>                subframes to accumulate per rank (default 16)\n"
+            "         --ranks <n>                 multi-GPU: fork n ranks on devices 0..n-1 (NCCL inside the library: sharded training,\n"
+            "                                     sample-partitioned frames, accumulation buffer reduced to rank 0)\n"
+            "         --rank r --world n --id-file f   the same with externally started ranks (rank 0 writes the NCCL id to f)\n"
             "         --alg pt|SPCBPT_eye         integrator (the reference toggles these with Space)\n"
             "         --K <n> --K-light <n> --connections <n> --max-depth <n>\n"
             "         --train-samples <n> --q-samples <n> --tree-samples <n> --batch <n> --epochs <n> --lr <f>\n"
@@ -119,6 +129,10 @@ bool parse_args(int argc, char** argv, Options& o) {
         else if (a == "--pretrace-padding") o.pre_padding = atoi(need("--pretrace-padding"));
         else if (a == "--seed-offset") o.seed_offset = (unsigned)strtoul(need("--seed-offset"), nullptr, 10);
         else if (a == "--seed-stride") o.seed_stride = (unsigned)strtoul(need("--seed-stride"), nullptr, 10);
+        else if (a == "--ranks") o.ranks = atoi(need("--ranks"));
+        else if (a == "--rank") o.rank = atoi(need("--rank"));
+        else if (a == "--world") o.world = atoi(need("--world"));
+        else if (a == "--id-file") o.id_file = need("--id-file");
         else if (a == "--no-pipeline") o.pipeline = false;
         else if (a == "--no-render") o.render = false;
         else if (a == "--no-images") o.write_images = false;
@@ -127,6 +141,9 @@ bool parse_args(int argc, char** argv, Options& o) {
     }
     if (o.lanes < 1 || o.lanes > 16) throw std::runtime_error("--lanes must be in 1..16");
     if (o.seed_stride < 1) throw std::runtime_error("--seed-stride must be >= 1");
+    if (o.ranks < 1 || o.ranks > 64 || o.world < 1 || o.rank < 0 || o.rank >= o.world) throw std::runtime_error("bad --ranks / --rank / --world");
+    if (o.world > 1 && o.id_file.empty()) throw std::runtime_error("--world needs --id-file");
+    if ((o.ranks > 1 || o.world > 1) && o.batch % (o.ranks > 1 ? o.ranks : o.world) != 0) throw std::runtime_error("--batch must divide by the number of ranks");
     if (o.K_light <= 0) o.K_light = (int)(0.2 * o.K);   // NUM_SUBSPACE_LIGHTSOURCE (optixPathTracer.h:32)
     return !(o.scene.empty() && o.cache.empty());
 }
@@ -208,7 +225,7 @@ struct App {
     }
 
     void launch_light_trace() {
-        params.lt.launch_frame += 1;
+        params.lt.launch_frame += lt_stride;
         SPC_CHECK(spc_set_params(ctx, &params));
         SPC_CHECK(spc_launch_named(ctx, "light trace", params.lt.num_core, 1));
     }
@@ -219,7 +236,7 @@ struct App {
     }
 
     int launch_pretrace() {
-        params.pre_tracer.iteration += 1;
+        params.pre_tracer.iteration += pretrace_stride;
         SPC_CHECK(spc_set_params(ctx, &params));
         SPC_CHECK(spc_launch_named(ctx, "pretrace", params.pre_tracer.num_core, 1));
         int valid_samples = 0;
@@ -249,11 +266,22 @@ struct App {
         return nodes;
     }
 
-    // preprocessing() (optixPathTracer.cpp:552-608)
+    // multi-GPU shard plan (the same arithmetic as spcbpt-optix7_b200/parallel.py shard_plan)
+    int  pretrace_stride = 1, lt_stride = 1;
+
+    // preprocessing() (optixPathTracer.cpp:552-608).  With world > 1 this rank traces its shard of the training paths and of the Q
+    // launches; the library all-reduces the statistics over NCCL (csrc/comm.cu) and rank 0's trees are broadcast.
     void preprocessing() {
+        const int rank = opt.rank, world = opt.world;
+        const int local_samples = (opt.train_samples + world - 1) / world, local_q = (opt.q_samples + world - 1) / world, local_batch = opt.batch / world;
+        if (world > 1) {
+            pretrace_stride = lt_stride = world;
+            params.pre_tracer.iteration = rank + 1 - world;
+            params.lt.launch_frame = rank + 1 - world;
+        }
         double t0 = now_s();
         int current = 0;
-        while (current < opt.train_samples) {
+        while (current < local_samples) {
             const int got = launch_pretrace();
             current += got;
             if (got == 0 && params.pre_tracer.iteration > 64 && current == 0) throw std::runtime_error("pretrace finds no valid path: is any light visible from the camera's paths?");
@@ -264,8 +292,17 @@ struct App {
         t_pretrace = t1 - t0;
 
         SPC_CHECK(spc_sample_reweight(ctx));
-        eye_tree = build_tree(true, opt.K);
-        light_tree = build_tree(false, opt.K - opt.K_light);
+        if (rank == 0) {
+            eye_tree = build_tree(true, opt.K);
+            light_tree = build_tree(false, opt.K - opt.K_light);
+        }
+        if (world > 1)
+            for (std::vector<spc_tree_node>* t : {&eye_tree, &light_tree}) {
+                int n = (int)t->size();
+                SPC_CHECK(spc_comm_bcast_host(ctx, &n, sizeof(n), 0));
+                t->resize((size_t)n);
+                SPC_CHECK(spc_comm_bcast_host(ctx, t->data(), (size_t)n * sizeof(spc_tree_node), 0));
+            }
         SPC_CHECK(spc_tree_to_device(ctx, 1, eye_tree.data(), (int)eye_tree.size(), &params.subspace_info.eye_tree));
         SPC_CHECK(spc_tree_to_device(ctx, 0, light_tree.data(), (int)light_tree.size(), &params.subspace_info.light_tree));
         double t2 = now_s();
@@ -274,7 +311,7 @@ struct App {
         int acc = 0;
         bool first = true;
         float* Q = nullptr;
-        while (acc < opt.q_samples) {
+        while (acc < local_q) {
             launch_light_trace();
             int cumulative = 0;
             SPC_CHECK(spc_preprocess_getQ(ctx, params.lt.ans, params.lt.validState, n_lvc, first ? 1 : 0, &Q, &cumulative));
@@ -282,23 +319,29 @@ struct App {
             acc += cumulative;   // sic: the reference adds the running total each time (:590, device_thrust.cu:408)
             if (cumulative == 0) throw std::runtime_error("light trace produced no paths");
         }
+        SPC_CHECK(spc_allreduce_training_stats(ctx));   // no-op on one GPU
         SPC_CHECK(spc_Q_zero_handle(ctx));
         SPC_CHECK(spc_node_label(ctx, params.subspace_info.eye_tree, params.subspace_info.light_tree));
 
-        const int usable = current < opt.train_samples ? current : opt.train_samples;
-        const int n_train = (usable / opt.batch) * opt.batch;
+        const int usable = current < local_samples ? current : local_samples;
+        int n_train = (usable / local_batch) * local_batch;
+        if (world > 1) SPC_CHECK(spc_comm_allreduce_host(ctx, &n_train, 1, SPC_COMM_I32, SPC_COMM_MIN));   // same number of Adam steps everywhere
         SPC_CHECK(spc_build_optimal_E_train_data(ctx, n_train));
         float* gamma = nullptr;
         SPC_CHECK(spc_preprocess_getGamma(ctx, &gamma));
         loss.assign(4096, 0.0f);
         int n_batches = 0;
-        SPC_CHECK(spc_train_optimal_E(ctx, opt.batch, opt.epochs, opt.lr, &gamma, loss.data(), (int)loss.size(), &n_batches));
+        SPC_CHECK(spc_train_optimal_E(ctx, local_batch, opt.epochs, opt.lr, &gamma, loss.data(), (int)loss.size(), &n_batches));
         loss.resize((size_t)(n_batches < (int)loss.size() ? n_batches : (int)loss.size()));
         params.subspace_info.Q = Q;
         gamma_dev = gamma;
         SPC_CHECK(spc_Gamma2CMFGamma(ctx, gamma, &params.subspace_info.CMFGamma));
         SPC_CHECK(spc_synchronize(ctx));
         t_qgamma = now_s() - t2;
+        if (world > 1) {   // the render loop's light-trace frames: disjoint from the training frames and from the other ranks'
+            lt_stride = 1;
+            params.lt.launch_frame = 1000003 * (rank + 1);
+        }
     }
 
     // trained state to / from the reference's debug text files (host/train_state.hpp)
@@ -444,6 +487,39 @@ int main(int argc, char** argv) {
             usage(argv[0]);
             return argc > 1 ? 0 : 1;
         }
+        if (app.opt.ranks > 1) {
+            // one process per GPU: fork the ranks before anything touches CUDA; rank r drives device r
+            Options& o = app.opt;
+            o.world = o.ranks;
+            o.id_file = "/tmp/spcbpt_nccl_id_" + std::to_string((long)getpid());
+            remove(o.id_file.c_str());
+            std::vector<pid_t> kids;
+            int my_rank = -1;
+            for (int r = 0; r < o.ranks && my_rank < 0; r++) {
+                const pid_t pid = fork();
+                if (pid < 0) throw std::runtime_error("fork failed");
+                if (pid == 0) my_rank = r;
+                else kids.push_back(pid);
+            }
+            if (my_rank < 0) {
+                int worst = 0;
+                for (pid_t pid : kids) {
+                    int st = 0;
+                    waitpid(pid, &st, 0);
+                    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) worst = 1;
+                }
+                remove(o.id_file.c_str());
+                return worst;
+            }
+            o.rank = my_rank;
+            o.device = my_rank;
+            o.ranks = 1;
+            if (my_rank != 0) o.quiet = true;
+        }
+        if (app.opt.world > 1) {   // sample partition across ranks, composed with the frame lanes below
+            app.opt.seed_offset = (unsigned)app.opt.rank;
+            app.opt.seed_stride = (unsigned)app.opt.world;
+        }
         const Options& opt = app.opt;
         double t0 = now_s();
         app.scene = load_scene(opt);
@@ -462,12 +538,32 @@ int main(int argc, char** argv) {
         // ---- Scene::finalize(): context + upload + BVH ------------------------------------------------------------
         app.scene_ref = &app.scene;
         double t_upload = 0;
+        const double t_e2e0 = now_s();   // end-to-end clock: scene upload + BVH -> training -> frames -> accumulation buffer on the host
         app.create_and_upload(&t_upload);
         spc_bvh_stats bs;
         SPC_CHECK(spc_bvh_stats_get(app.ctx, &bs));
         if (!opt.quiet) printf("bvh: %u triangles, %u 8-wide nodes, depth %u, SAH %.2f, device build %.2f ms (upload + build %.1f ms)\n", bs.n_triangles, bs.n_nodes, bs.max_depth,
                                bs.sah_cost, bs.build_ms, t_upload * 1e3);
         if (opt.seed_offset || opt.seed_stride != 1) SPC_CHECK(spc_set_seed_mapping(app.ctx, opt.seed_offset, opt.seed_stride));
+        if (opt.world > 1) {
+            // NCCL rendezvous through a file: rank 0 creates the unique id, the others wait for it
+            unsigned char id[SPC_COMM_ID_BYTES];
+            if (opt.rank == 0) {
+                if (spc_comm_unique_id(id) != SPC_OK) throw std::runtime_error(std::string("spc_comm_unique_id: ") + spc_last_error());
+                const std::string tmp = opt.id_file + ".tmp";
+                std::ofstream(tmp, std::ios::binary).write(reinterpret_cast<const char*>(id), sizeof(id));
+                if (rename(tmp.c_str(), opt.id_file.c_str()) != 0) throw std::runtime_error("cannot write " + opt.id_file);
+            } else {
+                bool got = false;
+                for (int tries = 0; tries < 1200 && !got; tries++) {
+                    std::ifstream f(opt.id_file, std::ios::binary);
+                    got = f && f.read(reinterpret_cast<char*>(id), sizeof(id)) && f.gcount() == (std::streamsize)sizeof(id);
+                    if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+                }
+                if (!got) throw std::runtime_error("timed out waiting for the NCCL id in " + opt.id_file);
+            }
+            SPC_CHECK(spc_comm_init(app.ctx, opt.rank, opt.world, id));
+        }
 
         app.init_launch_params();
         const bool lanes_on = opt.lanes > 1;
@@ -502,6 +598,7 @@ int main(int argc, char** argv) {
 
         // ---- render loop ----------------------------------------------------------------------------------------------
         SPC_CHECK(spc_synchronize(app.ctx));
+        SPC_CHECK(spc_comm_barrier(app.ctx));
         int64_t launches = 0;
         for (App* l : lanes) launches -= spc_launch_count(l->ctx);
         t0 = now_s();
@@ -524,7 +621,8 @@ int main(int argc, char** argv) {
             for (auto& e : errors)
                 if (e) std::rethrow_exception(e);
         }
-        const double t_render = now_s() - t0;
+        double t_render = now_s() - t0;
+        if (opt.world > 1) SPC_CHECK(spc_comm_allreduce_host(app.ctx, &t_render, 1, SPC_COMM_F64, SPC_COMM_MAX));   // the slowest rank
         for (App* l : lanes) launches += spc_launch_count(l->ctx);
 
         if (lanes_on) {   // read-out: merge the running means, weights = share of the subframes each lane rendered
@@ -541,11 +639,26 @@ int main(int argc, char** argv) {
             app.params.accum_buffer = merged;
         }
 
+        if (opt.world > 1) {
+            // read-out over NCCL: every rank rendered opt.frames subframes -> the image is the mean of the per-rank running means
+            SPC_CHECK(spc_reduce_accum(app.ctx, app.params.accum_buffer, opt.width * opt.height, 1.0f / (float)opt.world, 0));
+            SPC_CHECK(spc_synchronize(app.ctx));
+            if (opt.rank == 0) {   // display transform of the merged image
+                const spc_float4* one = app.params.accum_buffer;
+                const float w1 = 1.0f;
+                SPC_CHECK(spc_merge_accum(app.ctx, &one, &w1, 1, opt.width * opt.height, nullptr, app.params.frame_buffer));
+            } else {
+                for (auto& l : extra) spc_destroy(l->ctx);
+                spc_destroy(app.ctx);
+                return 0;
+            }
+        }
         const size_t P = (size_t)opt.width * opt.height;
         std::vector<float> accum(P * 4);
         std::vector<uint32_t> frame(P);
         SPC_CHECK(spc_download(app.ctx, accum.data(), app.params.accum_buffer, accum.size() * sizeof(float)));
         SPC_CHECK(spc_download(app.ctx, frame.data(), app.params.frame_buffer, frame.size() * sizeof(uint32_t)));
+        const double t_e2e = now_s() - t_e2e0;
         double mean = 0;
         for (size_t i = 0; i < P; i++) mean += accum[4 * i] + accum[4 * i + 1] + accum[4 * i + 2];
         mean /= (double)(3 * P);
@@ -553,10 +666,12 @@ int main(int argc, char** argv) {
             if (!spchost::write_ppm_from_uchar4(opt.out + ".ppm", frame.data(), opt.width, opt.height)) throw std::runtime_error("cannot write " + opt.out + ".ppm");
             if (!spchost::write_pfm_from_float4(opt.out + ".pfm", accum.data(), opt.width, opt.height)) throw std::runtime_error("cannot write " + opt.out + ".pfm");
         }
-        printf("{\"alg\": \"%s\", \"width\": %d, \"height\": %d, \"frames\": %d, \"triangles\": %zu, \"K\": %d, \"lanes\": %d, \"pipelined\": %s, \"render_s\": %.6f, \"ms_per_frame\": %.4f, "
-               "\"samples_per_s\": %.1f, \"kernel_launches\": %lld, \"train_paths\": %d, \"pretrace_s\": %.4f, \"trees_s\": %.4f, \"q_gamma_s\": %.4f, \"image_mean\": %.9g}\n",
-               opt.alg.c_str(), opt.width, opt.height, opt.frames, app.scene.n_triangles(), opt.K, opt.lanes, app.main_stream ? "true" : "false", t_render, t_render / opt.frames * 1e3,
-               (double)P * opt.frames / t_render, (long long)launches, app.train_paths, app.t_pretrace, app.t_trees, app.t_qgamma, mean);
+        printf("{\"alg\": \"%s\", \"width\": %d, \"height\": %d, \"frames\": %d, \"ranks\": %d, \"triangles\": %zu, \"K\": %d, \"lanes\": %d, \"pipelined\": %s, \"render_s\": %.6f, \"ms_per_frame\": %.4f, "
+               "\"samples_per_s\": %.1f, \"kernel_launches\": %lld, \"train_paths\": %d, \"pretrace_s\": %.4f, \"trees_s\": %.4f, \"q_gamma_s\": %.4f, \"upload_s\": %.4f, \"e2e_s\": %.4f, "
+               "\"e2e_samples_per_s\": %.1f, \"h2d_bytes\": %zu, \"d2h_bytes\": %zu, \"image_mean\": %.9g}\n",
+               opt.alg.c_str(), opt.width, opt.height, opt.frames, opt.world, app.scene.n_triangles(), opt.K, opt.lanes, app.main_stream ? "true" : "false", t_render, t_render / opt.frames * 1e3,
+               (double)P * opt.frames * opt.world / t_render, (long long)launches, app.train_paths, app.t_pretrace, app.t_trees, app.t_qgamma, t_upload, t_e2e,
+               (double)P * opt.frames * opt.world / t_e2e, app.scene.upload_bytes(), P * 20, mean);
         for (auto& l : extra) spc_destroy(l->ctx);
         spc_destroy(app.ctx);
     } catch (std::exception& e) {

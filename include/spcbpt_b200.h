@@ -490,6 +490,39 @@ SPC_API int  spc_download(spc_context* ctx, void* host, const void* dev, size_t 
  * written when it exceeds cap) or a negative spc_status; *max_label receives the largest label used. */
 SPC_API int  spc_build_tree(const spc_divide_weight* samples, int n, int K, int label_bias, spc_tree_node* out, int cap, int* max_label);
 
+/* -------------------------------- multi-GPU (NCCL over NVLink / NVSwitch) ------------------------ */
+/* One process per GPU, one context per process; every rank holds a replica of scene + BVH and renders its own subframes
+ * (spc_set_seed_mapping).  The reference is single-GPU: these calls have no counterpart there (its unused tile partition is
+ * sutil/WorkDistribution.h:34-91); SURVEY.md section 8b/8e lists them.  Rank 0 creates the id (ncclGetUniqueId), the host ships the
+ * 128 bytes to the other ranks by any means (a file, a pipe, MPI, torch.distributed), every rank calls spc_comm_init.
+ * Once a context has a communicator of world > 1 the training calls exchange what the single-GPU code sums over the whole training
+ * set (every rank holds a SHARD of the training paths and of the Q light-trace launches):
+ *   spc_sample_reweight            all-reduces the 10x10-pixel reweighting grid
+ *   spc_allreduce_training_stats   folds the per-rank Q estimates (call once after the last spc_preprocess_getQ)
+ *   spc_build_optimal_E_train_data takes rank 0's outlier threshold
+ *   spc_preprocess_getGamma        all-reduces the Gamma histogram before its row normalisation
+ *   spc_train_optimal_E            all-reduces the K x K gradient of every Adam step (global batch = world x batch_size; every rank
+ *                                  must hold the same number of batches)
+ * so that all ranks end with the same Q / Gamma, equal (up to fp32 summation order) to a single-GPU run over the union of the shards. */
+enum { SPC_COMM_ID_BYTES = 128 };
+enum { SPC_COMM_I32 = 0, SPC_COMM_F32 = 1, SPC_COMM_F64 = 2 };
+enum { SPC_COMM_SUM = 0, SPC_COMM_MIN = 1, SPC_COMM_MAX = 2 };
+SPC_API int  spc_comm_unique_id(void* id_out /* SPC_COMM_ID_BYTES */);
+SPC_API int  spc_comm_init(spc_context* ctx, int rank, int world, const void* id);
+SPC_API int  spc_comm_destroy(spc_context* ctx);
+SPC_API int  spc_comm_info(spc_context* ctx, int* rank, int* world);
+SPC_API int  spc_comm_barrier(spc_context* ctx);
+/* small HOST arrays (counts, timings) all-reduced in place / broadcast from root, staged through the device */
+SPC_API int  spc_comm_allreduce_host(spc_context* ctx, void* host_buf, int count, int dtype, int op);
+SPC_API int  spc_comm_bcast_host(spc_context* ctx, void* host_buf, size_t bytes, int root);
+SPC_API int  spc_allreduce_training_stats(spc_context* ctx);
+/* read-out of a sample-partitioned render: accum <- weight * accum summed over ranks into root's buffer (root < 0: into every rank's) */
+SPC_API int  spc_reduce_accum(spc_context* ctx, spc_float4* accum_dev, int n_pixels, float weight, int root);
+/* import of a training set / Q (the counterparts of spc_train_set_read and of the Q pointer spc_preprocess_getQ returns): restores
+ * the state spc_valid_sample_gather / spc_preprocess_getQ build up, e.g. to re-train from a saved set */
+SPC_API int  spc_train_set_write(spc_context* ctx, const spc_train_path* paths_host, int n_paths, const spc_train_conn* conns_host, int n_conns);
+SPC_API int  spc_train_Q_write(spc_context* ctx, const float* Q_host, int acc_paths);
+
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 SPC_API int64_t spc_launch_count(spc_context* ctx);
 

@@ -153,6 +153,17 @@ def _bind_optional(L):
         "spc_launch_named": [vp, ctypes.c_char_p, i32, i32],
         "spc_set_debug_outputs": [vp, vp, vp],
         "spc_eye_stats_get": [vp, vp],
+        "spc_comm_unique_id": [vp],
+        "spc_comm_init": [vp, i32, i32, vp],
+        "spc_comm_destroy": [vp],
+        "spc_comm_info": [vp, vp, vp],
+        "spc_comm_barrier": [vp],
+        "spc_comm_allreduce_host": [vp, vp, i32, i32, i32],
+        "spc_comm_bcast_host": [vp, vp, ctypes.c_size_t, i32],
+        "spc_allreduce_training_stats": [vp],
+        "spc_reduce_accum": [vp, vp, i32, f32, i32],
+        "spc_train_set_write": [vp, vp, i32, vp, i32],
+        "spc_train_Q_write": [vp, vp, i32],
         "spc_set_option": [vp, ctypes.c_char_p, i64],
         "spc_get_option": [vp, ctypes.c_char_p, vp],
         "spc_set_seed_offset": [vp, ctypes.c_uint32],
@@ -336,6 +347,55 @@ class Context:
         v = ctypes.c_int64(0)
         self._ck(self._L.spc_get_option(self.h, name.encode(), ctypes.byref(v)), "spc_get_option(%s)" % name)
         return v.value
+
+    # -- multi-GPU: NCCL inside the library (csrc/comm.cu) ---------------------------------------
+    def comm_unique_id(self):
+        buf = ctypes.create_string_buffer(128)
+        rc = self._L.spc_comm_unique_id(buf)
+        if rc != 0:
+            raise SpcError("spc_comm_unique_id failed (%d): %s" % (rc, self._L.spc_last_error().decode()))
+        return buf.raw
+
+    def comm_init(self, rank, world, id_bytes):
+        self._ck(self._L.spc_comm_init(self.h, rank, world, ctypes.c_char_p(id_bytes) if id_bytes else None), "spc_comm_init")
+
+    def comm_info(self):
+        r, w = ctypes.c_int(0), ctypes.c_int(1)
+        self._ck(self._L.spc_comm_info(self.h, ctypes.byref(r), ctypes.byref(w)), "spc_comm_info")
+        return r.value, w.value
+
+    def comm_barrier(self):
+        self._ck(self._L.spc_comm_barrier(self.h), "spc_comm_barrier")
+
+    def comm_allreduce_host(self, arr, op="sum"):
+        """small numpy array (int32 / float32 / float64) all-reduced over the ranks, returned"""
+        a = np.ascontiguousarray(arr).copy()
+        dt = {"int32": 0, "float32": 1, "float64": 2}[a.dtype.name]
+        self._ck(self._L.spc_comm_allreduce_host(self.h, a.ctypes.data, a.size, dt, {"sum": 0, "min": 1, "max": 2}[op]), "spc_comm_allreduce_host")
+        return a
+
+    def comm_bcast_array(self, arr, dtype, root=0):
+        """numpy struct array from `root` to every rank (size first, then the bytes)"""
+        rank, world = self.comm_info()
+        n = np.array([arr.shape[0] if rank == root else 0], np.int32)
+        self._ck(self._L.spc_comm_bcast_host(self.h, n.ctypes.data, 4, root), "spc_comm_bcast_host")
+        out = np.ascontiguousarray(arr, dtype) if rank == root else np.zeros(int(n[0]), dtype)
+        self._ck(self._L.spc_comm_bcast_host(self.h, out.ctypes.data, out.nbytes, root), "spc_comm_bcast_host")
+        return out
+
+    def allreduce_training_stats(self):
+        self._ck(self._L.spc_allreduce_training_stats(self.h), "spc_allreduce_training_stats")
+
+    def reduce_accum(self, accum_dev, n_pixels, weight, root=0):
+        self._ck(self._L.spc_reduce_accum(self.h, _ptr(accum_dev), n_pixels, weight, root), "spc_reduce_accum")
+
+    def train_set_write(self, paths, conns):
+        paths, conns = np.ascontiguousarray(paths, TRAIN_PATH), np.ascontiguousarray(conns, TRAIN_CONN)
+        self._ck(self._L.spc_train_set_write(self.h, paths.ctypes.data, paths.shape[0], conns.ctypes.data, conns.shape[0]), "spc_train_set_write")
+
+    def train_Q_write(self, Q, acc_paths):
+        Q = np.ascontiguousarray(Q, np.float32)
+        self._ck(self._L.spc_train_Q_write(self.h, Q.ctypes.data, acc_paths), "spc_train_Q_write")
 
     def eye_stats(self):
         """work counters (+ per-stage device ms under option stage_timing) of the last eye pass"""

@@ -132,6 +132,7 @@ void spc_destroy(spc_context* ctx) {
         if (st) cudaStreamDestroy(st);
     if (ctx->c.pipe_event) cudaEventDestroy(ctx->c.pipe_event);
     spc::gamma_guide_forget(&ctx->c, true);
+    spc_comm_destroy(ctx);
     delete ctx;
 }
 

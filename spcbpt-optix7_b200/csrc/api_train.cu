@@ -172,6 +172,32 @@ int spc_train_data_read(spc_context* ctx, int* N, int* M, float* outlier_thresho
     SPC_CUDA(cudaStreamSynchronize(c.stream));
     SPC_API_END
 }
+int spc_train_set_write(spc_context* ctx, const spc_train_path* paths_host, int n_paths, const spc_train_conn* conns_host, int n_conns) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(n_paths >= 0 && n_conns >= 0 && (paths_host || !n_paths) && (conns_host || !n_conns), SPC_ERR_INVALID, "spc_train_set_write: bad arguments");
+    for (int i = 0; i < n_paths; i++)
+        SPC_REQUIRE(paths_host[i].begin_ind >= 0 && paths_host[i].begin_ind <= paths_host[i].end_ind && paths_host[i].end_ind <= n_conns, SPC_ERR_INVALID,
+                    "spc_train_set_write: path %d spans connections [%d, %d) of %d", i, paths_host[i].begin_ind, paths_host[i].end_ind, n_conns);
+    c.train.paths.alloc((size_t)n_paths);
+    c.train.conns.alloc((size_t)n_conns);
+    if (n_paths) SPC_CUDA(cudaMemcpyAsync(c.train.paths.p, paths_host, (size_t)n_paths * sizeof(spc_train_path), cudaMemcpyHostToDevice, c.stream));
+    if (n_conns) SPC_CUDA(cudaMemcpyAsync(c.train.conns.p, conns_host, (size_t)n_conns * sizeof(spc_train_conn), cudaMemcpyHostToDevice, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    c.train.n_paths = (size_t)n_paths;
+    c.train.n_conns = (size_t)n_conns;
+    c.train.N = c.train.M = 0;
+    SPC_API_END
+}
+int spc_train_Q_write(spc_context* ctx, const float* Q_host, int acc_paths) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(Q_host && acc_paths >= 0, SPC_ERR_INVALID, "spc_train_Q_write: bad arguments");
+    c.train.Q.alloc(c.K);
+    SPC_CUDA(cudaMemcpyAsync(c.train.Q.p, Q_host, (size_t)c.K * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    c.train.has_Q = true;
+    c.train.acc_valid_path = acc_paths;
+    SPC_API_END
+}
 int spc_train_reset(spc_context* ctx) {
     SPC_API_BEGIN
     c.train.n_paths = c.train.n_conns = 0;

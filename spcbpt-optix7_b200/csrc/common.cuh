@@ -203,6 +203,10 @@ struct Context {
     bool          lvc_attr_set = false;        // lvc.cu: dynamic shared-memory opt-in of the binning kernels
     int           persist_blocks[2] = {0, 0};  // trace.cu: resident blocks per SM of k_trace_persist<ANYHIT> on this device (0 = not queried)
     int64_t       opt[OPT_COUNT] = {};         // spc_set_option switches (api_render.cu), all 0 by default
+    // multi-GPU (comm.cu): NCCL communicator of this rank, or null (world 1)
+    void*         comm = nullptr;
+    int           comm_rank = 0, comm_world = 1;
+    DevBuf<uint8_t> comm_scratch;
 };
 
 void build_bvh(Context& ctx, const float4* d_tri_pos /*3 per prim*/, uint32_t n_prims);
@@ -236,6 +240,10 @@ void   train_build_data(Context& c, int n_samples);
 float* train_get_gamma(Context& c);
 float* train_optimal_E(Context& c, int batch_size, int epochs, float lr, float* loss_out_host, int loss_cap, int* n_loss);
 float* train_gamma_to_cmf(Context& c, const float* gamma_dev);
+void   train_allreduce_Q(Context& c);
+// comm.cu: no-ops when the context has no communicator (world 1)
+void   comm_allreduce_sum(Context& c, float* dev, size_t n);
+void   comm_bcast(Context& c, void* dev, size_t bytes, int root);
 // compact copy of a classification tree uploaded by spc_tree_to_device, found by the reference-layout device pointer (or null)
 const float4* ctree_lookup(const spc_tree_node* tree_dev);
 void ctree_register(const spc_tree_node* tree_dev, const float4* ctree_dev, const void* owner);

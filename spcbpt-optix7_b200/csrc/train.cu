@@ -179,16 +179,32 @@ __global__ void k_reweight_apply(spc_train_path* __restrict__ p, int n, const sp
     const float3 c = f3(p[i].contri.x, p[i].contri.y, p[i].contri.z) / w;
     p[i].contri = spc_float3{c.x, c.y, c.z};
 }
+// sum_pmf of every bin <-> a dense float array (for the all-reduce of a sharded training set)
+__global__ void k_bins_get(const spc_subspace* __restrict__ bins, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = bins[i].sum_pmf;
+}
+__global__ void k_bins_put(spc_subspace* __restrict__ bins, int n, const float* __restrict__ in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bins[i].sum_pmf = in[i];
+}
 void train_reweight(Context& c) {
     TrainBuffers& t = c.train;
     const int n = (int)t.n_paths;
-    if (n == 0) return;
+    if (n == 0 && c.comm_world <= 1) return;
     LvcBuffers& b = c.bins_tmp;
     b.key.alloc(n); b.weight.alloc(n); b.totals.alloc(kReweightBins + 8);
     SPC_CUDA(cudaMemsetAsync(b.totals.p + kReweightBins, 0, 8 * sizeof(int), c.stream));
-    k_reweight_keys<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, n, b.key.p, b.weight.p);
+    if (n) k_reweight_keys<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, n, b.key.p, b.weight.p);
     bin_ordered(c, b, n, kReweightBins, b.totals.p + kReweightBins);
-    k_reweight_apply<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, n, b.subspace.p);
+    if (c.comm_world > 1) {   // the grid sums run over the whole training set: add the other ranks' shards
+        t.sort_vals.alloc(kReweightBins);
+        k_bins_get<<<(kReweightBins + 255) / 256, 256, 0, c.stream>>>(b.subspace.p, kReweightBins, t.sort_vals.p);
+        comm_allreduce_sum(c, t.sort_vals.p, kReweightBins);
+        k_bins_put<<<(kReweightBins + 255) / 256, 256, 0, c.stream>>>(b.subspace.p, kReweightBins, t.sort_vals.p);
+        c.launches += 2;
+    }
+    if (n) k_reweight_apply<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, n, b.subspace.p);
     c.launches += 2;
     SPC_CUDA(cudaGetLastError());
 }
@@ -288,6 +304,33 @@ int train_get_Q(Context& c, const spc_vertex* lvc, const uint8_t* valid, int n, 
     SPC_CUDA(cudaGetLastError());
     return t.acc_valid_path;
 }
+__global__ void k_q_scale(float* __restrict__ Q, int K, float s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) Q[i] *= s;
+}
+// spc_allreduce_training_stats: Q <- sum_r n_r Q_r / sum_r n_r (n_r = light paths behind rank r's estimate)
+void train_allreduce_Q(Context& c) {
+    TrainBuffers& t = c.train;
+    SPC_REQUIRE(t.has_Q, SPC_ERR_INVALID, "spc_allreduce_training_stats before preprocess_getQ");
+    if (c.comm_world <= 1) return;
+    const int K = c.K;
+    t.sort_vals.alloc(K + 1);
+    k_q_scale<<<(K + 127) / 128, 128, 0, c.stream>>>(t.Q.p, K, (float)t.acc_valid_path);
+    const float n_r = (float)t.acc_valid_path;
+    SPC_CUDA(cudaMemcpyAsync(t.sort_vals.p, t.Q.p, K * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+    SPC_CUDA(cudaMemcpyAsync(t.sort_vals.p + K, &n_r, sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));   // n_r is a stack variable
+    comm_allreduce_sum(c, t.sort_vals.p, (size_t)K + 1);
+    float total = 0.f;
+    SPC_CUDA(cudaMemcpyAsync(&total, t.sort_vals.p + K, sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    SPC_REQUIRE(total > 0.f, SPC_ERR_INVALID, "spc_allreduce_training_stats: no light paths on any rank");
+    SPC_CUDA(cudaMemcpyAsync(t.Q.p, t.sort_vals.p, K * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+    k_q_scale<<<(K + 127) / 128, 128, 0, c.stream>>>(t.Q.p, K, 1.0f / total);
+    t.acc_valid_path = (int)total;
+    c.launches += 2;
+    SPC_CUDA(cudaGetLastError());
+}
 void train_Q_zero_handle(Context& c) {
     TrainBuffers& t = c.train;
     SPC_REQUIRE(t.has_Q, SPC_ERR_INVALID, "Q_zero_handle before preprocess_getQ");
@@ -356,6 +399,12 @@ void train_build_data(Context& c, int n_samples) {
     SPC_CUDA(cudaStreamSynchronize(st));
     std::sort(h, h + 1000);   // thrust::sort + [999] (device_thrust.cu:3282-3284); NaNs cannot occur past the loss clamp unless Q is NaN
     t.outlier_threshold = h[999];
+    if (c.comm_world > 1) {   // sharded set: the first 1000 paths of the whole set are rank 0's
+        SPC_CUDA(cudaMemcpyAsync(t.outlier.p, &t.outlier_threshold, sizeof(float), cudaMemcpyHostToDevice, st));
+        comm_bcast(c, t.outlier.p, sizeof(float), 0);
+        SPC_CUDA(cudaMemcpyAsync(&t.outlier_threshold, t.outlier.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+        SPC_CUDA(cudaStreamSynchronize(st));
+    }
     const int np = (int)t.n_paths;
     k_outlier_clean<<<(np + 255) / 256, 256, 0, st>>>(t.paths.p, np, t.conns.p, t.Q.p, t.outlier_threshold);
     t.N = n_samples;
@@ -439,6 +488,7 @@ float* train_get_gamma(Context& c) {
         k_segment_sum_ordered<<<(n + 255) / 256, 256, 0, c.stream>>>(t.sort_keys2.p, t.sort_vals2.p, n, t.gamma.p);
         c.launches += 3;
     }
+    comm_allreduce_sum(c, t.gamma.p, (size_t)K * K);   // sharded set: the histogram runs over every rank's connections
     k_gamma_rownorm<<<(K + 63) / 64, 64, 0, c.stream>>>(t.gamma.p, K);
     c.launches += 1;
     SPC_CUDA(cudaGetLastError());
@@ -647,6 +697,9 @@ float* train_optimal_E(Context& c, int batch_size, int epochs, float lr, float* 
             const int hi = bias_sample + batch_size < t.N ? t.h_P2N[bias_sample + batch_size] : t.M;
             if (hi > lo)
                 k_train_dE_ordered<<<(hi - lo + 255) / 256, 256, 0, st>>>(t.sort_idx2.p, t.sort_keys2.p, lo, hi, t.peak.p, t.node_path.p, t.path_d.p, t.label_E.p, t.dE.p);
+            // sharded training set: this rank's batch is 1/world of the global batch -- sum the K x K gradient over the ranks
+            // (NCCL over NVLink, 4 MB per step at K = 1000) so that every rank takes the same Adam step
+            comm_allreduce_sum(c, t.dE.p, n);
             k_sum_fixed<<<1, 256, 0, st>>>(t.path_loss.p, batch_size, t.loss.p + (step - 1));
             k_train_step<<<K, 256, 0, st>>>(t.theta.p, t.adam_m.p, t.adam_v.p, t.E.p, t.Esum.p, t.dE.p, K, step, lr, 0.9f, 0.999f, 1e-8f);
             c.launches += 5;
@@ -654,13 +707,14 @@ float* train_optimal_E(Context& c, int batch_size, int epochs, float lr, float* 
     k_train_toE<<<K, 256, 0, st>>>(t.theta.p, K, t.gamma.p);
     c.launches++;
     SPC_CUDA(cudaGetLastError());
+    comm_allreduce_sum(c, t.loss.p, (size_t)step);
     if (n_loss) *n_loss = step;
     if (loss_out_host && loss_cap > 0) {
         const int m = std::min(loss_cap, step);
         std::vector<float> h(m);
         SPC_CUDA(cudaMemcpyAsync(h.data(), t.loss.p, m * sizeof(float), cudaMemcpyDeviceToHost, st));
         SPC_CUDA(cudaStreamSynchronize(st));
-        for (int i = 0; i < m; i++) loss_out_host[i] = h[i] / (float)batch_size;
+        for (int i = 0; i < m; i++) loss_out_host[i] = h[i] / ((float)batch_size * (float)c.comm_world);
     }
     return t.gamma.p;
 }

@@ -1,13 +1,17 @@
-"""Multi-GPU plumbing of the render core: one process per GPU (torch.distributed, NCCL over NVLink / NVSwitch), every
-rank holds a replica of the scene + BVH.  The path shards by samples: rank r renders its own
-subframes (own light-vertex cache per frame, own seeds) into its own running mean; there is NO per-bounce or per-frame
-collective.  Collectives appear in exactly two places:
+"""Multi-GPU host plumbing of the render core: one process per GPU, every rank holds a replica of scene + BVH (SURVEY.md
+section 8e).  The data-path collectives are NCCL calls INSIDE libspcbpt_b200.so (csrc/comm.cu, include/spcbpt_b200.h
+"multi-GPU"); this module only does what a host launcher does -- ship the NCCL unique id to the ranks and plan the shards:
 
-  * training, once:  trees are built on rank 0's host and broadcast; Q [K], the Gamma histogram [K*K] and the trained
-    matrix [K*K] are all-reduced (averaged) so that every rank samples from the same subspace statistics;
-  * read-out:        the accumulation buffers [W*H*4] fp32 are all-reduced (averaged over ranks).
+  * training, once:  the NEE training paths and the Q light-trace launches are sharded across ranks (rank r traces pretrace
+    iterations r+1, r+1+W, ... and light-trace frames likewise); the library all-reduces the reweighting grid, Q, the Gamma
+    histogram and the K x K gradient of every Adam step, so every rank ends with the same Q / Gamma as a single-GPU run over
+    the union of the shards (up to fp32 summation order); trees are built on rank 0's host and broadcast;
+  * rendering:       rank r renders its own subframes (own light-vertex cache, own seeds) into its own running mean -- no
+    per-bounce or per-frame collective;
+  * read-out:        spc_reduce_accum sums the weighted running means into rank 0's buffer.
 
-All helpers work with the gloo backend on CPU tensors as well, which is how the host logic is tested without GPUs."""
+torch.distributed is used for the rendezvous only (broadcast of 128 id bytes, barriers, max of timings): with the gloo
+backend on CPU this host logic is testable without GPUs (tests/test_parallel_cpu.py)."""
 import numpy as np
 
 
@@ -17,71 +21,76 @@ class DistEnv:
         self.rank = self.dist.get_rank() if self.dist else 0
         self.world = self.dist.get_world_size() if self.dist else 1
 
-    # -- statistics: in-place average over ranks --------------------------------------------------
+    def _dev(self):
+        import torch
+        return torch.device("cuda", torch.cuda.current_device()) if self.dist.get_backend() == "nccl" else torch.device("cpu")
+
+    # -- rank-0 bytes to everyone (the NCCL unique id, tree arrays in the CPU tests) ----------------
+    def broadcast_bytes(self, raw, nbytes=None):
+        """raw: bytes on rank 0 (ignored elsewhere); returns rank 0's bytes on every rank"""
+        if not self.dist or self.world == 1:
+            return bytes(raw)
+        import torch
+        dev = self._dev()
+        meta = torch.zeros(1, dtype=torch.int64, device=dev)
+        if self.rank == 0:
+            meta[0] = len(raw)
+        self.dist.broadcast(meta, 0)
+        n = int(meta[0].item())
+        buf = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev) if self.rank == 0 else torch.empty(n, dtype=torch.uint8, device=dev)
+        self.dist.broadcast(buf, 0)
+        return buf.cpu().numpy().tobytes()
+
     def allreduce_mean(self, tensor):
+        """in-place mean over ranks of a torch tensor (host-side statistics such as timings)"""
         if self.dist and self.world > 1:
             self.dist.all_reduce(tensor, op=self.dist.ReduceOp.SUM)
             tensor.div_(self.world)
         return tensor
-
-    # -- rank-0 objects (numpy arrays) to everyone ------------------------------------------------
-    def broadcast(self, obj):
-        """broadcast(None) -> this rank; broadcast(obj) -> rank 0's obj (tuples of numpy arrays are sent as byte tensors)"""
-        if obj is None:
-            return self.rank
-        if not self.dist or self.world == 1:
-            return obj
-        import torch
-        backend_cuda = self.dist.get_backend() == "nccl"
-        dev = torch.device("cuda", torch.cuda.current_device()) if backend_cuda else torch.device("cpu")
-        out = []
-        for k in range(len(obj)):
-            a = obj[k]
-            meta = torch.zeros(2, dtype=torch.int64, device=dev)
-            if self.rank == 0:
-                raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
-                meta[0], meta[1] = raw.shape[0], a.dtype.itemsize
-            self.dist.broadcast(meta, 0)
-            n = int(meta[0].item())
-            buf = torch.from_numpy(raw.copy()).to(dev) if self.rank == 0 else torch.empty(n, dtype=torch.uint8, device=dev)
-            self.dist.broadcast(buf, 0)
-            out.append(buf.cpu().numpy())
-        return out
 
     def barrier(self):
         if self.dist and self.world > 1:
             self.dist.barrier()
 
 
-def preprocess_distributed(renderer, env, tree_dtype, **kw):
-    """Renderer.preprocessing with the two training exchanges wired to `env`: every rank traces its own training paths
-    (pretrace iterations are offset by rank so that the sets are disjoint), rank 0 builds the trees."""
-    renderer.P["pre_tracer"]["iteration"] = 1000003 * env.rank
-    renderer.P["lt"]["launch_frame"] = 1000003 * env.rank
-
-    def bcast(obj):
-        r = env.broadcast(obj)
-        if obj is None:
-            return r
-        return tuple(np.frombuffer(x.tobytes(), dtype=tree_dtype).copy() for x in r) if env.world > 1 else obj
-
-    def allreduce(t):
-        # the statistic was produced on the context's stream and is consumed there again; the collective runs on torch's
-        # streams, so fence both sides (three times per training run: cost is irrelevant)
-        renderer.ctx.synchronize()
-        env.allreduce_mean(t)
-        if getattr(t, "is_cuda", False):
-            renderer.torch.cuda.synchronize(t.device)
-    return renderer.preprocessing(allreduce=allreduce if env.world > 1 else None, broadcast=bcast if env.world > 1 else None, **kw)
+def shard_plan(rank, world, target_samples, target_Q_samples, batch_size):
+    """who traces what: pure arithmetic, shared by renderer.py and host/spcbpt_main.cpp (tests/test_parallel_cpu.py)"""
+    assert world >= 1 and 0 <= rank < world
+    assert batch_size % world == 0, "the Adam batch (%d) must divide by the number of ranks (%d)" % (batch_size, world)
+    return dict(rank=rank, world=world,
+                local_samples=-(-target_samples // world),          # ceil: NEE training paths this rank traces
+                local_Q_samples=-(-target_Q_samples // world),      # light paths behind this rank's Q estimate
+                local_batch=batch_size // world,                    # this rank's share of every Adam batch
+                first_iteration=rank + 1, iteration_stride=world,   # pretrace iterations rank+1, rank+1+W, ...
+                first_lt_frame=rank + 1, lt_frame_stride=world,     # light-trace frames of the Q estimate likewise
+                render_lt_base=1000003 * (rank + 1))                # light-trace frames of the render loop: disjoint from all of the above
 
 
-def reduce_accum(renderer, env):
-    """average the per-rank running means (every rank rendered the same number of subframes): the read-out collective.
-    `renderer` is a Renderer or a LaneRenderer (whose lanes are merged first)."""
+def comm_init(ctx, env):
+    """give `ctx` the NCCL communicator of this job: rank 0 creates the unique id, torch.distributed ships the 128 bytes"""
+    if env.world == 1:
+        return
+    raw = ctx.comm_unique_id() if env.rank == 0 else b""
+    ctx.comm_init(env.rank, env.world, env.broadcast_bytes(raw))
+
+
+def preprocess_distributed(renderer, env, tree_dtype=None, **kw):
+    """Renderer.preprocessing with the training set sharded over the ranks of `env` (collectives inside the library)"""
+    if env.world > 1 and renderer.ctx.comm_info()[1] == 1:
+        comm_init(renderer.ctx, env)
+    plan = shard_plan(env.rank, env.world, kw.get("target_samples", 2000000), kw.get("target_Q_samples", 2000000), kw.get("batch_size", 20000))
+    return renderer.preprocessing(plan=plan, **kw)
+
+
+def reduce_accum(renderer, env, root=0):
+    """read-out: every rank rendered the same number of subframes, so the image is the plain mean of the per-rank running means,
+    summed into `root`'s buffer by NCCL (spc_reduce_accum).  `renderer` is a Renderer or a LaneRenderer (lanes merged first).
+    Returns the accumulation tensor (valid on `root`; root < 0: on every rank)."""
     if hasattr(renderer, "merge"):
         renderer.merge()
-    renderer.ctx.synchronize()
-    out = env.allreduce_mean(renderer.accum)
-    if getattr(out, "is_cuda", False):
-        renderer.torch.cuda.synchronize(out.device)
-    return out
+    ctx = renderer.ctx
+    ctx.synchronize()
+    if env.world > 1:
+        ctx.reduce_accum(renderer.accum, renderer.w * renderer.h, 1.0 / env.world, root)
+    ctx.synchronize()
+    return renderer.accum

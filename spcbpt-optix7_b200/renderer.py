@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-from . import (LAUNCH_LIGHT_TRACE, LAUNCH_PRETRACE, LAUNCH_PT, LAUNCH_SPCBPT_EYE, PARAMS, TRAIN_CONN, TRAIN_PATH, VERTEX, Context, build_tree)
+from . import (LAUNCH_LIGHT_TRACE, LAUNCH_PRETRACE, LAUNCH_PT, LAUNCH_SPCBPT_EYE, PARAMS, TRAIN_CONN, TRAIN_PATH, TREE_NODE, VERTEX, Context, build_tree)
 
 
 class Renderer:
@@ -49,10 +49,11 @@ class Renderer:
         self.subframe = 0
         self.stats = {}
         self._pipe = None
+        self.pretrace_stride = self.lt_stride = 1     # multi-GPU training shards the launches: parallel.shard_plan
 
     # ---- launch helpers (optixPathTracer.cpp:491-549) ------------------------------------------
     def launch_light_trace(self):
-        self.P["lt"]["launch_frame"] += 1
+        self.P["lt"]["launch_frame"] += self.lt_stride
         self.ctx.set_params(self.P)
         self.ctx.launch(LAUNCH_LIGHT_TRACE, int(self.P["lt"]["num_core"][0]), 1)
 
@@ -62,7 +63,7 @@ class Renderer:
 
     def launch_pretrace(self):
         pt = self.P["pre_tracer"]
-        pt["iteration"] += 1
+        pt["iteration"] += self.pretrace_stride
         self.ctx.set_params(self.P)
         n = int(pt["num_core"][0])
         self.ctx.launch(LAUNCH_PRETRACE, n, 1)
@@ -75,52 +76,63 @@ class Renderer:
 
     # ---- preprocessing() (optixPathTracer.cpp:552-608) -----------------------------------------
     def preprocessing(self, target_samples=2000000, target_Q_samples=2000000, tree_samples=100000, batch_size=20000, epochs=1, lr=0.01,
-                      allreduce=None, broadcast=None, verbose=False):
-        """the subspace-training schedule.  Multi-GPU (parallel.py): `allreduce(tensor)` averages a statistic across ranks in
-        place, `broadcast(None)` returns this rank and `broadcast(obj)` returns rank 0's object."""
+                      plan=None, verbose=False):
+        """the subspace-training schedule.  Multi-GPU: `plan` = parallel.shard_plan(...) and the context has a communicator
+        (parallel.comm_init): this rank traces its shard of the training paths and of the Q launches, the library all-reduces
+        the statistics (csrc/comm.cu), rank 0 builds the trees."""
         ctx, K = self.ctx, self.K
+        rank, world = (plan["rank"], plan["world"]) if plan else (0, 1)
+        local_samples = plan["local_samples"] if plan else target_samples
+        local_Q = plan["local_Q_samples"] if plan else target_Q_samples
+        local_batch = plan["local_batch"] if plan else batch_size
+        pt, lt = self.P["pre_tracer"], self.P["lt"]
+        if plan:
+            self.pretrace_stride, self.lt_stride = plan["iteration_stride"], plan["lt_frame_stride"]
+            pt["iteration"] = plan["first_iteration"] - self.pretrace_stride
+            lt["launch_frame"] = plan["first_lt_frame"] - self.lt_stride
         t0 = time.perf_counter()
         n = 0
-        while n < target_samples:
+        while n < local_samples:
             n += self.launch_pretrace()
+        ctx.synchronize()
         t1 = time.perf_counter()
         ctx.sample_reweight()
-        if broadcast is None or broadcast(None) == 0:    # the tree build stays on rank 0's host (SURVEY.md section 8e)
+        if rank == 0:    # the tree build stays on rank 0's host (SURVEY.md section 8e), from rank 0's shard of the paths
             eye_tree, _ = build_tree(ctx.get_tree_points(True, tree_samples), K, 0)
             light_tree, _ = build_tree(ctx.get_tree_points(False, tree_samples), K - self.K_light, 0)
         else:
             eye_tree = light_tree = None
-        if broadcast is not None:
-            eye_tree, light_tree = broadcast((eye_tree, light_tree))
+        if world > 1:
+            eye_tree, light_tree = (ctx.comm_bcast_array(t, TREE_NODE, 0) for t in (eye_tree, light_tree))
         self.eye_tree, self.light_tree = eye_tree, light_tree
         si = self.P["subspace_info"]
         si["eye_tree"] = ctx.tree_to_device(True, eye_tree)
         si["light_tree"] = ctx.tree_to_device(False, light_tree)
         t2 = time.perf_counter()
         acc, first, q_dev = 0, True, 0
-        while acc < target_Q_samples:
+        while acc < local_Q:
             self.launch_light_trace()
             q_dev, cum = ctx.preprocess_getQ(self.lvc, self.valid, self.n_lvc, reset=first)
             first = False
             acc += cum      # sic: the reference adds the CUMULATIVE count each time (optixPathTracer.cpp:590, device_thrust.cu:408)
-        if allreduce is not None:
-            allreduce(self._as_tensor(q_dev, K))
+        ctx.allreduce_training_stats()      # no-op on one GPU
         ctx.Q_zero_handle()
         ctx.node_label(int(si["eye_tree"][0]), int(si["light_tree"][0]))
-        n_train = (min(n, target_samples) // batch_size) * batch_size
+        n_train = (min(n, local_samples) // local_batch) * local_batch
+        if world > 1:       # every rank must run the same number of Adam steps
+            n_train = int(ctx.comm_allreduce_host(np.array([n_train], np.int32), "min")[0])
         ctx.build_optimal_E_train_data(n_train)
         g_dev = ctx.preprocess_getGamma()
-        if allreduce is not None:
-            allreduce(self._as_tensor(g_dev, K * K))
-        g_dev, loss = ctx.train_optimal_E(batch_size, epochs, lr)
-        if allreduce is not None:
-            allreduce(self._as_tensor(g_dev, K * K))
+        g_dev, loss = ctx.train_optimal_E(local_batch, epochs, lr)
         si["Q"] = q_dev
         self.gamma_dev = g_dev
         si["CMFGamma"] = ctx.Gamma2CMFGamma(g_dev)
         ctx.synchronize()
         t3 = time.perf_counter()
-        self.stats.update(train_paths=n, pretrace_s=t1 - t0, trees_s=t2 - t1, q_gamma_s=t3 - t2, loss_first=float(loss[0]) if len(loss) else None,
+        if plan:
+            self.lt_stride = 1
+            lt["launch_frame"] = plan["render_lt_base"]
+        self.stats.update(train_paths=n, train_paths_used=n_train, pretrace_s=t1 - t0, trees_s=t2 - t1, q_gamma_s=t3 - t2, loss_first=float(loss[0]) if len(loss) else None,
                           loss_last=float(loss[-1]) if len(loss) else None, eye_tree_nodes=int(eye_tree.shape[0]), light_tree_nodes=int(light_tree.shape[0]))
         if verbose:
             print(self.stats)

@@ -1,5 +1,7 @@
-"""CPU tests (gloo, world_size 2) of the multi-GPU host logic in spcbpt-optix7_b200/parallel.py: statistics are averaged
-in place, rank-0 trees reach every rank bit-for-bit, accumulation buffers reduce to the mean of the ranks."""
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic in spcbpt-optix7_b200/parallel.py: the rendezvous that ships the
+NCCL unique id (rank-0 bytes reach every rank bit-for-bit), host-side statistics, and the shard plan (which rank traces which
+pretrace iterations / light-trace frames, how the Adam batch splits).  The data-path collectives themselves are NCCL calls inside
+the library and are tested on GPUs (tests/test_multigpu_gpu.py)."""
 import os
 import socket
 import sys
@@ -28,7 +30,7 @@ def _worker(rank, world, port, q):
     pkg = spcbpt_loader.load()
     from spcbpt_optix7_b200.parallel import DistEnv
     env = DistEnv(dist)
-    ok = env.rank == rank and env.world == world and env.broadcast(None) == rank
+    ok = env.rank == rank and env.world == world
     # statistics: Q-like vector and a Gamma-like matrix
     qv = torch.full((16,), float(rank + 1))
     env.allreduce_mean(qv)
@@ -45,8 +47,11 @@ def _worker(rank, world, port, q):
         obj = (eye, light)
     else:
         obj = (np.zeros(0, pkg.TREE_NODE), np.zeros(0, pkg.TREE_NODE))
-    got = env.broadcast(obj)
-    trees = [np.frombuffer(x.tobytes(), dtype=pkg.TREE_NODE) for x in got]
+    got = [env.broadcast_bytes(x.tobytes() if rank == 0 else b"") for x in obj]
+    trees = [np.frombuffer(x, dtype=pkg.TREE_NODE) for x in got]
+    # the 128-byte NCCL unique id travels the same way (parallel.comm_init)
+    uid = bytes(range(128)) if rank == 0 else b""
+    ok &= env.broadcast_bytes(uid) == bytes(range(128))
     digest = [int(t["label"].sum()) + int(t["child"].sum()) + t.shape[0] for t in trees]
     # accumulation buffers: mean over ranks
     acc = torch.full((32, 4), float(rank))
@@ -72,3 +77,29 @@ def test_distenv_gloo_world2():
     res.sort()
     assert all(r[1] for r in res)
     assert res[0][2] == res[1][2] and res[0][2][0] > 10     # identical trees on both ranks
+
+
+def test_shard_plan_partitions_the_work():
+    sys.path.insert(0, ROOT)
+    import spcbpt_loader
+    spcbpt_loader.load()
+    from spcbpt_optix7_b200.parallel import shard_plan
+    for world in (1, 2, 4, 8):
+        plans = [shard_plan(r, world, 2000000, 2000000, 20000) for r in range(world)]
+        assert sum(p["local_batch"] for p in plans) == 20000
+        assert sum(p["local_samples"] for p in plans) >= 2000000 and plans[0]["local_samples"] == -(-2000000 // world)
+        # pretrace iterations / Q light-trace frames of the ranks are disjoint and cover 1, 2, 3, ...
+        its = sorted(p["first_iteration"] + k * p["iteration_stride"] for p in plans for k in range(5))
+        assert its == list(range(1, 5 * world + 1))
+        fr = sorted(p["first_lt_frame"] + k * p["lt_frame_stride"] for p in plans for k in range(5))
+        assert fr == list(range(1, 5 * world + 1))
+        # render-loop light-trace frames never collide with training frames or with another rank's
+        bases = [p["render_lt_base"] for p in plans]
+        assert len(set(bases)) == world and min(bases) > 100000
+    one = shard_plan(0, 1, 2000000, 2000000, 20000)
+    assert (one["local_samples"], one["local_batch"], one["first_iteration"], one["iteration_stride"]) == (2000000, 20000, 1, 1)
+    try:
+        shard_plan(0, 3, 2000000, 2000000, 20000)
+        assert False, "20000 does not divide by 3"
+    except AssertionError as ex:
+        assert "divide" in str(ex)

@@ -37,7 +37,9 @@ def test_reference_device_programs_agree_with_product(gpu_ctx):
     from spcbpt_optix7_b200.renderer import Renderer
     sc = pkg.scenes.scaled(varied_cornell(pkg), 0.01)
     w, h = 160, 120
-    kw = dict(K=1000, lt_num_core=200, lt_core_padding=400, lt_M_per_core=50, pretrace_num_core=20000)
+    # 300 x 400 LVC slots = the size tests/test_ref_thrust_gpu.py uses: the reference's LVC_Process sizes its function-static scratch
+    # vectors on the FIRST call of the process (device_thrust.cu:247-250) and overruns them when a later call is larger
+    kw = dict(K=1000, lt_num_core=300, lt_core_padding=400, lt_M_per_core=50, pretrace_num_core=20000)
     r = Renderer(sc, w, h, **kw)
     st = r.preprocessing(target_samples=200000, target_Q_samples=100000, tree_samples=50000, batch_size=20000)
     assert np.isfinite(st["loss_last"])
