@@ -387,7 +387,10 @@ def equal_time_block(pkg, torch, scene, seconds, gt_spp, lanes):
     for fast in (False, True):
         lr = LaneRenderer(scene, w, h, lanes=lanes, K=1000, fast=fast)
         lr.preprocessing()
-        run("SPCBPT_eye %s flavour (%d lanes)" % ("fast" if fast else "exact", lanes), lambda: lr.render(lanes), lr.image, lanes)
+        if fast:
+            for lane in lr.lanes:
+                lane.ctx.set_option("light_trace_mode", 1)
+        run("SPCBPT_eye %s (%d lanes)" % ("fast flavour + parallel light tracer" if fast else "exact flavour", lanes), lambda: lr.render(lanes), lr.image, lanes)
         out["rows"][-1]["spp"] += lanes
         if not fast:
             trained = lr
@@ -413,7 +416,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     size class (the shipped house scene is reference data and does not travel).  Samples are partitioned across ranks
     (each rank renders its own subframes); the accumulation buffers are averaged over NCCL at read-out."""
     from spcbpt_optix7_b200.renderer import LaneRenderer
-    from spcbpt_optix7_b200.parallel import DistEnv, preprocess_distributed, reduce_accum
+    from spcbpt_optix7_b200.parallel import DistEnv, comm_init, preprocess_distributed, reduce_accum
     env = DistEnv(dist)
     # the shipped scene when its .spcscene cache is present (written by __graft_entry__.build() from the reference's data with our
     # own loader, host/), else a synthetic scene of the same size class
@@ -434,6 +437,8 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     lr_ = LaneRenderer(scene, w, h, lanes=lanes, device=local_rank, K=K, K_light=K_light, max_depth=max_depth)
     r = lr_.lanes[0]
     lr_.seed_mapping(rank, world)
+    comm_init(r.ctx, env)       # NCCL communicator of this rank (csrc/comm.cu), outside the timed preprocessing
+    env.barrier()
     t0 = time.perf_counter()
     st = preprocess_distributed(r, env, pkg.TREE_NODE, target_samples=2000000, target_Q_samples=2000000, tree_samples=100000,
                                 batch_size=20000, epochs=1, lr=0.01)
@@ -469,6 +474,10 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     if not args.no_fast:
         lf = LaneRenderer(scene, w, h, lanes=lanes, device=local_rank, K=K, K_light=K_light, max_depth=max_depth, fast=True)
         lf.seed_mapping(rank, world)
+        comm_init(lf.lanes[0].ctx, env)
+        for lane in lf.lanes:   # per-path light-tracer streams as well (not bit-comparable with the reference either way)
+            lane.ctx.set_option("light_trace_mode", 1)
+        env.barrier()
         t0 = time.perf_counter()
         stf = preprocess_distributed(lf.lanes[0], env, pkg.TREE_NODE, target_samples=2000000, target_Q_samples=2000000, tree_samples=100000,
                                      batch_size=20000, epochs=1, lr=0.01)
@@ -487,7 +496,8 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
         out["fast_flavour"] = {"samples_per_s": w * h * args.render_frames * world / dtf, "ms_per_frame": dtf / args.render_frames * 1e3,
                                "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_f], "preprocess_s": pre_f,
                                "loss_last": stf["loss_last"], "image_mean": float(lf.image().mean()),
-                               "flags": "-fmad=true -prec-div=false -prec-sqrt=false -DSPC_FAST_MATH (render.cu, pt.cu, pretrace.cu); traversal / binning / training unchanged"}
+                               "flags": "-fmad=true -prec-div=false -prec-sqrt=false -DSPC_FAST_MATH (render.cu, pt.cu, pretrace.cu); traversal / binning / training unchanged; "
+                                        "light_trace_mode 1 (one lane per light path)"}
         del lf
     if rank == 0:
         # in-frame work and stage times: lane 0 alone, sequential frames, every stage of every bounce bracketed by CUDA events

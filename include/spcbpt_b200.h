@@ -420,6 +420,11 @@ SPC_API int  spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_de
  *   "count_canonical"   1: the *_counted entry points count the nodes / triangles of the strict front-to-back, t-pruned traversal
  *                          (one ray per lane, one node per step: the traversal SURVEY.md section 8d defines the algorithmic bytes
  *                          by) instead of the visits of the production kernel's own schedule
+ *   "light_trace_mode"  0 (default): the reference's RNG streams -- the M_per_core paths of a core share two streams
+ *                          (raygen.cu:624-628), so a core is traced serially and the LVC equals the reference's bit for bit;
+ *                       1: one lane per light path with per-path streams, seed tea<4>(0x80000000 | path, launch_frame), vertices
+ *                          packed densely in path order: same estimator and distribution, different random numbers (NOT bit-comparable
+ *                          with mode 0), an order of magnitude faster
  *   "stage_timing"      1: the eye pass brackets every stage of every bounce with CUDA events (slower: for spc_eye_stats_get) */
 SPC_API int  spc_set_option(spc_context* ctx, const char* name, int64_t value);
 SPC_API int  spc_get_option(spc_context* ctx, const char* name, int64_t* value);

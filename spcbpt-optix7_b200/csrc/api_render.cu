@@ -113,6 +113,7 @@ static int64_t* option_slot(Context& c, const char* name, int64_t* lo, int64_t* 
         {"blocking_sync", &c.opt[spc::OPT_BLOCKING_SYNC], 0, 1},
         {"count_canonical", &c.opt[spc::OPT_COUNT_CANONICAL], 0, 1},
         {"stage_timing", &c.opt[spc::OPT_STAGE_TIMING], 0, 1},
+        {"light_trace_mode", &c.opt[spc::OPT_LIGHT_TRACE_MODE], 0, 1},
     };
     for (const Opt& o : table)
         if (!strcmp(o.name, name)) {

@@ -161,7 +161,7 @@ struct TrainBuffers {
 };
 
 // spc_set_option switches (include/spcbpt_b200.h documents each)
-enum Option { OPT_REFERENCE_SEARCH = 0, OPT_BLOCKING_SYNC, OPT_COUNT_CANONICAL, OPT_STAGE_TIMING, OPT_COUNT };
+enum Option { OPT_REFERENCE_SEARCH = 0, OPT_BLOCKING_SYNC, OPT_COUNT_CANONICAL, OPT_STAGE_TIMING, OPT_LIGHT_TRACE_MODE, OPT_COUNT };
 
 struct Context {
     int           device = 0;
@@ -197,6 +197,7 @@ struct Context {
     int*          h_pinned = nullptr;          // small pinned staging block for counter read-backs
     cudaEvent_t   eye_events[8] = {};          // lagged queue-size read-backs of the eye pass (render.cu)
     DevBuf<spc_vertex> pretrace_scratch;       // per-lane eye-vertex buffers of the training tracer
+    DevBuf<int>   lt_counts;                   // parallel light tracer: per-path vertex counts + offsets (render.cu)
     TrainBuffers  train;
     LvcBuffers    bins_tmp;                    // ordered-binning scratch of getQ / sample_reweight
     // per-context one-time setup (function attributes and occupancy are per DEVICE, and spc_create accepts any device)

@@ -64,6 +64,61 @@ void build_material_tables(Context& c) {
 // =============================================================================================
 constexpr int kLtWarps = 4;
 
+// One light sub-path (the body of the `while (true)` of __raygen__lightTrace, raygen.cu:636-679, with the closest-hit programs
+// inlined): draws from `seed` (raygen side: light pick, point, direction) and `hit_seed` (hit side: BSDF sample + Russian roulette),
+// hands every vertex to emit(vertex) in path order; emit returns false when the output is full, which ends the path.
+// Returns false when emit refused a vertex.
+template <class Emit>
+__device__ __forceinline__ bool light_path(const DevFrame& fr, uint32_t& seed, uint32_t& hit_seed, uint2* stack, int sstride, const TravLut& lut, Emit& emit) {
+    unsigned cn = 0, ct = 0;
+    const int li = pick_light(fr, seed);
+    LightSample ls;
+    {
+        const float r1 = rnd(seed);
+        const float r2 = rnd(seed);
+        light_reverse_sample(fr, li, r1, r2, ls);   // lightSample::operator(), cuProg.h:602-621
+    }
+    light_trace_mode(ls, seed);
+    float3 ray_direction = ls.direction;
+    float3 ray_origin = ls.position;
+    Vtx cur;
+    vtx_zero(cur);
+    init_vertex_from_light_sample(ls, cur);
+    float3 pre_flux = f3(0.f);
+    float pre_singlePdf = ls.dir_pdf;   // init_lightSubPath_from_lightSample, raygen.cu:196-213
+    if (!emit(cur)) return false;
+    bool done = false;
+    int depth = 0;
+    while (true) {
+        TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
+        TravHit h;
+        bool pushed = false;
+        if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, stack, sstride, h, cn, ct, lut)) {
+            done = true;                                   // __miss__BDPTVertex, raygen.cu:699-704
+        } else {
+            const LocalGeom g = hit_geometry(fr.sc, h.prim, h.u, h.v);
+            if (g.light >= 0) {
+                done = true;                               // __closesthit__lightSource_subpath, hit_program.cu:239-244
+            } else {
+                Vtx mid;
+                SurfaceOut so;
+                surface_hit(fr, cur, pre_flux, pre_singlePdf, g, h.t, ray_direction, true, hit_seed, mid, so);
+                cur = mid;
+                pre_flux = so.next_flux;
+                pre_singlePdf = so.next_singlePdf;
+                ray_direction = so.dir;
+                ray_origin = g.P;
+                done = so.done;
+                pushed = true;
+            }
+        }
+        if (pushed && !emit(cur)) return false;
+        if (done || depth > fr.max_depth) break;
+        depth += 1;
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFrame fr, int lanes) {
     __shared__ uint2 s_stack[kSmStack * kLtWarps * 32];
     __shared__ TravLut s_lut;
@@ -78,67 +133,75 @@ __global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFr
     const unsigned bias = (unsigned)lt.core_padding * (unsigned)core;
     unsigned n_vert = 0, n_path = 0;
     const unsigned cap = (unsigned)lt.core_padding;
-    unsigned cn = 0, ct = 0;
-
-    while (true) {
-        const int li = pick_light(fr, seed);
-        LightSample ls;
-        {
-            const float r1 = rnd(seed);
-            const float r2 = rnd(seed);
-            light_reverse_sample(fr, li, r1, r2, ls);   // lightSample::operator(), cuProg.h:602-621
-        }
-        light_trace_mode(ls, seed);
-        float3 ray_direction = ls.direction;
-        float3 ray_origin = ls.position;
-        Vtx cur;
-        vtx_zero(cur);
-        init_vertex_from_light_sample(ls, cur);
-        float3 pre_flux = f3(0.f);
-        float pre_singlePdf = ls.dir_pdf;   // init_lightSubPath_from_lightSample, raygen.cu:196-213
-        vtx_store(lt.ans + bias + n_vert, cur);
+    auto emit = [&](const Vtx& v) {   // pushVertexToLVC (raygen.cu:613-619) + the window check of :656,:676
+        vtx_store(lt.ans + bias + n_vert, v);
         lt.validState[bias + n_vert] = 1;
         n_vert++;
-        if (!(n_vert < cap)) break;
-        bool done = false;
-        int depth = 0;
-        while (true) {
-            TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
-            TravHit h;
-            bool pushed = false;
-            if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, s_stack + threadIdx.x, kLtWarps * 32, h, cn, ct, s_lut)) {
-                done = true;                                   // __miss__BDPTVertex, raygen.cu:699-704
-            } else {
-                const LocalGeom g = hit_geometry(fr.sc, h.prim, h.u, h.v);
-                if (g.light >= 0) {
-                    done = true;                               // __closesthit__lightSource_subpath, hit_program.cu:239-244
-                } else {
-                    Vtx mid;
-                    SurfaceOut so;
-                    surface_hit(fr, cur, pre_flux, pre_singlePdf, g, h.t, ray_direction, true, hit_seed, mid, so);
-                    cur = mid;
-                    pre_flux = so.next_flux;
-                    pre_singlePdf = so.next_singlePdf;
-                    ray_direction = so.dir;
-                    ray_origin = g.P;
-                    done = so.done;
-                    pushed = true;
-                }
-            }
-            if (pushed) {
-                vtx_store(lt.ans + bias + n_vert, cur);
-                lt.validState[bias + n_vert] = 1;
-                n_vert++;
-                if (!(n_vert < cap)) break;
-            }
-            if (done || depth > fr.max_depth) break;
-            depth += 1;
-        }
+        return n_vert < cap;
+    };
+    while (true) {
+        if (!light_path(fr, seed, hit_seed, s_stack + threadIdx.x, kLtWarps * 32, s_lut, emit)) break;
         n_path++;
         if (n_path >= (unsigned)lt.M_per_core) break;
-        if (!(n_vert < cap)) break;
     }
     for (unsigned i = n_vert; i < cap; i++) lt.validState[bias + i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Parallel light tracer (spc_set_option "light_trace_mode" 1): one lane per light path instead of one per core.  Every path gets
+// its own streams, seed = tea<4>(0x80000000 | path index, launch_frame) (the reference couples the 100 paths of a core through two
+// shared streams, which is what forces k_light_trace_cores to run them serially): same estimator, same distribution, different
+// random numbers -- so frames are NOT bit-comparable with the reference-stream mode (tests/test_light_trace_modes_gpu.py compares
+// them statistically).  The vertices are packed densely in path order: pass 1 counts each path's vertices, an exclusive scan places
+// them, pass 2 traces the same paths again and writes -- deterministic and bit-reproducible, no atomics; the light sub-paths are
+// ~5 % of a frame's rays, so tracing them twice is cheaper than staging 120-byte vertices through scratch memory.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kLtPathBlock = 128;
+template <bool WRITE>
+__global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFrame fr, int n_paths, int* __restrict__ counts, const int* __restrict__ offsets, int n_slots) {
+    __shared__ uint2 s_stack[kSmStack * kLtPathBlock];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);
+    const int p = blockIdx.x * kLtPathBlock + threadIdx.x;
+    if (p >= n_paths) return;
+    const spc_light_trace_params& lt = fr.p.lt;
+    uint32_t seed = tea<4>(0x80000000u | (uint32_t)p, (uint32_t)lt.launch_frame);
+    uint32_t hit_seed = seed;
+    int n_vert = 0;
+    const int base = WRITE ? offsets[p] : 0;
+    auto emit = [&](const Vtx& v) {
+        if (WRITE) {
+            if (base + n_vert >= n_slots) return false;   // LVC full: the tail of the path order is dropped, deterministically
+            vtx_store(lt.ans + base + n_vert, v);
+            lt.validState[base + n_vert] = 1;
+        }
+        n_vert++;
+        return true;
+    };
+    light_path(fr, seed, hit_seed, s_stack + threadIdx.x, kLtPathBlock, s_lut, emit);
+    if (!WRITE) counts[p] = n_vert;
+}
+// exclusive scan of the per-path vertex counts (one block; 10^5 paths) and the validity flags of the unused tail
+__global__ void k_lt_scan(const int* __restrict__ counts, int n, int* __restrict__ offsets, int* __restrict__ total) {
+    __shared__ int s_part[1024];
+    const int per = (n + 1023) / 1024;
+    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += counts[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < 1024; i++) { const int v = s_part[i]; s_part[i] = run; run += v; }
+        *total = run;
+    }
+    __syncthreads();
+    int run = s_part[threadIdx.x];
+    for (int i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
+}
+__global__ void k_lt_clear_tail(uint8_t* __restrict__ valid, const int* __restrict__ total, int n_slots) {
+    const int first = min(*total, n_slots);
+    for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) valid[i] = 0;
 }
 
 void launch_light_trace(Context& c) {
@@ -147,6 +210,21 @@ void launch_light_trace(Context& c) {
     SPC_REQUIRE(lt.num_core > 0 && lt.core_padding > 0 && lt.ans && lt.validState, SPC_ERR_INVALID, "spc_launch(light trace): MyParams::lt is not set up");
     SPC_REQUIRE(c.geom.n_lights > 0, SPC_ERR_NO_SCENE, "spc_launch(light trace): the scene has no lights");
     const DevFrame fr = make_dev_frame(c);
+    if (c.opt[OPT_LIGHT_TRACE_MODE] == 1) {
+        const int n_paths = lt.num_core * lt.M_per_core, n_slots = lt.num_core * lt.core_padding;
+        c.lt_counts.alloc((size_t)2 * n_paths + 1);
+        int* counts = c.lt_counts.p;
+        int* offsets = counts + n_paths;
+        int* total = offsets + n_paths;
+        const int grid = (n_paths + kLtPathBlock - 1) / kLtPathBlock;
+        k_light_trace_paths<false><<<grid, kLtPathBlock, 0, c.stream>>>(fr, n_paths, counts, nullptr, n_slots);
+        k_lt_scan<<<1, 1024, 0, c.stream>>>(counts, n_paths, offsets, total);
+        k_light_trace_paths<true><<<grid, kLtPathBlock, 0, c.stream>>>(fr, n_paths, nullptr, offsets, n_slots);
+        k_lt_clear_tail<<<c.sm_count, 256, 0, c.stream>>>(lt.validState, total, n_slots);
+        SPC_CUDA(cudaGetLastError());
+        c.launches += 4;
+        return;
+    }
     static const int lanes = []() {
         const char* e = getenv("SPC_LT_LANES");
         return e ? std::max(1, std::min(32, atoi(e))) : 1;
