@@ -425,6 +425,8 @@ SPC_API int  spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_de
  *                       1: one lane per light path with per-path streams, seed tea<4>(0x80000000 | path, launch_frame), vertices
  *                          packed densely in path order: same estimator and distribution, different random numbers (NOT bit-comparable
  *                          with mode 0), an order of magnitude faster
+ *   "tail_threshold"    live-path count below which the eye pass stops launching per-bounce wavefront stages and finishes every
+ *                          surviving path in one kernel (0 = default 32768, -1 = never); frames are bit-identical for every value
  *   "stage_timing"      1: the eye pass brackets every stage of every bounce with CUDA events (slower: for spc_eye_stats_get) */
 SPC_API int  spc_set_option(spc_context* ctx, const char* name, int64_t value);
 SPC_API int  spc_get_option(spc_context* ctx, const char* name, int64_t* value);

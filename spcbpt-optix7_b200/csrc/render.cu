@@ -695,6 +695,105 @@ __global__ void __launch_bounds__(128) k_eye_connect(const DevFrame fr, const Ey
     if (lane == 0 && n_visible) atomicAdd(a.stat + 1, (unsigned long long)n_visible);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Tail of the eye pass.  After a few bounces a frame has a few thousand live paths left, yet every further bounce of the wavefront
+// costs six kernel launches whose duration is the latency of ONE path's dependent loads (~250 us per bounce, ~18 bounces on the
+// shipped scene: half of a sequential frame).  Once the live-path count has dropped below `tail_threshold` the remaining bounces of
+// every surviving path run to completion in this one kernel, one lane per path: closest hit -> surface program -> classification ->
+// C two-stage samples -> shadow rays -> connections, the loop body of __raygen__SPCBPT (raygen.cu:357-421) for that path.
+// Same draws in the same order and the same fp32 accumulation order as the wavefront stages (emitter term, then the connection
+// terms in connection order), so frames are bit-identical with and without the tail (tests/test_pipeline_gpu.py).
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kTailBlock = 128;
+template <int CT>
+__global__ void __launch_bounds__(kTailBlock) k_eye_tail(const DevFrame fr, const EyeArgs a, int first_bounce) {
+    __shared__ uint2 s_stack[kSmStack * kTailBlock];
+    __shared__ TravLut s_lut;
+    trav_lut_init(s_lut);
+    const int n = a.counts[first_bounce];
+    const int C = CT > 0 ? CT : fr.connections;
+    unsigned n_closest = 0, n_shadow = 0, n_visible = 0, cn = 0, ct = 0;
+    uint2* stack = s_stack + threadIdx.x;
+    for (int i = blockIdx.x * kTailBlock + threadIdx.x; i < n; i += gridDim.x * kTailBlock) {
+        const int pix = a.queue_cur[i];
+        const float4 ro4 = a.rays_cur[2 * (size_t)i], rd4 = a.rays_cur[2 * (size_t)i + 1];
+        float3 ray_origin = f3(ro4.x, ro4.y, ro4.z), ray_direction = f3(rd4.x, rd4.y, rd4.z);
+        Vtx last = vtx_load(a.ev + pix);
+        float4 pre = a.pre[pix];
+        float4 res = a.res[pix];
+        uint32_t seed = __float_as_uint(res.w);
+        int last_x = (int)a.xlab[pix];
+        for (int bounce = first_bounce; bounce <= fr.max_depth; bounce++) {
+            const TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
+            TravHit h;
+            n_closest++;
+            if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, stack, kTailBlock, h, cn, ct, s_lut)) break;   // miss
+            const LocalGeom g = hit_geometry(fr.sc, h.prim, h.u, h.v);
+            Vtx mid;
+            if (g.light >= 0) {
+                if (eye_hits_light(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, h.t, ray_direction, mid, last_x)) {
+                    const float3 ans = mid.flux / mid.pdf / mid.RMIS_pointer;
+                    if (!invalid3(ans)) { res.x += ans.x; res.y += ans.y; res.z += ans.z; }
+                }
+                break;
+            }
+            SurfaceOut so;
+            surface_hit(fr, last, f3(pre.x, pre.y, pre.z), pre.w, g, h.t, ray_direction, false, seed, mid, so, last_x, true);
+            int eye_subspace, cross;
+            if (fr.eye_ctree && fr.light_ctree) ctree_label2(fr.eye_ctree, fr.light_ctree, mid.position, mid.normal, eye_subspace, cross);
+            else tree_label2(fr.p.subspace_info.eye_tree, fr.p.subspace_info.light_tree, mid.position, mid.normal, eye_subspace, cross);
+            mid.subspaceId = (short)eye_subspace;
+            ConnPick pick[CT > 0 ? CT : 16];
+            bool sampled = false;
+            if (CT > 0) sampled = eye_sample_lockstep<(CT > 0 ? CT : 1)>(fr, eye_subspace, seed, pick);
+            if (!sampled) eye_sample_serial(fr, eye_subspace, C, seed, pick);
+#pragma unroll 1
+            for (int j = 0; j < C; j++) {
+                const int lv = pick[j].lv;
+                if (lv < 0) continue;
+                const Vtx light = vtx_load(fr.p.sampler.LVC + lv);
+                // visibilityTest (cuProg.h:489-502 -> :463-487)
+                const float3 bias_pos = light.position - mid.position;
+                const float len = length(bias_pos);
+                const float3 dir = bias_pos / len;
+                n_shadow++;
+                const float tmax = len - SPC_SCENE_EPS;
+                bool visible = true;
+                if (tmax > SPC_SCENE_EPS) {   // an empty interval hits nothing (k_trace_persist skips it the same way)
+                    const TravRay sr{mid.position.x, mid.position.y, mid.position.z, dir.x, dir.y, dir.z, SPC_SCENE_EPS, tmax};
+                    TravHit sh;
+                    visible = !traverse_bvh8<true, false>(fr.sc.nodes, fr.sc.tris, sr, false, stack, kTailBlock, sh, cn, ct, s_lut);
+                }
+                if (!visible) continue;
+                n_visible++;
+                const float3 c = connect_vertices(fr, mid, light, nullptr, cross, fr.lvc_xlabel ? (int)__ldg(fr.lvc_xlabel + lv) : -1);
+                const float3 rr = c / pick[j].pmf;
+                if (!invalid3(rr)) {
+                    const float3 term = rr / (float)C;
+                    res.x += term.x; res.y += term.y; res.z += term.z;   // connection order, as k_eye_gather
+                }
+            }
+            if (so.done) break;
+            last = mid;
+            last_x = cross;
+            pre = make_float4(so.next_flux.x, so.next_flux.y, so.next_flux.z, so.next_singlePdf);
+            ray_origin = g.P;
+            ray_direction = so.dir;
+        }
+        res.w = __uint_as_float(seed);
+        a.res[pix] = res;
+    }
+    // work counters (spc_eye_stats_get): [2] closest-hit rays of the tail
+    n_closest = __reduce_add_sync(0xffffffffu, n_closest);
+    n_shadow = __reduce_add_sync(0xffffffffu, n_shadow);
+    n_visible = __reduce_add_sync(0xffffffffu, n_visible);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_closest) atomicAdd(a.stat + 2, (unsigned long long)n_closest);
+        if (n_shadow) atomicAdd(a.stat + 0, (unsigned long long)n_shadow);
+        if (n_visible) atomicAdd(a.stat + 1, (unsigned long long)n_visible);
+    }
+}
+
 // result += res / CONNECTION_N, in connection order (raygen.cu:415)
 __global__ void k_eye_gather(const DevFrame fr, const EyeArgs a) {
     const int C = fr.connections;
@@ -863,6 +962,7 @@ void launch_eye_pass(Context& c, int width, int height) {
     // it stops when a queue was empty and shrinks the grids, but it never drains the stream (a full synchronisation every 4th
     // bounce left the GPU idle for a host round trip each time and made the frame time follow the host's scheduling noise).
     constexpr int kLag = 3, kRing = 8;
+    const int64_t tail_threshold = c.opt[OPT_TAIL_THRESHOLD] < 0 ? 0 : (c.opt[OPT_TAIL_THRESHOLD] == 0 ? 32768 : c.opt[OPT_TAIL_THRESHOLD]);
     if (!c.eye_events[0])
         for (int k = 0; k < kRing; k++)
             SPC_CUDA(cudaEventCreateWithFlags(&c.eye_events[k], cudaEventDisableTiming | (c.opt[OPT_BLOCKING_SYNC] ? cudaEventBlockingSync : 0)));
@@ -904,6 +1004,23 @@ void launch_eye_pass(Context& c, int width, int height) {
                 SPC_CUDA(cudaEventSynchronize(c.eye_events[pb % kRing]));
                 n_max = h_ring[pb % kRing];
                 if (n_max == 0) break;
+                if (tail_threshold > 0 && n_max <= tail_threshold && b + 1 <= fr.max_depth) {
+                    // few paths left: the remaining bounces of every survivor in one kernel (queue of bounce b + 1 = the `next` buffers)
+                    a.bounce = b + 1;
+                    a.rays_cur = (float4*)e.rays[(b + 1) & 1].p;
+                    a.queue_cur = e.queue[(b + 1) & 1].p;
+                    const int gt = (int)std::min<int64_t>((n_max + kTailBlock - 1) / kTailBlock, grid_cap);
+                    switch (C) {
+                        case 1: k_eye_tail<1><<<gt, kTailBlock, 0, st>>>(fr, a, b + 1); break;
+                        case 2: k_eye_tail<2><<<gt, kTailBlock, 0, st>>>(fr, a, b + 1); break;
+                        case 3: k_eye_tail<3><<<gt, kTailBlock, 0, st>>>(fr, a, b + 1); break;
+                        case 4: k_eye_tail<4><<<gt, kTailBlock, 0, st>>>(fr, a, b + 1); break;
+                        default: k_eye_tail<0><<<gt, kTailBlock, 0, st>>>(fr, a, b + 1); break;
+                    }
+                    c.launches++;
+                    SPC_CUDA(cudaGetLastError());
+                    break;
+                }
             }
         }
     }
@@ -925,7 +1042,8 @@ void eye_stats(Context& c, spc_eye_stats* out) {
     SPC_CUDA(cudaMemcpy(stat, e.stat.p, sizeof(stat), cudaMemcpyDeviceToHost));
     out->bounces = e.last_bounces;
     for (int v : counts) out->closest_rays += (uint64_t)v;
-    out->shadow_slots = out->closest_rays * (uint64_t)c.connections;
+    out->shadow_slots = out->closest_rays * (uint64_t)c.connections;   // slots the occlusion KERNEL scanned (the tail kernel traces its own)
+    out->closest_rays += stat[2];                                       // rays of the tail kernel
     out->shadow_rays = stat[0];
     out->visible_connections = stat[1];
     if (e.last_timed) {

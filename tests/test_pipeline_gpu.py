@@ -134,3 +134,35 @@ def test_shipped_scene_spcbpt_beats_pt_at_equal_spp(gpu_ctx):
     print("house 480x250 vs pt@2048spp: relMSE SPCBPT 64spp %.4f, pt 64spp %.4f, means %.4f / %.4f" % (e_spc, e_pt, img.mean(), ref.mean()))
     assert np.isfinite(img).all() and abs(img.mean() / ref.mean() - 1) < 0.02
     assert e_spc < 0.5 * e_pt and e_spc < 0.2
+
+
+def test_tail_kernel_leaves_frames_bit_identical(gpu_ctx):
+    """the eye pass finishes the last few thousand paths in one kernel (spc_set_option "tail_threshold"): whatever the threshold
+    -- never, the default, or "as early as the lagged queue read-back allows" -- the frames are the same, every bit, and the
+    work counters agree"""
+    pkg = gpu_ctx
+    from spcbpt_optix7_b200.renderer import Renderer
+    sc = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=12, box_cells=8), 0.01)
+    kw = dict(K=64, K_light=12, lt_num_core=100, lt_core_padding=300, lt_M_per_core=40, pretrace_num_core=20000)
+    r = Renderer(sc, 320, 200, **kw)
+    r.preprocessing(target_samples=40000, target_Q_samples=20000, tree_samples=20000, batch_size=20000)
+    frame0 = int(r.P["lt"]["launch_frame"][0])
+    out = []
+    for thr in (-1, 0, 4096, 1 << 30):
+        r.ctx.set_option("tail_threshold", thr)
+        r.reset_accumulation()
+        r.P["lt"]["launch_frame"] = frame0
+        l0 = r.ctx.launch_count()
+        for _ in range(4):
+            r.render_frame()
+        st = r.ctx.eye_stats()
+        out.append((r.image().copy(), st, r.ctx.launch_count() - l0))
+    r.ctx.set_option("tail_threshold", 0)
+    base = out[0]
+    assert base[0].mean() > 0.01
+    for img, st, launches in out[1:]:
+        assert np.array_equal(base[0].view(np.uint32), img.view(np.uint32))
+        assert (st["closest_rays"], st["shadow_rays"], st["visible_connections"]) == (base[1]["closest_rays"], base[1]["shadow_rays"], base[1]["visible_connections"])
+    print("launches for 4 frames: no tail %d, default %d, 4096 %d, earliest %d; wavefront bounces %s" % (
+        out[0][2], out[1][2], out[2][2], out[3][2], [o[1]["bounces"] for o in out]))
+    assert out[3][2] < out[1][2] <= out[0][2] and out[3][1]["bounces"] == 4
