@@ -57,6 +57,7 @@ struct Options {
     // with --rank r --world N --id-file <path> (rank 0 writes the NCCL unique id there, the others wait for it)
     int  ranks = 1, rank = 0, world = 1;
     std::string id_file;
+    std::vector<std::pair<std::string, long long>> options;   // --option name=value -> spc_set_option on every context
 };
 
 void usage(const char* argv0) {
@@ -65,6 +66,7 @@ void usage(const char* argv0) {
             "         --dim=<width>x<height>      image dimensions; defaults to 1920x1000\n"
             "         --data-root <dir>           directory the .scene's file names are relative to\n"
             "         --frames <n>                subframes to accumulate per rank (default 16)\n"
+            "         --option name=value         context switch (spc_set_option): light_trace_mode=1, tail_threshold=-1, ...\n"
             "         --ranks <n>                 multi-GPU: fork n ranks on devices 0..n-1 (NCCL inside the library: sharded training,\n"
             "                                     sample-partitioned frames, accumulation buffer reduced to rank 0)\n"
             "         --rank r --world n --id-file f   the same with externally started ranks (rank 0 writes the NCCL id to f)\n"
@@ -129,6 +131,12 @@ bool parse_args(int argc, char** argv, Options& o) {
         else if (a == "--pretrace-padding") o.pre_padding = atoi(need("--pretrace-padding"));
         else if (a == "--seed-offset") o.seed_offset = (unsigned)strtoul(need("--seed-offset"), nullptr, 10);
         else if (a == "--seed-stride") o.seed_stride = (unsigned)strtoul(need("--seed-stride"), nullptr, 10);
+        else if (a == "--option") {
+            const std::string kv = need("--option");
+            const size_t eq = kv.find('=');
+            if (eq == std::string::npos) throw std::runtime_error("--option expects name=value");
+            o.options.emplace_back(kv.substr(0, eq), atoll(kv.c_str() + eq + 1));
+        }
         else if (a == "--ranks") o.ranks = atoi(need("--ranks"));
         else if (a == "--rank") o.rank = atoi(need("--rank"));
         else if (a == "--world") o.world = atoi(need("--world"));
@@ -418,6 +426,7 @@ struct App {
                                    (int)scene_ref->lights.size(), textures.data(), (int)textures.size()));
         SPC_CHECK(spc_synchronize(ctx));
         if (upload_s) *upload_s = now_s() - t0;
+        for (const auto& kv : opt.options) SPC_CHECK(spc_set_option(ctx, kv.first.c_str(), kv.second));
     }
 
     void become_lane(int k, int n, const App& trained) {
