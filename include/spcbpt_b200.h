@@ -422,7 +422,8 @@ SPC_API int  spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_de
  *                          by) instead of the visits of the production kernel's own schedule
  *   "light_trace_mode"  0 (default): the reference's RNG streams -- the M_per_core paths of a core share two streams
  *                          (raygen.cu:624-628), so a core is traced serially and the LVC equals the reference's bit for bit;
- *                       1: one lane per light path with per-path streams, seed tea<4>(0x80000000 | path, launch_frame), vertices
+ *                       1: one lane per light path with per-path streams (seeds tea<4>(0x80000000 | path, launch_frame) for the
+ *                          raygen side, tea<4>(0x40000000 | path, launch_frame) for the hit side), vertices
  *                          packed densely in path order: same estimator and distribution, different random numbers (NOT bit-comparable
  *                          with mode 0), an order of magnitude faster
  *   "tail_threshold"    live-path count below which the eye pass stops launching per-bounce wavefront stages and finishes every

@@ -39,7 +39,7 @@ FAST_SWAP = {"-prec-div=true": "-prec-div=false", "-prec-sqrt=true": "-prec-sqrt
 NVCC_FLAGS_FAST = [FAST_SWAP.get(f, f) for f in NVCC_FLAGS] + ["-DSPC_FAST_MATH=1"]
 
 
-LINK_LIBS = ["-lnccl"]   # comm.cu: the system NCCL (/usr/include/nccl.h, libnccl.so.2)
+LINK_LIBS = ["-ldl"]   # comm.cu binds libnccl.so.2 at the first spc_comm_* call (types from /usr/include/nccl.h)
 
 
 def sources():

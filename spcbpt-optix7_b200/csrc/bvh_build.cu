@@ -570,6 +570,7 @@ static void stage_mark(cudaStream_t st, const char* what) {
 }
 
 void build_bvh(Context& ctx, const float4* d_tri_pos, uint32_t n) {
+    NvtxRange range("spc: BVH build");
     SPC_REQUIRE(n >= 1, SPC_ERR_INVALID, "scene has no triangles");
     cudaStream_t st = ctx.stream;
     static std::mutex g_build_mutex;

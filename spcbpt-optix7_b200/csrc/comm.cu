@@ -7,12 +7,68 @@
 //     of every Adam step right after k_train_dE_ordered (train.cu); trees are built on rank 0's host and broadcast;
 //   * read-out: the accumulation buffers are reduced to the root (spc_reduce_accum).
 // The reference is single-GPU (no counterpart); sutil/WorkDistribution.h:34-91 is its unused multi-GPU tile partition.
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <cstring>
+#include <mutex>
 #include "common.cuh"
 
 namespace spc {
+
+// NCCL is bound at the first spc_comm_* call, not at link time: a process may already hold a libnccl.so.2 (PyTorch ships its own and
+// resolves it by the same SONAME -- linking ours eagerly would make whichever library loads first win for both), and single-GPU
+// users need none at all.  RTLD_NOLOAD first: reuse the copy the process has; else the system library.
+namespace {
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    const char* (*GetErrorString)(ncclResult_t);
+};
+NcclApi g_nccl = {};
+bool g_nccl_ready = false;
+std::mutex g_nccl_mutex;
+}  // namespace
+
+static const NcclApi& nccl_api() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (g_nccl_ready) return g_nccl;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+        set_error("multi-GPU needs NCCL: cannot load libnccl.so.2 (%s)", dlerror());
+        throw CudaFailure{SPC_ERR_INVALID};
+    }
+    auto sym = [&](const char* name) {
+        void* p = dlsym(h, name);
+        if (!p) {
+            set_error("libnccl.so.2 lacks %s", name);
+            throw CudaFailure{SPC_ERR_INVALID};
+        }
+        return p;
+    };
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(sym("ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(sym("ncclAllReduce"));
+    g_nccl.Reduce = reinterpret_cast<decltype(g_nccl.Reduce)>(sym("ncclReduce"));
+    g_nccl.Broadcast = reinterpret_cast<decltype(g_nccl.Broadcast)>(sym("ncclBroadcast"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
+    g_nccl_ready = true;
+    return g_nccl;
+}
+// the calls below read like plain NCCL
+#define ncclGetUniqueId spc::nccl_api().GetUniqueId
+#define ncclCommInitRank spc::nccl_api().CommInitRank
+#define ncclCommDestroy spc::nccl_api().CommDestroy
+#define ncclAllReduce spc::nccl_api().AllReduce
+#define ncclReduce spc::nccl_api().Reduce
+#define ncclBroadcast spc::nccl_api().Broadcast
+#define ncclGetErrorString spc::nccl_api().GetErrorString
 
 #define SPC_NCCL(call)                                                                                   \
     do {                                                                                                 \

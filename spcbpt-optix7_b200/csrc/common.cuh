@@ -1,6 +1,7 @@
 // common.cuh -- shared declarations of libspcbpt_b200 (sm_100a only; no CPU fallback anywhere).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -32,6 +33,15 @@ struct CudaFailure { int code; };
             throw spc::CudaFailure{code};                                                        \
         }                                                                                        \
     } while (0)
+
+// NVTX range (header-only NVTX3: a no-op unless a profiler is attached): one per API-level stage and per wavefront stage of the
+// eye pass, so that an Nsight timeline reads "light trace / LVC_Process / eye pass: bounce b: trace, shade, ..."
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // RAII device buffer (cudaMalloc; buffers are sized for B200's 180 GB, no pooling needed)
 template <typename T>

@@ -217,6 +217,7 @@ int* lvc_bin(Context& c, LvcBuffers& b, const spc_vertex* lvc, const uint8_t* va
 }
 
 void lvc_process(Context& c, const spc_vertex* lvc, const uint8_t* valid, int n, spc_subspace_sampler* out) {
+    NvtxRange range("spc: LVC_Process");
     SPC_REQUIRE(lvc && valid && n > 0 && out, SPC_ERR_INVALID, "spc_lvc_process: bad arguments");
     LvcBuffers& b = c.lvc;
     if (!c.h_pinned) SPC_CUDA(cudaMallocHost((void**)&c.h_pinned, 64 * sizeof(int)));

@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(kPtBlock) k_pretrace(const DevFrame fr, spc_ve
 DevFrame make_dev_frame(Context& c);
 
 void launch_pretrace(Context& c) {
+    NvtxRange range("spc: pretrace");
     SPC_REQUIRE(c.has_params, SPC_ERR_INVALID, "spc_launch: spc_set_params has not been called");
     const spc_pretrace_params& pt = c.params.pre_tracer;
     SPC_REQUIRE(pt.num_core > 0 && pt.padding > 0 && pt.padding <= kMaxTrainVerts && pt.paths && pt.conns, SPC_ERR_INVALID,

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(kPtPixBlock) k_pt(const DevFrame fr, int n_pix
 }
 
 void launch_pt(Context& c, int width, int height) {
+    NvtxRange range("spc: pt");
     SPC_REQUIRE(c.has_params, SPC_ERR_INVALID, "spc_launch: spc_set_params has not been called");
     SPC_REQUIRE(width > 0 && height > 0 && (unsigned)width == c.params.width && (unsigned)height == c.params.height, SPC_ERR_INVALID,
                 "spc_launch(pt): launch size %dx%d differs from MyParams %ux%u", width, height, c.params.width, c.params.height);

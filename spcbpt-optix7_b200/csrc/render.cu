@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFr
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // Parallel light tracer (spc_set_option "light_trace_mode" 1): one lane per light path instead of one per core.  Every path gets
-// its own streams, seed = tea<4>(0x80000000 | path index, launch_frame) (the reference couples the 100 paths of a core through two
+// its own streams, seeds tea<4>(0x80000000 | path, launch_frame) and tea<4>(0x40000000 | path, launch_frame) (the reference couples the 100 paths of a core through two
 // shared streams, which is what forces k_light_trace_cores to run them serially): same estimator, same distribution, different
 // random numbers -- so frames are NOT bit-comparable with the reference-stream mode (tests/test_light_trace_modes_gpu.py compares
 // them statistically).  The vertices are packed densely in path order: pass 1 counts each path's vertices, an exclusive scan places
@@ -157,18 +157,23 @@ __global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFr
 // ~5 % of a frame's rays, so tracing them twice is cheaper than staging 120-byte vertices through scratch memory.
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int kLtPathBlock = 128;
+// Persistent lanes: a lane that finishes its path claims the next path index at once (the output depends on the path index only, so
+// any assignment of paths to lanes gives the same LVC), and the loop body is ONE bounce of whatever path the lane holds -- a warp
+// never idles behind its longest path (path lengths range from 1 to max_depth + 2 vertices).
 template <bool WRITE>
-__global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFrame fr, int n_paths, int* __restrict__ counts, const int* __restrict__ offsets, int n_slots) {
+__global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFrame fr, int n_paths, int* __restrict__ counts, const int* __restrict__ offsets, int n_slots,
+                                                                    int* __restrict__ next_path) {
     __shared__ uint2 s_stack[kSmStack * kLtPathBlock];
     __shared__ TravLut s_lut;
     trav_lut_init(s_lut);
-    const int p = blockIdx.x * kLtPathBlock + threadIdx.x;
-    if (p >= n_paths) return;
     const spc_light_trace_params& lt = fr.p.lt;
-    uint32_t seed = tea<4>(0x80000000u | (uint32_t)p, (uint32_t)lt.launch_frame);
-    uint32_t hit_seed = seed;
-    int n_vert = 0;
-    const int base = WRITE ? offsets[p] : 0;
+    uint2* stack = s_stack + threadIdx.x;
+    unsigned cn = 0, ct = 0;
+    int p = -1, n_vert = 0, base = 0, depth = 0;
+    uint32_t seed = 0, hit_seed = 0;
+    Vtx cur;
+    float3 pre_flux = f3(0.f), ray_origin = f3(0.f), ray_direction = f3(0.f);
+    float pre_singlePdf = 0.f;
     auto emit = [&](const Vtx& v) {
         if (WRITE) {
             if (base + n_vert >= n_slots) return false;   // LVC full: the tail of the path order is dropped, deterministically
@@ -178,8 +183,65 @@ __global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFra
         n_vert++;
         return true;
     };
-    light_path(fr, seed, hit_seed, s_stack + threadIdx.x, kLtPathBlock, s_lut, emit);
-    if (!WRITE) counts[p] = n_vert;
+    while (true) {
+        if (p < 0) {
+            p = atomicAdd(next_path, 1);
+            if (p >= n_paths) break;
+            // the two streams of a path (raygen side / hit side, raygen.cu:624-628) get their own seeds: started from one state, as the
+            // reference's first path of a core is, the hit side would replay the raygen side's draws on EVERY path
+            seed = tea<4>(0x80000000u | (uint32_t)p, (uint32_t)lt.launch_frame);
+            hit_seed = tea<4>(0x40000000u | (uint32_t)p, (uint32_t)lt.launch_frame);
+            n_vert = 0;
+            depth = 0;
+            base = WRITE ? offsets[p] : 0;
+            const int li = pick_light(fr, seed);
+            LightSample ls;
+            const float r1 = rnd(seed);
+            const float r2 = rnd(seed);
+            light_reverse_sample(fr, li, r1, r2, ls);
+            light_trace_mode(ls, seed);
+            ray_direction = ls.direction;
+            ray_origin = ls.position;
+            vtx_zero(cur);
+            init_vertex_from_light_sample(ls, cur);
+            pre_flux = f3(0.f);
+            pre_singlePdf = ls.dir_pdf;
+            if (!emit(cur)) {
+                p = -1;
+                continue;
+            }
+        }
+        // one bounce of the path this lane holds (the loop body of light_path)
+        const TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
+        TravHit h;
+        bool done = false, pushed = false;
+        if (!traverse_bvh8<false, false>(fr.sc.nodes, fr.sc.tris, r, true, stack, kLtPathBlock, h, cn, ct, s_lut)) {
+            done = true;
+        } else {
+            const LocalGeom g = hit_geometry(fr.sc, h.prim, h.u, h.v);
+            if (g.light >= 0) {
+                done = true;
+            } else {
+                Vtx mid;
+                SurfaceOut so;
+                surface_hit(fr, cur, pre_flux, pre_singlePdf, g, h.t, ray_direction, true, hit_seed, mid, so);
+                cur = mid;
+                pre_flux = so.next_flux;
+                pre_singlePdf = so.next_singlePdf;
+                ray_direction = so.dir;
+                ray_origin = g.P;
+                done = so.done;
+                pushed = true;
+            }
+        }
+        if (pushed && !emit(cur)) done = true;
+        if (done || depth > fr.max_depth) {
+            if (!WRITE) counts[p] = n_vert;
+            p = -1;
+        } else {
+            depth += 1;
+        }
+    }
 }
 // exclusive scan of the per-path vertex counts (one block; 10^5 paths) and the validity flags of the unused tail
 __global__ void k_lt_scan(const int* __restrict__ counts, int n, int* __restrict__ offsets, int* __restrict__ total) {
@@ -205,6 +267,7 @@ __global__ void k_lt_clear_tail(uint8_t* __restrict__ valid, const int* __restri
 }
 
 void launch_light_trace(Context& c) {
+    NvtxRange range("spc: light trace");
     SPC_REQUIRE(c.has_params, SPC_ERR_INVALID, "spc_launch: spc_set_params has not been called");
     const spc_light_trace_params& lt = c.params.lt;
     SPC_REQUIRE(lt.num_core > 0 && lt.core_padding > 0 && lt.ans && lt.validState, SPC_ERR_INVALID, "spc_launch(light trace): MyParams::lt is not set up");
@@ -212,14 +275,16 @@ void launch_light_trace(Context& c) {
     const DevFrame fr = make_dev_frame(c);
     if (c.opt[OPT_LIGHT_TRACE_MODE] == 1) {
         const int n_paths = lt.num_core * lt.M_per_core, n_slots = lt.num_core * lt.core_padding;
-        c.lt_counts.alloc((size_t)2 * n_paths + 1);
+        c.lt_counts.alloc((size_t)2 * n_paths + 4);
         int* counts = c.lt_counts.p;
         int* offsets = counts + n_paths;
         int* total = offsets + n_paths;
-        const int grid = (n_paths + kLtPathBlock - 1) / kLtPathBlock;
-        k_light_trace_paths<false><<<grid, kLtPathBlock, 0, c.stream>>>(fr, n_paths, counts, nullptr, n_slots);
+        int* next_path = total + 1;   // two counters, one per pass
+        SPC_CUDA(cudaMemsetAsync(next_path, 0, 2 * sizeof(int), c.stream));
+        const int grid = std::min((n_paths + kLtPathBlock - 1) / kLtPathBlock, c.sm_count * 2);
+        k_light_trace_paths<false><<<grid, kLtPathBlock, 0, c.stream>>>(fr, n_paths, counts, nullptr, n_slots, next_path);
         k_lt_scan<<<1, 1024, 0, c.stream>>>(counts, n_paths, offsets, total);
-        k_light_trace_paths<true><<<grid, kLtPathBlock, 0, c.stream>>>(fr, n_paths, nullptr, offsets, n_slots);
+        k_light_trace_paths<true><<<grid, kLtPathBlock, 0, c.stream>>>(fr, n_paths, nullptr, offsets, n_slots, next_path + 1);
         k_lt_clear_tail<<<c.sm_count, 256, 0, c.stream>>>(lt.validState, total, n_slots);
         SPC_CUDA(cudaGetLastError());
         c.launches += 4;
@@ -877,6 +942,7 @@ void merge_accum(Context& c, const spc_float4* const* bufs_host, const float* we
 }
 
 void launch_eye_pass(Context& c, int width, int height) {
+    NvtxRange range("spc: SPCBPT_eye");
     SPC_REQUIRE(c.has_params, SPC_ERR_INVALID, "spc_launch: spc_set_params has not been called");
     SPC_REQUIRE(width > 0 && height > 0 && (unsigned)width == c.params.width && (unsigned)height == c.params.height, SPC_ERR_INVALID,
                 "spc_launch(SPCBPT_eye): launch size %dx%d differs from MyParams %ux%u", width, height, c.params.width, c.params.height);
@@ -973,8 +1039,11 @@ void launch_eye_pass(Context& c, int width, int height) {
         a.rays_cur = (float4*)e.rays[b & 1].p; a.rays_next = (float4*)e.rays[(b + 1) & 1].p;
         a.queue_cur = e.queue[b & 1].p; a.queue_next = e.queue[(b + 1) & 1].p;
         mark(b, 0);
+        nvtxRangePushA("eye: closest hits");
         launch_trace_closest_q(c, (const spc_ray*)a.rays_cur, e.counts.p + b, 1, n_max, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);
+        nvtxRangePop();
         mark(b, 1);
+        nvtxRangePushA("eye: shade + sample");
         const int g1 = (int)std::min<int64_t>((n_max + 127) / 128, grid_cap);
         k_eye_shade<<<g1, 128, 0, st>>>(fr, a);
         mark(b, 2);
@@ -985,13 +1054,18 @@ void launch_eye_pass(Context& c, int width, int height) {
             case 4: k_eye_sample<4><<<g1, 128, 0, st>>>(fr, a); break;
             default: k_eye_sample<0><<<g1, 128, 0, st>>>(fr, a); break;
         }
+        nvtxRangePop();
         mark(b, 3);
+        nvtxRangePushA("eye: shadow rays");
         launch_trace_occlusion_q(c, (const spc_ray*)a.shadow, e.counts.p + b, C, n_max * C, e.visible.p);
+        nvtxRangePop();
         mark(b, 4);
+        nvtxRangePushA("eye: connect + gather");
         const int g2 = (int)std::min<int64_t>((n_max * C + 127) / 128, grid_cap);
         k_eye_connect<<<g2, 128, 0, st>>>(fr, a);
         mark(b, 5);
         k_eye_gather<<<g1, 128, 0, st>>>(fr, a);
+        nvtxRangePop();
         mark(b, 6);
         e.last_bounces = b + 1;
         c.launches += 4;
@@ -1005,6 +1079,7 @@ void launch_eye_pass(Context& c, int width, int height) {
                 n_max = h_ring[pb % kRing];
                 if (n_max == 0) break;
                 if (tail_threshold > 0 && n_max <= tail_threshold && b + 1 <= fr.max_depth) {
+                    NvtxRange tail_range("eye: tail kernel");
                     // few paths left: the remaining bounces of every survivor in one kernel (queue of bounce b + 1 = the `next` buffers)
                     a.bounce = b + 1;
                     a.rays_cur = (float4*)e.rays[(b + 1) & 1].p;

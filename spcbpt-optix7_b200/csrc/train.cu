@@ -657,6 +657,7 @@ __global__ void k_train_toE(const float* __restrict__ theta, int K, float* __res
 }
 
 float* train_optimal_E(Context& c, int batch_size, int epochs, float lr, float* loss_out_host, int loss_cap, int* n_loss) {
+    NvtxRange range("spc: train_optimal_E");
     TrainBuffers& t = c.train;
     SPC_REQUIRE(t.N > 0 && t.gamma.p, SPC_ERR_INVALID, "train_optimal_E needs build_optimal_E_train_data and preprocess_getGamma first");
     SPC_REQUIRE(batch_size > 0 && t.N >= batch_size, SPC_ERR_INVALID, "train_optimal_E: batch %d > %d training paths", batch_size, t.N);
