@@ -427,7 +427,7 @@ SPC_API int  spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_de
  *                          packed densely in path order: same estimator and distribution, different random numbers (NOT bit-comparable
  *                          with mode 0), an order of magnitude faster
  *   "tail_threshold"    live-path count below which the eye pass stops launching per-bounce wavefront stages and finishes every
- *                          surviving path in one kernel (0 = default 32768, -1 = never); frames are bit-identical for every value
+ *                          surviving path in one kernel (0 = default 131072, -1 = never); frames are bit-identical for every value
  *   "stage_timing"      1: the eye pass brackets every stage of every bounce with CUDA events (slower: for spc_eye_stats_get) */
 SPC_API int  spc_set_option(spc_context* ctx, const char* name, int64_t value);
 SPC_API int  spc_get_option(spc_context* ctx, const char* name, int64_t* value);
@@ -530,6 +530,18 @@ SPC_API int  spc_reduce_accum(spc_context* ctx, spc_float4* accum_dev, int n_pix
  * the state spc_valid_sample_gather / spc_preprocess_getQ build up, e.g. to re-train from a saved set */
 SPC_API int  spc_train_set_write(spc_context* ctx, const spc_train_path* paths_host, int n_paths, const spc_train_conn* conns_host, int n_conns);
 SPC_API int  spc_train_Q_write(spc_context* ctx, const float* Q_host, int acc_paths);
+
+/* Device-side tree build (csrc/tree_build.cu): the same trees as spc_build_tree / the reference's host builder, bit for bit, built on
+ * the GPU -- nearest-centre labelling (N x K) and a level-synchronous octree split.
+ * spc_build_tree_gpu: spc_build_tree with host samples in / host nodes out on the GPU of `ctx` (*n_nodes = node count; nodes are
+ *   written when they fit `cap`).
+ * spc_build_tree_from_training_set: get_weighted_point_for_tree_building + buildTreeBaseOnExistSample + eye/light_tree_to_device in
+ *   one call with the weighted points never leaving the device (optixPathTracer.cpp:563-571); the tree becomes the context's eye /
+ *   light tree like after spc_tree_to_device; nodes_host (optional, cap entries) receives a host copy for checkpoints. */
+SPC_API int  spc_build_tree_gpu(spc_context* ctx, const spc_divide_weight* samples_host, int n, int K, int label_bias, spc_tree_node* out_host, int cap,
+                                int* max_label, int* n_nodes);
+SPC_API int  spc_build_tree_from_training_set(spc_context* ctx, int eye_side, int max_size, int subspaces, int label_bias, spc_tree_node** dev_out, int* n_nodes,
+                                              spc_tree_node* nodes_host, int cap);
 
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 SPC_API int64_t spc_launch_count(spc_context* ctx);

@@ -164,6 +164,8 @@ def _bind_optional(L):
         "spc_reduce_accum": [vp, vp, i32, f32, i32],
         "spc_train_set_write": [vp, vp, i32, vp, i32],
         "spc_train_Q_write": [vp, vp, i32],
+        "spc_build_tree_gpu": [vp, vp, i32, i32, i32, vp, i32, vp, vp],
+        "spc_build_tree_from_training_set": [vp, i32, i32, i32, i32, vp, vp, vp, i32],
         "spc_set_option": [vp, ctypes.c_char_p, i64],
         "spc_get_option": [vp, ctypes.c_char_p, vp],
         "spc_set_seed_offset": [vp, ctypes.c_uint32],
@@ -434,6 +436,26 @@ class Context:
         out = np.zeros(max(n.value, 1), DIVIDE_WEIGHT)
         self._ck(self._L.spc_get_tree_points(self.h, int(eye_side), max_size, out.ctypes.data, out.shape[0], ctypes.byref(n)), "spc_get_tree_points")
         return out[:n.value]
+
+    def build_tree_gpu(self, samples, K, label_bias=0):
+        """spc_build_tree on the GPU (csrc/tree_build.cu): host samples in, (tree_node[], max_label) out -- the same tree, bit for bit"""
+        samples = np.ascontiguousarray(samples, DIVIDE_WEIGHT)
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, TREE_NODE)
+            ml, nn = ctypes.c_int(0), ctypes.c_int(0)
+            self._ck(self._L.spc_build_tree_gpu(self.h, samples.ctypes.data, samples.shape[0], K, label_bias, out.ctypes.data, cap, ctypes.byref(ml), ctypes.byref(nn)),
+                     "spc_build_tree_gpu")
+            if nn.value <= cap:
+                return out[:nn.value].copy(), ml.value
+            cap = nn.value
+
+    def build_tree_from_training_set(self, eye_side, max_size, subspaces, label_bias=0):
+        """tree points -> tree -> installed as the context's eye / light tree, all on the device; returns (device pointer, host copy)"""
+        p, nn = ctypes.c_void_p(), ctypes.c_int(0)
+        self._ck(self._L.spc_build_tree_from_training_set(self.h, int(eye_side), max_size, subspaces, label_bias, ctypes.byref(p), ctypes.byref(nn), None, 0),
+                 "spc_build_tree_from_training_set")
+        return p.value, self.download(p.value, TREE_NODE, nn.value)
 
     def tree_to_device(self, eye_side, nodes):
         nodes = np.ascontiguousarray(nodes, TREE_NODE)

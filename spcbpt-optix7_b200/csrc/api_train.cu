@@ -26,6 +26,63 @@ using spc::Context;
     }                                                                                            \
     return SPC_OK;
 
+namespace spc {
+// Installs a classification tree as the context's eye / light tree: validation, reference-layout device copy (uploaded unless it is
+// already there: upload = false after a device-side build) and the compact copy for the device-side walks.
+void tree_install(Context& c, int eye_side, const spc_tree_node* nodes_host, int n, bool upload) {
+    // A malformed tree (hand-edited tree_*.txt, a state trained with another K) would send the device walks out of bounds or into a
+    // cycle, and labels >= K index Q / the CMFGamma rows out of bounds: reject it here.  Well-formed = what the builder emits
+    // (classTree_host.h:103-284 appends the 8 children of a split behind their parent): root at 0, every child index in (parent, n)
+    // and referenced once, node types 0..2, leaf labels in [0, K).
+    {
+        std::vector<uint8_t> seen((size_t)n, 0);
+        for (int i = 0; i < n; i++) {
+            const spc_tree_node& nd = nodes_host[i];
+            if (nd.leaf) {
+                SPC_REQUIRE(nd.label >= 0 && nd.label < c.K, SPC_ERR_INVALID, "tree: node %d: leaf label %d outside [0, %d)", i, nd.label, c.K);
+                continue;
+            }
+            SPC_REQUIRE(nd.type >= 0 && nd.type <= 2, SPC_ERR_INVALID, "tree: node %d: type %d", i, nd.type);
+            for (int k = 0; k < 8; k++) {
+                const int ch = nd.child[k];
+                SPC_REQUIRE(ch > i && ch < n, SPC_ERR_INVALID, "tree: node %d: child %d = %d outside (%d, %d)", i, k, ch, i, n);
+                SPC_REQUIRE(!seen[ch], SPC_ERR_INVALID, "tree: node %d is the child of two nodes", ch);
+                seen[ch] = 1;
+            }
+        }
+    }
+    DevBuf<spc_tree_node>& b = eye_side ? c.train.eye_tree : c.train.light_tree;
+    if (upload) {
+        ctree_register(b.p, nullptr, &c);
+        b.alloc(n);
+        SPC_CUDA(cudaMemcpyAsync(b.p, nodes_host, (size_t)n * sizeof(spc_tree_node), cudaMemcpyHostToDevice, c.stream));
+    }
+    // compact copy for the device-side walks (shade.cuh "compact trees"): 48 B per node = {mid, type} + 8 children, a leaf child
+    // carries its label in the parent's entry (0x80000000 | label), a leaf root in the root's type word
+    std::vector<float> ct((size_t)n * 12, 0.f);
+    for (int i = 0; i < n; i++) {
+        const spc_tree_node& nd = nodes_host[i];
+        uint32_t w[12] = {};
+        memcpy(&w[0], &nd.mid.x, 4); memcpy(&w[1], &nd.mid.y, 4); memcpy(&w[2], &nd.mid.z, 4);
+        if (nd.leaf) {
+            w[3] = 0x80000000u | (uint32_t)nd.label;
+        } else {
+            w[3] = (uint32_t)nd.type;
+            for (int k = 0; k < 8; k++) {
+                const int ch = nd.child[k];
+                w[4 + k] = nodes_host[ch].leaf ? (0x80000000u | (uint32_t)nodes_host[ch].label) : (uint32_t)ch;
+            }
+        }
+        memcpy(&ct[(size_t)i * 12], w, sizeof(w));
+    }
+    DevBuf<float4>& cb = eye_side ? c.train.eye_ctree : c.train.light_ctree;
+    cb.alloc((size_t)n * 3);
+    SPC_CUDA(cudaMemcpyAsync(cb.p, ct.data(), ct.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
+    ctree_register(b.p, cb.p, &c);
+}
+}  // namespace spc
+
 extern "C" {
 
 int spc_valid_sample_gather(spc_context* ctx, const spc_train_path* raw_paths_dev, int max_paths, const spc_train_conn* raw_conns_dev,
@@ -47,61 +104,46 @@ int spc_get_tree_points(spc_context* ctx, int eye_side, int max_size, spc_divide
     *n = spc::train_tree_points(c, eye_side, max_size, out_host, cap);
     SPC_API_END
 }
+
 int spc_tree_to_device(spc_context* ctx, int eye_side, const spc_tree_node* nodes_host, int n, spc_tree_node** dev_out) {
     SPC_API_BEGIN
     SPC_REQUIRE(nodes_host && n > 0 && dev_out, SPC_ERR_INVALID, "spc_tree_to_device: bad arguments");
-    // A malformed tree (hand-edited tree_*.txt, a state trained with another K) would send the device walks out of bounds or into a
-    // cycle, and labels >= K index Q / the CMFGamma rows out of bounds: reject it here.  Well-formed = what the builder emits
-    // (classTree_host.h:103-284 appends the 8 children of a split behind their parent): root at 0, every child index in (parent, n)
-    // and referenced once, node types 0..2, leaf labels in [0, K).
-    {
-        std::vector<uint8_t> seen((size_t)n, 0);
-        for (int i = 0; i < n; i++) {
-            const spc_tree_node& nd = nodes_host[i];
-            if (nd.leaf) {
-                SPC_REQUIRE(nd.label >= 0 && nd.label < c.K, SPC_ERR_INVALID, "spc_tree_to_device: node %d: leaf label %d outside [0, %d)", i, nd.label, c.K);
-                continue;
-            }
-            SPC_REQUIRE(nd.type >= 0 && nd.type <= 2, SPC_ERR_INVALID, "spc_tree_to_device: node %d: type %d", i, nd.type);
-            for (int k = 0; k < 8; k++) {
-                const int ch = nd.child[k];
-                SPC_REQUIRE(ch > i && ch < n, SPC_ERR_INVALID, "spc_tree_to_device: node %d: child %d = %d outside (%d, %d)", i, k, ch, i, n);
-                SPC_REQUIRE(!seen[ch], SPC_ERR_INVALID, "spc_tree_to_device: node %d is the child of two nodes", ch);
-                seen[ch] = 1;
-            }
-        }
-    }
+    spc::tree_install(c, eye_side, nodes_host, n, true);
+    *dev_out = (eye_side ? c.train.eye_tree : c.train.light_tree).p;
+    SPC_API_END
+}
+// Device-side counterpart of spc_get_tree_points + spc_build_tree + spc_tree_to_device: the weighted points never leave the device.
+int spc_build_tree_from_training_set(spc_context* ctx, int eye_side, int max_size, int subspaces, int label_bias, spc_tree_node** dev_out, int* n_nodes,
+                                     spc_tree_node* nodes_host, int cap) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(dev_out && subspaces >= 1, SPC_ERR_INVALID, "spc_build_tree_from_training_set: bad arguments");
+    const int n_pts = spc::train_tree_points_device(c, eye_side, max_size);
+    SPC_REQUIRE(n_pts >= 2, SPC_ERR_INVALID, "spc_build_tree_from_training_set: the training set holds %d points", n_pts);
     spc::DevBuf<spc_tree_node>& b = eye_side ? c.train.eye_tree : c.train.light_tree;
     spc::ctree_register(b.p, nullptr, &c);
-    b.alloc(n);
-    SPC_CUDA(cudaMemcpyAsync(b.p, nodes_host, (size_t)n * sizeof(spc_tree_node), cudaMemcpyHostToDevice, c.stream));
-    // compact copy for the device-side walks (shade.cuh "compact trees"): 48 B per node = {mid, type} + 8 children, a leaf child
-    // carries its label in the parent's entry (0x80000000 | label), a leaf root in the root's type word
-    const bool compact_ok = true;   // guaranteed by the validation above
-    std::vector<float> ct((size_t)n * 12, 0.f);
-    for (int i = 0; i < n; i++) {
-        const spc_tree_node& nd = nodes_host[i];
-        uint32_t w[12] = {};
-        memcpy(&w[0], &nd.mid.x, 4); memcpy(&w[1], &nd.mid.y, 4); memcpy(&w[2], &nd.mid.z, 4);
-        if (nd.leaf) {
-            w[3] = 0x80000000u | (uint32_t)nd.label;
-        } else {
-            w[3] = (uint32_t)nd.type;
-            for (int k = 0; k < 8; k++) {
-                const int ch = nd.child[k];
-                w[4 + k] = nodes_host[ch].leaf ? (0x80000000u | (uint32_t)nodes_host[ch].label) : (uint32_t)ch;
-            }
-        }
-        memcpy(&ct[(size_t)i * 12], w, sizeof(w));
-    }
-    spc::DevBuf<float4>& cb = eye_side ? c.train.eye_ctree : c.train.light_ctree;
-    if (compact_ok) {
-        cb.alloc((size_t)n * 3);
-        SPC_CUDA(cudaMemcpyAsync(cb.p, ct.data(), ct.size() * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-    }
+    const int n = spc::tree_build_device(c, c.train.tree_pts.p, n_pts, subspaces, label_bias, b, nullptr);
+    std::vector<spc_tree_node> h((size_t)n);
+    SPC_CUDA(cudaMemcpyAsync(h.data(), b.p, (size_t)n * sizeof(spc_tree_node), cudaMemcpyDeviceToHost, c.stream));
     SPC_CUDA(cudaStreamSynchronize(c.stream));
-    if (compact_ok) spc::ctree_register(b.p, cb.p, &c);
+    spc::tree_install(c, eye_side, h.data(), n, false);
+    if (n_nodes) *n_nodes = n;
+    if (nodes_host && n <= cap) memcpy(nodes_host, h.data(), (size_t)n * sizeof(spc_tree_node));
     *dev_out = b.p;
+    SPC_API_END
+}
+// spc_build_tree on the GPU of `ctx`: same arguments and result (host samples in, host nodes out), for callers that hold the samples
+int spc_build_tree_gpu(spc_context* ctx, const spc_divide_weight* samples_host, int n, int K, int label_bias, spc_tree_node* out_host, int cap, int* max_label,
+                       int* n_nodes) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(samples_host && n >= 2 && K >= 1 && n_nodes, SPC_ERR_INVALID, "spc_build_tree_gpu: bad arguments");
+    spc::DevBuf<spc_divide_weight> s;
+    spc::DevBuf<spc_tree_node> nodes;
+    s.alloc(n);
+    SPC_CUDA(cudaMemcpyAsync(s.p, samples_host, (size_t)n * sizeof(spc_divide_weight), cudaMemcpyHostToDevice, c.stream));
+    const int cnt = spc::tree_build_device(c, s.p, n, K, label_bias, nodes, max_label);
+    *n_nodes = cnt;
+    if (out_host && cnt <= cap) SPC_CUDA(cudaMemcpyAsync(out_host, nodes.p, (size_t)cnt * sizeof(spc_tree_node), cudaMemcpyDeviceToHost, c.stream));
+    SPC_CUDA(cudaStreamSynchronize(c.stream));
     SPC_API_END
 }
 int spc_preprocess_getQ(spc_context* ctx, const spc_vertex* lvc_dev, const uint8_t* valid_dev, int count_range, int reset, float** Q_dev, int* acc_paths) {

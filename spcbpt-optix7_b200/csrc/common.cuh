@@ -244,6 +244,9 @@ int* lvc_bin(Context& c, LvcBuffers& b, const spc_vertex* lvc, const uint8_t* va
 int    train_gather(Context& c, const spc_train_path* raw_paths, int max_paths, const spc_train_conn* raw_conns, int max_conns);
 void   train_reweight(Context& c);
 int    train_tree_points(Context& c, int eye_side, int max_size, spc_divide_weight* out_host, int cap);
+int    train_tree_points_device(Context& c, int eye_side, int max_size);
+int    tree_build_device(Context& c, const spc_divide_weight* samples_dev, int n, int K, int label_bias, DevBuf<spc_tree_node>& out, int* max_label_host);
+void   tree_install(Context& c, int eye_side, const spc_tree_node* nodes_host, int n, bool upload);
 void   train_node_label(Context& c, const spc_tree_node* eye_tree, const spc_tree_node* light_tree);
 int    train_get_Q(Context& c, const spc_vertex* lvc, const uint8_t* valid, int n, int reset);
 void   train_Q_zero_handle(Context& c);

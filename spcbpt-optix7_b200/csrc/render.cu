@@ -763,7 +763,8 @@ __global__ void __launch_bounds__(128) k_eye_connect(const DevFrame fr, const Ey
 // ---------------------------------------------------------------------------------------------------------------------------
 // Tail of the eye pass.  After a few bounces a frame has a few thousand live paths left, yet every further bounce of the wavefront
 // costs six kernel launches whose duration is the latency of ONE path's dependent loads (~250 us per bounce, ~18 bounces on the
-// shipped scene: half of a sequential frame).  Once the live-path count has dropped below `tail_threshold` the remaining bounces of
+// shipped scene: half of a sequential frame).  Once the live-path count has dropped below `tail_threshold` (default 131072: house scene,
+// sequential 1080p frames 10.4 ms without the tail, 9.7 / 9.5 / 9.3 ms with 32 k / 128 k / 512 k, profiles/r2e_summary.md) the remaining bounces of
 // every surviving path run to completion in this one kernel, one lane per path: closest hit -> surface program -> classification ->
 // C two-stage samples -> shadow rays -> connections, the loop body of __raygen__SPCBPT (raygen.cu:357-421) for that path.
 // Same draws in the same order and the same fp32 accumulation order as the wavefront stages (emitter term, then the connection
@@ -1028,7 +1029,7 @@ void launch_eye_pass(Context& c, int width, int height) {
     // it stops when a queue was empty and shrinks the grids, but it never drains the stream (a full synchronisation every 4th
     // bounce left the GPU idle for a host round trip each time and made the frame time follow the host's scheduling noise).
     constexpr int kLag = 3, kRing = 8;
-    const int64_t tail_threshold = c.opt[OPT_TAIL_THRESHOLD] < 0 ? 0 : (c.opt[OPT_TAIL_THRESHOLD] == 0 ? 32768 : c.opt[OPT_TAIL_THRESHOLD]);
+    const int64_t tail_threshold = c.opt[OPT_TAIL_THRESHOLD] < 0 ? 0 : (c.opt[OPT_TAIL_THRESHOLD] == 0 ? 131072 : c.opt[OPT_TAIL_THRESHOLD]);
     if (!c.eye_events[0])
         for (int k = 0; k < kRing; k++)
             SPC_CUDA(cudaEventCreateWithFlags(&c.eye_events[k], cudaEventDisableTiming | (c.opt[OPT_BLOCKING_SYNC] ? cudaEventBlockingSync : 0)));

@@ -233,7 +233,8 @@ __global__ void k_tree_points(const spc_train_path* __restrict__ paths, const sp
     }
     out[j] = t;
 }
-int train_tree_points(Context& c, int eye_side, int max_size, spc_divide_weight* out_host, int cap) {
+// the weighted points stay on the device (t.tree_pts): input of the device-side tree build (tree_build.cu)
+int train_tree_points_device(Context& c, int eye_side, int max_size) {
     TrainBuffers& t = c.train;
     if (t.n_paths == 0) return 0;
     pinned(c);
@@ -242,10 +243,25 @@ int train_tree_points(Context& c, int eye_side, int max_size, spc_divide_weight*
     SPC_CUDA(cudaMemcpyAsync(&last, t.paths.p + limit - 1, sizeof(last), cudaMemcpyDeviceToHost, c.stream));
     SPC_CUDA(cudaStreamSynchronize(c.stream));
     const int n = last.end_ind;
-    if (n > cap || !out_host) return n;
     t.tree_pts.alloc(n);
-    k_tree_points<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, t.conns.p, n, eye_side, t.tree_pts.p);
+    if (n) k_tree_points<<<(n + 255) / 256, 256, 0, c.stream>>>(t.paths.p, t.conns.p, n, eye_side, t.tree_pts.p);
     c.launches++;
+    SPC_CUDA(cudaGetLastError());
+    return n;
+}
+int train_tree_points(Context& c, int eye_side, int max_size, spc_divide_weight* out_host, int cap) {
+    TrainBuffers& t = c.train;
+    if (t.n_paths == 0) return 0;
+    if (!out_host) {   // size query
+        pinned(c);
+        const size_t limit = max_size == 0 ? t.n_paths : std::min(t.n_paths, (size_t)max_size);
+        spc_train_path last;
+        SPC_CUDA(cudaMemcpyAsync(&last, t.paths.p + limit - 1, sizeof(last), cudaMemcpyDeviceToHost, c.stream));
+        SPC_CUDA(cudaStreamSynchronize(c.stream));
+        return last.end_ind;
+    }
+    const int n = train_tree_points_device(c, eye_side, max_size);
+    if (n > cap) return n;
     SPC_CUDA(cudaMemcpyAsync(out_host, t.tree_pts.p, (size_t)n * sizeof(spc_divide_weight), cudaMemcpyDeviceToHost, c.stream));
     SPC_CUDA(cudaStreamSynchronize(c.stream));
     return n;

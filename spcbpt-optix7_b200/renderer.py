@@ -50,6 +50,7 @@ class Renderer:
         self.stats = {}
         self._pipe = None
         self.pretrace_stride = self.lt_stride = 1     # multi-GPU training shards the launches: parallel.shard_plan
+        self.device_trees = True                      # classification trees built on the GPU (False: the host builder, as the reference)
 
     # ---- launch helpers (optixPathTracer.cpp:491-549) ------------------------------------------
     def launch_light_trace(self):
@@ -97,17 +98,21 @@ class Renderer:
         ctx.synchronize()
         t1 = time.perf_counter()
         ctx.sample_reweight()
-        if rank == 0:    # the tree build stays on rank 0's host, from rank 0's shard of the paths
-            eye_tree, _ = build_tree(ctx.get_tree_points(True, tree_samples), K, 0)
-            light_tree, _ = build_tree(ctx.get_tree_points(False, tree_samples), K - self.K_light, 0)
-        else:
-            eye_tree = light_tree = None
+        si = self.P["subspace_info"]
+        eye_tree = light_tree = None
+        if rank == 0:    # rank 0 builds the trees from its shard of the paths
+            if self.device_trees:    # on the device: the weighted points never leave HBM (csrc/tree_build.cu; same trees bit for bit)
+                si["eye_tree"], eye_tree = ctx.build_tree_from_training_set(True, tree_samples, K, 0)
+                si["light_tree"], light_tree = ctx.build_tree_from_training_set(False, tree_samples, K - self.K_light, 0)
+            else:                    # the reference's way: points to the host, host builder, tree back to the device
+                eye_tree, _ = build_tree(ctx.get_tree_points(True, tree_samples), K, 0)
+                light_tree, _ = build_tree(ctx.get_tree_points(False, tree_samples), K - self.K_light, 0)
         if world > 1:
             eye_tree, light_tree = (ctx.comm_bcast_array(t, TREE_NODE, 0) for t in (eye_tree, light_tree))
         self.eye_tree, self.light_tree = eye_tree, light_tree
-        si = self.P["subspace_info"]
-        si["eye_tree"] = ctx.tree_to_device(True, eye_tree)
-        si["light_tree"] = ctx.tree_to_device(False, light_tree)
+        if not (rank == 0 and self.device_trees):
+            si["eye_tree"] = ctx.tree_to_device(True, eye_tree)
+            si["light_tree"] = ctx.tree_to_device(False, light_tree)
         t2 = time.perf_counter()
         acc, first, q_dev = 0, True, 0
         while acc < local_Q:

@@ -63,7 +63,8 @@ def test_parallel_light_tracer_contract_and_statistics(gpu_ctx):
     q0, q1 = sum(t[2] for t in s0), sum(t[2] for t in s1)
     print("vertices: serial cores %d, parallel paths %d; depth histograms %s / %s" % (n0, n1, d0[:6], d1[:6]))
     assert abs(n1 / n0 - 1) < 0.02
-    assert np.allclose(d1[:5], d0[:5], rtol=0.03)
+    # two independent Poisson-like counts per depth: 4.5 standard deviations of their difference
+    assert (np.abs(d1[:6].astype(float) - d0[:6]) <= 4.5 * np.sqrt(d0[:6] + d1[:6] + 1.0)).all()
     assert abs(q1.sum() / q0.sum() - 1) < 0.02
     big = q0 > 0.01 * q0.sum()
     assert big.sum() >= 5 and np.allclose(q1[big], q0[big], rtol=0.1)

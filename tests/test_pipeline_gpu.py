@@ -165,4 +165,4 @@ def test_tail_kernel_leaves_frames_bit_identical(gpu_ctx):
         assert (st["closest_rays"], st["shadow_rays"], st["visible_connections"]) == (base[1]["closest_rays"], base[1]["shadow_rays"], base[1]["visible_connections"])
     print("launches for 4 frames: no tail %d, default %d, 4096 %d, earliest %d; wavefront bounces %s" % (
         out[0][2], out[1][2], out[2][2], out[3][2], [o[1]["bounces"] for o in out]))
-    assert out[3][2] < out[1][2] <= out[0][2] and out[3][1]["bounces"] == 4
+    assert out[3][2] <= out[1][2] < out[0][2] and out[3][2] < out[2][2] < out[0][2] and out[3][1]["bounces"] == 4
