@@ -53,6 +53,7 @@ struct Options {
     int  pre_cores = 10000, pre_padding = 10;                    // preTracer_params_setup
     unsigned seed_offset = 0, seed_stride = 1;
     bool pipeline = true, render = true, quiet = false, write_images = true;
+    bool host_trees = false;   // classification trees by the host builder (the reference's way) instead of the device-side build
     // multi-GPU: one process per GPU.  `--ranks N` forks N ranks on devices 0..N-1 of this node; or start the ranks yourself
     // with --rank r --world N --id-file <path> (rank 0 writes the NCCL unique id there, the others wait for it)
     int  ranks = 1, rank = 0, world = 1;
@@ -66,6 +67,7 @@ void usage(const char* argv0) {
             "         --dim=<width>x<height>      image dimensions; defaults to 1920x1000\n"
             "         --data-root <dir>           directory the .scene's file names are relative to\n"
             "         --frames <n>                subframes to accumulate per rank (default 16)\n"
+            "         --host-trees                build the classification trees on the host (the reference's way; default: on the GPU)\n"
             "         --option name=value         context switch (spc_set_option): light_trace_mode=1, tail_threshold=-1, ...\n"
             "         --ranks <n>                 multi-GPU: fork n ranks on devices 0..n-1 (NCCL inside the library: sharded training,\n"
             "                                     sample-partitioned frames, accumulation buffer reduced to rank 0)\n"
@@ -141,6 +143,7 @@ bool parse_args(int argc, char** argv, Options& o) {
         else if (a == "--rank") o.rank = atoi(need("--rank"));
         else if (a == "--world") o.world = atoi(need("--world"));
         else if (a == "--id-file") o.id_file = need("--id-file");
+        else if (a == "--host-trees") o.host_trees = true;
         else if (a == "--no-pipeline") o.pipeline = false;
         else if (a == "--no-render") o.render = false;
         else if (a == "--no-images") o.write_images = false;
@@ -300,9 +303,24 @@ struct App {
         t_pretrace = t1 - t0;
 
         SPC_CHECK(spc_sample_reweight(ctx));
+        bool installed = false;
         if (rank == 0) {
-            eye_tree = build_tree(true, opt.K);
-            light_tree = build_tree(false, opt.K - opt.K_light);
+            if (opt.host_trees) {
+                eye_tree = build_tree(true, opt.K);
+                light_tree = build_tree(false, opt.K - opt.K_light);
+            } else {
+                // device-side build: the weighted points never leave HBM; same trees bit for bit (csrc/tree_build.cu)
+                for (int eye_side = 1; eye_side >= 0; eye_side--) {
+                    std::vector<spc_tree_node>& t = eye_side ? eye_tree : light_tree;
+                    spc_tree_node** dev = eye_side ? &params.subspace_info.eye_tree : &params.subspace_info.light_tree;
+                    int n = 0;
+                    SPC_CHECK(spc_build_tree_from_training_set(ctx, eye_side, opt.tree_samples, eye_side ? opt.K : opt.K - opt.K_light, 0, dev, &n, nullptr, 0));
+                    t.resize((size_t)n);
+                    SPC_CHECK(spc_download(ctx, t.data(), *dev, (size_t)n * sizeof(spc_tree_node)));
+                    if (!opt.quiet) printf("class tree building complete:size %d (device)\n", n);
+                }
+                installed = true;
+            }
         }
         if (world > 1)
             for (std::vector<spc_tree_node>* t : {&eye_tree, &light_tree}) {
@@ -311,8 +329,10 @@ struct App {
                 t->resize((size_t)n);
                 SPC_CHECK(spc_comm_bcast_host(ctx, t->data(), (size_t)n * sizeof(spc_tree_node), 0));
             }
-        SPC_CHECK(spc_tree_to_device(ctx, 1, eye_tree.data(), (int)eye_tree.size(), &params.subspace_info.eye_tree));
-        SPC_CHECK(spc_tree_to_device(ctx, 0, light_tree.data(), (int)light_tree.size(), &params.subspace_info.light_tree));
+        if (!installed) {
+            SPC_CHECK(spc_tree_to_device(ctx, 1, eye_tree.data(), (int)eye_tree.size(), &params.subspace_info.eye_tree));
+            SPC_CHECK(spc_tree_to_device(ctx, 0, light_tree.data(), (int)light_tree.size(), &params.subspace_info.light_tree));
+        }
         double t2 = now_s();
         t_trees = t2 - t1;
 
