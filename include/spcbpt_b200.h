@@ -428,6 +428,9 @@ SPC_API int  spc_merge_accum(spc_context* ctx, const spc_float4* const* accum_de
  *                          with mode 0), an order of magnitude faster
  *   "tail_threshold"    live-path count below which the eye pass stops launching per-bounce wavefront stages and finishes every
  *                          surviving path in one kernel (0 = default 131072, -1 = never); frames are bit-identical for every value
+ *   "sort_hits"         1: from the second bounce on, the wavefront queue is re-ordered by the Morton code of the hit points after the
+ *                          closest-hit pass (counting sort), so that shading, subspace sampling, shadow rays and the next bounce's rays
+ *                          run on spatially coherent entries; frames are bit-identical with and without
  *   "stage_timing"      1: the eye pass brackets every stage of every bounce with CUDA events (slower: for spc_eye_stats_get) */
 SPC_API int  spc_set_option(spc_context* ctx, const char* name, int64_t value);
 SPC_API int  spc_get_option(spc_context* ctx, const char* name, int64_t* value);

@@ -112,6 +112,11 @@ struct EyeBuffers {
     DevBuf<spc_ray>    rays[2];   // ping-pong ray queues (queue order)
     DevBuf<int>        queue[2];  // ping-pong pixel ids (queue order)
     DevBuf<spc_hit>    hits;
+    DevBuf<spc_ray>    rays_sorted;   // option "sort_hits": the queue of a bounce re-ordered by hit-point Morton code (render.cu)
+    DevBuf<int>        queue_sorted;
+    DevBuf<spc_hit>    hits_sorted;
+    DevBuf<uint32_t>   sort_keys;
+    DevBuf<int>        sort_hist;
     DevBuf<spc_ray>    shadow;    // `connections` shadow rays per queue entry
     DevBuf<uint8_t>    visible;
     DevBuf<int>        conn_lvc;  // LVC index of every connection (-1: none)
@@ -171,7 +176,7 @@ struct TrainBuffers {
 };
 
 // spc_set_option switches (include/spcbpt_b200.h documents each)
-enum Option { OPT_REFERENCE_SEARCH = 0, OPT_BLOCKING_SYNC, OPT_COUNT_CANONICAL, OPT_STAGE_TIMING, OPT_LIGHT_TRACE_MODE, OPT_TAIL_THRESHOLD, OPT_COUNT };
+enum Option { OPT_REFERENCE_SEARCH = 0, OPT_BLOCKING_SYNC, OPT_COUNT_CANONICAL, OPT_STAGE_TIMING, OPT_LIGHT_TRACE_MODE, OPT_TAIL_THRESHOLD, OPT_SORT_HITS, OPT_COUNT };
 
 struct Context {
     int           device = 0;

@@ -942,6 +942,70 @@ void merge_accum(Context& c, const spc_float4* const* bufs_host, const float* we
     c.launches++;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Sorting between bounces (spc_set_option "sort_hits").  From the second bounce on the hit points of a wavefront are scattered over
+// the scene although the queue is still in (compacted) pixel order.  After the closest-hit pass of bounce b >= 1 the queue entries
+// {pixel, ray, hit} are re-ordered by the Morton code of their hit point (5 bits per axis of the scene box, misses last): every
+// later stage of the bounce then works on spatially coherent entries -- material / texture fetches in k_eye_shade, the eye-subspace
+// row of the Gamma CDF in k_eye_sample, shadow-ray origins, and the next bounce's rays (their origins ARE these hit points).
+// A counting sort over 2^15 + 1 bins: keys + histogram, one-block scan, scatter.  The order inside a bin is whatever the atomics
+// give: nothing depends on queue order (every result is written per pixel or per queue slot and summed in connection order), so
+// frames stay bit-identical with and without the sort (tests/test_pipeline_gpu.py).
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kSortBits = 15, kSortBins = (1 << kSortBits) + 1;
+__device__ __forceinline__ uint32_t morton_spread5(uint32_t v) {   // 5 bits -> every third bit
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6) | ((v & 16u) << 8);
+}
+__global__ void k_sort_keys(const float4* __restrict__ rays, const float4* __restrict__ hits, const int* __restrict__ n_dev, float3 lo, float3 inv_extent,
+                            uint32_t* __restrict__ keys, int* __restrict__ hist) {
+    const int n = *n_dev;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 h = hits[i];
+        uint32_t key = kSortBins - 1;   // miss
+        if (__float_as_int(h.w) >= 0) {
+            const float4 ro = rays[2 * (size_t)i], rd = rays[2 * (size_t)i + 1];
+            const float px = (ro.x + h.x * rd.x - lo.x) * inv_extent.x, py = (ro.y + h.x * rd.y - lo.y) * inv_extent.y, pz = (ro.z + h.x * rd.z - lo.z) * inv_extent.z;
+            const uint32_t qx = (uint32_t)min(31, max(0, (int)(px * 32.f))), qy = (uint32_t)min(31, max(0, (int)(py * 32.f))), qz = (uint32_t)min(31, max(0, (int)(pz * 32.f)));
+            key = morton_spread5(qx) | (morton_spread5(qy) << 1) | (morton_spread5(qz) << 2);
+        }
+        keys[i] = key;
+        atomicAdd(hist + key, 1);
+    }
+}
+__global__ void k_sort_scan(int* __restrict__ hist) {   // exclusive scan of kSortBins counters, one block of 1024
+    __shared__ int s_part[1024];
+    constexpr int per = (kSortBins + 1023) / 1024;
+    const int lo = min(kSortBins, (int)threadIdx.x * per), hi = min(kSortBins, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += hist[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {   // Hillis-Steele inclusive scan
+        const int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = s_part[threadIdx.x] - sum;
+    for (int i = lo; i < hi; i++) {
+        const int v = hist[i];
+        hist[i] = run;
+        run += v;
+    }
+}
+__global__ void k_sort_scatter(const uint32_t* __restrict__ keys, int* __restrict__ offsets, const int* __restrict__ n_dev, const float4* __restrict__ rays,
+                               const float4* __restrict__ hits, const int* __restrict__ queue, float4* __restrict__ rays_out, float4* __restrict__ hits_out,
+                               int* __restrict__ queue_out) {
+    const int n = *n_dev;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int dst = atomicAdd(offsets + keys[i], 1);
+        rays_out[2 * (size_t)dst] = rays[2 * (size_t)i];
+        rays_out[2 * (size_t)dst + 1] = rays[2 * (size_t)i + 1];
+        hits_out[dst] = hits[i];
+        queue_out[dst] = queue[i];
+    }
+}
+
 void launch_eye_pass(Context& c, int width, int height) {
     NvtxRange range("spc: SPCBPT_eye");
     SPC_REQUIRE(c.has_params, SPC_ERR_INVALID, "spc_launch: spc_set_params has not been called");
@@ -961,6 +1025,7 @@ void launch_eye_pass(Context& c, int width, int height) {
         e.ev.alloc(P); e.pre.alloc(P); e.res.alloc(P); e.xlab.alloc(P);
         for (int k = 0; k < 2; k++) { e.rays[k].alloc(P); e.queue[k].alloc(P); }
         e.hits.alloc(P);
+        e.rays_sorted.alloc(P); e.queue_sorted.alloc(P); e.hits_sorted.alloc(P); e.sort_keys.alloc(P); e.sort_hist.alloc(kSortBins);
         e.shadow.alloc(P * C); e.visible.alloc(P * C); e.conn_lvc.alloc(P * C); e.conn_pmf.alloc(P * C); e.contrib.alloc(P * C);
         e.pixels = P; e.conns = C;
     }
@@ -1029,6 +1094,11 @@ void launch_eye_pass(Context& c, int width, int height) {
     // it stops when a queue was empty and shrinks the grids, but it never drains the stream (a full synchronisation every 4th
     // bounce left the GPU idle for a host round trip each time and made the frame time follow the host's scheduling noise).
     constexpr int kLag = 3, kRing = 8;
+    const bool sort_hits = c.opt[OPT_SORT_HITS] != 0;
+    const int64_t sort_min = 4096;   // below this a bounce is latency-bound anyway (and the tail kernel takes over soon)
+    const float3 sort_lo = make_float3(c.geom.scene_lo[0], c.geom.scene_lo[1], c.geom.scene_lo[2]);
+    const float3 sort_inv = make_float3(1.0f / std::max(1e-30f, c.geom.scene_hi[0] - c.geom.scene_lo[0]), 1.0f / std::max(1e-30f, c.geom.scene_hi[1] - c.geom.scene_lo[1]),
+                               1.0f / std::max(1e-30f, c.geom.scene_hi[2] - c.geom.scene_lo[2]));
     const int64_t tail_threshold = c.opt[OPT_TAIL_THRESHOLD] < 0 ? 0 : (c.opt[OPT_TAIL_THRESHOLD] == 0 ? 131072 : c.opt[OPT_TAIL_THRESHOLD]);
     if (!c.eye_events[0])
         for (int k = 0; k < kRing; k++)
@@ -1042,6 +1112,21 @@ void launch_eye_pass(Context& c, int width, int height) {
         mark(b, 0);
         nvtxRangePushA("eye: closest hits");
         launch_trace_closest_q(c, (const spc_ray*)a.rays_cur, e.counts.p + b, 1, n_max, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);
+        if (sort_hits && b >= 1 && n_max >= sort_min) {
+            // re-order the queue by hit-point Morton code (see k_sort_keys): the rest of the bounce reads the sorted copies
+            const int gs = (int)std::min<int64_t>((n_max + 255) / 256, grid_cap);
+            SPC_CUDA(cudaMemsetAsync(e.sort_hist.p, 0, kSortBins * sizeof(int), st));
+            k_sort_keys<<<gs, 256, 0, st>>>(a.rays_cur, (const float4*)e.hits.p, e.counts.p + b, sort_lo, sort_inv, e.sort_keys.p, e.sort_hist.p);
+            k_sort_scan<<<1, 1024, 0, st>>>(e.sort_hist.p);
+            k_sort_scatter<<<gs, 256, 0, st>>>(e.sort_keys.p, e.sort_hist.p, e.counts.p + b, a.rays_cur, (const float4*)e.hits.p, a.queue_cur, (float4*)e.rays_sorted.p,
+                                               (float4*)e.hits_sorted.p, e.queue_sorted.p);
+            c.launches += 3;
+            a.rays_cur = (float4*)e.rays_sorted.p;
+            a.queue_cur = e.queue_sorted.p;
+            a.hits = (const float4*)e.hits_sorted.p;
+        } else {
+            a.hits = (const float4*)e.hits.p;
+        }
         nvtxRangePop();
         mark(b, 1);
         nvtxRangePushA("eye: shade + sample");

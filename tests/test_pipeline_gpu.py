@@ -166,3 +166,32 @@ def test_tail_kernel_leaves_frames_bit_identical(gpu_ctx):
     print("launches for 4 frames: no tail %d, default %d, 4096 %d, earliest %d; wavefront bounces %s" % (
         out[0][2], out[1][2], out[2][2], out[3][2], [o[1]["bounces"] for o in out]))
     assert out[3][2] <= out[1][2] < out[0][2] and out[3][2] < out[2][2] < out[0][2] and out[3][1]["bounces"] == 4
+
+
+def test_sorting_between_bounces_leaves_frames_bit_identical(gpu_ctx):
+    """spc_set_option "sort_hits": the wavefront queue re-ordered by hit-point Morton code from the second bounce on -- nothing
+    depends on queue order, so frames and work counters are the same, every bit"""
+    pkg = gpu_ctx
+    from spcbpt_optix7_b200.renderer import Renderer
+    sc = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=12, box_cells=8), 0.01)
+    kw = dict(K=64, K_light=12, lt_num_core=100, lt_core_padding=300, lt_M_per_core=40, pretrace_num_core=20000)
+    r = Renderer(sc, 480, 300, **kw)
+    r.preprocessing(target_samples=40000, target_Q_samples=20000, tree_samples=20000, batch_size=20000)
+    r.ctx.set_option("tail_threshold", 8192)      # keep several wavefront bounces (the sort acts on bounces >= 1 of the wavefront)
+    frame0 = int(r.P["lt"]["launch_frame"][0])
+    out = []
+    for sort in (0, 1):
+        r.ctx.set_option("sort_hits", sort)
+        r.reset_accumulation()
+        r.P["lt"]["launch_frame"] = frame0
+        l0 = r.ctx.launch_count()
+        for _ in range(4):
+            r.render_frame()
+        st = r.ctx.eye_stats()
+        out.append((r.image().copy(), st, r.ctx.launch_count() - l0))
+    r.ctx.set_option("sort_hits", 0)
+    r.ctx.set_option("tail_threshold", 0)
+    assert out[0][0].mean() > 0.01 and np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    for k in ("closest_rays", "shadow_rays", "visible_connections", "bounces"):
+        assert out[0][1][k] == out[1][1][k], k
+    assert out[1][2] > out[0][2]        # the sort kernels did run
