@@ -374,11 +374,7 @@ __global__ void __launch_bounds__(128) k_eye_shade(const DevFrame fr, const EyeA
             pix = a.queue_cur[i];
             const float4 hit = a.hits[i];
             const int prim = __float_as_int(hit.w);
-            for (int j = 0; j < C; j++) {   // default: no connection in this slot (an empty-interval shadow ray)
-                a.conn_lvc[(size_t)i * C + j] = -1;
-                a.shadow[2 * ((size_t)i * C + j)] = make_float4(0.f, 0.f, 0.f, 1.0f);
-                a.shadow[2 * ((size_t)i * C + j) + 1] = make_float4(0.f, 0.f, 1.f, -1.0f);
-            }
+            a.conn_lvc[(size_t)i * C] = -1;   // no surface vertex (yet): k_eye_sample fills the slots either way
             if (a.bounce == 0 && a.first_prim) a.first_prim[pix] = prim;
             if (prim >= 0) {
                 const float4 rd4 = a.rays_cur[2 * (size_t)i + 1];
@@ -647,7 +643,14 @@ __global__ void __launch_bounds__(128, 8) k_eye_sample(const DevFrame fr, const 
     const int C = CT > 0 ? CT : fr.connections;
     unsigned n_shadow = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (a.conn_lvc[(size_t)i * C] != -2) continue;   // miss, emitter hit or no surface vertex: slots stay empty
+        if (a.conn_lvc[(size_t)i * C] != -2) {   // miss, emitter hit or no surface vertex: empty slots (an empty-interval shadow ray each)
+            for (int j = 0; j < C; j++) {
+                a.conn_lvc[(size_t)i * C + j] = -1;
+                a.shadow[2 * ((size_t)i * C + j)] = make_float4(0.f, 0.f, 0.f, 1.0f);
+                a.shadow[2 * ((size_t)i * C + j) + 1] = make_float4(0.f, 0.f, 1.f, -1.0f);
+            }
+            continue;
+        }
         const int pix = a.queue_cur[i];
         spc_vertex* ev = a.ev + pix;
         const float3 pos = f3(ev->position.x, ev->position.y, ev->position.z);
@@ -668,11 +671,17 @@ __global__ void __launch_bounds__(128, 8) k_eye_sample(const DevFrame fr, const 
 #pragma unroll
         for (int j = 0; j < (CT > 0 ? CT : 16); j++) {
             if (j >= C) break;
-            const int lv = pick[j].lv;
-            a.conn_lvc[(size_t)i * C + j] = lv;
-            if (lv < 0) continue;
-            const spc_vertex* L = fr.p.sampler.LVC + lv;
+            int lv = pick[j].lv;
+            const spc_vertex* L = fr.p.sampler.LVC + max(lv, 0);
             const float3 lp = f3(L->position.x, L->position.y, L->position.z);
+            // endpoints facing away from each other: the contribution is exactly zero, no shadow ray and no evaluation (shade.cuh)
+            if (lv >= 0 && connection_is_dead(pos, nrm, lp, f3(L->normal.x, L->normal.y, L->normal.z), L->isOrigin != 0)) lv = -1;
+            a.conn_lvc[(size_t)i * C + j] = lv;
+            if (lv < 0) {   // empty subspace or a connection that cannot contribute: an empty-interval shadow ray
+                a.shadow[2 * ((size_t)i * C + j)] = make_float4(0.f, 0.f, 0.f, 1.0f);
+                a.shadow[2 * ((size_t)i * C + j) + 1] = make_float4(0.f, 0.f, 1.f, -1.0f);
+                continue;
+            }
             // visibilityTest (cuProg.h:489-502 -> :463-487)
             const float3 bias_pos = lp - pos;
             const float len = length(bias_pos);
@@ -818,6 +827,7 @@ __global__ void __launch_bounds__(kTailBlock) k_eye_tail(const DevFrame fr, cons
                 const int lv = pick[j].lv;
                 if (lv < 0) continue;
                 const Vtx light = vtx_load(fr.p.sampler.LVC + lv);
+                if (connection_is_dead(mid.position, mid.normal, light.position, light.normal, light.isOrigin != 0)) continue;   // contributes +0
                 // visibilityTest (cuProg.h:489-502 -> :463-487)
                 const float3 bias_pos = light.position - mid.position;
                 const float len = length(bias_pos);

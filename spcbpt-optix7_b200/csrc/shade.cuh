@@ -705,6 +705,19 @@ __device__ __forceinline__ float3 connect_vertices(const DevFrame& fr, const Vtx
     return invalid3(ans) ? f3(0.0f) : ans;
 }
 
+// A connection whose endpoints face away from each other contributes exactly zero whatever the shadow ray finds: connect_vertices
+// multiplies by fa = Eval(a, N_a, -connectDir, .) and fb = Eval(b, N_b, connectDir, .) (or the one-sided emitter term), and Eval
+// returns 0 when dot(N, L) <= 0 (cuProg.h:741-742).  The reference traces the shadow ray first and finds out afterwards
+// (raygen.cu:405-413); here the same two dot products -- the very expressions connect_vertices / bsdf_eval evaluate -- are checked
+// before the ray is queued.  A culled connection adds +0 to the pixel, as it would have: frames are bit-identical.
+__device__ __forceinline__ bool connection_is_dead(float3 a_position, float3 a_normal, float3 b_position, float3 b_normal, bool b_is_origin) {
+    const float3 connectVec = a_position - b_position;
+    const float3 connectDir = normalize(connectVec);
+    if (dot(a_normal, -connectDir) <= 0.0f) return true;                 // fa == 0
+    if (b_is_origin) return dot(b_normal, -connectDir) > 0.0f;            // fb == 0 (one-sided emitter, raygen.cu:280-290)
+    return dot(b_normal, connectDir) <= 0.0f;                             // fb == 0
+}
+
 // binary_sample (cuProg.h:245-264): the reference's own bisect; returns l and its pmf
 __device__ __forceinline__ int binary_sample(const float* __restrict__ cmf, int size, uint32_t& seed, float& pmf) {
     const float index = rnd(seed) * 1.0f;
