@@ -213,6 +213,7 @@ struct Context {
     cudaEvent_t   eye_events[8] = {};          // lagged queue-size read-backs of the eye pass (render.cu)
     DevBuf<spc_vertex> pretrace_scratch;       // per-lane eye-vertex buffers of the training tracer
     DevBuf<int>   lt_counts;                   // parallel light tracer: per-path vertex counts + offsets (render.cu)
+    DevBuf<spc_vertex> lt_scratch;             // ... and its per-path vertex windows (max_depth + 3 vertices each)
     TrainBuffers  train;
     LvcBuffers    bins_tmp;                    // ordered-binning scratch of getQ / sample_reweight
     // per-context one-time setup (function attributes and occupancy are per DEVICE, and spc_create accepts any device)

@@ -152,16 +152,15 @@ __global__ void __launch_bounds__(kLtWarps * 32) k_light_trace_cores(const DevFr
 // its own streams, seeds tea<4>(0x80000000 | path, launch_frame) and tea<4>(0x40000000 | path, launch_frame) (the reference couples the 100 paths of a core through two
 // shared streams, which is what forces k_light_trace_cores to run them serially): same estimator, same distribution, different
 // random numbers -- so frames are NOT bit-comparable with the reference-stream mode (tests/test_light_trace_modes_gpu.py compares
-// them statistically).  The vertices are packed densely in path order: pass 1 counts each path's vertices, an exclusive scan places
-// them, pass 2 traces the same paths again and writes -- deterministic and bit-reproducible, no atomics; the light sub-paths are
-// ~5 % of a frame's rays, so tracing them twice is cheaper than staging 120-byte vertices through scratch memory.
+// them statistically).  The vertices are packed densely in path order: the trace pass writes every path's vertices into its own
+// scratch window and counts them, an exclusive scan of the counts places the paths, a compaction kernel moves them from a per-path scratch window (max_depth + 3 vertices) to the LVC -- deterministic and
+// bit-reproducible (the assignment of paths to lanes is dynamic, the output depends on the path index only).
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr int kLtPathBlock = 128;
 // Persistent lanes: a lane that finishes its path claims the next path index at once (the output depends on the path index only, so
 // any assignment of paths to lanes gives the same LVC), and the loop body is ONE bounce of whatever path the lane holds -- a warp
 // never idles behind its longest path (path lengths range from 1 to max_depth + 2 vertices).
-template <bool WRITE>
-__global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFrame fr, int n_paths, int* __restrict__ counts, const int* __restrict__ offsets, int n_slots,
+__global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFrame fr, int n_paths, int* __restrict__ counts, spc_vertex* __restrict__ scratch, int stride,
                                                                     int* __restrict__ next_path) {
     __shared__ uint2 s_stack[kSmStack * kLtPathBlock];
     __shared__ TravLut s_lut;
@@ -175,11 +174,8 @@ __global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFra
     float3 pre_flux = f3(0.f), ray_origin = f3(0.f), ray_direction = f3(0.f);
     float pre_singlePdf = 0.f;
     auto emit = [&](const Vtx& v) {
-        if (WRITE) {
-            if (base + n_vert >= n_slots) return false;   // LVC full: the tail of the path order is dropped, deterministically
-            vtx_store(lt.ans + base + n_vert, v);
-            lt.validState[base + n_vert] = 1;
-        }
+        if (n_vert >= stride) return false;   // (cannot happen: stride = max_depth + 3 vertices)
+        vtx_store(scratch + (size_t)base * stride + n_vert, v);
         n_vert++;
         return true;
     };
@@ -193,7 +189,7 @@ __global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFra
             hit_seed = tea<4>(0x40000000u | (uint32_t)p, (uint32_t)lt.launch_frame);
             n_vert = 0;
             depth = 0;
-            base = WRITE ? offsets[p] : 0;
+            base = p;
             const int li = pick_light(fr, seed);
             LightSample ls;
             const float r1 = rnd(seed);
@@ -206,10 +202,7 @@ __global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFra
             init_vertex_from_light_sample(ls, cur);
             pre_flux = f3(0.f);
             pre_singlePdf = ls.dir_pdf;
-            if (!emit(cur)) {
-                p = -1;
-                continue;
-            }
+            emit(cur);
         }
         // one bounce of the path this lane holds (the loop body of light_path)
         const TravRay r{ray_origin.x, ray_origin.y, ray_origin.z, ray_direction.x, ray_direction.y, ray_direction.z, SPC_SCENE_EPS, 1e16f};
@@ -236,7 +229,7 @@ __global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFra
         }
         if (pushed && !emit(cur)) done = true;
         if (done || depth > fr.max_depth) {
-            if (!WRITE) counts[p] = n_vert;
+            counts[p] = n_vert;
             p = -1;
         } else {
             depth += 1;
@@ -261,6 +254,18 @@ __global__ void k_lt_scan(const int* __restrict__ counts, int n, int* __restrict
     int run = s_part[threadIdx.x];
     for (int i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
 }
+// dense LVC: path p's vertices go to slots offsets[p].. in path order (one warp per path, 15 x 64-bit words per vertex)
+__global__ void k_lt_compact(const spc_vertex* __restrict__ scratch, int stride, const int* __restrict__ counts, const int* __restrict__ offsets, int n_paths, int n_slots,
+                             spc_vertex* __restrict__ lvc, uint8_t* __restrict__ valid) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n_paths) return;
+    const int cnt = counts[p], base = offsets[p];
+    const uint2* src = reinterpret_cast<const uint2*>(scratch + (size_t)p * stride);
+    uint2* dst = reinterpret_cast<uint2*>(lvc + base);
+    const int keep = max(0, min(cnt, n_slots - base));   // LVC full: the tail of the path order is dropped, deterministically
+    for (int w = lane; w < keep * 15; w += 32) dst[w] = src[w];
+    for (int k = lane; k < keep; k += 32) valid[base + k] = 1;
+}
 __global__ void k_lt_clear_tail(uint8_t* __restrict__ valid, const int* __restrict__ total, int n_slots) {
     const int first = min(*total, n_slots);
     for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) valid[i] = 0;
@@ -279,12 +284,14 @@ void launch_light_trace(Context& c) {
         int* counts = c.lt_counts.p;
         int* offsets = counts + n_paths;
         int* total = offsets + n_paths;
-        int* next_path = total + 1;   // two counters, one per pass
-        SPC_CUDA(cudaMemsetAsync(next_path, 0, 2 * sizeof(int), c.stream));
+        int* next_path = total + 1;
+        SPC_CUDA(cudaMemsetAsync(next_path, 0, sizeof(int), c.stream));
+        const int stride = fr.max_depth + 3;   // the emitter vertex + one vertex per bounce 0 .. max_depth + 1
+        c.lt_scratch.alloc((size_t)n_paths * stride);
         const int grid = std::min((n_paths + kLtPathBlock - 1) / kLtPathBlock, c.sm_count * 2);
-        k_light_trace_paths<false><<<grid, kLtPathBlock, 0, c.stream>>>(fr, n_paths, counts, nullptr, n_slots, next_path);
+        k_light_trace_paths<<<grid, kLtPathBlock, 0, c.stream>>>(fr, n_paths, counts, c.lt_scratch.p, stride, next_path);
         k_lt_scan<<<1, 1024, 0, c.stream>>>(counts, n_paths, offsets, total);
-        k_light_trace_paths<true><<<grid, kLtPathBlock, 0, c.stream>>>(fr, n_paths, nullptr, offsets, n_slots, next_path + 1);
+        k_lt_compact<<<(n_paths * 32 + 255) / 256, 256, 0, c.stream>>>(c.lt_scratch.p, stride, counts, offsets, n_paths, n_slots, lt.ans, lt.validState);
         k_lt_clear_tail<<<c.sm_count, 256, 0, c.stream>>>(lt.validState, total, n_slots);
         SPC_CUDA(cudaGetLastError());
         c.launches += 4;
@@ -325,7 +332,32 @@ struct EyeArgs {
     int         bounce;
 };
 
-// raygen part of __raygen__SPCBPT (raygen.cu:321-353) + init_EyeSubpath (:216-231)
+// init_EyeSubpath (raygen.cu:216-231): the vertex at the camera
+__device__ __forceinline__ Vtx camera_vertex(float3 eye, float3 d) {
+    Vtx v;
+    vtx_zero(v);
+    v.position = eye;
+    v.flux = f3(1.0f);
+    v.pdf = 1.0f;
+    v.RMIS_pointer = 0;
+    v.normal = d;
+    v.isOrigin = 1;
+    v.depth = 0;
+    v.singlePdf = 1.0f;
+    return v;
+}
+// the path's RNG state after the pixel jitter (raygen.cu:332-336)
+__device__ __forceinline__ uint32_t first_seed(const DevFrame& fr, int pix) {
+    const uint32_t sample_index = fr.p.subframe_index * fr.seed_stride + fr.seed_offset;
+    uint32_t seed = tea<4>((uint32_t)pix, sample_index);
+    if (sample_index != 0) {
+        rnd(seed);
+        rnd(seed);
+    }
+    return seed;
+}
+
+// raygen part of __raygen__SPCBPT (raygen.cu:321-353)
 __global__ void k_eye_init(const DevFrame fr, const EyeArgs a, int n_pix) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pix) return;
@@ -340,19 +372,8 @@ __global__ void k_eye_init(const DevFrame fr, const EyeArgs a, int n_pix) {
     }
     const float3 eye = ld3(fr.p.eye);
     const float3 d = camera_dir_exact(ld3(fr.p.U), ld3(fr.p.V), ld3(fr.p.W), x, y, W, H, jx, jy);
-    Vtx v;
-    vtx_zero(v);
-    v.position = eye;
-    v.flux = f3(1.0f);
-    v.pdf = 1.0f;
-    v.RMIS_pointer = 0;
-    v.normal = d;
-    v.isOrigin = 1;
-    v.depth = 0;
-    v.singlePdf = 1.0f;
-    vtx_store(a.ev + i, v);
-    a.pre[i] = make_float4(0.f, 0.f, 0.f, 1.0f);
-    a.res[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(seed));
+    // The camera vertex, the pre-loaded BSDF value and the per-pixel result are NOT written here: the first bounce's k_eye_shade
+    // rebuilds them in registers from the ray (camera_vertex / first_seed below), which saves 152 B written + read per pixel.
     a.queue_cur[i] = i;
     a.rays_cur[2 * (size_t)i] = make_float4(eye.x, eye.y, eye.z, SPC_SCENE_EPS);
     a.rays_cur[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, 1e16f);
@@ -376,14 +397,18 @@ __global__ void __launch_bounds__(128) k_eye_shade(const DevFrame fr, const EyeA
             const int prim = __float_as_int(hit.w);
             a.conn_lvc[(size_t)i * C] = -1;   // no surface vertex (yet): k_eye_sample fills the slots either way
             if (a.bounce == 0 && a.first_prim) a.first_prim[pix] = prim;
+            if (prim < 0 && a.bounce == 0) a.res[pix] = make_float4(0.f, 0.f, 0.f, __uint_as_float(first_seed(fr, pix)));   // a miss: the pixel's result is 0
             if (prim >= 0) {
                 const float4 rd4 = a.rays_cur[2 * (size_t)i + 1];
                 const float3 ray_direction = f3(rd4.x, rd4.y, rd4.z);
-                const Vtx last = vtx_load(a.ev + pix);
-                const float4 pre = a.pre[pix];
-                const int last_x = a.bounce > 0 ? (int)a.xlab[pix] : -1;   // written by k_eye_sample of the previous bounce
-                float4 res = a.res[pix];
+                const bool first = a.bounce == 0;
+                const float4 ro4 = a.rays_cur[2 * (size_t)i];
+                const Vtx last = first ? camera_vertex(f3(ro4.x, ro4.y, ro4.z), ray_direction) : vtx_load(a.ev + pix);
+                const float4 pre = first ? make_float4(0.f, 0.f, 0.f, 1.0f) : a.pre[pix];
+                const int last_x = first ? -1 : (int)a.xlab[pix];   // written by k_eye_sample of the previous bounce
+                float4 res = first ? make_float4(0.f, 0.f, 0.f, __uint_as_float(first_seed(fr, pix))) : a.res[pix];
                 uint32_t seed = __float_as_uint(res.w);
+                if (first) a.res[pix] = res;   // (the emitter / surface branches below overwrite it where they add to it)
                 const LocalGeom g = hit_geometry(fr.sc, prim, hit.y, hit.z);
                 Vtx mid;
                 if (g.light >= 0) {
