@@ -148,6 +148,11 @@ int spc_comm_init(spc_context* ctx, int rank, int world, const void* id) {
         ncclComm_t comm = nullptr;
         SPC_NCCL(ncclCommInitRank(&comm, world, uid, rank));
         c.comm = comm;
+        // NCCL sets its channels up lazily, on the first collective (~1 s with 8 ranks): pay for it here, not inside the training
+        c.comm_scratch.alloc(4);
+        SPC_CUDA(cudaMemsetAsync(c.comm_scratch.p, 0, 4, c.stream));
+        SPC_NCCL(ncclAllReduce(c.comm_scratch.p, c.comm_scratch.p, 1, ncclInt32, ncclSum, comm, c.stream));
+        SPC_CUDA(cudaStreamSynchronize(c.stream));
     }
     c.comm_rank = rank;
     c.comm_world = world;

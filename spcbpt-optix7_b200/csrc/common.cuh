@@ -111,6 +111,8 @@ struct EyeBuffers {
     DevBuf<float4>     res;       // {radiance estimate of this subframe, seed bits}
     DevBuf<spc_ray>    rays[2];   // ping-pong ray queues (queue order)
     DevBuf<int>        queue[2];  // ping-pong pixel ids (queue order)
+    DevBuf<int>        queue_ident;   // the first bounce's queue: pixel i at entry i (filled once)
+    size_t             ident_pixels = 0;
     DevBuf<spc_hit>    hits;
     DevBuf<spc_ray>    rays_sorted;   // option "sort_hits": the queue of a bounce re-ordered by hit-point Morton code (render.cu)
     DevBuf<int>        queue_sorted;
@@ -235,6 +237,13 @@ void launch_trace_occlusion(Context& ctx, const spc_ray* rays, int64_t n, uint8_
                             unsigned long long* counters /*nullable*/);
 
 void launch_trace_closest_q(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits);
+// the pinhole camera of one subframe (raygen.cu:321-344): the first bounce's closest-hit pass generates its rays itself (ray i = pixel i)
+struct CamGen {
+    float3   eye, U, V, W;
+    unsigned width, height;
+    uint32_t sample_index;   // subframe_index * seed_stride + seed_offset
+};
+void launch_trace_closest_camera(Context& ctx, const CamGen& cam, int64_t n_pixels, int flags, spc_hit* hits);
 void launch_trace_occlusion_q(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, uint8_t* visible);
 
 void launch_light_trace(Context& ctx);                       // "light trace" raygen

@@ -357,29 +357,29 @@ __device__ __forceinline__ uint32_t first_seed(const DevFrame& fr, int pix) {
     return seed;
 }
 
-// raygen part of __raygen__SPCBPT (raygen.cu:321-353)
-__global__ void k_eye_init(const DevFrame fr, const EyeArgs a, int n_pix) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pix) return;
+// The raygen part of __raygen__SPCBPT (raygen.cu:321-353) has no kernel of its own: the first closest-hit pass generates the camera
+// rays itself (trace.cu, k_trace_persist<.., RAYGEN>) and the first k_eye_shade rebuilds ray, camera vertex and RNG state in
+// registers (camera_ray / camera_vertex / first_seed); queue entry i of the first bounce is pixel i (a cached identity array).
+// That removes 188 B written and 220 B read per pixel and frame.
+__device__ __forceinline__ void camera_ray(const DevFrame& fr, int pix, float3& eye, float3& dir) {
     const unsigned W = fr.p.width, H = fr.p.height;
-    const unsigned x = (unsigned)i % W, y = (unsigned)i / W;
     const uint32_t sample_index = fr.p.subframe_index * fr.seed_stride + fr.seed_offset;   // = subframe_index in the reference
-    uint32_t seed = tea<4>((uint32_t)i, sample_index);
+    uint32_t seed = tea<4>((uint32_t)pix, sample_index);
     float jx = 0.5f, jy = 0.5f;
     if (sample_index != 0) {   // make_float2(rnd(seed), rnd(seed)): nvcc evaluates left to right
         jx = rnd(seed);
         jy = rnd(seed);
     }
-    const float3 eye = ld3(fr.p.eye);
-    const float3 d = camera_dir_exact(ld3(fr.p.U), ld3(fr.p.V), ld3(fr.p.W), x, y, W, H, jx, jy);
-    // The camera vertex, the pre-loaded BSDF value and the per-pixel result are NOT written here: the first bounce's k_eye_shade
-    // rebuilds them in registers from the ray (camera_vertex / first_seed below), which saves 152 B written + read per pixel.
-    a.queue_cur[i] = i;
-    a.rays_cur[2 * (size_t)i] = make_float4(eye.x, eye.y, eye.z, SPC_SCENE_EPS);
-    a.rays_cur[2 * (size_t)i + 1] = make_float4(d.x, d.y, d.z, 1e16f);
+    eye = ld3(fr.p.eye);
+    dir = camera_dir_exact(ld3(fr.p.U), ld3(fr.p.V), ld3(fr.p.W), (unsigned)pix % W, (unsigned)pix / W, W, H, jx, jy);
+}
+__global__ void k_eye_begin(const EyeArgs a, int n_pix, int n_work, int* __restrict__ ident, int fill_ident) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) a.counts[0] = n_pix;
+    if (i >= n_work || n_work < n_pix) return;   // n_work = n_pix only when there is per-pixel work
+    if (fill_ident) ident[i] = i;
     if (a.first_prim) a.first_prim[i] = -1;
     if (a.first_label) a.first_label[i] = -1;
-    if (i == 0) a.counts[0] = n_pix;
 }
 
 // closest-hit programs + connection sampling of one bounce; one lane per live path
@@ -399,11 +399,15 @@ __global__ void __launch_bounds__(128) k_eye_shade(const DevFrame fr, const EyeA
             if (a.bounce == 0 && a.first_prim) a.first_prim[pix] = prim;
             if (prim < 0 && a.bounce == 0) a.res[pix] = make_float4(0.f, 0.f, 0.f, __uint_as_float(first_seed(fr, pix)));   // a miss: the pixel's result is 0
             if (prim >= 0) {
-                const float4 rd4 = a.rays_cur[2 * (size_t)i + 1];
-                const float3 ray_direction = f3(rd4.x, rd4.y, rd4.z);
                 const bool first = a.bounce == 0;
-                const float4 ro4 = a.rays_cur[2 * (size_t)i];
-                const Vtx last = first ? camera_vertex(f3(ro4.x, ro4.y, ro4.z), ray_direction) : vtx_load(a.ev + pix);
+                float3 ray_direction, cam_eye = f3(0.f);
+                if (first) {
+                    camera_ray(fr, pix, cam_eye, ray_direction);
+                } else {
+                    const float4 rd4 = a.rays_cur[2 * (size_t)i + 1];
+                    ray_direction = f3(rd4.x, rd4.y, rd4.z);
+                }
+                const Vtx last = first ? camera_vertex(cam_eye, ray_direction) : vtx_load(a.ev + pix);
                 const float4 pre = first ? make_float4(0.f, 0.f, 0.f, 1.0f) : a.pre[pix];
                 const int last_x = first ? -1 : (int)a.xlab[pix];   // written by k_eye_sample of the previous bounce
                 float4 res = first ? make_float4(0.f, 0.f, 0.f, __uint_as_float(first_seed(fr, pix))) : a.res[pix];
@@ -1121,8 +1125,22 @@ void launch_eye_pass(Context& c, int width, int height) {
         fr.lvc_xlabel = nullptr;
     }
     const int nP = (int)P;
-    k_eye_init<<<(nP + 255) / 256, 256, 0, st>>>(fr, a, nP);
+    // queue of the first bounce = pixel order: an identity array filled once per allocation; per frame only counts[0] (and the
+    // optional parity dumps) are initialised
+    const bool fill_ident = e.ident_pixels != P;
+    if (fill_ident) e.queue_ident.alloc(P);
+    const int n_work = (fill_ident || a.first_prim || a.first_label) ? nP : 1;
+    k_eye_begin<<<(n_work + 255) / 256, 256, 0, st>>>(a, nP, n_work, e.queue_ident.p, fill_ident ? 1 : 0);
+    e.ident_pixels = P;
     c.launches++;
+    CamGen cam;
+    cam.eye = make_float3(c.params.eye.x, c.params.eye.y, c.params.eye.z);
+    cam.U = make_float3(c.params.U.x, c.params.U.y, c.params.U.z);
+    cam.V = make_float3(c.params.V.x, c.params.V.y, c.params.V.z);
+    cam.W = make_float3(c.params.W.x, c.params.W.y, c.params.W.z);
+    cam.width = c.params.width;
+    cam.height = c.params.height;
+    cam.sample_index = c.params.subframe_index * c.seed_stride + c.seed_offset;
     const int grid_cap = c.sm_count * 16;
     int64_t n_max = nP;   // host-side upper bound on the live paths (refreshed by the lagged read-backs)
     // The size of every bounce's queue is copied to pinned memory behind the bounce, and the host looks at it kLag bounces later:
@@ -1143,10 +1161,11 @@ void launch_eye_pass(Context& c, int width, int height) {
     for (int b = 0; b <= fr.max_depth; b++) {
         a.bounce = b;
         a.rays_cur = (float4*)e.rays[b & 1].p; a.rays_next = (float4*)e.rays[(b + 1) & 1].p;
-        a.queue_cur = e.queue[b & 1].p; a.queue_next = e.queue[(b + 1) & 1].p;
+        a.queue_cur = b == 0 ? e.queue_ident.p : e.queue[b & 1].p; a.queue_next = e.queue[(b + 1) & 1].p;
         mark(b, 0);
         nvtxRangePushA("eye: closest hits");
-        launch_trace_closest_q(c, (const spc_ray*)a.rays_cur, e.counts.p + b, 1, n_max, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);
+        if (b == 0) launch_trace_closest_camera(c, cam, nP, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);   // generates the camera rays itself
+        else launch_trace_closest_q(c, (const spc_ray*)a.rays_cur, e.counts.p + b, 1, n_max, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);
         if (sort_hits && b >= 1 && n_max >= sort_min) {
             // re-order the queue by hit-point Morton code (see k_sort_keys): the rest of the bounce reads the sorted copies
             const int gs = (int)std::min<int64_t>((n_max + 255) / 256, grid_cap);

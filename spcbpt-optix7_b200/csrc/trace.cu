@@ -4,6 +4,7 @@
 // memory (kSmStack entries per lane) with a local-memory tail.
 #include <algorithm>
 #include <cstdlib>
+#include "geom.cuh"
 #include "traverse.cuh"
 
 namespace spc {
@@ -81,12 +82,14 @@ k_trace_occlusion(const float4* __restrict__ nodes, const float4* __restrict__ t
 // idle lanes claim new rays with one warp-aggregated atomicAdd, so lanes stay busy until the batch is drained.
 // The grid is sized to the resident capacity of the GPU (SM count x blocks per SM), not to the ray count.
 // ---------------------------------------------------------------------------------------------
-template <bool ANYHIT, bool COUNT = false>
+// RAYGEN: ray i is the camera ray of pixel i, generated here (seed tea<4>(i, sample_index), jitter, camera_dir_exact -- the very
+// arithmetic k_eye_shade repeats for the first bounce) instead of being read from a ray buffer another kernel would have to write.
+template <bool ANYHIT, bool COUNT = false, bool RAYGEN = false>
 __global__ void __launch_bounds__(kTraceBlock, SPC_PERSIST_MIN_BLOCKS)
 k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float4* __restrict__ rays,
                 const int* __restrict__ n_dev, int mult, int64_t n_host, int cull_back, int fetch_threshold, int postpone_div,
                 float4* __restrict__ hits, uint8_t* __restrict__ visible, unsigned long long* __restrict__ counter,
-                unsigned long long* __restrict__ visit_counters = nullptr) {
+                unsigned long long* __restrict__ visit_counters = nullptr, const CamGen cam = CamGen()) {
     __shared__ uint2 s_stack[kSmStack * kTraceBlock];
     __shared__ TravLut s_lut;
     trav_lut_init(s_lut);
@@ -112,8 +115,21 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
                 if (ray < 0) {
                     const int64_t my = (int64_t)base + __popc(idle & lt_mask);
                     if (my < n) {
-                        const float4 ro = __ldg(rays + 2 * my);
-                        const float4 rd = __ldg(rays + 2 * my + 1);
+                        float4 ro, rd;
+                        if (RAYGEN) {
+                            uint32_t seed = tea<4>((uint32_t)my, cam.sample_index);
+                            float jx = 0.5f, jy = 0.5f;
+                            if (cam.sample_index != 0) {
+                                jx = rnd(seed);
+                                jy = rnd(seed);
+                            }
+                            const float3 d = camera_dir_exact(cam.U, cam.V, cam.W, (unsigned)my % cam.width, (unsigned)my / cam.width, cam.width, cam.height, jx, jy);
+                            ro = make_float4(cam.eye.x, cam.eye.y, cam.eye.z, 1e-3f);   // SCENE_EPSILON
+                            rd = make_float4(d.x, d.y, d.z, 1e16f);
+                        } else {
+                            ro = __ldg(rays + 2 * my);
+                            rd = __ldg(rays + 2 * my + 1);
+                        }
                         if (ANYHIT && !(rd.w > ro.w)) {
                             visible[my] = 1;   // empty interval: an unused connection slot
                         } else {
@@ -158,15 +174,20 @@ static int trace_env(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+struct Knobs {
+    int max_blocks, fetch_t, postpone_div;
+};
+static const Knobs& persist_knobs() {
+    static const Knobs knobs = {trace_env("SPC_TRACE_BLOCKS_PER_SM", 16), trace_env("SPC_FETCH_THRESHOLD", 6), trace_env("SPC_POSTPONE_DIV", 5)};
+    return knobs;
+}
+
 template <bool ANYHIT>
 static void launch_persist(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits, uint8_t* visible,
                            unsigned long long* visit_counters = nullptr) {
     // process-wide tuning knobs (environment, read once) and the per-device occupancy of this kernel (queried once per context:
     // occupancy is a property of the device the context lives on)
-    struct Knobs {
-        int max_blocks, fetch_t, postpone_div;
-    };
-    static const Knobs knobs = {trace_env("SPC_TRACE_BLOCKS_PER_SM", 16), trace_env("SPC_FETCH_THRESHOLD", 6), trace_env("SPC_POSTPONE_DIV", 5)};
+    const Knobs& knobs = persist_knobs();
     int& cached = ctx.persist_blocks[ANYHIT ? 1 : 0];
     if (cached == 0) {
         int b = 0;
@@ -241,6 +262,29 @@ k_trace_occlusion_q(const float4* __restrict__ nodes, const float4* __restrict__
         const bool blocked = traverse_bvh8<true, false>(nodes, tris, r, false, s_stack + threadIdx.x, kTraceBlock, h, cn, ct, s_lut);
         visible[i] = blocked ? 0 : 1;
     }
+}
+
+void launch_trace_closest_camera(Context& ctx, const CamGen& cam, int64_t n_pixels, int flags, spc_hit* hits) {
+    if (n_pixels <= 0) return;
+    int& cached = ctx.persist_blocks[0];
+    if (cached == 0) {
+        int b = 0;
+        SPC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace_persist<false>, kTraceBlock, 0));
+        cached = std::max(1, std::min(b, persist_knobs().max_blocks));
+    }
+    if (ctx.fetch_counters.n < 256) {
+        ctx.fetch_counters.alloc(256);
+        ctx.fetch_slot = 0;
+    }
+    unsigned long long* counter = ctx.fetch_counters.p + (ctx.fetch_slot++ & 255);
+    SPC_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx.stream));
+    const int bps = ctx.trace_blocks_per_sm > 0 ? std::min(ctx.trace_blocks_per_sm, cached) : cached;
+    const int64_t blocks = std::min<int64_t>((n_pixels + kTraceBlock - 1) / kTraceBlock, (int64_t)ctx.sm_count * bps);
+    k_trace_persist<false, false, true><<<(unsigned)blocks, kTraceBlock, 0, ctx.stream>>>(
+        ctx.bvh.nodes.p, ctx.bvh.tris.p, nullptr, nullptr, 1, n_pixels, (flags & SPC_RAYFLAG_CULL_BACK_FACING) ? 1 : 0, persist_knobs().fetch_t,
+        persist_knobs().postpone_div, (float4*)hits, nullptr, counter, nullptr, cam);
+    SPC_CUDA(cudaGetLastError());
+    ctx.launches++;
 }
 
 void launch_trace_closest_q(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, int flags, spc_hit* hits) {
