@@ -28,5 +28,7 @@ bool write_rgba8_cache(const std::string& path, const ImageRGBA8& img);
 // PPM is written top row first (flipped), PFM bottom row first (its native order, negative scale = little endian).
 bool write_ppm_from_uchar4(const std::string& path, const uint32_t* frame, int width, int height);
 bool write_pfm_from_float4(const std::string& path, const float* accum4, int width, int height);
+// 8-bit RGB PNG of the frame buffer (top row first; deflate by the system zlib, filter 0), for viewers that do not read PPM
+bool write_png_from_uchar4(const std::string& path, const uint32_t* frame, int width, int height);
 
 }  // namespace spchost

@@ -194,4 +194,48 @@ bool decode_png_rgba8(const uint8_t* data, size_t size, ImageRGBA8& img, std::st
     return true;
 }
 
+// ---- writer: IHDR / IDAT / IEND, colour type 2 (RGB), 8 bit, filter method 0 on every row ---------------------------------------
+namespace {
+void png_chunk(FILE* f, const char type[4], const uint8_t* data, size_t n) {
+    const uint8_t len[4] = {(uint8_t)(n >> 24), (uint8_t)(n >> 16), (uint8_t)(n >> 8), (uint8_t)n};
+    fwrite(len, 1, 4, f);
+    fwrite(type, 1, 4, f);
+    if (n) fwrite(data, 1, n, f);
+    uLong crc = crc32(0L, reinterpret_cast<const Bytef*>(type), 4);
+    if (n) crc = crc32(crc, data, (uInt)n);
+    const uint8_t c[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+    fwrite(c, 1, 4, f);
+}
+}  // namespace
+
+bool write_png_from_uchar4(const std::string& path, const uint32_t* frame, int width, int height) {
+    if (width <= 0 || height <= 0) return false;
+    std::vector<uint8_t> raw((size_t)height * (1 + (size_t)width * 3));
+    size_t o = 0;
+    for (int y = height - 1; y >= 0; y--) {   // the render's row 0 is the bottom row (image_io.hpp)
+        raw[o++] = 0;                          // filter type: none
+        const uint8_t* s = reinterpret_cast<const uint8_t*>(frame + (size_t)y * width);
+        for (int x = 0; x < width; x++) {
+            raw[o++] = s[4 * x];
+            raw[o++] = s[4 * x + 1];
+            raw[o++] = s[4 * x + 2];
+        }
+    }
+    uLongf zn = compressBound((uLong)raw.size());
+    std::vector<uint8_t> z(zn);
+    if (compress2(z.data(), &zn, raw.data(), (uLong)raw.size(), 6) != Z_OK) return false;
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    fwrite(sig, 1, 8, f);
+    const uint8_t ihdr[13] = {(uint8_t)(width >> 24), (uint8_t)(width >> 16), (uint8_t)(width >> 8), (uint8_t)width,
+                              (uint8_t)(height >> 24), (uint8_t)(height >> 16), (uint8_t)(height >> 8), (uint8_t)height, 8, 2, 0, 0, 0};
+    png_chunk(f, "IHDR", ihdr, sizeof(ihdr));
+    png_chunk(f, "IDAT", z.data(), zn);
+    png_chunk(f, "IEND", nullptr, 0);
+    const bool ok = !ferror(f);
+    fclose(f);
+    return ok;
+}
+
 }  // namespace spchost

@@ -1,6 +1,7 @@
 // scene_tool.cpp -- scene conversion and texture decoding without a GPU (no dependency on libspcbpt_b200.so):
 //   spc_scene_tool convert <file.scene> <out.spcscene> [--data-root dir] [--K-light n]   .scene + OBJ + textures -> cache
 //   spc_scene_tool decode  <image> <out.rgba8>                                          JPEG/PNG/PNM -> raw RGBA8 cache
+//   spc_scene_tool png     <image> <out.png>                                            re-encode through the driver's PNG writer
 //   spc_scene_tool scene   <file.scene> <out.txt> [data-root]                          parsed .scene as text (LoadScene check)
 //   spc_scene_tool obj     <file.obj> <out.bin>      shapes as: u32 n_shapes; per shape u32 nv, nt, nuv; f32 pos[3nv]; u32 idx[3nt]; f32 uv[nuv]
 // Used by tests/test_host_loader.py to compare the loaders with the reference's own tinyobj / stb_image / LoadScene.
@@ -40,6 +41,16 @@ int main(int argc, char** argv) {
         ImageRGBA8 img;
         if (!load_image_rgba8(argv[2], img, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
         if (!write_rgba8_cache(argv[3], img)) { fprintf(stderr, "cannot write %s\n", argv[3]); return 1; }
+        printf("%d %d\n", img.width, img.height);
+        return 0;
+    }
+    if (cmd == "png") {   // image -> PNG through the driver's writer (frame-buffer convention: row 0 = bottom row)
+        ImageRGBA8 img;
+        if (!load_image_rgba8(argv[2], img, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        std::vector<uint32_t> frame((size_t)img.width * img.height);
+        for (int y = 0; y < img.height; y++)
+            memcpy(&frame[(size_t)(img.height - 1 - y) * img.width], &img.rgba[(size_t)y * img.width * 4], (size_t)img.width * 4);
+        if (!write_png_from_uchar4(argv[3], frame.data(), img.width, img.height)) { fprintf(stderr, "cannot write %s\n", argv[3]); return 1; }
         printf("%d %d\n", img.width, img.height);
         return 0;
     }

@@ -7,7 +7,7 @@
 // reference's timing read-out (sutil::displayStats) replaced by a summary line.  Every GPU step is one call into the
 // library; this file only sequences them (the Python twin is spcbpt-optix7_b200/renderer.py, used by the tests).
 //
-// Display is replaced by files: <out>.ppm (tone-mapped frame buffer) and <out>.pfm (accumulation buffer).
+// Display is replaced by files: <out>.ppm / <out>.png (tone-mapped frame buffer) and <out>.pfm (accumulation buffer).
 #include <cuda_runtime_api.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -57,6 +57,7 @@ struct Options {
     // multi-GPU: one process per GPU.  `--ranks N` forks N ranks on devices 0..N-1 of this node; or start the ranks yourself
     // with --rank r --world N --id-file <path> (rank 0 writes the NCCL unique id there, the others wait for it)
     int  ranks = 1, rank = 0, world = 1;
+    bool tiles = false;   // multi-GPU by image tiles (spc_set_tile_partition) instead of by samples: frame latency scales, not throughput
     std::string id_file;
     std::vector<std::pair<std::string, long long>> options;   // --option name=value -> spc_set_option on every context
 };
@@ -72,6 +73,8 @@ void usage(const char* argv0) {
             "         --ranks <n>                 multi-GPU: fork n ranks on devices 0..n-1 (NCCL inside the library: sharded training,\n"
             "                                     sample-partitioned frames, accumulation buffer reduced to rank 0)\n"
             "         --rank r --world n --id-file f   the same with externally started ranks (rank 0 writes the NCCL id to f)\n"
+            "         --tiles                     with several ranks: partition every frame by 8x4 pixel tiles (sutil/WorkDistribution.h) instead of\n"
+            "                                     partitioning the samples: all ranks render the same subframes, each its own tiles\n"
             "         --alg pt|SPCBPT_eye         integrator (the reference toggles these with Space)\n"
             "         --K <n> --K-light <n> --connections <n> --max-depth <n>\n"
             "         --train-samples <n> --q-samples <n> --tree-samples <n> --batch <n> --epochs <n> --lr <f>\n"
@@ -143,6 +146,7 @@ bool parse_args(int argc, char** argv, Options& o) {
         else if (a == "--rank") o.rank = atoi(need("--rank"));
         else if (a == "--world") o.world = atoi(need("--world"));
         else if (a == "--id-file") o.id_file = need("--id-file");
+        else if (a == "--tiles") o.tiles = true;
         else if (a == "--host-trees") o.host_trees = true;
         else if (a == "--no-pipeline") o.pipeline = false;
         else if (a == "--no-render") o.render = false;
@@ -368,7 +372,7 @@ struct App {
         t_qgamma = now_s() - t2;
         if (world > 1) {   // the render loop's light-trace frames: disjoint from the training frames and from the other ranks'
             lt_stride = 1;
-            params.lt.launch_frame = 1000003 * (rank + 1);
+            params.lt.launch_frame = 1000003 * (opt.tiles ? 1 : rank + 1);   // tile partition: every rank traces the same light paths
         }
     }
 
@@ -398,6 +402,8 @@ struct App {
         SPC_CHECK(spc_upload(ctx, gamma_dev, st.gamma.data(), st.gamma.size() * sizeof(float)));
         params.subspace_info.Q = q;
         SPC_CHECK(spc_Gamma2CMFGamma(ctx, gamma_dev, &params.subspace_info.CMFGamma));
+        // sample partition: every rank needs light paths of its own (as after preprocessing()); tile partition: the same everywhere
+        if (opt.world > 1 && !opt.tiles) params.lt.launch_frame = 1000003 * (opt.rank + 1);
     }
 
     // launchSubframe (:609-635)
@@ -447,6 +453,7 @@ struct App {
         SPC_CHECK(spc_synchronize(ctx));
         if (upload_s) *upload_s = now_s() - t0;
         for (const auto& kv : opt.options) SPC_CHECK(spc_set_option(ctx, kv.first.c_str(), kv.second));
+        if (opt.tiles && opt.world > 1) SPC_CHECK(spc_set_tile_partition(ctx, opt.rank, opt.world));
     }
 
     void become_lane(int k, int n, const App& trained) {
@@ -545,7 +552,7 @@ int main(int argc, char** argv) {
             o.ranks = 1;
             if (my_rank != 0) o.quiet = true;
         }
-        if (app.opt.world > 1) {   // sample partition across ranks, composed with the frame lanes below
+        if (app.opt.world > 1 && !app.opt.tiles) {   // sample partition across ranks, composed with the frame lanes below
             app.opt.seed_offset = (unsigned)app.opt.rank;
             app.opt.seed_stride = (unsigned)app.opt.world;
         }
@@ -670,7 +677,8 @@ int main(int argc, char** argv) {
 
         if (opt.world > 1) {
             // read-out over NCCL: every rank rendered opt.frames subframes -> the image is the mean of the per-rank running means
-            SPC_CHECK(spc_reduce_accum(app.ctx, app.params.accum_buffer, opt.width * opt.height, 1.0f / (float)opt.world, 0));
+            // (tile partition: every pixel is non-zero on exactly one rank -> weight 1)
+            SPC_CHECK(spc_reduce_accum(app.ctx, app.params.accum_buffer, opt.width * opt.height, opt.tiles ? 1.0f : 1.0f / (float)opt.world, 0));
             SPC_CHECK(spc_synchronize(app.ctx));
             if (opt.rank == 0) {   // display transform of the merged image
                 const spc_float4* one = app.params.accum_buffer;
@@ -693,14 +701,16 @@ int main(int argc, char** argv) {
         mean /= (double)(3 * P);
         if (opt.write_images) {
             if (!spchost::write_ppm_from_uchar4(opt.out + ".ppm", frame.data(), opt.width, opt.height)) throw std::runtime_error("cannot write " + opt.out + ".ppm");
+            if (!spchost::write_png_from_uchar4(opt.out + ".png", frame.data(), opt.width, opt.height)) throw std::runtime_error("cannot write " + opt.out + ".png");
             if (!spchost::write_pfm_from_float4(opt.out + ".pfm", accum.data(), opt.width, opt.height)) throw std::runtime_error("cannot write " + opt.out + ".pfm");
         }
+        const int sample_ranks = opt.tiles ? 1 : opt.world;   // tile partition: the ranks share the subframes instead of adding their own
         printf("{\"alg\": \"%s\", \"width\": %d, \"height\": %d, \"frames\": %d, \"ranks\": %d, \"triangles\": %zu, \"K\": %d, \"lanes\": %d, \"pipelined\": %s, \"render_s\": %.6f, \"ms_per_frame\": %.4f, "
                "\"samples_per_s\": %.1f, \"kernel_launches\": %lld, \"train_paths\": %d, \"pretrace_s\": %.4f, \"trees_s\": %.4f, \"q_gamma_s\": %.4f, \"upload_s\": %.4f, \"e2e_s\": %.4f, "
                "\"e2e_samples_per_s\": %.1f, \"h2d_bytes\": %zu, \"d2h_bytes\": %zu, \"image_mean\": %.9g}\n",
                opt.alg.c_str(), opt.width, opt.height, opt.frames, opt.world, app.scene.n_triangles(), opt.K, opt.lanes, app.main_stream ? "true" : "false", t_render, t_render / opt.frames * 1e3,
-               (double)P * opt.frames * opt.world / t_render, (long long)launches, app.train_paths, app.t_pretrace, app.t_trees, app.t_qgamma, t_upload, t_e2e,
-               (double)P * opt.frames * opt.world / t_e2e, app.scene.upload_bytes(), P * 20, mean);
+               (double)P * opt.frames * sample_ranks / t_render, (long long)launches, app.train_paths, app.t_pretrace, app.t_trees, app.t_qgamma, t_upload, t_e2e,
+               (double)P * opt.frames * sample_ranks / t_e2e, app.scene.upload_bytes(), P * 20, mean);
         for (auto& l : extra) spc_destroy(l->ctx);
         spc_destroy(app.ctx);
     } catch (std::exception& e) {

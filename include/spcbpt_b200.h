@@ -402,6 +402,13 @@ SPC_API int  spc_set_seed_offset(spc_context* ctx, uint32_t offset);
  * global subframes lane, lane + n_lanes, ...: this is how several contexts on one GPU render alternate subframes concurrently
  * (host/spcbpt_main.cpp --lanes) and how ranks partition subframes across GPUs. */
 SPC_API int  spc_set_seed_mapping(spc_context* ctx, uint32_t offset, uint32_t stride);
+/* Tile partition of the image (the other way to shard a frame; sutil/WorkDistribution.h:34-91 StaticWorkDistribution, which the reference
+ * ships but never wires up): with num_gpus > 1 the SPCBPT_eye launch renders only the pixels of this GPU's 8 x 4 tiles (strips of num_gpus
+ * tiles, the GPU's tile shifted by one per strip row) and leaves the other pixels of accum_buffer untouched (the caller zero-fills it).
+ * A pixel's estimate depends on its own path and on the light-vertex cache only, so ranks that trace the same light paths (same
+ * lt.launch_frame) produce, tile by tile, exactly the single-GPU image: read-out is spc_reduce_accum with weight 1.  Latency, not
+ * throughput, scales (strong scaling: every rank still traces the light paths).  (0, 1) = the whole image (default). */
+SPC_API int  spc_set_tile_partition(spc_context* ctx, int gpu_idx, int num_gpus);
 /* Resident thread blocks per SM of the persistent traversal kernels launched by this context (0 = default: as many as fit, 9).
  * No counterpart in the reference (OptiX schedules its own launches).  A context that shares the GPU with other contexts (frame
  * lanes) leaves room for their small latency-bound kernels by asking for fewer: 7 measured best on the shipped scene with 4 lanes

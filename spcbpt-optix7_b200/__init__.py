@@ -171,6 +171,7 @@ def _bind_optional(L):
         "spc_set_seed_offset": [vp, ctypes.c_uint32],
         "spc_set_seed_mapping": [vp, ctypes.c_uint32, ctypes.c_uint32],
         "spc_set_trace_blocks": [vp, i32],
+        "spc_set_tile_partition": [vp, i32, i32],
         "spc_merge_accum": [vp, vp, vp, i32, i32, vp, vp],
         "spc_lvc_process": [vp, vp, vp, i32, vp],
         "spc_build_tree": [vp, i32, i32, i32, vp, i32, vp],
@@ -332,6 +333,9 @@ class Context:
 
     def set_seed_mapping(self, offset, stride):
         self._ck(self._L.spc_set_seed_mapping(self.h, offset, stride), "spc_set_seed_mapping")
+
+    def set_tile_partition(self, gpu_idx, num_gpus):
+        self._ck(self._L.spc_set_tile_partition(self.h, gpu_idx, num_gpus), "spc_set_tile_partition")
 
     def set_trace_blocks(self, blocks_per_sm):
         self._ck(self._L.spc_set_trace_blocks(self.h, blocks_per_sm), "spc_set_trace_blocks")

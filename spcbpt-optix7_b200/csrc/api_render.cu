@@ -91,6 +91,14 @@ int spc_set_seed_mapping(spc_context* ctx, uint32_t offset, uint32_t stride) {
     SPC_API_END
 }
 
+int spc_set_tile_partition(spc_context* ctx, int gpu_idx, int num_gpus) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(num_gpus >= 1 && gpu_idx >= 0 && gpu_idx < num_gpus, SPC_ERR_INVALID, "spc_set_tile_partition: gpu %d of %d", gpu_idx, num_gpus);
+    c.tile_rank = gpu_idx;
+    c.tile_world = num_gpus;
+    SPC_API_END
+}
+
 int spc_set_trace_blocks(spc_context* ctx, int blocks_per_sm) {
     SPC_API_BEGIN
     SPC_REQUIRE(blocks_per_sm >= 0 && blocks_per_sm <= 32, SPC_ERR_INVALID, "spc_set_trace_blocks: %d is outside 0..32", blocks_per_sm);

@@ -222,6 +222,10 @@ struct Context {
     bool          lvc_attr_set = false;        // lvc.cu: dynamic shared-memory opt-in of the binning kernels
     int           persist_blocks[2] = {0, 0};  // trace.cu: resident blocks per SM of k_trace_persist<ANYHIT> on this device (0 = not queried)
     int64_t       opt[OPT_COUNT] = {};         // spc_set_option switches (api_render.cu), all 0 by default
+    // tile partition of the image across GPUs (spc_set_tile_partition; sutil/WorkDistribution.h): this rank's pixel list
+    int           tile_rank = 0, tile_world = 1, n_tile_pixels = 0;
+    int           tile_key[4] = {0, 0, 0, 0};
+    DevBuf<int>   tile_pixels;
     // multi-GPU (comm.cu): NCCL communicator of this rank, or null (world 1)
     void*         comm = nullptr;
     int           comm_rank = 0, comm_world = 1;
@@ -242,6 +246,7 @@ struct CamGen {
     float3   eye, U, V, W;
     unsigned width, height;
     uint32_t sample_index;   // subframe_index * seed_stride + seed_offset
+    const int* pixels;       // ray i belongs to pixel pixels[i] (tile partition), or null: pixel i
 };
 void launch_trace_closest_camera(Context& ctx, const CamGen& cam, int64_t n_pixels, int flags, spc_hit* hits);
 void launch_trace_occlusion_q(Context& ctx, const spc_ray* rays, const int* n_dev, int mult, int64_t n_max, uint8_t* visible);

@@ -373,9 +373,9 @@ __device__ __forceinline__ void camera_ray(const DevFrame& fr, int pix, float3& 
     eye = ld3(fr.p.eye);
     dir = camera_dir_exact(ld3(fr.p.U), ld3(fr.p.V), ld3(fr.p.W), (unsigned)pix % W, (unsigned)pix / W, W, H, jx, jy);
 }
-__global__ void k_eye_begin(const EyeArgs a, int n_pix, int n_work, int* __restrict__ ident, int fill_ident) {
+__global__ void k_eye_begin(const EyeArgs a, int n_pix, int n_first, int n_work, int* __restrict__ ident, int fill_ident) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) a.counts[0] = n_pix;
+    if (i == 0) a.counts[0] = n_first;   // entries of the first bounce's queue: all pixels, or this rank's tiles
     if (i >= n_work || n_work < n_pix) return;   // n_work = n_pix only when there is per-pixel work
     if (fill_ident) ident[i] = i;
     if (a.first_prim) a.first_prim[i] = -1;
@@ -927,9 +927,10 @@ __device__ __forceinline__ float to_srgb(float c) {
     const float powed = cm_powf(c, invGamma);
     return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
 }
-__global__ void k_accumulate(const DevFrame fr, const float4* __restrict__ res, int n_pix) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pix) return;
+__global__ void k_accumulate(const DevFrame fr, const float4* __restrict__ res, int n_pix, const int* __restrict__ pixels /* null: all pixels */) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pix) return;
+    const int i = pixels ? pixels[k] : k;
     const float4 r = res[i];
     float3 c = f3(r.x, r.y, r.z);
     if (fr.p.subframe_index > 0) {
@@ -1126,12 +1127,38 @@ void launch_eye_pass(Context& c, int width, int height) {
     }
     const int nP = (int)P;
     // queue of the first bounce = pixel order: an identity array filled once per allocation; per frame only counts[0] (and the
-    // optional parity dumps) are initialised
-    const bool fill_ident = e.ident_pixels != P;
+    // optional parity dumps) are initialised.  Tile partition (spc_set_tile_partition): the queue is this rank's pixel list instead.
+    const bool tiled = c.tile_world > 1;
+    int n_first = nP;
+    if (tiled) {
+        if (c.tile_key[0] != width || c.tile_key[1] != height || c.tile_key[2] != c.tile_rank || c.tile_key[3] != c.tile_world) {
+            // StaticWorkDistribution::getSamplePixel (sutil/WorkDistribution.h:59-82): 8 x 4 tiles, strips of `world` tiles, the
+            // rank's tile shifted by one per strip row; pixels beyond the image are dropped
+            constexpr int TW = 8, TH = 4;
+            const int G = c.tile_world, strip_w = TW * G;
+            const int cols = (width + strip_w - 1) / strip_w, rows = (height + TH - 1) / TH;
+            std::vector<int> px;
+            px.reserve((size_t)P / G + 64);
+            for (int sidx = 0; sidx < rows * cols * TW * TH; sidx++) {
+                const int strip = sidx / (TW * TH), sy = strip / cols, sx = strip - sy * cols;
+                const int tp = sidx - strip * TW * TH, ty = tp / TW, tx = tp - ty * TW;
+                const int x = sx * strip_w + tx + (c.tile_rank + sy % G) % G * TW, y = sy * TH + ty;
+                if (x < width && y < height) px.push_back(y * width + x);
+            }
+            c.tile_pixels.alloc(px.size());
+            SPC_CUDA(cudaMemcpyAsync(c.tile_pixels.p, px.data(), px.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+            SPC_CUDA(cudaStreamSynchronize(st));
+            c.n_tile_pixels = (int)px.size();
+            c.tile_key[0] = width; c.tile_key[1] = height; c.tile_key[2] = c.tile_rank; c.tile_key[3] = c.tile_world;
+        }
+        n_first = c.n_tile_pixels;
+    }
+    const bool fill_ident = !tiled && e.ident_pixels != P;
     if (fill_ident) e.queue_ident.alloc(P);
     const int n_work = (fill_ident || a.first_prim || a.first_label) ? nP : 1;
-    k_eye_begin<<<(n_work + 255) / 256, 256, 0, st>>>(a, nP, n_work, e.queue_ident.p, fill_ident ? 1 : 0);
-    e.ident_pixels = P;
+    k_eye_begin<<<(n_work + 255) / 256, 256, 0, st>>>(a, nP, n_first, n_work, e.queue_ident.p, fill_ident ? 1 : 0);
+    if (fill_ident) e.ident_pixels = P;
+    const int* first_queue = tiled ? c.tile_pixels.p : e.queue_ident.p;
     c.launches++;
     CamGen cam;
     cam.eye = make_float3(c.params.eye.x, c.params.eye.y, c.params.eye.z);
@@ -1141,8 +1168,9 @@ void launch_eye_pass(Context& c, int width, int height) {
     cam.width = c.params.width;
     cam.height = c.params.height;
     cam.sample_index = c.params.subframe_index * c.seed_stride + c.seed_offset;
+    cam.pixels = tiled ? c.tile_pixels.p : nullptr;
     const int grid_cap = c.sm_count * 16;
-    int64_t n_max = nP;   // host-side upper bound on the live paths (refreshed by the lagged read-backs)
+    int64_t n_max = n_first;   // host-side upper bound on the live paths (refreshed by the lagged read-backs)
     // The size of every bounce's queue is copied to pinned memory behind the bounce, and the host looks at it kLag bounces later:
     // it stops when a queue was empty and shrinks the grids, but it never drains the stream (a full synchronisation every 4th
     // bounce left the GPU idle for a host round trip each time and made the frame time follow the host's scheduling noise).
@@ -1161,10 +1189,10 @@ void launch_eye_pass(Context& c, int width, int height) {
     for (int b = 0; b <= fr.max_depth; b++) {
         a.bounce = b;
         a.rays_cur = (float4*)e.rays[b & 1].p; a.rays_next = (float4*)e.rays[(b + 1) & 1].p;
-        a.queue_cur = b == 0 ? e.queue_ident.p : e.queue[b & 1].p; a.queue_next = e.queue[(b + 1) & 1].p;
+        a.queue_cur = b == 0 ? const_cast<int*>(first_queue) : e.queue[b & 1].p; a.queue_next = e.queue[(b + 1) & 1].p;
         mark(b, 0);
         nvtxRangePushA("eye: closest hits");
-        if (b == 0) launch_trace_closest_camera(c, cam, nP, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);   // generates the camera rays itself
+        if (b == 0) launch_trace_closest_camera(c, cam, n_first, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);   // generates the camera rays itself
         else launch_trace_closest_q(c, (const spc_ray*)a.rays_cur, e.counts.p + b, 1, n_max, SPC_RAYFLAG_CULL_BACK_FACING, e.hits.p);
         if (sort_hits && b >= 1 && n_max >= sort_min) {
             // re-order the queue by hit-point Morton code (see k_sort_keys): the rest of the bounce reads the sorted copies
@@ -1239,7 +1267,7 @@ void launch_eye_pass(Context& c, int width, int height) {
             }
         }
     }
-    k_accumulate<<<(nP + 255) / 256, 256, 0, st>>>(fr, e.res.p, nP);
+    k_accumulate<<<(n_first + 255) / 256, 256, 0, st>>>(fr, e.res.p, n_first, tiled ? c.tile_pixels.p : nullptr);
     c.launches++;
     if (timed) SPC_CUDA(cudaEventRecord(e.stage_ev[1], st));
     SPC_CUDA(cudaGetLastError());

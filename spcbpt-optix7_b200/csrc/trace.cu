@@ -117,13 +117,14 @@ k_trace_persist(const float4* __restrict__ nodes, const float4* __restrict__ tri
                     if (my < n) {
                         float4 ro, rd;
                         if (RAYGEN) {
-                            uint32_t seed = tea<4>((uint32_t)my, cam.sample_index);
+                            const unsigned pixel = cam.pixels ? (unsigned)__ldg(cam.pixels + my) : (unsigned)my;
+                            uint32_t seed = tea<4>(pixel, cam.sample_index);
                             float jx = 0.5f, jy = 0.5f;
                             if (cam.sample_index != 0) {
                                 jx = rnd(seed);
                                 jy = rnd(seed);
                             }
-                            const float3 d = camera_dir_exact(cam.U, cam.V, cam.W, (unsigned)my % cam.width, (unsigned)my / cam.width, cam.width, cam.height, jx, jy);
+                            const float3 d = camera_dir_exact(cam.U, cam.V, cam.W, pixel % cam.width, pixel / cam.width, cam.width, cam.height, jx, jy);
                             ro = make_float4(cam.eye.x, cam.eye.y, cam.eye.z, 1e-3f);   // SCENE_EPSILON
                             rd = make_float4(d.x, d.y, d.z, 1e16f);
                         } else {

@@ -136,6 +136,37 @@ def test_python_lane_renderer_equals_sequential(gpu_ctx, tmp_path):
     assert np.abs(lr.frame_rgba8().astype(int) - seq.frame_rgba8().astype(int)).max() <= 1
 
 
+def test_cpp_driver_writes_png(gpu_ctx, tmp_path):
+    """<out>.png (host/png_decode.cpp write_png_from_uchar4) holds the pixels of <out>.ppm"""
+    from PIL import Image
+    pkg = gpu_ctx
+    sc = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=6, box_cells=4), 0.01)
+    path = pkg.scenes.export_scene(sc, str(tmp_path), "cb")
+    run_driver("--scene", path, "--dim=64x48", "--frames", 2, "--alg", "pt", "--out", tmp_path / "p", *SMALL)
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "p.png").convert("RGB")), read_ppm(tmp_path / "p.ppm"))
+
+
+def test_cpp_driver_tile_partition_two_ranks(gpu_ctx, tmp_path):
+    """--ranks 2 --tiles: the two GPUs render the same subframes, each the pixels of its 8 x 4 tiles (spc_set_tile_partition,
+    sutil/WorkDistribution.h:34-91); the NCCL read-out reassembles exactly the single-GPU image"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    pkg = gpu_ctx
+    sc = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=12, box_cells=8), 0.01)
+    path = pkg.scenes.export_scene(sc, str(tmp_path), "cb")
+    dim, frames = "--dim=100x70", 4
+    run_driver("--scene", path, dim, "--frames", 1, "--out", tmp_path / "t", "--save-state", tmp_path / "st_", "--no-images", *SMALL)
+    one, _ = run_driver("--scene", path, dim, "--frames", frames, "--out", tmp_path / "one", "--load-state", tmp_path / "st_", *SMALL)
+    two, _ = run_driver("--scene", path, dim, "--frames", frames, "--out", tmp_path / "two", "--load-state", tmp_path / "st_", "--ranks", 2, "--tiles", *SMALL)
+    assert two["ranks"] == 2 and one["image_mean"] > 0.01
+    assert np.array_equal(read_pfm(tmp_path / "one.pfm").view(np.uint32), read_pfm(tmp_path / "two.pfm").view(np.uint32))
+    assert np.array_equal(read_ppm(tmp_path / "one.ppm"), read_ppm(tmp_path / "two.ppm"))
+    # with frame lanes on each rank as well
+    two4, _ = run_driver("--scene", path, dim, "--frames", frames, "--out", tmp_path / "two4", "--load-state", tmp_path / "st_", "--ranks", 2, "--tiles", "--lanes", 2, *SMALL)
+    assert np.allclose(read_pfm(tmp_path / "two4.pfm"), read_pfm(tmp_path / "one.pfm"), rtol=2e-6, atol=1e-7)
+
+
 def test_cpp_driver_errors(gpu_ctx, tmp_path):
     r = subprocess.run([BIN, "--scene", str(tmp_path / "nope.scene")], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open scene file" in r.stderr

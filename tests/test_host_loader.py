@@ -80,6 +80,23 @@ def test_jpeg_and_png_decoders_equal_stb_image(tool, tmp_path):
         assert mine.shape == gold[name].shape and np.array_equal(mine, gold[name]), name
 
 
+def test_png_writer_roundtrip(tool, tmp_path):
+    """the driver's PNG output (host/png_decode.cpp write_png_from_uchar4): PIL and our own decoder read back the very pixels"""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    src = tmp_path / "in.ppm"
+    with open(src, "wb") as f:
+        f.write(b"P6\n53 37\n255\n" + rgb.tobytes())
+    out = tmp_path / "out.png"
+    run(tool, "png", str(src), str(out))
+    assert np.array_equal(np.asarray(Image.open(out).convert("RGB")), rgb)
+    back = tmp_path / "back.rgba8"
+    run(tool, "decode", str(out), str(back))
+    mine = np.fromfile(back, np.uint8)[16:].reshape(37, 53, 4)
+    assert np.array_equal(mine[..., :3], rgb) and (mine[..., 3] == 255).all()
+
+
 def test_progressive_jpeg_is_rejected_loudly(tool, tmp_path):
     from PIL import Image
     p = tmp_path / "prog.jpg"

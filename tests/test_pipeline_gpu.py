@@ -195,3 +195,51 @@ def test_sorting_between_bounces_leaves_frames_bit_identical(gpu_ctx):
     for k in ("closest_rays", "shadow_rays", "visible_connections", "bounces"):
         assert out[0][1][k] == out[1][1][k], k
     assert out[1][2] > out[0][2]        # the sort kernels did run
+
+
+@pytest.mark.parametrize("world,dim", [(2, (320, 200)), (3, (203, 77))])
+def test_tile_partition_reassembles_the_single_gpu_image(gpu_ctx, world, dim):
+    """spc_set_tile_partition (sutil/WorkDistribution.h:34-91 StaticWorkDistribution): every "GPU" renders only the pixels of its
+    8 x 4 tiles; ranks that trace the same light paths reproduce, tile by tile, the single-GPU frames bit for bit, the tiles are
+    disjoint and cover the image -- also when the image is not a multiple of the strip size"""
+    pkg = gpu_ctx
+    from spcbpt_optix7_b200.renderer import Renderer
+    sc = pkg.scenes.scaled(pkg.scenes.cornell_scene(wall_cells=12, box_cells=8), 0.01)
+    kw = dict(K=64, K_light=12, lt_num_core=100, lt_core_padding=300, lt_M_per_core=40, pretrace_num_core=20000)
+    w, h = dim
+    r = Renderer(sc, w, h, **kw)
+    r.preprocessing(target_samples=40000, target_Q_samples=20000, tree_samples=20000, batch_size=20000)
+    frame0 = int(r.P["lt"]["launch_frame"][0])
+
+    def render(gpu_idx, num_gpus):
+        r.ctx.set_tile_partition(gpu_idx, num_gpus)
+        r.ctx.synchronize()
+        r.accum.zero_()
+        r.frame.zero_()
+        r.reset_accumulation()
+        r.P["lt"]["launch_frame"] = frame0
+        for _ in range(3):
+            r.render_frame()
+        r.ctx.synchronize()
+        return r.accum.cpu().numpy().reshape(h, w, 4).copy(), r.frame.cpu().numpy().reshape(h, w).copy()
+
+    full, full_frame = render(0, 1)
+    assert full[..., :3].mean() > 0.01 and (full[..., 3] == 1.0).all()
+    owner = np.full((h, w), -1)
+    acc, frm = np.zeros_like(full), np.zeros_like(full_frame)
+    for g in range(world):
+        a, f = render(g, world)
+        mine = a[..., 3] == 1.0
+        assert (owner[mine] == -1).all(), "tiles of two GPUs overlap"
+        owner[mine] = g
+        assert (a[~mine] == 0).all() and (f[~mine] == 0).all(), "a rank wrote outside its tiles"
+        acc += a
+        frm += f
+    r.ctx.set_tile_partition(0, 1)
+    assert (owner >= 0).all(), "tiles do not cover the image"
+    # the reference's layout: pixel (x, y) belongs to GPU ((x / 8) - (y / 4)) mod world   (WorkDistribution.h:67-80)
+    yy, xx = np.mgrid[0:h, 0:w]
+    assert np.array_equal(owner, (xx // 8 - yy // 4) % world)
+    assert np.array_equal(acc.view(np.uint32), full.view(np.uint32)) and np.array_equal(frm, full_frame)
+    with pytest.raises(Exception):
+        r.ctx.set_tile_partition(2, 2)
