@@ -434,7 +434,11 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
         scene_name = "cornell-class medium scene %d triangles" % scene.n_triangles
     w, h = args.render_dim
     lanes = args.lanes
+    torch.cuda.synchronize()
+    t_up0 = time.perf_counter()
     lr_ = LaneRenderer(scene, w, h, lanes=lanes, device=local_rank, K=K, K_light=K_light, max_depth=max_depth)
+    torch.cuda.synchronize()
+    upload_s = time.perf_counter() - t_up0     # contexts + scene upload (host arrays -> device) + BVH build, all lanes
     r = lr_.lanes[0]
     lr_.seed_mapping(rank, world)
     comm_init(r.ctx, env)       # NCCL communicator of this rank (csrc/comm.cu), outside the timed preprocessing
@@ -461,7 +465,10 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     reduce_accum(r, env)
     e1.record(torch.cuda.current_stream())
     torch.cuda.synchronize()
-    mean = float(r.image().mean())
+    t_ro0 = time.perf_counter()
+    img = r.image()                            # merge of the lanes' running means + device -> host copy of the accumulation buffer
+    readout_s = time.perf_counter() - t_ro0
+    mean = float(img.mean())
     assert st["loss_last"] is not None and np.isfinite(st["loss_last"]) and np.isfinite(mean) and mean > 0, \
         "SPCBPT section: training or render produced no valid result (loss %r, image mean %r)" % (st["loss_last"], mean)
     out = {"workload": "SPCBPT_eye %dx%d, 1 spp per frame, K=%d (K_light %d), connections 3, %s, "
@@ -469,6 +476,15 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
            "samples_per_s": w * h * args.render_frames * world / dt_max, "ms_per_frame": dt_max / args.render_frames * 1e3, "frames": args.render_frames,
            "preprocess_s": pre_s, "train_paths": st["train_paths"], "loss_first": st["loss_first"], "loss_last": st["loss_last"],
            "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_s], "kernel_launches": int(launches), "accum_allreduce_ms": e0.elapsed_time(e1) if world > 1 else 0.0, "image_mean": mean}
+    # end to end through the public API, host data in, host image out: scene upload + BVH build, training, the timed frames, read-out
+    scene_bytes = int(sum(m["positions"].nbytes + m["indices"].nbytes + (m["texcoords"].nbytes if m.get("texcoords") is not None else 0) for m in scene.meshes)
+                      + scene.materials.nbytes + scene.lights.nbytes + sum(t.nbytes for t in scene.textures))
+    e2e_s = upload_s + pre_s + dt_max + readout_s
+    out["e2e"] = {"what": "host scene arrays -> %d contexts (upload + BVH build) -> training -> %d frames -> merged accumulation buffer on the host" % (lanes, args.render_frames),
+                  "upload_s": upload_s, "preprocess_s": pre_s, "render_s": dt_max, "readout_s": readout_s,
+                  "h2d_bytes": scene_bytes * lanes, "d2h_bytes": w * h * 12,
+                  "samples_per_s": w * h * args.render_frames * world / e2e_s,
+                  "samples_per_s_without_training": w * h * args.render_frames * world / (upload_s + dt_max + readout_s)}
     # the fast-arithmetic flavour of the same library (FMA contraction + hardware special functions in the shading kernels, as the
     # reference's own --use_fast_math build; csrc/shade.cuh SPC_FAST_MATH, tests/test_fast_flavour_gpu.py): same schedule, own training
     if not args.no_fast:

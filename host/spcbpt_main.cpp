@@ -573,7 +573,7 @@ int main(int argc, char** argv) {
 
         // ---- Scene::finalize(): context + upload + BVH ------------------------------------------------------------
         app.scene_ref = &app.scene;
-        double t_upload = 0;
+        double t_upload = 0, t_comm = 0;
         const double t_e2e0 = now_s();   // end-to-end clock: scene upload + BVH -> training -> frames -> accumulation buffer on the host
         app.create_and_upload(&t_upload);
         spc_bvh_stats bs;
@@ -598,7 +598,9 @@ int main(int argc, char** argv) {
                 }
                 if (!got) throw std::runtime_error("timed out waiting for the NCCL id in " + opt.id_file);
             }
+            const double tc0 = now_s();
             SPC_CHECK(spc_comm_init(app.ctx, opt.rank, opt.world, id));
+            t_comm = now_s() - tc0;   // NCCL bootstrap + communicator + warm-up collective: tens of seconds for 8 ranks on a cold node
         }
 
         app.init_launch_params();
@@ -706,10 +708,10 @@ int main(int argc, char** argv) {
         }
         const int sample_ranks = opt.tiles ? 1 : opt.world;   // tile partition: the ranks share the subframes instead of adding their own
         printf("{\"alg\": \"%s\", \"width\": %d, \"height\": %d, \"frames\": %d, \"ranks\": %d, \"triangles\": %zu, \"K\": %d, \"lanes\": %d, \"pipelined\": %s, \"render_s\": %.6f, \"ms_per_frame\": %.4f, "
-               "\"samples_per_s\": %.1f, \"kernel_launches\": %lld, \"train_paths\": %d, \"pretrace_s\": %.4f, \"trees_s\": %.4f, \"q_gamma_s\": %.4f, \"upload_s\": %.4f, \"e2e_s\": %.4f, "
+               "\"samples_per_s\": %.1f, \"kernel_launches\": %lld, \"train_paths\": %d, \"pretrace_s\": %.4f, \"trees_s\": %.4f, \"q_gamma_s\": %.4f, \"upload_s\": %.4f, \"comm_init_s\": %.4f, \"e2e_s\": %.4f, "
                "\"e2e_samples_per_s\": %.1f, \"h2d_bytes\": %zu, \"d2h_bytes\": %zu, \"image_mean\": %.9g}\n",
                opt.alg.c_str(), opt.width, opt.height, opt.frames, opt.world, app.scene.n_triangles(), opt.K, opt.lanes, app.main_stream ? "true" : "false", t_render, t_render / opt.frames * 1e3,
-               (double)P * opt.frames * sample_ranks / t_render, (long long)launches, app.train_paths, app.t_pretrace, app.t_trees, app.t_qgamma, t_upload, t_e2e,
+               (double)P * opt.frames * sample_ranks / t_render, (long long)launches, app.train_paths, app.t_pretrace, app.t_trees, app.t_qgamma, t_upload, t_comm, t_e2e,
                (double)P * opt.frames * sample_ranks / t_e2e, app.scene.upload_bytes(), P * 20, mean);
         for (auto& l : extra) spc_destroy(l->ctx);
         spc_destroy(app.ctx);
