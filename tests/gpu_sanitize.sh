@@ -12,3 +12,5 @@ for tool in memcheck racecheck; do
 done
 timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_trace_gpu.py -m gpu -q -x > gpurun_out/sanitize_memcheck_trace_tests.log 2>&1
 echo "memcheck trace tests exit $?: $(grep -E 'ERROR SUMMARY' gpurun_out/sanitize_memcheck_trace_tests.log | tail -1) $(grep -E 'passed|failed' gpurun_out/sanitize_memcheck_trace_tests.log | tail -1)"
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_pipeline_gpu.py -m gpu -q -x -k "tile_partition" > gpurun_out/sanitize_memcheck_tile_partition.log 2>&1
+echo "memcheck tile partition exit $?: $(grep -E 'ERROR SUMMARY' gpurun_out/sanitize_memcheck_tile_partition.log | tail -1) $(grep -E 'passed|failed' gpurun_out/sanitize_memcheck_tile_partition.log | tail -1)"
