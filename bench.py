@@ -474,7 +474,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     out = {"workload": "SPCBPT_eye %dx%d, 1 spp per frame, K=%d (K_light %d), connections 3, %s, "
                        "light trace 1000x100 paths per frame, %d frame lanes per GPU" % (w, h, K, K_light, scene_name, lanes),
            "samples_per_s": w * h * args.render_frames * world / dt_max, "ms_per_frame": dt_max / args.render_frames * 1e3, "frames": args.render_frames,
-           "preprocess_s": pre_s, "train_paths": st["train_paths"], "loss_first": st["loss_first"], "loss_last": st["loss_last"],
+           "preprocess_s": pre_s, "preprocess_phases_s": {k: st[k] for k in ("pretrace_s", "trees_s", "q_gamma_s")}, "train_paths": st["train_paths"], "loss_first": st["loss_first"], "loss_last": st["loss_last"],
            "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_s], "kernel_launches": int(launches), "accum_allreduce_ms": e0.elapsed_time(e1) if world > 1 else 0.0, "image_mean": mean}
     # end to end through the public API, host data in, host image out: scene upload + BVH build, training, the timed frames, read-out
     scene_bytes = int(sum(m["positions"].nbytes + m["indices"].nbytes + (m["texcoords"].nbytes if m.get("texcoords") is not None else 0) for m in scene.meshes)
@@ -511,6 +511,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
         reduce_accum(lf, env)
         out["fast_flavour"] = {"samples_per_s": w * h * args.render_frames * world / dtf, "ms_per_frame": dtf / args.render_frames * 1e3,
                                "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_f], "preprocess_s": pre_f,
+                               "preprocess_phases_s": {k: stf[k] for k in ("pretrace_s", "trees_s", "q_gamma_s")},
                                "loss_last": stf["loss_last"], "image_mean": float(lf.image().mean()),
                                "flags": "-fmad=true -prec-div=false -prec-sqrt=false -DSPC_FAST_MATH (render.cu, pt.cu, pretrace.cu); traversal / binning / training unchanged; "
                                         "light_trace_mode 1 (one lane per light path)"}

@@ -294,6 +294,7 @@ struct App {
             params.pre_tracer.iteration = rank + 1 - world;
             params.lt.launch_frame = rank + 1 - world;
         }
+        SPC_CHECK(spc_set_option(ctx, "train_reserve_paths", local_samples));   // size the training set once instead of doubling up to it
         double t0 = now_s();
         int current = 0;
         while (current < local_samples) {

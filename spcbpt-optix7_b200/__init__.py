@@ -120,6 +120,12 @@ def _load(path):
     if not os.path.exists(path):
         raise SpcError("%s is not built: run `python spcbpt-optix7_b200/build.py` "
                        "(there is no Python or CPU fallback)" % os.path.basename(path))
+    # One sequential pass over the file before mapping it: on a freshly provisioned box the library's 10 MB of device code are paged
+    # in on demand, kernel by kernel, at the first launch of each (CUDA loads modules lazily) -- seconds of scattered page faults that
+    # would land inside whatever phase happens to launch a kernel first (measured: 0.1 -> 1.7 s on the first tree build).
+    with open(path, "rb") as fh:
+        while fh.read(1 << 24):
+            pass
     L = ctypes.CDLL(path)
     vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
     L.spc_last_error.restype = ctypes.c_char_p

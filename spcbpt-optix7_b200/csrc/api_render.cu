@@ -124,6 +124,7 @@ static int64_t* option_slot(Context& c, const char* name, int64_t* lo, int64_t* 
         {"light_trace_mode", &c.opt[spc::OPT_LIGHT_TRACE_MODE], 0, 1},
         {"tail_threshold", &c.opt[spc::OPT_TAIL_THRESHOLD], -1, 1 << 30},
         {"sort_hits", &c.opt[spc::OPT_SORT_HITS], 0, 1},
+        {"train_reserve_paths", &c.opt[spc::OPT_TRAIN_RESERVE], 0, 1 << 30},
     };
     for (const Opt& o : table)
         if (!strcmp(o.name, name)) {

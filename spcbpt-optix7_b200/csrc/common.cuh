@@ -178,7 +178,7 @@ struct TrainBuffers {
 };
 
 // spc_set_option switches (include/spcbpt_b200.h documents each)
-enum Option { OPT_REFERENCE_SEARCH = 0, OPT_BLOCKING_SYNC, OPT_COUNT_CANONICAL, OPT_STAGE_TIMING, OPT_LIGHT_TRACE_MODE, OPT_TAIL_THRESHOLD, OPT_SORT_HITS, OPT_COUNT };
+enum Option { OPT_REFERENCE_SEARCH = 0, OPT_BLOCKING_SYNC, OPT_COUNT_CANONICAL, OPT_STAGE_TIMING, OPT_LIGHT_TRACE_MODE, OPT_TAIL_THRESHOLD, OPT_SORT_HITS, OPT_TRAIN_RESERVE, OPT_COUNT };
 
 struct Context {
     int           device = 0;

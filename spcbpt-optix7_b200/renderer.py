@@ -91,6 +91,7 @@ class Renderer:
             self.pretrace_stride, self.lt_stride = plan["iteration_stride"], plan["lt_frame_stride"]
             pt["iteration"] = plan["first_iteration"] - self.pretrace_stride
             lt["launch_frame"] = plan["first_lt_frame"] - self.lt_stride
+        ctx.set_option("train_reserve_paths", int(local_samples))   # size the training set once instead of doubling up to it
         t0 = time.perf_counter()
         n = 0
         while n < local_samples:
