@@ -77,7 +77,7 @@ class Renderer:
 
     # ---- preprocessing() (optixPathTracer.cpp:552-608) -----------------------------------------
     def preprocessing(self, target_samples=2000000, target_Q_samples=2000000, tree_samples=100000, batch_size=20000, epochs=1, lr=0.01,
-                      plan=None, verbose=False):
+                      plan=None, verbose=False, adam=True):
         """the subspace-training schedule.  Multi-GPU: `plan` = parallel.shard_plan(...) and the context has a communicator
         (parallel.comm_init): this rank traces its shard of the training paths and of the Q launches, the library all-reduces
         the statistics (csrc/comm.cu), rank 0 builds the trees."""
@@ -129,7 +129,9 @@ class Renderer:
             n_train = int(ctx.comm_allreduce_host(np.array([n_train], np.int32), "min")[0])
         ctx.build_optimal_E_train_data(n_train)
         g_dev = ctx.preprocess_getGamma()
-        g_dev, loss = ctx.train_optimal_E(local_batch, epochs, lr)
+        loss = np.zeros(0, np.float32)
+        if adam:    # (adam=False keeps the row-normalised histogram Gamma: the study in tests/quick_adam_vs_histogram.py)
+            g_dev, loss = ctx.train_optimal_E(local_batch, epochs, lr)
         si["Q"] = q_dev
         self.gamma_dev = g_dev
         si["CMFGamma"] = ctx.Gamma2CMFGamma(g_dev)
