@@ -455,11 +455,21 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     # three timed segments of `render_frames` frames each; the figure reported is the MEDIAN segment (the GPU boxes are VMs: an
     # occasional host hiccup stretches one segment by tens of per cent, tests/quick_variance.sh), all three are listed
     dt, seg_s, launches = time_lane_frames(lr_, args.render_frames, torch, env)
+    # the same library with the parallel light tracer (light_trace_mode 1: per-path RNG streams instead of the reference's coupled
+    # per-core streams -- same estimator, not bit-comparable with the reference's light paths), timed the same way
+    for lane in lr_.lanes:
+        lane.ctx.set_option("light_trace_mode", 1)
+    lr_.render(2 * lanes)
+    torch.cuda.synchronize()
+    env.barrier()
+    dt_lt1, seg_lt1, _ = time_lane_frames(lr_, args.render_frames, torch, env)
+    for lane in lr_.lanes:
+        lane.ctx.set_option("light_trace_mode", 0)
     r = lr_
-    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([dt, dt_lt1], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt_max = float(tt.item())
+    dt_max, dt_lt1 = float(tt[0].item()), float(tt[1].item())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(torch.cuda.current_stream())
     reduce_accum(r, env)
@@ -475,7 +485,9 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
                        "light trace 1000x100 paths per frame, %d frame lanes per GPU" % (w, h, K, K_light, scene_name, lanes),
            "samples_per_s": w * h * args.render_frames * world / dt_max, "ms_per_frame": dt_max / args.render_frames * 1e3, "frames": args.render_frames,
            "preprocess_s": pre_s, "preprocess_phases_s": {k: st[k] for k in ("pretrace_s", "trees_s", "q_gamma_s")}, "train_paths": st["train_paths"], "loss_first": st["loss_first"], "loss_last": st["loss_last"],
-           "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_s], "kernel_launches": int(launches), "accum_allreduce_ms": e0.elapsed_time(e1) if world > 1 else 0.0, "image_mean": mean}
+           "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_s], "kernel_launches": int(launches), "accum_allreduce_ms": e0.elapsed_time(e1) if world > 1 else 0.0, "image_mean": mean,
+           "exact_flavour_parallel_light_tracer": {"samples_per_s": w * h * args.render_frames * world / dt_lt1, "ms_per_frame": dt_lt1 / args.render_frames * 1e3,
+                                                   "segments_ms_per_frame": [x / args.render_frames * 1e3 for x in seg_lt1]}}
     # end to end through the public API, host data in, host image out: scene upload + BVH build, training, the timed frames, read-out
     scene_bytes = int(sum(m["positions"].nbytes + m["indices"].nbytes + (m["texcoords"].nbytes if m.get("texcoords") is not None else 0) for m in scene.meshes)
                       + scene.materials.nbytes + scene.lights.nbytes + sum(t.nbytes for t in scene.textures))
