@@ -236,23 +236,43 @@ __global__ void __launch_bounds__(kLtPathBlock) k_light_trace_paths(const DevFra
         }
     }
 }
-// exclusive scan of the per-path vertex counts (one block; 10^5 paths) and the validity flags of the unused tail
-__global__ void k_lt_scan(const int* __restrict__ counts, int n, int* __restrict__ offsets, int* __restrict__ total) {
-    __shared__ int s_part[1024];
-    const int per = (n + 1023) / 1024;
-    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
-    int sum = 0;
-    for (int i = lo; i < hi; i++) sum += counts[i];
-    s_part[threadIdx.x] = sum;
+// exclusive scan of the per-path vertex counts (one block; 10^5 paths): tiles of 1024 counts, coalesced, warp-shuffle scan per tile
+// with a running carry (a strided per-thread serial walk of ~100 counts plus a serial pass over 1024 partials took 100 us)
+__global__ void __launch_bounds__(1024) k_lt_scan(const int* __restrict__ counts, int n, int* __restrict__ offsets, int* __restrict__ total) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int i = 0; i < 1024; i++) { const int v = s_part[i]; s_part[i] = run; run += v; }
-        *total = run;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        const int v = i < n ? counts[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_warp[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;   // exclusive prefix of the warp sums
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (i < n) offsets[i] = carry + s_warp[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + incl;
+        __syncthreads();
     }
-    __syncthreads();
-    int run = s_part[threadIdx.x];
-    for (int i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
+    if (threadIdx.x == 0) *total = s_carry;
 }
 // dense LVC: path p's vertices go to slots offsets[p].. in path order (one warp per path, 15 x 64-bit words per vertex)
 __global__ void k_lt_compact(const spc_vertex* __restrict__ scratch, int stride, const int* __restrict__ counts, const int* __restrict__ offsets, int n_paths, int n_slots,
