@@ -36,7 +36,7 @@ def _centroids(sc, cap=20000, seed=0):
     return P, N
 
 
-def _chain_vs_oracle(pkg, orc, sc, K, KL, w, h, cfg, subframes, max_bad, seed):
+def _chain_vs_oracle(pkg, orc, sc, K, KL, w, h, cfg, subframes, max_bad, seed, max_depth=0):
     """light trace -> LVC_Process -> eye pass on GPU and oracle; returns (first_prim, first_label, accum) of the last subframe"""
     import torch
     P, N = _centroids(sc)
@@ -49,6 +49,7 @@ def _chain_vs_oracle(pkg, orc, sc, K, KL, w, h, cfg, subframes, max_bad, seed):
     df.P["subspace_info"]["eye_tree"] = ctx.tree_to_device(True, eye_tree)
     df.P["subspace_info"]["light_tree"] = ctx.tree_to_device(False, light_tree)
     hf.set_trees(eye_tree, light_tree)
+    df.P["max_depth"] = hf.P["max_depth"] = max_depth      # MyParams::max_depth (0: the reference's literal 50)
     df.set_q_gamma(Q, cmf)   # a caller-made CDF: searched with the reference's bisect (guide tables exist only for tables the library built)
     hf.set_q_gamma(Q, cmf)
     osc = orc.Scene(pkg, sc)
@@ -66,10 +67,10 @@ def _chain_vs_oracle(pkg, orc, sc, K, KL, w, h, cfg, subframes, max_bad, seed):
         ctx.set_params(df.P)
         ctx.launch(pkg.LAUNCH_SPCBPT_EYE, w, h)
         ctx.synchronize()
-        orc.light_trace(osc, hf.P, K, threads=8)
+        orc.light_trace(osc, hf.P, K, max_depth=max_depth, threads=8)
         sub, cmfs, jump, vc, pc = orc.lvc_process(pkg, hf.lvc, hf.valid, K)
         hf.set_sampler(sub, cmfs, jump, vc, pc)
-        ofp, ofl = orc.eye_pass(osc, hf.P, K, 3, 0, threads=8, want_first=True)
+        ofp, ofl = orc.eye_pass(osc, hf.P, K, 3, max_depth, threads=8, want_first=True)
         lvc, valid = df.lvc_host()
         badv = compare_lvc(pkg, lvc, valid, hf.lvc, hf.valid, exact=True)
         assert not badv, "subframe %d LVC: %s" % (sf, badv)
@@ -125,6 +126,17 @@ def test_house_scene_low_res_bit_exact(gpu_ctx, orc):
     fp, fl, acc, vc = _chain_vs_oracle(pkg, orc, sc, 1000, 200, 320, 180, cfg, (0, 1), 4, seed=6)
     assert (fp >= 0).mean() > 0.9 and len(np.unique(fl[fl >= 0])) > 50 and vc > 30000
     assert np.isfinite(acc).all() and acc[:, :3].mean() > 0.05
+
+
+def test_config5_class_glossy_many_emitters_depth12_bit_exact(gpu_ctx, orc):
+    """BASELINE.json configs[4] in miniature: the large-scene generator at 96 x 96 quads (18 432 terrain triangles, rough-metal and
+    glossy materials, 16 quad emitters with one subspace each), max depth 12, K = 80 with 16 emitter subspaces"""
+    pkg = gpu_ctx
+    sc = pkg.scenes.large_scene(96, 4)
+    assert sc.lights.shape[0] == 16
+    cfg = dict(num_core=64, core_padding=400, M_per_core=40)
+    fp, fl, acc, vc = _chain_vs_oracle(pkg, orc, sc, 80, 16, 256, 144, cfg, (0, 1), 4, seed=12, max_depth=12)
+    assert (fp >= 0).mean() > 0.9 and vc > 3000 and np.isfinite(acc).all() and acc[:, :3].mean() > 1e-3
 
 
 def test_config2_heightfield_bench_ray_sets_vs_oracle(gpu_ctx, orc):
