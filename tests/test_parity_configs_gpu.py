@@ -139,6 +139,17 @@ def test_config5_class_glossy_many_emitters_depth12_bit_exact(gpu_ctx, orc):
     assert (fp >= 0).mean() > 0.9 and vc > 3000 and np.isfinite(acc).all() and acc[:, :3].mean() > 1e-3
 
 
+@pytest.mark.parametrize("dim", [(1, 1), (7, 5), (33, 1), (1, 40)])
+def test_tiny_and_odd_image_sizes_bit_exact(gpu_ctx, orc, dim):
+    """edge sizes of the launch (a single pixel, fewer pixels than a warp, one row, one column): queues, compaction and the tail kernel
+    at their boundaries"""
+    pkg = gpu_ctx
+    sc = pkg.scenes.cornell_scene(wall_cells=6, box_cells=4)
+    cfg = dict(num_core=16, core_padding=120, M_per_core=20)
+    fp, fl, acc, vc = _chain_vs_oracle(pkg, orc, sc, 64, 12, dim[0], dim[1], cfg, (0, 1, 2), 0, seed=3)
+    assert fp.shape[0] == dim[0] * dim[1] and np.isfinite(acc).all()
+
+
 def test_config2_heightfield_bench_ray_sets_vs_oracle(gpu_ctx, orc):
     """BASELINE.json configs[1]: the bench's own three ray sets on the 1 M-triangle height field, 2^18-ray sample each:
     prim ids, t/u/v bits and visibility against the oracle (bench.py repeats this on the full 2^24-ray sets)"""
