@@ -123,8 +123,11 @@ extern "C" {
 ORC_API void orc_set_jitter_rtl(int v) { g_jitter_rtl = v; }
 
 // optixLaunch of "light trace" (optixPathTracer.cpp:491-514): one sequential core per launch index
-ORC_API void orc_light_trace(void* sc, const spc_params* p, int K, int max_depth, int threads) {
-    const Frame fr = make_frame(sc, p, K, 3, max_depth);
+// (connections = CONNECTION_N, optixPathTracer.h:33: the light sub-path's MIS recursion multiplies by it, cuProg.h:70-78)
+ORC_API void orc_light_trace_c(void* sc, const spc_params* p, int K, int connections, int max_depth, int threads);
+ORC_API void orc_light_trace(void* sc, const spc_params* p, int K, int max_depth, int threads) { orc_light_trace_c(sc, p, K, 3, max_depth, threads); }
+ORC_API void orc_light_trace_c(void* sc, const spc_params* p, int K, int connections, int max_depth, int threads) {
+    const Frame fr = make_frame(sc, p, K, connections, max_depth);
     std::atomic<int> next(0);
     auto worker = [&]() {
         for (;;) {

@@ -111,6 +111,8 @@ def _bind_render(L):
     vp, i32 = ctypes.c_void_p, ctypes.c_int
     L.orc_light_trace.argtypes = [vp, vp, i32, i32, i32]
     L.orc_light_trace.restype = None
+    L.orc_light_trace_c.argtypes = [vp, vp, i32, i32, i32, i32]
+    L.orc_light_trace_c.restype = None
     L.orc_lvc_process.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.orc_lvc_process.restype = None
     L.orc_eye_pass.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
@@ -123,9 +125,9 @@ def _bind_render(L):
     L.orc_connect.restype = None
 
 
-def light_trace(scene, params, K, max_depth=0, threads=8):
+def light_trace(scene, params, K, max_depth=0, threads=8, connections=3):
     L = lib(); _bind_render(L)
-    L.orc_light_trace(scene.h, params.ctypes.data, K, max_depth, threads)
+    L.orc_light_trace_c(scene.h, params.ctypes.data, K, connections, max_depth, threads)
 
 
 def lvc_process(pkg, lvc, valid, K):

@@ -36,13 +36,15 @@ def _centroids(sc, cap=20000, seed=0):
     return P, N
 
 
-def _chain_vs_oracle(pkg, orc, sc, K, KL, w, h, cfg, subframes, max_bad, seed, max_depth=0):
+def _chain_vs_oracle(pkg, orc, sc, K, KL, w, h, cfg, subframes, max_bad, seed, max_depth=0, connections=3, options=()):
     """light trace -> LVC_Process -> eye pass on GPU and oracle; returns (first_prim, first_label, accum) of the last subframe"""
     import torch
     P, N = _centroids(sc)
     eye_tree, light_tree, Q, cmf = random_trees_and_gamma(pkg, P, N, K, KL, lambda p, s, k, b: p.build_tree(s, k, b), seed=seed)
-    ctx = pkg.Context(0, K=K, K_light=KL, connections=3)
+    ctx = pkg.Context(0, K=K, K_light=KL, connections=connections)
     ctx.upload_scene(sc)
+    for name, value in options:
+        ctx.set_option(name, value)
     df = DeviceFrame(pkg, sc, w, h, K=K, **cfg)
     hf = HostFrame(pkg, sc, w, h, K=K, **cfg)
     # trees go through spc_tree_to_device (compact copies, cross labels): the production path of the eye pass
@@ -67,10 +69,10 @@ def _chain_vs_oracle(pkg, orc, sc, K, KL, w, h, cfg, subframes, max_bad, seed, m
         ctx.set_params(df.P)
         ctx.launch(pkg.LAUNCH_SPCBPT_EYE, w, h)
         ctx.synchronize()
-        orc.light_trace(osc, hf.P, K, max_depth=max_depth, threads=8)
+        orc.light_trace(osc, hf.P, K, max_depth=max_depth, threads=8, connections=connections)
         sub, cmfs, jump, vc, pc = orc.lvc_process(pkg, hf.lvc, hf.valid, K)
         hf.set_sampler(sub, cmfs, jump, vc, pc)
-        ofp, ofl = orc.eye_pass(osc, hf.P, K, 3, max_depth, threads=8, want_first=True)
+        ofp, ofl = orc.eye_pass(osc, hf.P, K, connections, max_depth, threads=8, want_first=True)
         lvc, valid = df.lvc_host()
         badv = compare_lvc(pkg, lvc, valid, hf.lvc, hf.valid, exact=True)
         assert not badv, "subframe %d LVC: %s" % (sf, badv)
@@ -137,6 +139,27 @@ def test_config5_class_glossy_many_emitters_depth12_bit_exact(gpu_ctx, orc):
     cfg = dict(num_core=64, core_padding=400, M_per_core=40)
     fp, fl, acc, vc = _chain_vs_oracle(pkg, orc, sc, 80, 16, 256, 144, cfg, (0, 1), 4, seed=12, max_depth=12)
     assert (fp >= 0).mean() > 0.9 and vc > 3000 and np.isfinite(acc).all() and acc[:, :3].mean() > 1e-3
+
+
+@pytest.mark.parametrize("connections,options", [(1, ()), (2, ()), (4, ()), (6, ()), (6, (("tail_threshold", 1 << 30),)), (2, (("tail_threshold", -1),))])
+def test_other_connection_counts_bit_exact(gpu_ctx, orc, connections, options):
+    """CONNECTION_N is a runtime value here (optixPathTracer.h:33 fixes it at 3): the specialised kernels for 1, 2 and 4 connections and
+    the generic ones (> 4), through the wavefront stages and through the tail kernel"""
+    pkg = gpu_ctx
+    sc = pkg.scenes.cornell_scene(wall_cells=6, box_cells=4)
+    cfg = dict(num_core=32, core_padding=160, M_per_core=30)
+    fp, fl, acc, vc = _chain_vs_oracle(pkg, orc, sc, 64, 12, 96, 64, cfg, (0, 1), 2, seed=5, connections=connections, options=options)
+    assert np.isfinite(acc).all() and acc[:, :3].mean() > 0.01
+
+
+def test_light_vertex_cache_overflow_bit_exact(gpu_ctx, orc):
+    """a core whose window of `core_padding` slots fills up before its M_per_core paths are traced (raygen.cu:640-684: the path in flight
+    is cut, the remaining paths are skipped): same LVC, same sampler, same frames"""
+    pkg = gpu_ctx
+    sc = pkg.scenes.cornell_scene(wall_cells=6, box_cells=4)
+    cfg = dict(num_core=24, core_padding=24, M_per_core=20)
+    fp, fl, acc, vc = _chain_vs_oracle(pkg, orc, sc, 64, 12, 64, 48, cfg, (0, 1), 2, seed=8)
+    assert vc > 24 * 20 and np.isfinite(acc).all()      # the windows are (nearly) full
 
 
 @pytest.mark.parametrize("dim", [(1, 1), (7, 5), (33, 1), (1, 40)])
