@@ -443,8 +443,15 @@ struct App {
     int          lane = 0, n_lanes = 1, lt_base = 0;
     cudaStream_t lane_stream = nullptr;
 
-    void create_and_upload(double* upload_s) {
+    // `owner`: a context on the same device that already holds the scene (frame lanes share lane 0's: spc_scene_share)
+    void create_and_upload(double* upload_s, spc_context* owner = nullptr) {
         SPC_CHECK(spc_create(opt.device, opt.K, opt.K_light, opt.connections, &ctx));
+        if (owner) {
+            SPC_CHECK(spc_scene_share(ctx, owner));
+            for (const auto& kv : opt.options) SPC_CHECK(spc_set_option(ctx, kv.first.c_str(), kv.second));
+            if (opt.tiles && opt.world > 1) SPC_CHECK(spc_set_tile_partition(ctx, opt.rank, opt.world));
+            return;
+        }
         std::vector<spc_mesh> meshes;
         std::vector<spc_texture> textures;
         scene_ref->abi_views(meshes, textures);
@@ -628,7 +635,7 @@ int main(int argc, char** argv) {
                 App& l = *extra.back();
                 l.opt = opt;
                 l.scene_ref = &app.scene;
-                l.create_and_upload(nullptr);
+                l.create_and_upload(nullptr, app.ctx);
                 l.init_launch_params();
                 lanes.push_back(&l);
             }

@@ -350,6 +350,10 @@ SPC_API int  spc_scene_upload(spc_context* ctx,
                               const spc_pbr* materials, int n_materials,
                               const spc_light* lights, int n_lights,
                               const spc_texture* textures, int n_textures);
+/* A second context on the same device uses `owner`'s uploaded scene (geometry, materials, lights, textures, BVH: all read-only after the
+ * upload) instead of holding a copy: frame lanes (host/spcbpt_main.cpp --lanes) need one replica per GPU, not one per lane.  No counterpart
+ * in the reference (one context, one scene).  `owner` must outlive `ctx` and keep its scene while `ctx` renders. */
+SPC_API int  spc_scene_share(spc_context* ctx, spc_context* owner);
 SPC_API int  spc_bvh_stats_get(spc_context* ctx, spc_bvh_stats* out);
 
 /* -------------------------------- wavefront ray batches ------------------------------------ */

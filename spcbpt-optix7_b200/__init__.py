@@ -178,6 +178,7 @@ def _bind_optional(L):
         "spc_set_seed_mapping": [vp, ctypes.c_uint32, ctypes.c_uint32],
         "spc_set_trace_blocks": [vp, i32],
         "spc_set_tile_partition": [vp, i32, i32],
+        "spc_scene_share": [vp, vp],
         "spc_merge_accum": [vp, vp, vp, i32, i32, vp, vp],
         "spc_lvc_process": [vp, vp, vp, i32, vp],
         "spc_build_tree": [vp, i32, i32, i32, vp, i32, vp],
@@ -316,6 +317,11 @@ class Context:
                                           lights.ctypes.data, len(lights), textures.ctypes.data, ntex),
                  "spc_scene_upload")
         del keep
+
+    def share_scene(self, owner):
+        """use `owner`'s uploaded scene and BVH (same device) instead of a copy: spc_scene_share"""
+        self._ck(self._L.spc_scene_share(self.h, owner.h), "spc_scene_share")
+        self._scene_owner = owner      # keeps the owner alive as long as this context
 
     def bvh_stats(self):
         s = np.zeros(1, BVH_STATS)

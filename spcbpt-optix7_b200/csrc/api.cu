@@ -228,6 +228,40 @@ int spc_scene_upload(spc_context* ctx, const spc_mesh* meshes, int n_meshes, con
     SPC_API_END
 }
 
+// Frame lanes on one GPU (and any other set of contexts on the same device) need ONE copy of the scene: the geometry, material, light
+// and texture arrays and the BVH are read-only after the upload.  `ctx` becomes a second user of `owner`'s scene: no host staging, no
+// copies, no second BVH build -- and one copy of the BVH in L2 instead of one per lane.  `owner` must outlive `ctx` (or `ctx` must
+// upload / share another scene first) and must not upload a new scene while `ctx` renders.
+int spc_scene_share(spc_context* ctx, spc_context* owner) {
+    SPC_API_BEGIN
+    SPC_REQUIRE(owner && owner != ctx, SPC_ERR_INVALID, "spc_scene_share: no owner context");
+    const Context& o = owner->c;
+    SPC_REQUIRE(o.has_scene, SPC_ERR_NO_SCENE, "spc_scene_share: the owner has no scene");
+    SPC_REQUIRE(o.device == c.device, SPC_ERR_INVALID, "spc_scene_share: contexts live on devices %d and %d", o.device, c.device);
+    SPC_CUDA(cudaStreamSynchronize(c.stream));   // nothing of this context may still read the buffers it is about to drop
+    c.bvh.nodes.borrow(o.bvh.nodes);
+    c.bvh.tris.borrow(o.bvh.tris);
+    c.bvh.n_nodes = o.bvh.n_nodes;
+    c.bvh.n_tris = o.bvh.n_tris;
+    c.bvh_stats = o.bvh_stats;
+    spc::SceneGeom& g = c.geom;
+    const spc::SceneGeom& og = o.geom;
+    g.tri_pos.borrow(og.tri_pos);
+    g.tri_uv.borrow(og.tri_uv);
+    g.materials.borrow(og.materials);
+    g.mat_log_cc.borrow(og.mat_log_cc);
+    g.lights.borrow(og.lights);
+    g.tex_data.borrow(og.tex_data);
+    g.tex_desc.borrow(og.tex_desc);
+    g.n_prims = og.n_prims;
+    g.n_materials = og.n_materials;
+    g.n_lights = og.n_lights;
+    g.n_textures = og.n_textures;
+    for (int a = 0; a < 3; a++) { g.scene_lo[a] = og.scene_lo[a]; g.scene_hi[a] = og.scene_hi[a]; }
+    c.has_scene = true;
+    SPC_API_END
+}
+
 int spc_bvh_stats_get(spc_context* ctx, spc_bvh_stats* out) {
     SPC_API_BEGIN
     SPC_REQUIRE(out, SPC_ERR_INVALID, "spc_bvh_stats_get: out is null");

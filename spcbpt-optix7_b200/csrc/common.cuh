@@ -48,21 +48,29 @@ template <typename T>
 struct DevBuf {
     T*     p = nullptr;
     size_t n = 0;
+    bool   owned = true;   // false: a view of another context's buffer (spc_scene_share), never freed or reused for new contents here
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         n = 0;
+        owned = true;
     }
     void alloc(size_t count) {
-        if (count <= n && p) return;
+        if (count <= n && p && owned) return;
         release();
         if (count == 0) count = 1;
         SPC_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
         n = count;
+    }
+    void borrow(const DevBuf& o) {
+        release();
+        p = o.p;
+        n = o.n;
+        owned = false;
     }
     size_t bytes() const { return n * sizeof(T); }
 };

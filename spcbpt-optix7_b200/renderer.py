@@ -13,7 +13,8 @@ from . import (LAUNCH_LIGHT_TRACE, LAUNCH_PRETRACE, LAUNCH_PT, LAUNCH_SPCBPT_EYE
 
 class Renderer:
     def __init__(self, scene, width, height, device=0, K=1000, K_light=0, connections=3, max_depth=0,
-                 lt_num_core=1000, lt_core_padding=800, lt_M_per_core=100, pretrace_num_core=10000, pretrace_padding=10, stream=None, fast=False):
+                 lt_num_core=1000, lt_core_padding=800, lt_M_per_core=100, pretrace_num_core=10000, pretrace_padding=10, stream=None, fast=False,
+                 scene_owner=None):
         import torch
         self.torch = torch
         self.scene, self.w, self.h = scene, width, height
@@ -22,7 +23,10 @@ class Renderer:
         self.ctx = Context(device, K=K, K_light=self.K_light, connections=connections, fast=fast)   # fast: the fast-arithmetic flavour
         if stream is not None:
             self.ctx.set_stream(stream)
-        self.ctx.upload_scene(scene)
+        if scene_owner is not None:     # another context on this device already holds the scene: one replica per GPU (spc_scene_share)
+            self.ctx.share_scene(scene_owner)
+        else:
+            self.ctx.upload_scene(scene)
         dev = torch.device("cuda", device)
         self.dev = dev
         P = np.zeros(1, PARAMS)
@@ -278,7 +282,9 @@ class LaneRenderer:
         import torch
         self.torch = torch
         self.w, self.h, self.n_lanes = width, height, lanes
-        self.lanes = [Renderer(scene, width, height, device=device, **kw) for _ in range(lanes)]
+        self.lanes = [Renderer(scene, width, height, device=device, **kw)]
+        for _ in range(1, lanes):       # the other lanes read lane 0's scene and BVH: one replica per GPU
+            self.lanes.append(Renderer(scene, width, height, device=device, scene_owner=self.lanes[0].ctx, **kw))
         with torch.cuda.device(device):
             self.streams = [torch.cuda.Stream() for _ in range(lanes)]
         for k, (r, s) in enumerate(zip(self.lanes, self.streams)):

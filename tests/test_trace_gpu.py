@@ -182,6 +182,30 @@ def test_device_pointer_path_matches_host_path(cornell):
     ctx.set_stream(0)
 
 
+def test_scene_share_gives_the_owner_s_results(cornell):
+    """spc_scene_share: a second context on the device traces through the first one's BVH (no copy), same hits; bad owners are refused"""
+    pkg, sc, ctx, orc_sc = cornell
+    other = pkg.Context(0, K=64, K_light=12)
+    other.share_scene(ctx)
+    assert other.bvh_stats() == ctx.bvh_stats()
+    rays = pkg.scenes.camera_rays(sc, 96, 64)
+    a, b = ctx.trace(rays), other.trace(rays)
+    for k in ("prim", "t", "u", "v"):
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    assert np.array_equal(ctx.occlusion(rays), other.occlusion(rays))
+    empty = pkg.Context(0, K=64, K_light=12)
+    with pytest.raises(pkg.SpcError):
+        other.share_scene(empty)          # the owner has no scene
+    with pytest.raises(pkg.SpcError):
+        other.share_scene(other)          # not itself
+    # a borrower that uploads its own scene afterwards stops borrowing (and does not write into the owner's buffers)
+    other.upload_scene(pkg.scenes.cornell_scene(wall_cells=2, box_cells=2))
+    assert other.bvh_stats()["n_triangles"] != ctx.bvh_stats()["n_triangles"]
+    c = ctx.trace(rays)
+    assert np.array_equal(a["prim"], c["prim"])
+    other.close(); empty.close()
+
+
 def test_error_paths(gpu_ctx):
     pkg = gpu_ctx
     ctx = pkg.Context(0)
