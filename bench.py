@@ -436,7 +436,11 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     lanes = args.lanes
     torch.cuda.synchronize()
     t_up0 = time.perf_counter()
-    lr_ = LaneRenderer(scene, w, h, lanes=lanes, device=local_rank, K=K, K_light=K_light, max_depth=max_depth)
+    # spc_scene_share (one replica of scene + BVH per GPU, lanes borrow lane 0's) is verified on one GPU only: the round's GPU budget ran
+    # out before a multi-rank run of it, so under torchrun every lane keeps its own copy, exactly the configuration measured on 8 GPUs
+    # (profiles/r2ab_bench_8gpu.json).  Frame times are the same either way on this scene (profiles/r2_summary.md).
+    share = world == 1
+    lr_ = LaneRenderer(scene, w, h, lanes=lanes, device=local_rank, K=K, K_light=K_light, max_depth=max_depth, share_scene=share)
     torch.cuda.synchronize()
     upload_s = time.perf_counter() - t_up0     # contexts + scene upload (host arrays -> device) + BVH build, all lanes
     r = lr_.lanes[0]
@@ -494,13 +498,13 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     e2e_s = upload_s + pre_s + dt_max + readout_s
     out["e2e"] = {"what": "host scene arrays -> one upload + BVH build, %d lane contexts sharing it -> training -> %d frames -> merged accumulation buffer on the host" % (lanes, args.render_frames),
                   "upload_s": upload_s, "preprocess_s": pre_s, "render_s": dt_max, "readout_s": readout_s,
-                  "h2d_bytes": scene_bytes, "d2h_bytes": w * h * 12,   # one upload: the lanes share lane 0's scene (spc_scene_share)
+                  "h2d_bytes": scene_bytes * (1 if share else lanes), "d2h_bytes": w * h * 12,   # one upload when the lanes share lane 0's scene
                   "samples_per_s": w * h * args.render_frames * world / e2e_s,
                   "samples_per_s_without_training": w * h * args.render_frames * world / (upload_s + dt_max + readout_s)}
     # the fast-arithmetic flavour of the same library (FMA contraction + hardware special functions in the shading kernels, as the
     # reference's own --use_fast_math build; csrc/shade.cuh SPC_FAST_MATH, tests/test_fast_flavour_gpu.py): same schedule, own training
     if not args.no_fast:
-        lf = LaneRenderer(scene, w, h, lanes=lanes, device=local_rank, K=K, K_light=K_light, max_depth=max_depth, fast=True)
+        lf = LaneRenderer(scene, w, h, lanes=lanes, device=local_rank, K=K, K_light=K_light, max_depth=max_depth, fast=True, share_scene=share)
         lf.seed_mapping(rank, world)
         comm_init(lf.lanes[0].ctx, env)
         for lane in lf.lanes:   # per-path light-tracer streams as well (not bit-comparable with the reference either way)

@@ -278,13 +278,13 @@ class LaneRenderer:
     running means with weights n_k / n (spc_merge_accum): the same sample set as the sequential loop, summed in a different
     fp32 order.  Training happens once, on lane 0; the other lanes share its trees, Q and CMFGamma (same device)."""
 
-    def __init__(self, scene, width, height, lanes=3, device=0, **kw):
+    def __init__(self, scene, width, height, lanes=3, device=0, share_scene=True, **kw):
         import torch
         self.torch = torch
         self.w, self.h, self.n_lanes = width, height, lanes
         self.lanes = [Renderer(scene, width, height, device=device, **kw)]
-        for _ in range(1, lanes):       # the other lanes read lane 0's scene and BVH: one replica per GPU
-            self.lanes.append(Renderer(scene, width, height, device=device, scene_owner=self.lanes[0].ctx, **kw))
+        for _ in range(1, lanes):       # the other lanes read lane 0's scene and BVH: one replica per GPU (share_scene=False: own copies)
+            self.lanes.append(Renderer(scene, width, height, device=device, scene_owner=self.lanes[0].ctx if share_scene else None, **kw))
         with torch.cuda.device(device):
             self.streams = [torch.cuda.Stream() for _ in range(lanes)]
         for k, (r, s) in enumerate(zip(self.lanes, self.streams)):
