@@ -626,8 +626,14 @@ def main():
     ap.add_argument("--equal-time-seconds", type=float, default=1.5)
     ap.add_argument("--gt-spp", type=int, default=4096, help="ground-truth samples per pixel (pt) of the equal-time block")
     ap.add_argument("--lanes", type=int, default=4, help="frame lanes per GPU in the SPCBPT section (contexts rendering alternate subframes)")
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("SPC_BENCH_WATCHDOG_S", "1500")),
+                    help="seconds after which a run that is still going dumps every thread's stack to stderr and exits (0 = off): a hang -- "
+                         "a rank stuck in a collective, a lost GPU -- then costs a bounded time and says where it stood")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -746,7 +752,15 @@ def main():
 
     spcbpt = None
     if not args.no_render:
-        spcbpt = render_section(args, pkg, torch, dist if world > 1 else None, rank, local_rank, world, scene if large else None)
+        if world > 1:   # (ranks meet in collectives inside: a rank that swallowed its own exception would leave the others waiting)
+            spcbpt = render_section(args, pkg, torch, dist, rank, local_rank, world, scene if large else None)
+        else:
+            try:
+                spcbpt = render_section(args, pkg, torch, None, rank, local_rank, world, scene if large else None)
+            except Exception as ex:   # the headline line (traversal metric, roofline, parity) must not be lost to the extra section
+                import traceback
+                traceback.print_exc()
+                spcbpt = {"error": repr(ex)}
 
     if rank == 0:
         peak, peak_src = hbm_peak()
