@@ -496,7 +496,8 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     scene_bytes = int(sum(m["positions"].nbytes + m["indices"].nbytes + (m["texcoords"].nbytes if m.get("texcoords") is not None else 0) for m in scene.meshes)
                       + scene.materials.nbytes + scene.lights.nbytes + sum(t.nbytes for t in scene.textures))
     e2e_s = upload_s + pre_s + dt_max + readout_s
-    out["e2e"] = {"what": "host scene arrays -> one upload + BVH build, %d lane contexts sharing it -> training -> %d frames -> merged accumulation buffer on the host" % (lanes, args.render_frames),
+    out["e2e"] = {"what": "host scene arrays -> %s, %d lane contexts -> training -> %d frames -> merged accumulation buffer on the host" % (
+                      "one upload + BVH build shared by the lanes" if share else "one upload + BVH build per lane", lanes, args.render_frames),
                   "upload_s": upload_s, "preprocess_s": pre_s, "render_s": dt_max, "readout_s": readout_s,
                   "h2d_bytes": scene_bytes * (1 if share else lanes), "d2h_bytes": w * h * 12,   # one upload when the lanes share lane 0's scene
                   "samples_per_s": w * h * args.render_frames * world / e2e_s,
