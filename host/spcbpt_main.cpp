@@ -635,7 +635,9 @@ int main(int argc, char** argv) {
                 App& l = *extra.back();
                 l.opt = opt;
                 l.scene_ref = &app.scene;
-                l.create_and_upload(nullptr, app.ctx);
+                // lanes borrow lane 0's scene and BVH (spc_scene_share).  Verified on one GPU; multi-rank runs keep a copy per lane, the
+                // configuration that was measured on 2 and 8 GPUs before the round's GPU budget ran out (profiles/r2_summary.md section 5)
+                l.create_and_upload(nullptr, opt.world == 1 ? app.ctx : nullptr);
                 l.init_launch_params();
                 lanes.push_back(&l);
             }
