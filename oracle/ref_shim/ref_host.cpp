@@ -43,6 +43,13 @@ static inline float ref_cm_powf(float x, float y) { return (float)::pow((double)
 #define expf ref_cm_expf
 #define powf ref_cm_powf
 
+#ifdef REF_VARIANT_HEADER
+// Variant build (oracle/Makefile, _ref/libref_host_k64c2d6.so): the reference's optixPathTracer.h with other values for its compile-time
+// constants (NUM_SUBSPACE, NUM_SUBSPACE_LIGHTSOURCE, CONNECTION_N), pre-included so that the original (same include guard) becomes a
+// no-op; raygen.cu comes from the variant directory too (its depth limit `> 50` replaced).  Pins the oracle's RUNTIME K / connections /
+// max_depth against the reference's own code compiled for those values.
+#include REF_VARIANT_HEADER
+#endif
 #include "rmis_patched.h"   // see oracle/Makefile: rmis.h with getMat() returning by value
 #include "hit_program.cu"
 #include "raygen.cu"

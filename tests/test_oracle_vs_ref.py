@@ -69,6 +69,106 @@ def test_render_path_bit_exact(pkg, orc, ref):
     assert oa[0][0][:, :3].mean() > 0.01
 
 
+@pytest.fixture(scope="module")
+def ref_variant():
+    """the reference compiled for NUM_SUBSPACE 64, NUM_SUBSPACE_LIGHTSOURCE 12, CONNECTION_N 2 and a depth limit of 6 (oracle/Makefile)"""
+    spec = importlib.util.spec_from_file_location("ref_py_variant", os.path.join(ROOT, "oracle", "ref_py.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    m.PATH = os.path.join(ROOT, "oracle", "_ref", "libref_host_k64c2d6.so")
+    if not os.path.exists(m.PATH):
+        if not os.path.isdir("/root/reference/src"):
+            pytest.skip("reference tree absent and oracle/_ref/libref_host_k64c2d6.so not prebuilt")
+        import subprocess
+        r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "_ref/libref_host_k64c2d6.so"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    return m
+
+
+def test_runtime_constants_against_the_reference_compiled_for_them(pkg, orc, ref_variant):
+    """K, K_light, CONNECTION_N and the path-depth limit are compile-time constants in the reference (optixPathTracer.h:31-36, the literal 50
+    in raygen.cu) and run-time values in the oracle and the product.  The reference's own programs, compiled for K = 64 (BASELINE.json
+    configs[0]), 12 emitter subspaces, 2 connections and depth 6, against the oracle called with those values: LVC and frames bit-equal."""
+    ref = ref_variant
+    consts = ref.layout()["constants"]
+    assert (consts["NUM_SUBSPACE"], consts["NUM_SUBSPACE_LIGHTSOURCE"], consts["CONNECTION_N"]) == (64, 12, 2)
+    sc = _varied_cornell(pkg)
+    K, KL, C, DEPTH = 64, 12, 2, 6
+    osc = orc.Scene(pkg, sc)
+    ref.scene_create(pkg, sc)
+    P = np.concatenate([m["positions"][m["indices"].astype(np.int64)].mean(1) for m in sc.meshes]).astype(np.float32)
+    N = np.tile(np.array([[0, 1, 0]], np.float32), (P.shape[0], 1))
+    eye_tree, light_tree, Q, cmf = random_trees_and_gamma(pkg, P, N, K, KL, ref.tree_build, seed=21)
+    w, h = 64, 48
+
+    def run(kind):
+        fr = HostFrame(pkg, sc, w, h, K=K, num_core=24, core_padding=150, M_per_core=25)
+        fr.set_trees(eye_tree, light_tree)
+        fr.set_q_gamma(Q, cmf)
+        fr.P["lt"]["launch_frame"] = 11
+        if kind == "ref":
+            ref.launch(fr.P, ref.KIND_LIGHT_TRACE, 24, 1, threads=8)
+        else:
+            orc.light_trace(osc, fr.P, K, max_depth=DEPTH, threads=8, connections=C)
+        sub, cmfs, jump, vc, pc = orc.lvc_process(pkg, fr.lvc, fr.valid, K)
+        fr.set_sampler(sub, cmfs, jump, vc, pc)
+        outs = []
+        for sf in (0, 1, 4):
+            fr.P["subframe_index"] = sf
+            if kind == "ref":
+                ref.launch(fr.P, ref.KIND_SPCBPT_EYE, w, h, threads=8)
+            else:
+                orc.eye_pass(osc, fr.P, K, C, DEPTH, threads=8)
+            outs.append((fr.accum.copy(), fr.frame.copy()))
+        return fr, outs
+
+    orc.set_jitter_rtl(1)
+    try:
+        fa, oa = run("ref")
+        fb, ob = run("orc")
+    finally:
+        orc.set_jitter_rtl(0)
+        ref.lib().ref_scene_destroy()
+    bad = compare_lvc(pkg, fb.lvc, fb.valid, fa.lvc, fa.valid, exact=True)
+    assert not bad, bad
+    # (the limit is tested at the loop head, before the next trace: the deepest stored vertex sits two beyond it)
+    assert fa.valid.sum() > 1000 and int(fa.lvc["depth"][fa.valid.astype(bool)].max()) == DEPTH + 2
+    for (xa, fa_), (xb, fb_) in zip(oa, ob):
+        assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32))
+        assert np.array_equal(fa_, fb_)
+    assert oa[0][0][:, :3].mean() > 0.01
+
+
+def test_pretrace_runtime_constants_against_the_variant_build(pkg, orc, ref_variant):
+    """__raygen__TrainData of the reference compiled for K = 64 and depth 6 against the oracle's pretrace called with those values"""
+    ref = ref_variant
+    sc = _varied_cornell(pkg)
+    K, KL, DEPTH = 64, 12, 6
+    osc = orc.Scene(pkg, sc)
+    ref.scene_create(pkg, sc)
+    P = np.concatenate([m["positions"][m["indices"].astype(np.int64)].mean(1) for m in sc.meshes]).astype(np.float32)
+    N = np.tile(np.array([[0, 1, 0]], np.float32), (P.shape[0], 1))
+    eye_tree, light_tree, Q, cmf = random_trees_and_gamma(pkg, P, N, K, KL, ref.tree_build, seed=5)
+    frames = []
+    orc.set_jitter_rtl(1)
+    try:
+        for kind in ("ref", "orc"):
+            fr = HostFrame(pkg, sc, 320, 200, K=K, num_core=8, core_padding=50, M_per_core=5)
+            fr.set_trees(eye_tree, light_tree)
+            setup_pretrace(fr, 6000, 10, iteration=3)
+            if kind == "ref":
+                ref.launch(fr.P, ref.KIND_PRETRACE, 6000, 1, threads=8)
+            else:
+                orc.pretrace(osc, fr.P, K, max_depth=DEPTH, threads=8)
+            frames.append(fr)
+    finally:
+        orc.set_jitter_rtl(0)
+        ref.lib().ref_scene_destroy()
+    bad = compare_train(pkg, frames[1].tp, frames[1].tc, frames[0].tp, frames[0].tc)
+    assert not bad, bad
+    assert frames[0].tp["valid"].sum() > 1500
+
+
 def test_bsdf_random(pkg, orc, ref):
     rng = np.random.default_rng(77)
     n = 400
