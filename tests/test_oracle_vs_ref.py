@@ -69,6 +69,70 @@ def test_render_path_bit_exact(pkg, orc, ref):
     assert oa[0][0][:, :3].mean() > 0.01
 
 
+def test_shipped_house_scene_render_path_bit_exact(pkg, orc, ref):
+    """the shipped scene itself (119 140 triangles, 6 textures, two divLevel-10 quad lights, the .scene's camera): the reference's programs
+    on the host against the oracle -- light trace, three subframes of the eye pass and the NEE training tracer"""
+    cache = os.path.join(ROOT, "data", "_ref", "house.spcscene")
+    if not os.path.exists(cache):
+        pytest.skip("data/_ref/house.spcscene not present (built only where /root/reference exists)")
+    sc = pkg.scenes.load_spcscene(cache)
+    K, KL = 1000, 200
+    osc = orc.Scene(pkg, sc)
+    ref.scene_create(pkg, sc)
+    rng = np.random.default_rng(17)
+    tri = np.concatenate([m["positions"][m["indices"].astype(np.int64)] for m in sc.meshes])
+    sel = np.sort(rng.choice(tri.shape[0], 20000, replace=False))
+    P = tri[sel].mean(1).astype(np.float32)
+    nrm = np.cross(tri[sel, 1] - tri[sel, 0], tri[sel, 2] - tri[sel, 0])
+    N = (nrm / np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)).astype(np.float32)
+    eye_tree, light_tree, Q, cmf = random_trees_and_gamma(pkg, P, N, K, KL, ref.tree_build, seed=31)
+    w, h = 96, 54
+
+    def run(kind):
+        fr = HostFrame(pkg, sc, w, h, K=K, num_core=48, core_padding=400, M_per_core=50)
+        fr.set_trees(eye_tree, light_tree)
+        fr.set_q_gamma(Q, cmf)
+        fr.P["lt"]["launch_frame"] = 3
+        if kind == "ref":
+            ref.launch(fr.P, ref.KIND_LIGHT_TRACE, 48, 1, threads=8)
+        else:
+            orc.light_trace(osc, fr.P, K, threads=8)
+        sub, cmfs, jump, vc, pc = orc.lvc_process(pkg, fr.lvc, fr.valid, K)
+        fr.set_sampler(sub, cmfs, jump, vc, pc)
+        outs = []
+        for sf in (0, 1, 2):
+            fr.P["subframe_index"] = sf
+            if kind == "ref":
+                ref.launch(fr.P, ref.KIND_SPCBPT_EYE, w, h, threads=8)
+            else:
+                orc.eye_pass(osc, fr.P, K, 3, 0, threads=8)
+            outs.append((fr.accum.copy(), fr.frame.copy()))
+        setup_pretrace(fr, 4000, 10, iteration=2)
+        if kind == "ref":
+            ref.launch(fr.P, ref.KIND_PRETRACE, 4000, 1, threads=8)
+        else:
+            orc.pretrace(osc, fr.P, K, threads=8)
+        return fr, outs
+
+    orc.set_jitter_rtl(1)
+    try:
+        fa, oa = run("ref")
+        fb, ob = run("orc")
+    finally:
+        orc.set_jitter_rtl(0)
+        ref.lib().ref_scene_destroy()
+    bad = compare_lvc(pkg, fb.lvc, fb.valid, fa.lvc, fa.valid, exact=True)
+    assert not bad, bad
+    assert fa.valid.sum() > 3000
+    for (xa, fa_), (xb, fb_) in zip(oa, ob):
+        assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32))
+        assert np.array_equal(fa_, fb_)
+    assert oa[0][0][:, :3].mean() > 0.05
+    bad = compare_train(pkg, fb.tp, fb.tc, fa.tp, fa.tc)
+    assert not bad, bad
+    assert fa.tp["valid"].sum() > 500
+
+
 @pytest.fixture(scope="module")
 def ref_variant():
     """the reference compiled for NUM_SUBSPACE 64, NUM_SUBSPACE_LIGHTSOURCE 12, CONNECTION_N 2 and a depth limit of 6 (oracle/Makefile)"""
