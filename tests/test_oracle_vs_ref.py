@@ -334,3 +334,33 @@ def test_pt_integrator_bit_exact(pkg, orc, ref):
     for (a, fa), (b, fb) in zip(outs["ref"], outs["orc"]):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(fa, fb)
     assert outs["ref"][0][0][:, :3].mean() > 0.01
+
+
+def test_pt_integrator_on_the_shipped_scene_bit_exact(pkg, orc, ref):
+    """the same on the shipped house scene (textures, two lights): four subframes, accumulation and frame buffers bit-equal"""
+    cache = os.path.join(ROOT, "data", "_ref", "house.spcscene")
+    if not os.path.exists(cache):
+        pytest.skip("data/_ref/house.spcscene not present (built only where /root/reference exists)")
+    sc = pkg.scenes.load_spcscene(cache)
+    osc = orc.Scene(pkg, sc)
+    ref.scene_create(pkg, sc)
+    outs = {}
+    orc.set_jitter_rtl(1)
+    try:
+        for kind in ("ref", "orc"):
+            fr = HostFrame(pkg, sc, 96, 54, K=1000, num_core=8, core_padding=50, M_per_core=5)
+            res = []
+            for sf in (0, 1, 2, 9):
+                fr.P["subframe_index"] = sf
+                if kind == "ref":
+                    ref.launch(fr.P, ref.KIND_PT, 96, 54, threads=8)
+                else:
+                    orc.pt_pass(osc, fr.P, 1000, threads=8)
+                res.append((fr.accum.copy(), fr.frame.copy()))
+            outs[kind] = res
+    finally:
+        orc.set_jitter_rtl(0)
+        ref.lib().ref_scene_destroy()
+    for (a, fa), (b, fb) in zip(outs["ref"], outs["orc"]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(fa, fb)
+    assert np.nanmean(outs["ref"][0][0][:, :3]) > 0.05
