@@ -69,32 +69,27 @@ def test_render_path_bit_exact(pkg, orc, ref):
     assert oa[0][0][:, :3].mean() > 0.01
 
 
-def test_shipped_house_scene_render_path_bit_exact(pkg, orc, ref):
-    """the shipped scene itself (119 140 triangles, 6 textures, two divLevel-10 quad lights, the .scene's camera): the reference's programs
-    on the host against the oracle -- light trace, three subframes of the eye pass and the NEE training tracer"""
-    cache = os.path.join(ROOT, "data", "_ref", "house.spcscene")
-    if not os.path.exists(cache):
-        pytest.skip("data/_ref/house.spcscene not present (built only where /root/reference exists)")
-    sc = pkg.scenes.load_spcscene(cache)
+def _chain_ref_vs_oracle(pkg, orc, ref, sc, w, h, num_core, core_padding, M_per_core, seed, min_vertices, min_train):
+    """light trace -> LVC_Process -> three subframes of the eye pass -> NEE training tracer: the reference's programs on the host against
+    the oracle on scene `sc` (K = 1000, trees from the reference's builder over triangle centroids, seeded random Q / Gamma)"""
     K, KL = 1000, 200
     osc = orc.Scene(pkg, sc)
     ref.scene_create(pkg, sc)
-    rng = np.random.default_rng(17)
+    rng = np.random.default_rng(seed)
     tri = np.concatenate([m["positions"][m["indices"].astype(np.int64)] for m in sc.meshes])
-    sel = np.sort(rng.choice(tri.shape[0], 20000, replace=False))
+    sel = np.sort(rng.choice(tri.shape[0], min(20000, tri.shape[0]), replace=False))
     P = tri[sel].mean(1).astype(np.float32)
     nrm = np.cross(tri[sel, 1] - tri[sel, 0], tri[sel, 2] - tri[sel, 0])
     N = (nrm / np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)).astype(np.float32)
-    eye_tree, light_tree, Q, cmf = random_trees_and_gamma(pkg, P, N, K, KL, ref.tree_build, seed=31)
-    w, h = 96, 54
+    eye_tree, light_tree, Q, cmf = random_trees_and_gamma(pkg, P, N, K, KL, ref.tree_build, seed=seed)
 
     def run(kind):
-        fr = HostFrame(pkg, sc, w, h, K=K, num_core=48, core_padding=400, M_per_core=50)
+        fr = HostFrame(pkg, sc, w, h, K=K, num_core=num_core, core_padding=core_padding, M_per_core=M_per_core)
         fr.set_trees(eye_tree, light_tree)
         fr.set_q_gamma(Q, cmf)
         fr.P["lt"]["launch_frame"] = 3
         if kind == "ref":
-            ref.launch(fr.P, ref.KIND_LIGHT_TRACE, 48, 1, threads=8)
+            ref.launch(fr.P, ref.KIND_LIGHT_TRACE, num_core, 1, threads=8)
         else:
             orc.light_trace(osc, fr.P, K, threads=8)
         sub, cmfs, jump, vc, pc = orc.lvc_process(pkg, fr.lvc, fr.valid, K)
@@ -123,14 +118,31 @@ def test_shipped_house_scene_render_path_bit_exact(pkg, orc, ref):
         ref.lib().ref_scene_destroy()
     bad = compare_lvc(pkg, fb.lvc, fb.valid, fa.lvc, fa.valid, exact=True)
     assert not bad, bad
-    assert fa.valid.sum() > 3000
+    assert fa.valid.sum() > min_vertices, int(fa.valid.sum())
     for (xa, fa_), (xb, fb_) in zip(oa, ob):
         assert np.array_equal(xa.view(np.uint32), xb.view(np.uint32))
         assert np.array_equal(fa_, fb_)
-    assert oa[0][0][:, :3].mean() > 0.05
     bad = compare_train(pkg, fb.tp, fb.tc, fa.tp, fa.tc)
     assert not bad, bad
-    assert fa.tp["valid"].sum() > 500
+    assert fa.tp["valid"].sum() > min_train, int(fa.tp["valid"].sum())
+    return oa
+
+
+def test_shipped_house_scene_render_path_bit_exact(pkg, orc, ref):
+    """the shipped scene itself (119 140 triangles, 6 textures, two divLevel-10 quad lights, the .scene's camera): the reference's programs
+    on the host against the oracle -- light trace, three subframes of the eye pass and the NEE training tracer"""
+    cache = os.path.join(ROOT, "data", "_ref", "house.spcscene")
+    if not os.path.exists(cache):
+        pytest.skip("data/_ref/house.spcscene not present (built only where /root/reference exists)")
+    oa = _chain_ref_vs_oracle(pkg, orc, ref, pkg.scenes.load_spcscene(cache), 96, 54, 48, 400, 50, 31, 3000, 500)
+    assert oa[0][0][:, :3].mean() > 0.05
+
+
+def test_config5_class_scene_render_path_bit_exact(pkg, orc, ref):
+    """BASELINE.json configs[4] in miniature (the large-scene generator at 96 x 96 quads: rough-metal terrain with glossy ridges, 16 quad
+    emitters of one subspace each) through the reference's own programs: near-specular lobes and the many-light emitter pick"""
+    oa = _chain_ref_vs_oracle(pkg, orc, ref, pkg.scenes.large_scene(96, 4), 96, 54, 32, 300, 40, 41, 1500, 300)
+    assert np.isfinite(oa[0][0]).all() and oa[0][0][:, :3].mean() > 1e-3
 
 
 @pytest.fixture(scope="module")
