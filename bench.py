@@ -97,12 +97,80 @@ class ClockSampler:
 
 
 ORIG_AFFINITY = None
+BOUND_AFFINITY = None
 
 
 def restore_affinity():
     """the CPU baseline legs use every host core"""
     if ORIG_AFFINITY:
         os.sched_setaffinity(0, ORIG_AFFINITY)
+
+
+def rebind_affinity():
+    """back onto the GPU's NUMA node after a CPU baseline leg (no-op when bind_to_gpu_numa_node did not bind)"""
+    if BOUND_AFFINITY:
+        try:
+            os.sched_setaffinity(0, BOUND_AFFINITY)
+        except OSError:
+            pass
+
+
+class SectionGuard:
+    """Bounded time for the extra `spcbpt` section.  The headline line (traversal metric, roofline, parity, cpu_baseline) is complete
+    before the section starts; if the section is still running after `seconds` -- a rank stuck in a collective, a lost GPU -- every
+    rank dumps its threads' stacks to stderr and leaves with status 0, rank 0 after printing the headline line with the section
+    marked as timed out.  The line is printed exactly once: by finish() on the main thread or by the timer, never both."""
+
+    def __init__(self, seconds, rank, line):
+        self.seconds, self.rank, self.line = seconds, rank, line
+        self.lock = threading.Lock()
+        self.done = False
+        self.timer = None
+
+    def start(self):
+        if self.seconds > 0:
+            # rank 0 first: it owns the line; the others follow a few seconds later so that no peer disappears under it
+            self.timer = threading.Timer(self.seconds + (0 if self.rank == 0 else 5), self._fire)
+            self.timer.daemon = True
+            self.timer.start()
+        return self
+
+    def _fire(self):
+        with self.lock:
+            if self.done:
+                return
+            try:
+                import faulthandler
+                sys.stderr.write("bench.py: the SPCBPT section is still running after %d s on rank %d; thread stacks follow, the headline "
+                                 "line is printed without the section\n" % (self.seconds, self.rank))
+                faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+                sys.stderr.flush()
+                self._print("section timed out after %d s (thread stacks on stderr); headline unaffected" % self.seconds)
+            finally:
+                os._exit(0)
+
+    def _print(self, why):
+        if self.rank == 0 and self.line is not None:
+            self.line["spcbpt"] = {"error": why}
+            sys.stdout.write(json.dumps(self.line) + "\n")
+            sys.stdout.flush()
+
+    def abandon(self, why):
+        """the section failed on this rank of a multi-rank run: print the headline (rank 0) and leave the process; never returns"""
+        with self.lock:
+            try:
+                if not self.done:
+                    self._print(why)
+                sys.stderr.flush()
+            finally:
+                os._exit(0)
+
+    def finish(self):
+        """the section returned (or raised): from here on the main thread owns the line"""
+        with self.lock:
+            self.done = True
+        if self.timer is not None:
+            self.timer.cancel()
 
 
 def bind_to_gpu_numa_node(gpu_index):
@@ -119,12 +187,13 @@ def bind_to_gpu_numa_node(gpu_index):
         for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
-        global ORIG_AFFINITY
+        global ORIG_AFFINITY, BOUND_AFFINITY
         ORIG_AFFINITY = os.sched_getaffinity(0)
         cpus &= ORIG_AFFINITY
         if not cpus:
             return "numa: node %d has no usable cpu" % node
         os.sched_setaffinity(0, cpus)
+        BOUND_AFFINITY = cpus
         return "numa: bound to node %d (%d cpus)" % (node, len(cpus))
     except Exception as ex:   # topology files absent (VM without NUMA information): leave the affinity alone
         return "numa: not bound (%s)" % type(ex).__name__
@@ -627,6 +696,9 @@ def main():
     ap.add_argument("--equal-time-seconds", type=float, default=1.5)
     ap.add_argument("--gt-spp", type=int, default=4096, help="ground-truth samples per pixel (pt) of the equal-time block")
     ap.add_argument("--lanes", type=int, default=4, help="frame lanes per GPU in the SPCBPT section (contexts rendering alternate subframes)")
+    ap.add_argument("--section-timeout", type=int, default=int(os.environ.get("SPC_BENCH_SECTION_TIMEOUT_S", "-1")),
+                    help="seconds the SPCBPT section may take before the headline line is printed without it and every rank exits 0 "
+                         "(-1 = 360, or 1200 for --workload large; 0 = no limit).  A normal section takes 30-60 s")
     ap.add_argument("--watchdog", type=int, default=int(os.environ.get("SPC_BENCH_WATCHDOG_S", "1500")),
                     help="seconds after which a run that is still going dumps every thread's stack to stderr and exits (0 = off): a hang -- "
                          "a rank stuck in a collective, a lost GPU -- then costs a bounded time and says where it stood")
@@ -751,18 +823,7 @@ def main():
     # e2e results must equal the device-resident results (same kernels)
     assert torch.equal(oB.cuda()[:, 3].view(torch.int32), hitsB[:, 3].view(torch.int32)), "e2e hits differ from device-path hits"
 
-    spcbpt = None
-    if not args.no_render:
-        if world > 1:   # (ranks meet in collectives inside: a rank that swallowed its own exception would leave the others waiting)
-            spcbpt = render_section(args, pkg, torch, dist, rank, local_rank, world, scene if large else None)
-        else:
-            try:
-                spcbpt = render_section(args, pkg, torch, None, rank, local_rank, world, scene if large else None)
-            except Exception as ex:   # the headline line (traversal metric, roofline, parity) must not be lost to the extra section
-                import traceback
-                traceback.print_exc()
-                spcbpt = {"error": repr(ex)}
-
+    line = None
     if rank == 0:
         peak, peak_src = hbm_peak()
         nn, nt = canB["nodes_visited"] / canB["rays"], canB["tris_tested"] / canB["rays"]
@@ -819,6 +880,26 @@ def main():
             "cpu_baseline": {"value": cpu_val, "unit": "Mrays/s", "cores": threads, "kind": "port",
                              "sample": "first %d rays of each of the 3 sets (%d rays, %.1f s) on the oracle port" % (ns, cpu_n, cpu_s)},
         }
+    rebind_affinity()
+
+    # The headline line is complete at this point (rank 0 holds it); the SPCBPT section below is an extra key.  It runs under a
+    # guard: an exception in it (single GPU) or a hang in it (any N) must not take the headline down.
+    spcbpt = None
+    if not args.no_render:
+        guard = SectionGuard(args.section_timeout if args.section_timeout >= 0 else (1200 if large else 360), rank, line).start()
+        try:
+            spcbpt = render_section(args, pkg, torch, dist if world > 1 else None, rank, local_rank, world, scene if large else None)
+        except Exception as ex:
+            import traceback
+            traceback.print_exc()
+            if world > 1:
+                # the other ranks are (or will be) waiting for this one in a collective of the section: there is no orderly way on.
+                # Rank 0 prints the headline line now, any other rank just leaves; both with status 0 so that the launcher does not
+                # tear the remaining ranks down before THEIR guard has let rank 0 print
+                guard.abandon("exception on rank %d: %r" % (rank, ex))
+            spcbpt = {"error": repr(ex)}
+        guard.finish()
+    if rank == 0:
         if spcbpt is not None:
             line["spcbpt"] = spcbpt
         print(json.dumps(line), flush=True)

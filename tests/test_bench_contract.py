@@ -31,3 +31,60 @@ def test_reference_arm_is_silent_on_other_ranks():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+# ---- the guard around the extra SPCBPT section (bench.SectionGuard): the headline line must survive a hang or a failure in it ----
+_GUARD_SCRIPT = r"""
+import json, os, sys, time
+sys.path.insert(0, %(root)r)
+import bench
+rank, mode = int(sys.argv[1]), sys.argv[2]
+line = {"metric": "Mrays/s", "value": 1.0} if rank == 0 else None
+g = bench.SectionGuard(1, rank, line).start()
+if mode == "hang":
+    time.sleep(60)                      # a rank stuck in a collective
+elif mode == "abandon":
+    g.abandon("exception on rank %%d: boom" %% rank)
+elif mode == "ok":
+    time.sleep(0.2)
+    g.finish()
+    time.sleep(1.5)                     # the cancelled timer must not print a second line
+    if rank == 0:
+        line["spcbpt"] = {"samples_per_s": 2.0}
+        print(json.dumps(line), flush=True)
+    sys.exit(0)
+print("not reached")
+sys.exit(3)
+"""
+
+
+def _run_guard(rank, mode):
+    import time
+    t0 = time.perf_counter()
+    r = subprocess.run([sys.executable, "-c", _GUARD_SCRIPT % {"root": ROOT}, str(rank), mode], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    return r, time.perf_counter() - t0
+
+
+def test_section_guard_prints_the_headline_when_the_section_hangs():
+    r, dt = _run_guard(0, "hang")
+    assert r.returncode == 0 and dt < 30, (r.returncode, dt, r.stderr[-1000:])
+    lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1 and lines[0]["value"] == 1.0 and "timed out" in lines[0]["spcbpt"]["error"]
+    assert "still running" in r.stderr and "time.sleep" not in r.stdout       # the stacks go to stderr
+    # the other ranks leave quietly (a few seconds after rank 0), status 0
+    r, dt = _run_guard(1, "hang")
+    assert r.returncode == 0 and dt < 30 and not r.stdout.strip()
+
+
+def test_section_guard_prints_once_when_the_section_returns():
+    r, _ = _run_guard(0, "ok")
+    lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1 and lines[0]["spcbpt"] == {"samples_per_s": 2.0}
+
+
+def test_section_guard_abandon_keeps_the_headline():
+    r, _ = _run_guard(0, "abandon")
+    lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and len(lines) == 1 and "boom" in lines[0]["spcbpt"]["error"] and "not reached" not in r.stdout
+    r, _ = _run_guard(1, "abandon")
+    assert r.returncode == 0 and not r.stdout.strip()
