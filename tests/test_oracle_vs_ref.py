@@ -321,6 +321,44 @@ def test_tree_builder_vs_reference_K1000(pkg, ref):
         assert np.array_equal(a["mid"][inner].view(np.uint32), b["mid"][inner].view(np.uint32))
 
 
+def _same_tree(a, ma, b, mb):
+    assert a.shape == b.shape and ma == mb
+    assert np.array_equal(a["leaf"], b["leaf"]) and np.array_equal(a["label"], b["label"])
+    inner = b["leaf"] == 0
+    assert np.array_equal(a["type"][inner], b["type"][inner]) and np.array_equal(a["child"][inner], b["child"][inner])
+    assert np.array_equal(a["mid"][inner].view(np.uint32), b["mid"][inner].view(np.uint32))
+
+
+def test_tree_builder_vs_reference_edge_cases(pkg, ref):
+    """spc_build_tree vs the reference's builder where its quirks show: all coordinates negative (the bounding-box maximum starts at
+    FLT_MIN), exact weight ties in the majority vote, zero weights, duplicate positions on a lattice with axis normals, a label bias,
+    fewer samples than subspaces, two samples"""
+    rng = np.random.default_rng(5)
+
+    def unit(v):
+        return v / np.maximum(np.linalg.norm(v, axis=1, keepdims=True), 1e-20)
+    cases = [(2, 4, 0, "cloud"), (3, 1, 0, "cloud"), (17, 300, 200, "cloud"), (400, 16, 5, "negative"), (3000, 64, 0, "lattice"),
+             (3000, 8, 0, "ties"), (5000, 300, 7, "zeros"), (8000, 1000, 0, "negative")]
+    for n, K, bias, kind in cases:
+        s = np.zeros(n, pkg.DIVIDE_WEIGHT)
+        s["position"] = (rng.random((n, 3)) * 10).astype(np.float32)
+        s["normal"] = unit(rng.normal(0, 1, (n, 3))).astype(np.float32)
+        s["dir"] = unit(rng.normal(0, 1, (n, 3))).astype(np.float32)
+        s["weight"] = rng.random(n).astype(np.float32)
+        if kind == "negative":
+            s["position"] = (-rng.random((n, 3)) * 50 - 1).astype(np.float32)
+        elif kind == "lattice":
+            s["position"] = np.round(rng.random((n, 3)) * 4).astype(np.float32)
+            s["normal"] = (np.eye(3)[rng.integers(0, 3, n)] * rng.choice([-1, 1], (n, 1))).astype(np.float32)
+        elif kind == "ties":
+            s["weight"] = 1.0
+        elif kind == "zeros":
+            s["weight"][rng.random(n) < 0.3] = 0
+        a, ma = pkg.build_tree(s, K, bias)
+        b, mb = ref.tree_build(pkg, s, K, bias)
+        _same_tree(a, ma, b, mb)
+
+
 def test_pt_integrator_bit_exact(pkg, orc, ref):
     """oracle "pt" restatement vs the reference's own __raygen__pinhole / __closesthit__radiance / __closesthit__lightsource"""
     sc = _varied_cornell(pkg)
