@@ -190,8 +190,8 @@ def bind_to_gpu_numa_node(gpu_index):
         global ORIG_AFFINITY, BOUND_AFFINITY
         ORIG_AFFINITY = os.sched_getaffinity(0)
         cpus &= ORIG_AFFINITY
-        if not cpus:
-            return "numa: node %d has no usable cpu" % node
+        if len(cpus) < 8:     # a rank drives 4 frame lanes (spinning host threads) next to NCCL's proxy thread: do not squeeze them
+            return "numa: node %d offers %d usable cpus, not bound" % (node, len(cpus))
         os.sched_setaffinity(0, cpus)
         BOUND_AFFINITY = cpus
         return "numa: bound to node %d (%d cpus)" % (node, len(cpus))
