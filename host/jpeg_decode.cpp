@@ -1,4 +1,4 @@
-// jpeg_decode.cpp -- baseline (SOF0/SOF1, 8-bit, Huffman) JPEG -> RGBA8 for the textures of a .scene file.
+// jpeg_decode.cpp -- baseline and progressive (SOF0/SOF1/SOF2, 8-bit, Huffman) JPEG -> RGBA8 for the textures of a .scene file.
 //
 // The reference decodes textures with stb_image 2.x (scene_shift.cpp:39-40, stbi_load(..., STBI_rgb_alpha)) and
 // uploads the bytes unchanged, so texel values are part of the shading parity contract.  The entropy decoding is
@@ -9,8 +9,11 @@
 //     into 16-bit storage first (:2213-2230);
 //   * chroma up-sampling: centred bilinear 3:1 taps, (3a+b+2)>>2 and (3t0+t1+8)>>4 (:3411-3474), edges replicated;
 //   * YCbCr -> RGB: 20-bit fixed point with the Cb term of G masked to its upper 16 bits (:3605-3630).
+// Progressive files (SOF2: spectral selection + successive approximation, T.81 annex G) keep the whole image as 16-bit coefficients
+// across their scans and are de-quantised and inverse-transformed once at the end, block by block, in 16-bit storage as stb_image
+// does (:2084-2233 the two block decoders, :3208-3226 the final pass) -- the same three lossy stages, so the bytes agree as well.
 // tests/test_host_loader.py pins the decoder against the reference's own stb_image compiled from the reference tree.
-// Progressive and arithmetic-coded files are rejected (convert them to the .rgba8 cache, tools/convert_textures.py).
+// Arithmetic-coded, lossless and hierarchical files are rejected.
 #include <cstring>
 #include <memory>
 
@@ -44,6 +47,8 @@ struct Component {
     int w2 = 0, h2 = 0;    // allocated size: whole MCUs
     int dc_pred = 0;
     std::vector<uint8_t> data;
+    std::vector<int16_t> coeff;   // progressive only: 64 coefficients per block, blocks in raster order, coeff_w blocks per row
+    int coeff_w = 0;
 };
 
 struct Decoder {
@@ -62,6 +67,8 @@ struct Decoder {
     bool jfif = false;
     int  adobe_transform = -1, rgb_ids = 0;
     bool progressive = false;
+    int  spec_start = 0, spec_end = 63, succ_high = 0, succ_low = 0;   // the current scan's Ss, Se, Ah, Al
+    int  eob_run = 0;                                                   // progressive AC scans: blocks still covered by an end-of-band run
     std::string error;
 
     bool fail(const char* msg) {
@@ -116,6 +123,7 @@ struct Decoder {
         bitcnt = 0;
         nomore = false;
         marker = -1;
+        eob_run = 0;
         for (int i = 0; i < 4; i++) comp[i].dc_pred = 0;
     }
 };
@@ -254,6 +262,149 @@ bool decode_scan(Decoder& z, const int* order, int n_scan) {
     return true;
 }
 
+// ---- progressive scans (T.81 annex G) ----------------------------------------------------------------------------------------
+// zig-zag index with the 15 entries a corrupt run can overshoot by mapped onto the last coefficient (as stb_image's table)
+inline int zigzag_at(int k) { return k < 64 ? kZigzag[k] : 63; }
+
+// DC scan: first pass stores the predicted DC value scaled by 2^Al, refinement passes add one bit
+bool prog_dc(Decoder& z, Component& c, int16_t* blk) {
+    if (z.spec_end != 0) return z.fail("progressive scan mixes DC and AC");
+    if (z.succ_high == 0) {
+        memset(blk, 0, 64 * sizeof(int16_t));
+        const int t = z.huff(z.dc[c.td]);
+        if (t < 0 || t > 15) return z.fail("bad huffman code");
+        const int diff = t ? Decoder::extend(z.bits(t), t) : 0;
+        c.dc_pred += diff;
+        blk[0] = (int16_t)(c.dc_pred * (1 << z.succ_low));
+    } else if (z.bits(1)) {
+        blk[0] = (int16_t)(blk[0] + (int16_t)(1 << z.succ_low));
+    }
+    return true;
+}
+
+// one correction bit for an already non-zero coefficient (G.1.2.3): moves it away from zero by `bit` unless that bit is set
+inline void refine(Decoder& z, int16_t& v, int bit) {
+    if (z.bits(1) && (v & bit) == 0) v = (int16_t)(v > 0 ? v + bit : v - bit);
+}
+
+// AC scan over the band [Ss, Se] of one block
+bool prog_ac(Decoder& z, Component& c, int16_t* blk) {
+    if (z.spec_start == 0) return z.fail("progressive scan mixes DC and AC");
+    const HuffTable& ha = z.ac[c.ta];
+    if (z.succ_high == 0) {            // first pass of the band
+        if (z.eob_run) {
+            --z.eob_run;
+            return true;
+        }
+        int k = z.spec_start;
+        do {
+            const int rs = z.huff(ha);
+            if (rs < 0) return z.fail("bad huffman code");
+            const int r = rs >> 4, sz = rs & 15;
+            if (sz == 0) {
+                if (r < 15) {          // end of band for this block and the next 2^r + extra - 1 blocks
+                    z.eob_run = 1 << r;
+                    if (r) z.eob_run += z.bits(r);
+                    --z.eob_run;
+                    break;
+                }
+                k += 16;
+            } else {
+                k += r;
+                const int zig = zigzag_at(k++);
+                blk[zig] = (int16_t)(Decoder::extend(z.bits(sz), sz) * (1 << z.succ_low));
+            }
+        } while (k <= z.spec_end);
+        return true;
+    }
+    // refinement pass: every non-zero coefficient met gets a correction bit; new coefficients are +-2^Al after `r` zero ones
+    const int bit = 1 << z.succ_low;
+    if (z.eob_run) {
+        --z.eob_run;
+        for (int k = z.spec_start; k <= z.spec_end; k++) {
+            int16_t& v = blk[kZigzag[k]];
+            if (v != 0) refine(z, v, bit);
+        }
+        return true;
+    }
+    int k = z.spec_start;
+    do {
+        const int rs = z.huff(ha);
+        if (rs < 0) return z.fail("bad huffman code");
+        int r = rs >> 4, sz = rs & 15, val = 0;
+        if (sz == 0) {
+            if (r < 15) {
+                z.eob_run = (1 << r) - 1;
+                if (r) z.eob_run += z.bits(r);
+                r = 64;                // run to the end of the band, correcting what is there
+            }                          // (r == 15: sixteen zero coefficients -- a run of 15 followed by "placing" a zero)
+        } else {
+            if (sz != 1) return z.fail("bad huffman code");
+            val = z.bits(1) ? bit : -bit;
+        }
+        while (k <= z.spec_end) {
+            int16_t& v = blk[kZigzag[k++]];
+            if (v != 0) refine(z, v, bit);
+            else if (r == 0) {
+                v = (int16_t)val;
+                break;
+            } else --r;
+        }
+    } while (k <= z.spec_end);
+    return true;
+}
+
+bool decode_scan_progressive(Decoder& z, const int* order, int n_scan) {
+    z.reset_entropy();
+    int todo = z.restart_interval ? z.restart_interval : 0x7fffffff;
+    auto restart = [&]() -> bool {
+        if (z.bitcnt < 24) z.fill();
+        if (!(z.marker >= 0xd0 && z.marker <= 0xd7)) return false;
+        z.reset_entropy();
+        todo = z.restart_interval ? z.restart_interval : 0x7fffffff;
+        return true;
+    };
+    if (n_scan == 1) {
+        Component& c = z.comp[order[0]];
+        const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
+        for (int j = 0; j < bh; j++)
+            for (int i = 0; i < bw; i++) {
+                int16_t* blk = c.coeff.data() + 64 * ((size_t)i + (size_t)j * c.coeff_w);
+                if (!(z.spec_start == 0 ? prog_dc(z, c, blk) : prog_ac(z, c, blk))) return false;
+                if (--todo <= 0 && !restart()) return true;
+            }
+        return true;
+    }
+    for (int my = 0; my < z.mcus_y; my++)       // interleaved scans of a progressive file carry DC coefficients only
+        for (int mx = 0; mx < z.mcus_x; mx++) {
+            for (int k = 0; k < n_scan; k++) {
+                Component& c = z.comp[order[k]];
+                for (int y = 0; y < c.v; y++)
+                    for (int x = 0; x < c.h; x++) {
+                        const size_t bx = (size_t)mx * c.h + x, by = (size_t)my * c.v + y;
+                        if (!prog_dc(z, c, c.coeff.data() + 64 * (bx + by * c.coeff_w))) return false;
+                    }
+            }
+            if (--todo <= 0 && !restart()) return true;
+        }
+    return true;
+}
+
+// after the last scan: de-quantise in 16-bit storage and inverse-transform every block the image covers
+void finish_progressive(Decoder& z) {
+    for (int n = 0; n < z.ncomp; n++) {
+        Component& c = z.comp[n];
+        const uint16_t* dq = z.dequant[c.tq];
+        const int bw = (c.x + 7) >> 3, bh = (c.y + 7) >> 3;
+        for (int j = 0; j < bh; j++)
+            for (int i = 0; i < bw; i++) {
+                int16_t* blk = c.coeff.data() + 64 * ((size_t)i + (size_t)j * c.coeff_w);
+                for (int k = 0; k < 64; k++) blk[k] = (int16_t)(blk[k] * dq[k]);
+                idct_block(c.data.data() + (size_t)c.w2 * j * 8 + i * 8, c.w2, blk);
+            }
+    }
+}
+
 bool read_tables_and_frame(Decoder& z, int m) {
     const int len = z.get16() - 2;
     if (len < 0 || z.p + len > z.end) return z.fail("truncated segment");
@@ -325,6 +476,10 @@ bool read_tables_and_frame(Decoder& z, int m) {
                 c.w2 = z.mcus_x * c.h * 8;
                 c.h2 = z.mcus_y * c.v * 8;
                 c.data.assign((size_t)c.w2 * c.h2, 0);
+                if (z.progressive) {
+                    c.coeff_w = c.w2 / 8;
+                    c.coeff.assign((size_t)c.w2 * c.h2, 0);
+                }
             }
             break;
         }
@@ -410,7 +565,6 @@ bool decode_jpeg_rgba8(const uint8_t* data, size_t size, ImageRGBA8& img, std::s
         if (m >= 0xd0 && m <= 0xd7) continue;
         if (m == 0xda) {   // SOS
             if (!have_frame) { err = "SOS before SOF"; return false; }
-            if (z.progressive) { err = "progressive JPEG is not supported (convert to .rgba8)"; return false; }
             z.get16();
             const int n_scan = z.get8();
             if (n_scan < 1 || n_scan > z.ncomp) { err = "bad SOS"; return false; }
@@ -426,8 +580,18 @@ bool decode_jpeg_rgba8(const uint8_t* data, size_t size, ImageRGBA8& img, std::s
                 if (z.comp[which].td > 3 || z.comp[which].ta > 3) { err = "bad SOS table"; return false; }
                 order[i] = which;
             }
-            z.get8(); z.get8(); z.get8();   // Ss, Se, Ah/Al: fixed for sequential scans
-            if (!decode_scan(z, order, n_scan)) { err = z.error; return false; }
+            z.spec_start = z.get8();
+            z.spec_end = z.get8();
+            const int approx = z.get8();
+            z.succ_high = approx >> 4;
+            z.succ_low = approx & 15;
+            if (z.progressive) {
+                if (z.spec_start > 63 || z.spec_end > 63 || z.spec_start > z.spec_end || z.succ_high > 13 || z.succ_low > 13) { err = "bad SOS"; return false; }
+                if (!decode_scan_progressive(z, order, n_scan)) { err = z.error; return false; }
+            } else {
+                if (z.spec_start != 0 || z.succ_high != 0 || z.succ_low != 0) { err = "bad SOS"; return false; }
+                if (!decode_scan(z, order, n_scan)) { err = z.error; return false; }
+            }
             if (z.marker >= 0) pending = z.marker;
             z.marker = -1;
             continue;
@@ -443,6 +607,7 @@ bool decode_jpeg_rgba8(const uint8_t* data, size_t size, ImageRGBA8& img, std::s
         err = "no frame in JPEG";
         return false;
     }
+    if (z.progressive) finish_progressive(z);
 
     // ---- up-sample and colour-convert row by row (stb_image.h:3840-3905) -----------------------------------
     const int W = z.width, H = z.height;

@@ -70,7 +70,9 @@ def main():
     # small synthetic images: smooth gradient + noise so that every DCT coefficient and chroma tap is exercised
     rng = np.random.default_rng(5)
 
-    def picture(w, h, chan):
+    rng_prog = np.random.default_rng(6)    # (own stream for the progressive cases: the earlier fixtures keep their bytes)
+
+    def picture(w, h, chan, rng=rng):
         y, x = np.mgrid[0:h, 0:w]
         base = np.stack([(x * 255 // max(w - 1, 1)), (y * 255 // max(h - 1, 1)), ((x + y) * 255 // max(w + h - 2, 1))], -1)
         img = np.clip(base + rng.integers(-40, 40, (h, w, 3)), 0, 255).astype(np.uint8)
@@ -86,8 +88,15 @@ def main():
         ("jgray", 33, 20, "L", dict(quality=80)),
         ("j420_restart", 64, 48, "RGB", dict(subsampling=2, quality=70, restart_marker_blocks=3)),
         ("j420_opt", 40, 40, "RGB", dict(subsampling=2, quality=30, optimize=True)),
+        # progressive (SOF2): spectral selection + successive approximation, DC-only interleaved scans, end-of-band runs, restarts
+        ("jprog444", 37, 29, "RGB", dict(subsampling=0, quality=90, progressive=True)),
+        ("jprog420", 61, 43, "RGB", dict(subsampling=2, quality=60, progressive=True)),
+        ("jprog420_lowq", 96, 80, "RGB", dict(subsampling=2, quality=8, progressive=True)),
+        ("jprog422_restart", 50, 35, "RGB", dict(subsampling=1, quality=75, progressive=True, restart_marker_blocks=2)),
+        ("jprog_gray", 33, 20, "L", dict(quality=80, progressive=True)),
+        ("jprog_1px", 1, 1, "RGB", dict(subsampling=2, quality=95, progressive=True)),
     ]:
-        im = Image.fromarray(picture(w, h, 3 if mode == "RGB" else 1), mode)
+        im = Image.fromarray(picture(w, h, 3 if mode == "RGB" else 1, rng_prog if name.startswith("jprog") else rng), mode)
         p = os.path.join(OUT, name + ".jpg")
         im.save(p, "JPEG", **kw)
         cases.append(name + ".jpg")
@@ -137,9 +146,6 @@ def main():
             dig["obj"][f] = sha(tmp)
     for f in sorted(os.listdir(os.path.join(HOUSE, "textures"))):
         if f.lower().endswith((".jpg", ".png")):
-            im = Image.open(os.path.join(HOUSE, "textures", f))
-            if im.format == "JPEG" and im.info.get("progressive"):
-                continue
             ref("decode", os.path.join(HOUSE, "textures", f), tmp)
             dig["tex"][f] = sha(tmp)
     os.remove(tmp)

@@ -72,7 +72,7 @@ def test_obj_float_parser_matches_tinyobj_not_strtod(tool, tmp_path):
 
 def test_jpeg_and_png_decoders_equal_stb_image(tool, tmp_path):
     gold = np.load(os.path.join(GOLD, "stb_decodes.npz"))
-    assert len(gold.files) >= 15
+    assert len(gold.files) >= 21
     for name in gold.files:
         out = tmp_path / (name + ".rgba8")
         run(tool, "decode", os.path.join(GOLD, name), str(out))
@@ -97,12 +97,20 @@ def test_png_writer_roundtrip(tool, tmp_path):
     assert np.array_equal(mine[..., :3], rgb) and (mine[..., 3] == 255).all()
 
 
-def test_progressive_jpeg_is_rejected_loudly(tool, tmp_path):
+def test_progressive_jpeg_scans_are_decoded(tool, tmp_path):
+    """SOF2 files (5 of the shipped scene's 39 JPEG textures are progressive) go through the same golden comparison above; here: the
+    file really is progressive with several scans, and a file whose coding process is not supported is rejected loudly"""
     from PIL import Image
-    p = tmp_path / "prog.jpg"
-    Image.fromarray(np.zeros((16, 16, 3), np.uint8)).save(p, "JPEG", progressive=True)
+    for name in ("jprog444.jpg", "jprog420_lowq.jpg", "jprog422_restart.jpg"):
+        raw = open(os.path.join(GOLD, name), "rb").read()
+        assert b"\xff\xc2" in raw and raw.count(b"\xff\xda") >= 4 and Image.open(os.path.join(GOLD, name)).info.get("progressive")
+    raw = bytearray(open(os.path.join(GOLD, "j444.jpg"), "rb").read())
+    i = raw.index(b"\xff\xc0")
+    raw[i + 1] = 0xc9          # SOF9: arithmetic coding
+    p = tmp_path / "arith.jpg"
+    p.write_bytes(bytes(raw))
     r = subprocess.run([tool, "decode", str(p), str(tmp_path / "o.rgba8")], capture_output=True, text=True)
-    assert r.returncode != 0 and "progressive" in r.stderr
+    assert r.returncode != 0 and "unsupported JPEG coding process" in r.stderr
 
 
 def test_export_convert_roundtrip(tool, pkg, tmp_path):
@@ -221,7 +229,8 @@ def test_shipped_house_scene_equals_reference_loaders(tool, tmp_path):
         run(tool, "obj", os.path.join(HOUSE, "geometry", f), str(out))
         assert hashlib.sha256(out.read_bytes()).hexdigest() == h, f
     used = ("1-1PR0120602213_290_290.jpg", "5cceae599e438.jpg", "Chocofur_shaders_free_04_bump.jpg", "QUARTERSAWNTEAK.jpg", "Wood.jpg", "chair_wood.jpg")
-    for f in used + ("Country-Kitchen-JayHardy.png", "apple_leaf.JPG"):
+    assert set(used) <= set(dig["tex"]) and len(dig["tex"]) == 43     # every JPEG / PNG in the shipped texture directory, 5 of them progressive
+    for f in sorted(dig["tex"]):
         out = tmp_path / "t.rgba8"
         run(tool, "decode", os.path.join(HOUSE, "textures", f), str(out))
         assert hashlib.sha256(out.read_bytes()).hexdigest() == dig["tex"][f], f
