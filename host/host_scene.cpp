@@ -217,8 +217,16 @@ struct Writer {
 struct Reader {
     FILE* f;
     bool ok = true;
+    long size = -1;     // of the whole file, when known: a count read from the file may not announce more than the file still holds
     void get(void* p, size_t n) { ok = ok && (n == 0 || fread(p, 1, n, f) == n); }
     template <class T> T val() { T v{}; get(&v, sizeof(T)); return v; }
+    bool holds(uint64_t bytes) {   // call before sizing a buffer by a count from the file
+        if (size >= 0) {
+            const long at = ftell(f);
+            if (at < 0 || bytes > (uint64_t)(size - at)) ok = false;
+        }
+        return ok;
+    }
 };
 }  // namespace
 
@@ -259,6 +267,8 @@ bool load_scene_cache(const std::string& path, HostScene& s, std::string& err) {
         return false;
     }
     Reader r{f};
+    if (fseek(f, 0, SEEK_END) == 0) r.size = ftell(f);
+    fseek(f, 0, SEEK_SET);
     char magic[8];
     r.get(magic, 8);
     if (!r.ok || memcmp(magic, "SPCSCN01", 8) != 0) {
@@ -274,7 +284,7 @@ bool load_scene_cache(const std::string& path, HostScene& s, std::string& err) {
         const uint32_t nv = r.val<uint32_t>(), ntri = r.val<uint32_t>();
         m.material_id = r.val<int32_t>();
         m.light_id = r.val<int32_t>();
-        if (!r.ok || nv > (1u << 30) || ntri > (1u << 30)) { r.ok = false; break; }
+        if (!r.ok || nv > (1u << 30) || ntri > (1u << 30) || !r.holds((uint64_t)nv * 20 + (uint64_t)ntri * 12)) { r.ok = false; break; }
         m.positions.resize((size_t)nv * 3);
         m.indices.resize((size_t)ntri * 3);
         m.texcoords.resize((size_t)nv * 2);
@@ -283,7 +293,7 @@ bool load_scene_cache(const std::string& path, HostScene& s, std::string& err) {
         r.get(m.texcoords.data(), m.texcoords.size() * 4);
         s.meshes.push_back(std::move(m));
     }
-    if (r.ok && nmat < (1u << 24) && nl < (1u << 24)) {
+    if (r.ok && nmat < (1u << 24) && nl < (1u << 24) && r.holds((uint64_t)nmat * sizeof(spc_pbr) + (uint64_t)nl * sizeof(spc_light))) {
         s.materials.resize(nmat);
         s.lights.resize(nl);
         r.get(s.materials.data(), nmat * sizeof(spc_pbr));
@@ -295,7 +305,7 @@ bool load_scene_cache(const std::string& path, HostScene& s, std::string& err) {
         ImageRGBA8 t;
         t.width = r.val<int32_t>();
         t.height = r.val<int32_t>();
-        if (!r.ok || t.width <= 0 || t.height <= 0 || (size_t)t.width * t.height > (1u << 28)) { r.ok = false; break; }
+        if (!r.ok || t.width <= 0 || t.height <= 0 || (size_t)t.width * t.height > (1u << 28) || !r.holds((uint64_t)t.width * t.height * 4)) { r.ok = false; break; }
         t.rgba.resize((size_t)t.width * t.height * 4);
         r.get(t.rgba.data(), t.rgba.size());
         s.textures.push_back(std::move(t));

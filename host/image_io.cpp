@@ -14,7 +14,11 @@ static bool read_file(const std::string& path, std::vector<uint8_t>& out) {
     fseek(f, 0, SEEK_END);
     const long n = ftell(f);
     fseek(f, 0, SEEK_SET);
-    out.resize(n > 0 ? (size_t)n : 0);
+    if (n < 0 || n > (1L << 31)) {   // not a regular file (fopen succeeds on a directory, whose "size" is LONG_MAX), or no texture
+        fclose(f);
+        return false;
+    }
+    out.resize((size_t)n);
     const size_t got = out.empty() ? 0 : fread(out.data(), 1, out.size(), f);
     fclose(f);
     return got == out.size();

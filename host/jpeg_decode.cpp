@@ -27,6 +27,7 @@ struct HuffTable {
     uint8_t  bits[17] = {0};      // number of codes of each length
     uint8_t  vals[256] = {0};
     int      mincode[18], maxcode[18], valptr[18];
+    HuffTable() { build(); }      // a table no DHT segment defined has no codes: every look-up fails ("bad huffman code")
     void build() {
         int code = 0, k = 0;
         for (int len = 1; len <= 16; len++) {
@@ -53,13 +54,14 @@ struct Component {
 
 struct Decoder {
     const uint8_t* p;
+    const uint8_t* begin;
     const uint8_t* end;
     uint32_t bitbuf = 0;
     int      bitcnt = 0;
     int      marker = -1;     // marker met inside entropy data (0xD0.. etc.), -1 = none
     bool     nomore = false;
 
-    uint16_t dequant[4][64];
+    uint16_t dequant[4][64] = {};
     HuffTable dc[4], ac[4];
     Component comp[4];
     int ncomp = 0, width = 0, height = 0, hmax = 1, vmax = 1, mcu_w = 0, mcu_h = 0, mcus_x = 0, mcus_y = 0;
@@ -446,6 +448,9 @@ bool read_tables_and_frame(Decoder& z, int m) {
             z.width = z.get16();
             z.ncomp = z.get8();
             if (z.width <= 0 || z.height <= 0) return z.fail("bad JPEG size");
+            // untrusted files: no more than 2^28 pixels, and no frame the file cannot fill (every block costs at least one bit per scan)
+            if ((uint64_t)z.width * (uint64_t)z.height > (1ull << 28)) return z.fail("JPEG exceeds 2^28 pixels");
+            if ((uint64_t)z.width * (uint64_t)z.height > (uint64_t)(z.end - z.begin) * 1024 + (1u << 20)) return z.fail("JPEG frame size does not match its data");
             if (z.ncomp != 1 && z.ncomp != 3) return z.fail("only 1- and 3-component JPEG is supported");
             z.rgb_ids = 0;
             static const char rgb[3] = {'R', 'G', 'B'};
@@ -542,7 +547,7 @@ constexpr int f2f20(float x) { return ((int)(x * 4096.0f + 0.5f)) << 8; }
 bool decode_jpeg_rgba8(const uint8_t* data, size_t size, ImageRGBA8& img, std::string& err) {
     auto zp = std::make_unique<Decoder>();
     Decoder& z = *zp;
-    z.p = data;
+    z.p = z.begin = data;
     z.end = data + size;
     if (size < 4 || z.get8() != 0xff || z.get8() != 0xd8) {
         err = "not a JPEG file";

@@ -105,6 +105,12 @@ bool decode_png_rgba8(const uint8_t* data, size_t size, ImageRGBA8& img, std::st
         err = "bad PNG header";
         return false;
     }
+    // texture files are untrusted: a header may not ask for more memory than its data can fill (deflate expands at most ~1032 : 1)
+    // nor for an image beyond 2^28 pixels (1 GiB of RGBA8)
+    if ((uint64_t)W * (uint64_t)H > (1ull << 28) || (uint64_t)W * (uint64_t)H / 8 > (uint64_t)z.size() * 1040 + 1024) {
+        err = "PNG header does not match its data (or the image exceeds 2^28 pixels)";
+        return false;
+    }
     const int chan = chan_of[ctype];
     const int bits_pp = chan * depth;
     const int bpp = bits_pp >= 8 ? bits_pp / 8 : 1;

@@ -1,5 +1,6 @@
 // scene_tool.cpp -- scene conversion and texture decoding without a GPU (no dependency on libspcbpt_b200.so):
 //   spc_scene_tool convert <file.scene> <out.spcscene> [--data-root dir] [--K-light n]   .scene + OBJ + textures -> cache
+//   spc_scene_tool info    <file.spcscene> <out.txt>                                    cache -> one summary line (loader check)
 //   spc_scene_tool decode  <image> <out.rgba8>                                          JPEG/PNG/PNM -> raw RGBA8 cache
 //   spc_scene_tool png     <image> <out.png>                                            re-encode through the driver's PNG writer
 //   spc_scene_tool scene   <file.scene> <out.txt> [data-root]                          parsed .scene as text (LoadScene check)
@@ -37,6 +38,18 @@ int main(int argc, char** argv) {
         printf("%zu meshes %zu triangles %zu materials %zu lights %zu textures\n", hs.meshes.size(), hs.n_triangles(), hs.materials.size(), hs.lights.size(), hs.textures.size());
         return 0;
     }
+    if (cmd == "info") {
+        HostScene hs;
+        if (!load_scene_cache(argv[2], hs, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        FILE* f = fopen(argv[3], "w");
+        if (!f) return 1;
+        size_t texels = 0;
+        for (const auto& t : hs.textures) texels += (size_t)t.width * t.height;
+        fprintf(f, "%zu meshes %zu triangles %zu materials %zu lights %zu textures %zu texels %zu upload bytes\n", hs.meshes.size(), hs.n_triangles(), hs.materials.size(),
+                hs.lights.size(), hs.textures.size(), texels, hs.upload_bytes());
+        fclose(f);
+        return 0;
+    }
     if (cmd == "decode") {
         ImageRGBA8 img;
         if (!load_image_rgba8(argv[2], img, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
@@ -64,9 +77,9 @@ int main(int argc, char** argv) {
         for (const auto& s : shapes) {
             const uint32_t h[3] = {(uint32_t)(s.positions.size() / 3), (uint32_t)(s.indices.size() / 3), (uint32_t)s.texcoords.size()};
             fwrite(h, 4, 3, f);
-            fwrite(s.positions.data(), 4, s.positions.size(), f);
-            fwrite(s.indices.data(), 4, s.indices.size(), f);
-            fwrite(s.texcoords.data(), 4, s.texcoords.size(), f);
+            if (!s.positions.empty()) fwrite(s.positions.data(), 4, s.positions.size(), f);
+            if (!s.indices.empty()) fwrite(s.indices.data(), 4, s.indices.size(), f);
+            if (!s.texcoords.empty()) fwrite(s.texcoords.data(), 4, s.texcoords.size(), f);
         }
         fclose(f);
         printf("%u shapes\n", n);

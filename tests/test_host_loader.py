@@ -113,6 +113,55 @@ def test_progressive_jpeg_scans_are_decoded(tool, tmp_path):
     assert r.returncode != 0 and "unsupported JPEG coding process" in r.stderr
 
 
+def test_untrusted_files_are_rejected_not_trusted(tool, tmp_path):
+    """texture and cache files come from disk: a header may not make the loaders allocate what the file cannot fill, a directory is not
+    a file, a Huffman table nobody defined has no codes, a truncated cache is an error (found by fuzzing under ASan / UBSan)"""
+    def rc(*args):
+        return subprocess.run([tool] + [str(a) for a in args], capture_output=True, text=True, timeout=120)
+    # PNG whose IHDR claims 2^30 x 2^30 pixels
+    raw = bytearray(open(os.path.join(GOLD, "p_rgb.png"), "rb").read())
+    i = raw.index(b"IHDR") + 4
+    raw[i:i + 8] = bytes([0x40, 0, 0, 0, 0x40, 0, 0, 0])
+    (tmp_path / "huge.png").write_bytes(bytes(raw))
+    r = rc("decode", tmp_path / "huge.png", tmp_path / "o")
+    assert r.returncode == 1 and "PNG" in r.stderr
+    # JPEG whose frame header claims 65535 x 65535, and one whose scan names a Huffman table that no DHT defined
+    raw = bytearray(open(os.path.join(GOLD, "j444.jpg"), "rb").read())
+    i = raw.index(b"\xff\xc0") + 5
+    big = bytearray(raw)
+    big[i:i + 4] = b"\xff\xff\xff\xff"
+    (tmp_path / "huge.jpg").write_bytes(bytes(big))
+    r = rc("decode", tmp_path / "huge.jpg", tmp_path / "o")
+    assert r.returncode == 1 and "JPEG" in r.stderr
+    j = raw.index(b"\xff\xda")
+    nosuch = bytearray(raw)
+    nosuch[j + 6] = 0x33        # first scan component: DC table 3, AC table 3
+    (tmp_path / "tables.jpg").write_bytes(bytes(nosuch))
+    r = rc("decode", tmp_path / "tables.jpg", tmp_path / "o")
+    assert r.returncode == 1 and "huffman" in r.stderr
+    # a directory where a texture file is expected
+    (tmp_path / "dir.png").mkdir()
+    assert rc("decode", tmp_path / "dir.png", tmp_path / "o").returncode == 1
+    # .spcscene: the summary of a good cache, then truncated and with a vertex count the file cannot hold
+    sc_dir = tmp_path / "sc"
+    sc_dir.mkdir()
+    (sc_dir / "t.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    (sc_dir / "s.scene").write_text("material m\n{\n color 1 1 1\n}\nmesh\n{\n file t.obj\n material m\n}\n")
+    r = rc("convert", sc_dir / "s.scene", tmp_path / "s.spcscene", "--data-root", sc_dir)
+    assert r.returncode == 0, r.stderr
+    r = rc("info", tmp_path / "s.spcscene", tmp_path / "info.txt")
+    assert r.returncode == 0 and (tmp_path / "info.txt").read_text().startswith("1 meshes 1 triangles 1 materials 0 lights 0 textures")
+    good = (tmp_path / "s.spcscene").read_bytes()
+    (tmp_path / "cut.spcscene").write_bytes(good[:len(good) // 2])
+    r = rc("info", tmp_path / "cut.spcscene", tmp_path / "o")
+    assert r.returncode == 1 and "truncated or corrupt" in r.stderr
+    lie = bytearray(good)
+    lie[64:68] = (1 << 29).to_bytes(4, "little")       # first mesh: vertex count (after magic, 4 counts, camera)
+    (tmp_path / "lie.spcscene").write_bytes(bytes(lie))
+    r = rc("info", tmp_path / "lie.spcscene", tmp_path / "o")
+    assert r.returncode == 1 and "truncated or corrupt" in r.stderr
+
+
 def test_export_convert_roundtrip(tool, pkg, tmp_path):
     """scenes.export_scene -> .scene + OBJ + PPM textures -> C++ loader -> .spcscene -> scenes.load_spcscene: identical
     triangles (positions and uv bits per corner), materials, lights and camera; mesh order = file order then light quads"""
