@@ -88,3 +88,29 @@ def test_section_guard_abandon_keeps_the_headline():
     assert r.returncode == 0 and len(lines) == 1 and "boom" in lines[0]["spcbpt"]["error"] and "not reached" not in r.stdout
     r, _ = _run_guard(1, "abandon")
     assert r.returncode == 0 and not r.stdout.strip()
+
+
+def _dry_run(mode):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_dry_run.py"), mode], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    return r, lines
+
+
+def test_bench_main_flow_on_a_fake_device():
+    """bench.main() end to end on a fake CUDA surface (tests/bench_dry_run.py): one JSON line with every contract key, the parity leg
+    green, and the SPCBPT section's three outcomes -- result, exception, hang -- all leave the headline line intact"""
+    for mode, check in (("ok", lambda sp: sp == {"samples_per_s": 123.0}), ("raise", lambda sp: "boom in section" in sp["error"]),
+                        ("hang", lambda sp: "timed out" in sp["error"]), ("norender", lambda sp: sp is None)):
+        r, lines = _dry_run(mode)
+        assert r.returncode == 0 and len(lines) == 1, (mode, r.returncode, r.stdout[-500:], r.stderr[-1500:])
+        d = lines[0]
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                    "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "parity"):
+            assert key in d, (mode, key)
+        assert d["metric"] == "Mrays/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["value"] > 0
+        assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["roofline"]["bound"] == "hbm"
+        assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 3 * 48 * 48 * 32
+        assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["config"]["workload"]
+        p = d["parity"]
+        assert p["rays_checked"] == 3 * 48 * 48 and p["prim_mismatch"] == p["tuv_bit_mismatch"] == p["visibility_mismatch"] == 0
+        assert check(d.get("spcbpt")), (mode, d.get("spcbpt"))
