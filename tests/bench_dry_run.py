@@ -2,7 +2,9 @@
 pkg.Context by a fake context that answers the traversal calls through the oracle, on a tiny scene and 48 x 48 rays per set.  It
 exercises bench.py's control flow -- the order of the legs, the assembly and JSON encoding of the headline line, the parity
 check, the guard around the SPCBPT section -- and nothing of the product (the numbers it prints mean nothing).
-usage: python tests/bench_dry_run.py norender|ok|raise|hang"""
+usage: python tests/bench_dry_run.py norender|ok|raise|hang
+Under torchrun (WORLD_SIZE > 1; the process group is switched to gloo) the modes ok2 | hang1 | raise1 run the multi-rank flow: in
+hang1 / raise1 rank 1 gets stuck / fails inside the section while rank 0 waits for it in a collective."""
 import os
 import sys
 import time
@@ -95,13 +97,22 @@ def reg_empty(*a, **k):
 torch.empty = reg_empty
 pkg.scenes.heightfield_scene = lambda n: pkg.scenes.cornell_scene(wall_cells=4, box_cells=3)
 
+import torch.distributed as tdist
+_init = tdist.init_process_group
+tdist.init_process_group = lambda backend, **kw: _init("gloo")      # no NCCL without GPUs
+
+
 def fake_section(args, pkg_, torch_, dist, rank, local_rank, world, large_scene=None):
     if mode == "hang": time.sleep(60)
     if mode == "raise": raise RuntimeError("boom in section")
+    if mode == "hang1" and rank == 1: time.sleep(60)
+    if mode == "raise1" and rank == 1: raise RuntimeError("boom on rank 1")
+    if dist is not None:
+        dist.barrier()          # the section's collectives: rank 0 waits here for a rank that never comes
     return {"samples_per_s": 123.0}
 bench.render_section = fake_section
 argv = ["bench.py", "--steps", "2", "--warmup", "3"]
 if mode == "norender": argv.append("--no-render")
-if mode == "hang": argv += ["--section-timeout", "2"]
+if mode in ("hang", "hang1", "raise1"): argv += ["--section-timeout", "3"]
 sys.argv = argv
 bench.main()

@@ -114,3 +114,19 @@ def test_bench_main_flow_on_a_fake_device():
         p = d["parity"]
         assert p["rays_checked"] == 3 * 48 * 48 and p["prim_mismatch"] == p["tuv_bit_mismatch"] == p["visibility_mismatch"] == 0
         assert check(d.get("spcbpt")), (mode, d.get("spcbpt"))
+
+
+def test_bench_main_flow_two_ranks_under_torchrun():
+    """the same dry run launched as the driver launches N > 1 (torch.distributed.run, 2 ranks, gloo instead of NCCL): barriers and the max over
+    ranks run; a rank that hangs or fails inside the section neither takes the headline line down nor makes the launcher fail"""
+    import socket
+    for mode, check in (("ok2", lambda sp: sp == {"samples_per_s": 123.0}), ("hang1", lambda sp: "timed out" in sp["error"]),
+                        ("raise1", lambda sp: "error" in sp)):
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+                            os.path.join(ROOT, "tests", "bench_dry_run.py"), mode], capture_output=True, text=True, timeout=400, cwd=ROOT)
+        lines = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+        assert r.returncode == 0 and len(lines) == 1, (mode, r.returncode, r.stdout[-500:], r.stderr[-1500:])
+        assert lines[0]["n_gpus"] == 2 and lines[0]["value"] > 0 and lines[0]["parity"]["prim_mismatch"] == 0 and check(lines[0]["spcbpt"]), (mode, lines[0].get("spcbpt"))
