@@ -699,7 +699,7 @@ def main():
     ap.add_argument("--section-timeout", type=int, default=int(os.environ.get("SPC_BENCH_SECTION_TIMEOUT_S", "-1")),
                     help="seconds the SPCBPT section may take before the headline line is printed without it and every rank exits 0 "
                          "(-1 = 360, or 1200 for --workload large; 0 = no limit).  A normal section takes 30-60 s")
-    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("SPC_BENCH_WATCHDOG_S", "1500")),
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("SPC_BENCH_WATCHDOG_S", "900")),
                     help="seconds after which a run that is still going dumps every thread's stack to stderr and exits (0 = off): a hang -- "
                          "a rank stuck in a collective, a lost GPU -- then costs a bounded time and says where it stood")
     args = ap.parse_args()
