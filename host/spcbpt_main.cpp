@@ -9,9 +9,13 @@
 //
 // Display is replaced by files: <out>.ppm / <out>.png (tone-mapped frame buffer) and <out>.pfm (accumulation buffer).
 #include <cuda_runtime_api.h>
+#include <signal.h>
+#include <sys/prctl.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <cerrno>
 #include <chrono>
 #include <fstream>
 #include <exception>
@@ -542,15 +546,34 @@ int main(int argc, char** argv) {
             for (int r = 0; r < o.ranks && my_rank < 0; r++) {
                 const pid_t pid = fork();
                 if (pid < 0) throw std::runtime_error("fork failed");
-                if (pid == 0) my_rank = r;
-                else kids.push_back(pid);
+                if (pid == 0) {
+                    my_rank = r;
+                    prctl(PR_SET_PDEATHSIG, SIGKILL);   // a rank never outlives the launcher (it may be sitting in a collective)
+                } else kids.push_back(pid);
             }
             if (my_rank < 0) {
+                // Wait for the ranks.  Once one has failed the others get 30 s to finish on their own: a rank waiting in a collective
+                // for a peer that is gone would otherwise keep the launcher (and its GPU) forever.
                 int worst = 0;
-                for (pid_t pid : kids) {
+                double failed_at = -1.0;
+                while (!kids.empty()) {
                     int st = 0;
-                    waitpid(pid, &st, 0);
-                    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) worst = 1;
+                    const pid_t pid = waitpid(-1, &st, failed_at < 0 ? 0 : WNOHANG);
+                    if (pid > 0) {
+                        kids.erase(std::remove(kids.begin(), kids.end(), pid), kids.end());
+                        if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) {
+                            worst = 1;
+                            if (failed_at < 0) failed_at = now_s();
+                        }
+                    } else if (pid < 0 && errno != EINTR) {
+                        break;                              // no child left to wait for
+                    } else if (failed_at >= 0 && now_s() - failed_at > 30.0) {
+                        fprintf(stderr, "spcbpt_render: a rank failed; stopping the %zu rank(s) still running\n", kids.size());
+                        for (pid_t k : kids) kill(k, SIGKILL);
+                        failed_at = -1.0;                   // reap them with blocking waits
+                    } else if (pid == 0) {
+                        std::this_thread::sleep_for(std::chrono::milliseconds(100));
+                    }
                 }
                 remove(o.id_file.c_str());
                 return worst;

@@ -8,6 +8,7 @@
 import os
 import sys
 import tempfile
+import time
 
 import numpy as np
 import pytest
@@ -75,8 +76,16 @@ def test_two_ranks_sharded_training_and_reduced_image(gpu_ctx):
         procs = [ctx.Process(target=_worker, args=(r, world, os.path.join(d, "nccl_id"), d)) for r in range(world)]
         for p in procs:
             p.start()
+        deadline = time.monotonic() + 600
         for p in procs:
-            p.join(timeout=600)
+            p.join(timeout=max(1.0, deadline - time.monotonic()))
+        stuck = [p for p in procs if p.is_alive()]
+        for p in stuck:          # a rank waiting in a collective for a peer that failed: do not leave it (and its GPU) behind
+            p.kill()
+        for p in stuck:
+            p.join(timeout=30)
+        assert not stuck, "%d rank process(es) still running after 600 s" % len(stuck)
+        for p in procs:
             assert p.exitcode == 0, "rank process failed"
         ranks = [np.load(os.path.join(d, "rank%d.npz" % r)) for r in range(world)]
         image2 = np.load(os.path.join(d, "image.npy"))
