@@ -100,6 +100,7 @@ bool write_rgba8_cache(const std::string& path, const ImageRGBA8& img) {
 }
 
 bool write_ppm_from_uchar4(const std::string& path, const uint32_t* frame, int width, int height) {
+    if (!frame || width <= 0 || height <= 0) return false;
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) return false;
     fprintf(f, "P6\n%d %d\n255\n", width, height);
@@ -113,11 +114,12 @@ bool write_ppm_from_uchar4(const std::string& path, const uint32_t* frame, int w
         }
         fwrite(row.data(), 1, row.size(), f);
     }
-    fclose(f);
-    return true;
+    const bool ok = !ferror(f);
+    return fclose(f) == 0 && ok;
 }
 
 bool write_pfm_from_float4(const std::string& path, const float* accum4, int width, int height) {
+    if (!accum4 || width <= 0 || height <= 0) return false;
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) return false;
     fprintf(f, "PF\n%d %d\n-1.0\n", width, height);
@@ -131,8 +133,8 @@ bool write_pfm_from_float4(const std::string& path, const float* accum4, int wid
         }
         fwrite(row.data(), sizeof(float), row.size(), f);
     }
-    fclose(f);
-    return true;
+    const bool ok = !ferror(f);
+    return fclose(f) == 0 && ok;
 }
 
 }  // namespace spchost

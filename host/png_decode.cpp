@@ -215,7 +215,7 @@ void png_chunk(FILE* f, const char type[4], const uint8_t* data, size_t n) {
 }  // namespace
 
 bool write_png_from_uchar4(const std::string& path, const uint32_t* frame, int width, int height) {
-    if (width <= 0 || height <= 0) return false;
+    if (!frame || width <= 0 || height <= 0) return false;
     std::vector<uint8_t> raw((size_t)height * (1 + (size_t)width * 3));
     size_t o = 0;
     for (int y = height - 1; y >= 0; y--) {   // the render's row 0 is the bottom row (image_io.hpp)
@@ -240,8 +240,7 @@ bool write_png_from_uchar4(const std::string& path, const uint32_t* frame, int w
     png_chunk(f, "IDAT", z.data(), zn);
     png_chunk(f, "IEND", nullptr, 0);
     const bool ok = !ferror(f);
-    fclose(f);
-    return ok;
+    return fclose(f) == 0 && ok;      // (a full disk shows up at the flush)
 }
 
 }  // namespace spchost
