@@ -699,11 +699,13 @@ def main():
     ap.add_argument("--section-timeout", type=int, default=int(os.environ.get("SPC_BENCH_SECTION_TIMEOUT_S", "-1")),
                     help="seconds the SPCBPT section may take before the headline line is printed without it and every rank exits 0 "
                          "(-1 = 360, or 1200 for --workload large; 0 = no limit).  A normal section takes 30-60 s")
-    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("SPC_BENCH_WATCHDOG_S", "900")),
-                    help="seconds after which a run that is still going dumps every thread's stack to stderr and exits (0 = off): a hang -- "
-                         "a rank stuck in a collective, a lost GPU -- then costs a bounded time and says where it stood")
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("SPC_BENCH_WATCHDOG_S", "-1")),
+                    help="seconds after which a run that is still going dumps every thread's stack to stderr and exits (0 = off; -1 = 900, or 1800 "
+                         "for --workload large): a hang -- a rank stuck in a collective, a lost GPU -- then costs a bounded time and says where it stood")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.watchdog < 0:
+        args.watchdog = 1800 if args.workload == "large" else 900
     if args.watchdog > 0:
         import faulthandler
         faulthandler.dump_traceback_later(args.watchdog, exit=True)
