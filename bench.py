@@ -96,6 +96,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+T_START = time.perf_counter()
+
+
+def note(msg):
+    """progress line on stderr (stdout carries the one JSON line): when a run stops short, the log says where it stood"""
+    sys.stderr.write("[bench %7.1f s rank %s] %s\n" % (time.perf_counter() - T_START, os.environ.get("RANK", "0"), msg))
+    sys.stderr.flush()
+
+
 ORIG_AFFINITY = None
 BOUND_AFFINITY = None
 
@@ -514,14 +523,17 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     upload_s = time.perf_counter() - t_up0     # contexts + scene upload (host arrays -> device) + BVH build, all lanes
     r = lr_.lanes[0]
     lr_.seed_mapping(rank, world)
+    note("section: %d lanes up (%.2f s)" % (lanes, upload_s))
     comm_init(r.ctx, env)       # NCCL communicator of this rank (csrc/comm.cu), outside the timed preprocessing
     env.barrier()
+    note("section: communicator up, training")
     t0 = time.perf_counter()
     st = preprocess_distributed(r, env, pkg.TREE_NODE, target_samples=2000000, target_Q_samples=2000000, tree_samples=100000,
                                 batch_size=20000, epochs=1, lr=0.01)
     lr_.share_trained_state()
     torch.cuda.synchronize()
     pre_s = time.perf_counter() - t0
+    note("section: trained (%.2f s), rendering" % pre_s)
     lr_.render(2 * lanes)
     torch.cuda.synchronize()
     env.barrier()
@@ -552,6 +564,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
     img = r.image()                            # merge of the lanes' running means + device -> host copy of the accumulation buffer
     readout_s = time.perf_counter() - t_ro0
     mean = float(img.mean())
+    note("section: exact flavour rendered and read out")
     assert st["loss_last"] is not None and np.isfinite(st["loss_last"]) and np.isfinite(mean) and mean > 0, \
         "SPCBPT section: training or render produced no valid result (loss %r, image mean %r)" % (st["loss_last"], mean)
     out = {"workload": "SPCBPT_eye %dx%d, 1 spp per frame, K=%d (K_light %d), connections 3, %s, "
@@ -602,6 +615,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
                                "flags": "-fmad=true -prec-div=false -prec-sqrt=false -DSPC_FAST_MATH (render.cu, pt.cu, pretrace.cu); traversal / binning / training unchanged; "
                                         "light_trace_mode 1 (one lane per light path)"}
         del lf
+        note("section: fast flavour done")
     if rank == 0:
         # in-frame work and stage times: lane 0 alone, sequential frames, every stage of every bounce bracketed by CUDA events
         # (option "stage_timing"; slower than the production loop, used only to attribute the frame time and to state the
@@ -662,6 +676,7 @@ def render_section(args, pkg, torch, dist, rank, local_rank, world, large_scene=
                                    "sample": "one frame of the oracle port: light trace of 100k paths + LVC_Process (%.2f s) + eye pass on %dx%d (%.2f s), same trained state" % (t1 - t0, cw, ch, t2 - t1)}
         except Exception as ex:   # the CPU leg is informative only
             out["cpu_baseline"] = {"error": repr(ex)}
+        note("section: stage timing and CPU frame done")
         # GPU-side reference arm + relMSE at equal time (informative legs: a failure must not take the headline down)
         try:
             out["reference_gpu"] = reference_gpu_rate(pkg, torch, lr_.lanes[0], w, h)
@@ -726,7 +741,9 @@ def main():
     numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "numa: single rank, not bound"
     torch.cuda.set_device(local_rank)
     if world > 1:
+        note("process group: init (nccl, %d ranks)" % world)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        note("process group: up")
 
     large = args.workload == "large"
     if large:
@@ -740,6 +757,7 @@ def main():
         scene = pkg.scenes.heightfield_scene(708)
     ctx = pkg.Context(local_rank)
     ctx.upload_scene(scene)
+    note("scene uploaded, BVH built (%d triangles)" % scene.n_triangles)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     side = RAYS_SIDE
@@ -771,6 +789,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    note("ray sets and visit counts ready")
     for _ in range(args.warmup):
         step()
     barrier()
@@ -787,6 +806,7 @@ def main():
     barrier()
     launches = ctx.launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
+    note("timed region done: %.2f ms per step" % (ms_total / args.steps))
     clocks = sampler.stop()
     ms_B = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
@@ -824,6 +844,7 @@ def main():
     e2e_val = rays_per_step_all * e2e_steps / float(te.item()) / 1e6
     # e2e results must equal the device-resident results (same kernels)
     assert torch.equal(oB.cuda()[:, 3].view(torch.int32), hitsB[:, 3].view(torch.int32)), "e2e hits differ from device-path hits"
+    note("e2e leg done")
 
     line = None
     if rank == 0:
@@ -851,6 +872,7 @@ def main():
         parity = check_parity(pkg, (hits, hitsB), vis, cpu_res, ns)
         assert parity["prim_mismatch"] == 0 and parity["tuv_bit_mismatch"] == 0 and parity["visibility_mismatch"] == 0, \
             "GPU traversal differs from the oracle on the benchmarked rays: %r" % parity
+        note("oracle leg done: %d rays in %.1f s, parity %r" % (cpu_n, cpu_s, parity))
         st = ctx.bvh_stats()
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -901,6 +923,7 @@ def main():
                 guard.abandon("exception on rank %d: %r" % (rank, ex))
             spcbpt = {"error": repr(ex)}
         guard.finish()
+        note("SPCBPT section done")
     if rank == 0:
         if spcbpt is not None:
             line["spcbpt"] = spcbpt
