@@ -1,6 +1,7 @@
 // scene_tool.cpp -- scene conversion and texture decoding without a GPU (no dependency on libspcbpt_b200.so):
 //   spc_scene_tool convert <file.scene> <out.spcscene> [--data-root dir] [--K-light n]   .scene + OBJ + textures -> cache
 //   spc_scene_tool info    <file.spcscene> <out.txt>                                    cache -> one summary line (loader check)
+//   spc_scene_tool state   <in_prefix> <out_prefix> <K>                                 trained state (tree_eye/tree_light/Q/E .txt) read and re-written
 //   spc_scene_tool decode  <image> <out.rgba8>                                          JPEG/PNG/PNM -> raw RGBA8 cache
 //   spc_scene_tool png     <image> <out.png>                                            re-encode through the driver's PNG writer
 //   spc_scene_tool scene   <file.scene> <out.txt> [data-root]                          parsed .scene as text (LoadScene check)
@@ -12,6 +13,7 @@
 #include <string>
 
 #include "host_scene.hpp"
+#include "train_state.hpp"
 
 using namespace spchost;
 
@@ -36,6 +38,14 @@ int main(int argc, char** argv) {
         for (const auto& w : hs.warnings) fprintf(stderr, "warning: %s\n", w.c_str());
         if (!save_scene_cache(argv[3], hs)) { fprintf(stderr, "cannot write %s\n", argv[3]); return 1; }
         printf("%zu meshes %zu triangles %zu materials %zu lights %zu textures\n", hs.meshes.size(), hs.n_triangles(), hs.materials.size(), hs.lights.size(), hs.textures.size());
+        return 0;
+    }
+    if (cmd == "state") {   // host/train_state.cpp round trip: the reader and the writer of the reference's checkpoint text files
+        if (argc < 5) { fprintf(stderr, "usage: %s state <in_prefix> <out_prefix> <K>\n", argv[0]); return 2; }
+        TrainState st;
+        if (!load_train_state(argv[2], atoi(argv[4]), st, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        if (!save_train_state(argv[3], st)) { fprintf(stderr, "cannot write %s*.txt\n", argv[3]); return 1; }
+        printf("%zu + %zu tree nodes, %zu Q, %zu Gamma\n", st.eye_tree.size(), st.light_tree.size(), st.Q.size(), st.gamma.size());
         return 0;
     }
     if (cmd == "info") {

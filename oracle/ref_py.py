@@ -38,6 +38,8 @@ def lib():
         L.ref_rnd_stream.restype = None
         L.ref_tree_build.argtypes = [vp, i32, i32, i32, vp, i32, vp]
         L.ref_tree_index.argtypes = [vp, vp, vp, i32, vp]
+        if hasattr(L, "ref_tree_load"):
+            L.ref_tree_load.argtypes = [ctypes.c_char_p, vp, vp, vp, vp, i32]
         L.ref_tree_index.restype = None
         L.ref_bsdf.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
         L.ref_bsdf.restype = None
@@ -76,6 +78,15 @@ def tree_build(pkg, samples, K, label_bias=0):
     n = lib().ref_tree_build(samples.ctypes.data, samples.shape[0], K, label_bias, out.ctypes.data, cap, ctypes.byref(ml))
     assert n <= cap
     return out[:n].copy(), ml.value
+
+
+def tree_load(pkg, directory, cap=1 << 20):
+    """classTree::tree_load run in `directory` (reads tree_eye.txt / tree_light.txt) -> (eye tree_node[], light tree_node[])"""
+    eye, light = np.zeros(cap, pkg.TREE_NODE), np.zeros(cap, pkg.TREE_NODE)
+    ne, nl = ctypes.c_int(0), ctypes.c_int(0)
+    rc = lib().ref_tree_load(os.fsencode(directory), eye.ctypes.data, ctypes.byref(ne), light.ctypes.data, ctypes.byref(nl), cap)
+    assert rc == 0, "ref_tree_load failed"
+    return eye[:ne.value].copy(), light[:nl.value].copy()
 
 
 def tree_index(pkg, tree, pos, nrm):

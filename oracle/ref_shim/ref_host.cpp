@@ -11,6 +11,7 @@
 //     traversal = oracle/orc_scene.cpp (the intersection contract); texture filtering = the fp32
 //     bilinear/wrap fetch below (CUDA's 9-bit filter weights are not reproducible); libm instead
 //     of --use_fast_math intrinsics.
+#include <unistd.h>
 #include <optix.h>
 
 #include <algorithm>
@@ -219,6 +220,22 @@ REF_API int ref_tree_build(const spc_divide_weight* samples, int n, int K, int l
     delete[] t.v;
     delete[] t.center;
     return size;
+}
+// classTree::tree_load(eye, light) (classTree_host.h:15-60): reads tree_eye.txt / tree_light.txt from the working directory.  Run in `dir`
+// to check the files host/train_state.cpp writes.  Returns 0, or -1 when a tree exceeds `cap` / the directory cannot be entered.
+REF_API int ref_tree_load(const char* dir, spc_tree_node* eye, int* n_eye, spc_tree_node* light, int* n_light, int cap) {
+    char old[4096];
+    if (!getcwd(old, sizeof(old)) || chdir(dir) != 0) return -1;
+    std::vector<classTree::tree_node> e, l;
+    classTree::tree_load(e, l);
+    const int back = chdir(old);
+    (void)back;
+    *n_eye = (int)e.size();
+    *n_light = (int)l.size();
+    if ((int)e.size() > cap || (int)l.size() > cap) return -1;
+    if (!e.empty()) memcpy((void*)eye, e.data(), e.size() * sizeof(spc_tree_node));
+    if (!l.empty()) memcpy((void*)light, l.data(), l.size() * sizeof(spc_tree_node));
+    return 0;
 }
 // classTree::tree_index (classTree_common.h:39-51) == classTree::getLabel (classTree_device.h:8-11)
 REF_API void ref_tree_index(const spc_tree_node* tree, const float* pos, const float* nrm, int n, int* labels) {

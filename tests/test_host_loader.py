@@ -286,3 +286,54 @@ def test_shipped_house_scene_equals_reference_loaders(tool, tmp_path):
     out = tmp_path / "house.spcscene"
     r = run(tool, "convert", os.path.join(HOUSE, "house_uvrefine2.scene"), str(out))
     assert "28 meshes %d triangles 29 materials 2 lights 6 textures" % dig["triangles"] in r.stdout
+
+
+def test_trained_state_files_round_trip_and_the_reference_reads_them(tool, pkg, tmp_path):
+    """host/train_state.cpp: the checkpoint text files of the trained state (tree_eye.txt, tree_light.txt, Q.txt, E.txt -- the files the
+    reference's classTree::tree_load / load_Q_file / load_Gamma_file read).  Files in that format are read by the C++ reader and written
+    back value for value, and the reference's OWN tree_load (classTree_host.h:15-60, compiled from the reference tree) reads the C++
+    writer's files back to the very tree."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("spc_ref_py", os.path.join(ROOT, "oracle", "ref_py.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(4)
+    n, K, KL = 4000, 24, 6
+    s = np.zeros(n, pkg.DIVIDE_WEIGHT)
+    s["position"] = (rng.random((n, 3)) * 7 - 2).astype(np.float32)
+    v = rng.normal(0, 1, (n, 3))
+    s["normal"] = (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+    s["dir"] = s["normal"]
+    s["weight"] = rng.random(n).astype(np.float32)
+    eye, _ = pkg.build_tree(s, K, 0)
+    light, _ = pkg.build_tree(s[::2].copy(), K - KL, 0)
+    Q = (rng.random(K) * 1e-3).astype(np.float32)
+    Q[3] = np.float32(3.4028235e38)           # Q_zero_handle writes FLT_MAX into empty subspaces
+    E = rng.random((K, K)).astype(np.float32)
+    E /= E.sum(1, keepdims=True)
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir()
+    dst.mkdir()
+    for name, tree in (("tree_eye.txt", eye), ("tree_light.txt", light)):      # the format renderer.save_state writes (same as the C++ writer)
+        with open(src / name, "w") as f:
+            for nd in tree:
+                if nd["leaf"]:
+                    f.write("1 %d\n" % nd["label"])
+                else:
+                    f.write("0 %d %d %.9g %.9g %.9g %s\n" % (nd["label"], nd["type"], nd["mid"][0], nd["mid"][1], nd["mid"][2], " ".join(str(int(c)) for c in nd["child"])))
+    np.savetxt(src / "Q.txt", Q, fmt="%.9g")
+    np.savetxt(src / "E.txt", E, fmt="%.9g")
+    r = run(tool, "state", str(src) + "/", str(dst) + "/", str(K))
+    assert "%d + %d tree nodes, %d Q, %d Gamma" % (eye.shape[0], light.shape[0], K, K * K) in r.stdout
+    assert np.array_equal(np.loadtxt(dst / "Q.txt", dtype=np.float32).view(np.uint32), Q.view(np.uint32))
+    assert np.array_equal(np.loadtxt(dst / "E.txt", dtype=np.float32).view(np.uint32), E.view(np.uint32))
+    if ref.available() and hasattr(ref.lib(), "ref_tree_load"):
+        e2, l2 = ref.tree_load(pkg, str(dst))
+        for a, b in ((eye, e2), (light, l2)):
+            assert a.shape == b.shape and np.array_equal(a["leaf"], b["leaf"]) and np.array_equal(a["label"], b["label"])
+            inner = a["leaf"] == 0
+            assert np.array_equal(a["type"][inner], b["type"][inner]) and np.array_equal(a["child"][inner], b["child"][inner])
+            assert np.array_equal(a["mid"][inner].view(np.uint32), b["mid"][inner].view(np.uint32))
+    # a wrong K (a state trained with another subspace count) is an error, not a silent mismatch
+    bad = subprocess.run([tool, "state", str(src) + "/", str(dst) + "/", str(K + 1)], capture_output=True, text=True)
+    assert bad.returncode == 1 and "Q.txt" in bad.stderr
