@@ -60,16 +60,25 @@ def main():
     jobs = [(os.path.join(GOLD, f), "decode", False) for f in sorted(os.listdir(GOLD)) if f.endswith((".jpg", ".png"))]
     jobs += [(os.path.join(GOLD, "quirks.obj"), "obj", True), (os.path.join(sc, "s.scene"), "scene", True), (os.path.join(sc, "s.scene"), "convert", True),
              (os.path.join(sc, "s.spcscene"), "info", False)]
+    # trained-state checkpoint files (host/train_state.cpp): a two-node state, one file mutated at a time
+    st = os.path.join(tmp, "state")
+    os.makedirs(os.path.join(st, "out"))
+    for name, text_ in (("tree_eye.txt", "0 2 1 0.5 0.25 0.125 1 2 3 4 5 6 7 8\n" + "".join("1 %d\n" % i for i in range(8))), ("tree_light.txt", "1 0\n"),
+                        ("Q.txt", "0.5\n0.25\n0.125\n1\n"), ("E.txt", "0.25 0.25 0.25 0.25\n" * 4)):
+        with open(os.path.join(st, name), "w") as f:
+            f.write(text_)
+    jobs += [(os.path.join(st, n), "state", True) for n in ("tree_eye.txt", "Q.txt", "E.txt")]
     rng = np.random.default_rng(args.seed)
     runs = findings = 0
     for path, cmd, text in jobs:
         raw = open(path, "rb").read()
-        victim = os.path.join(sc if cmd in ("scene", "convert") else tmp, "fz" + os.path.splitext(path)[1])
+        victim = path if cmd == "state" else os.path.join(sc if cmd in ("scene", "convert") else tmp, "fz" + os.path.splitext(path)[1])
+        argv = [tool, "state", st + "/", os.path.join(st, "out") + "/", "4"] if cmd == "state" else [tool, cmd, victim, os.path.join(tmp, "out")]
         for _ in range(args.runs):
             with open(victim, "wb") as f:
                 f.write(mutate(raw, rng, text))
             try:
-                r = subprocess.run([tool, cmd, victim, os.path.join(tmp, "out")], capture_output=True, timeout=120)
+                r = subprocess.run(argv, capture_output=True, timeout=120)
                 err = r.stderr.decode(errors="replace")
                 bad = r.returncode not in (0, 1, 2) or "Sanitizer" in err or "runtime error" in err
             except subprocess.TimeoutExpired:
@@ -78,8 +87,12 @@ def main():
             if bad:
                 findings += 1
                 keep = os.path.join(tmp, "finding_%d%s" % (findings, os.path.splitext(path)[1]))
-                os.replace(victim, keep)
+                with open(keep, "wb") as f:
+                    f.write(open(victim, "rb").read())
                 print("FINDING", cmd, os.path.basename(path), "->", keep, "\n", err[-1500:])
+        if cmd == "state":
+            with open(path, "wb") as f:
+                f.write(raw)
     print("runs %d findings %d (work dir %s)" % (runs, findings, tmp))
     return 1 if findings else 0
 
