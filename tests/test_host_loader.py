@@ -325,6 +325,8 @@ def test_trained_state_files_round_trip_and_the_reference_reads_them(tool, pkg, 
     np.savetxt(src / "E.txt", E, fmt="%.9g")
     r = run(tool, "state", str(src) + "/", str(dst) + "/", str(K))
     assert "%d + %d tree nodes, %d Q, %d Gamma" % (eye.shape[0], light.shape[0], K, K * K) in r.stdout
+    for name in ("tree_eye.txt", "tree_light.txt", "Q.txt", "E.txt"):       # the C++ writer and the Python twin's writer produce the same bytes
+        assert (dst / name).read_bytes() == (src / name).read_bytes(), name
     assert np.array_equal(np.loadtxt(dst / "Q.txt", dtype=np.float32).view(np.uint32), Q.view(np.uint32))
     assert np.array_equal(np.loadtxt(dst / "E.txt", dtype=np.float32).view(np.uint32), E.view(np.uint32))
     if ref.available() and hasattr(ref.lib(), "ref_tree_load"):
