@@ -2,6 +2,7 @@
 //   spc_scene_tool convert <file.scene> <out.spcscene> [--data-root dir] [--K-light n]   .scene + OBJ + textures -> cache
 //   spc_scene_tool info    <file.spcscene> <out.txt>                                    cache -> one summary line (loader check)
 //   spc_scene_tool state   <in_prefix> <out_prefix> <K>                                 trained state (tree_eye/tree_light/Q/E .txt) read and re-written
+//   spc_scene_tool camera  <file.spcscene> <out.txt> <width> <height>                   eye, U, V, W of the launch parameters (Camera::UVWFrame check)
 //   spc_scene_tool decode  <image> <out.rgba8>                                          JPEG/PNG/PNM -> raw RGBA8 cache
 //   spc_scene_tool png     <image> <out.png>                                            re-encode through the driver's PNG writer
 //   spc_scene_tool scene   <file.scene> <out.txt> [data-root]                          parsed .scene as text (LoadScene check)
@@ -46,6 +47,18 @@ int main(int argc, char** argv) {
         if (!load_train_state(argv[2], atoi(argv[4]), st, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
         if (!save_train_state(argv[3], st)) { fprintf(stderr, "cannot write %s*.txt\n", argv[3]); return 1; }
         printf("%zu + %zu tree nodes, %zu Q, %zu Gamma\n", st.eye_tree.size(), st.light_tree.size(), st.Q.size(), st.gamma.size());
+        return 0;
+    }
+    if (cmd == "camera") {
+        if (argc < 6) { fprintf(stderr, "usage: %s camera <file.spcscene> <out.txt> <width> <height>\n", argv[0]); return 2; }
+        HostScene hs;
+        if (!load_scene_cache(argv[2], hs, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        float U[3], V[3], W[3];
+        hs.camera_frame(atoi(argv[4]), atoi(argv[5]), U, V, W);
+        FILE* f = fopen(argv[3], "w");
+        if (!f) return 1;
+        fprintf(f, "%.9g %.9g %.9g\n%.9g %.9g %.9g\n%.9g %.9g %.9g\n%.9g %.9g %.9g\n", hs.eye[0], hs.eye[1], hs.eye[2], U[0], U[1], U[2], V[0], V[1], V[2], W[0], W[1], W[2]);
+        fclose(f);
         return 0;
     }
     if (cmd == "info") {

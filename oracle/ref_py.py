@@ -80,6 +80,17 @@ def tree_build(pkg, samples, K, label_bias=0):
     return out[:n].copy(), ml.value
 
 
+def camera_uvw(eye, lookat, up, fov_y, aspect):
+    """sutil::Camera(eye, lookat, up, fovY, aspect).UVWFrame -> (U, V, W), the reference's own Camera.cpp"""
+    L = lib()
+    L.ref_camera_uvw.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_float, ctypes.c_float, ctypes.c_void_p]
+    L.ref_camera_uvw.restype = None
+    a = [np.ascontiguousarray(v, np.float32) for v in (eye, lookat, up)]
+    out = np.zeros(9, np.float32)
+    L.ref_camera_uvw(a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, float(np.float32(fov_y)), float(np.float32(aspect)), out.ctypes.data)
+    return out[0:3].copy(), out[3:6].copy(), out[6:9].copy()
+
+
 def tree_load(pkg, directory, cap=1 << 20):
     """classTree::tree_load run in `directory` (reads tree_eye.txt / tree_light.txt) -> (eye tree_node[], light tree_node[])"""
     eye, light = np.zeros(cap, pkg.TREE_NODE), np.zeros(cap, pkg.TREE_NODE)

@@ -221,6 +221,17 @@ REF_API int ref_tree_build(const spc_divide_weight* samples, int n, int K, int l
     delete[] t.center;
     return size;
 }
+// sutil::Camera::UVWFrame (sutil/Camera.cpp:32-43), compiled from the reference's own Camera.cpp: the camera frame the host hands to the
+// raygen program (optixPathTracer.cpp:371-380 updateState / handleCameraUpdate).  out = U[3], V[3], W[3]
+#include <sutil/Camera.cpp>
+REF_API void ref_camera_uvw(const float* eye, const float* lookat, const float* up, float fov_y, float aspect, float* out) {
+    const sutil::Camera cam(make_float3(eye[0], eye[1], eye[2]), make_float3(lookat[0], lookat[1], lookat[2]), make_float3(up[0], up[1], up[2]), fov_y, aspect);
+    float3 U, V, W;
+    cam.UVWFrame(U, V, W);
+    const float3 v[3] = {U, V, W};
+    for (int k = 0; k < 3; k++) { out[3 * k] = v[k].x; out[3 * k + 1] = v[k].y; out[3 * k + 2] = v[k].z; }
+}
+
 // classTree::tree_load(eye, light) (classTree_host.h:15-60): reads tree_eye.txt / tree_light.txt from the working directory.  Run in `dir`
 // to check the files host/train_state.cpp writes.  Returns 0, or -1 when a tree exceeds `cap` / the directory cannot be entered.
 REF_API int ref_tree_load(const char* dir, spc_tree_node* eye, int* n_eye, spc_tree_node* light, int* n_light, int cap) {

@@ -40,22 +40,32 @@ class SceneData:
         return int(sum(m["indices"].shape[0] for m in self.meshes))
 
     def camera_frame(self, width, height):
-        """sutil::Camera::UVWFrame (sutil/Camera.cpp:32-43), fp32."""
+        """sutil::Camera::UVWFrame (sutil/Camera.cpp:32-43) in the reference's own fp32 operation order (vec_math.h dot / cross /
+        normalize written out on scalars: numpy's dot may sum in another order); tests/test_host_loader.py compares it, and the C++
+        driver's HostScene::camera_frame, with the reference's Camera.cpp bit for bit."""
         f = np.float32
-        eye = np.asarray(self.camera["eye"], f)
-        lookat = np.asarray(self.camera["lookat"], f)
-        up = np.asarray(self.camera["up"], f)
-        W = lookat - eye
-        wlen = f(np.sqrt(np.dot(W, W)))
-        U = np.cross(W, up).astype(f)
-        U = U * (f(1) / f(np.sqrt(np.dot(U, U))))
-        V = np.cross(U, W).astype(f)
-        V = V * (f(1) / f(np.sqrt(np.dot(V, V))))
+
+        def dot(a, b):
+            return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+
+        def cross(a, b):
+            return [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+
+        def normalize(a):
+            inv = f(1) / f(np.sqrt(dot(a, a)))
+            return [a[0] * inv, a[1] * inv, a[2] * inv]
+        eye = [f(x) for x in self.camera["eye"]]
+        lookat = [f(x) for x in self.camera["lookat"]]
+        up = [f(x) for x in self.camera["up"]]
+        W = [lookat[k] - eye[k] for k in range(3)]          # not normalised: its length is the focal distance
+        wlen = f(np.sqrt(dot(W, W)))
+        U = normalize(cross(W, up))
+        V = normalize(cross(U, W))
         vlen = f(wlen * _tanf(f(0.5) * f(self.camera["fov"]) * f(np.pi) / f(180.0)))
-        V = (V * vlen).astype(f)
-        ulen = f(vlen * f(width / height))
-        U = (U * ulen).astype(f)
-        return eye, U, V, W.astype(f)
+        V = [v * vlen for v in V]
+        ulen = f(vlen * (f(width) / f(height)))
+        U = [u * ulen for u in U]
+        return np.asarray(eye, f), np.asarray(U, f), np.asarray(V, f), np.asarray(W, f)
 
 
 def make_pbr(n):

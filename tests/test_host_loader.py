@@ -339,3 +339,38 @@ def test_trained_state_files_round_trip_and_the_reference_reads_them(tool, pkg, 
     # a wrong K (a state trained with another subspace count) is an error, not a silent mismatch
     bad = subprocess.run([tool, "state", str(src) + "/", str(dst) + "/", str(K + 1)], capture_output=True, text=True)
     assert bad.returncode == 1 and "Q.txt" in bad.stderr
+
+
+def test_camera_frame_equals_the_reference_camera(tool, pkg, tmp_path):
+    """eye, U, V, W of the launch parameters: the reference's own sutil::Camera::UVWFrame (Camera.cpp:32-43 compiled from the reference
+    tree) against the C++ driver's HostScene::camera_frame and the Python twin's Scene.camera_frame, bit for bit, on the shipped scene's
+    camera, the Cornell camera and random ones, at several aspect ratios"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("spc_ref_py", os.path.join(ROOT, "oracle", "ref_py.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    if not (ref.available() and hasattr(ref.lib(), "ref_camera_uvw")):
+        pytest.skip("oracle/_ref/libref_host.so without ref_camera_uvw (built where /root/reference exists)")
+    rng = np.random.default_rng(8)
+    cams = [dict(eye=[-0.813158, 5.627658, -7.363544], lookat=[-0.2, 1.7, 2.0], up=[0, 1, 0], fov=60.0),     # house_uvrefine2.scene's eye
+            dict(eye=[278, 273, -800], lookat=[278, 273, 0], up=[0, 1, 0], fov=39.3)]
+    for _ in range(6):
+        cams.append(dict(eye=(rng.normal(0, 10, 3)).tolist(), lookat=(rng.normal(0, 10, 3)).tolist(), up=(rng.normal(0, 1, 3)).tolist(), fov=float(rng.uniform(10, 120))))
+    sc = pkg.scenes.cornell_scene(wall_cells=2, box_cells=2)
+    for k, cam in enumerate(cams):
+        for key in ("eye", "lookat", "up"):
+            sc.camera[key] = np.asarray(cam[key], np.float32)
+        sc.camera["fov"] = np.float32(cam["fov"])
+        d = tmp_path / ("cam%d" % k)
+        d.mkdir()
+        path = pkg.scenes.export_scene(sc, str(d), "c")
+        run(tool, "convert", path, str(d / "c.spcscene"))
+        for w, h in ((1920, 1080), (512, 512), (1920, 1000), (3840, 2160), (96, 64), (7, 13)):
+            U, V, W = ref.camera_uvw(sc.camera["eye"], sc.camera["lookat"], sc.camera["up"], sc.camera["fov"], np.float32(w) / np.float32(h))
+            want = np.concatenate([np.asarray(sc.camera["eye"], np.float32), U, V, W])
+            eye, U2, V2, W2 = sc.camera_frame(w, h)
+            mine = np.concatenate([eye, U2, V2, W2]).astype(np.float32)
+            assert np.array_equal(mine.view(np.uint32), want.view(np.uint32)), ("python", k, w, h, mine, want)
+            run(tool, "camera", str(d / "c.spcscene"), str(d / "cam.txt"), str(w), str(h))
+            cpp = np.loadtxt(d / "cam.txt", dtype=np.float32).reshape(-1)
+            assert np.array_equal(cpp.view(np.uint32), want.view(np.uint32)), ("c++", k, w, h, cpp, want)
