@@ -91,6 +91,15 @@ def camera_uvw(eye, lookat, up, fov_y, aspect):
     return out[0:3].copy(), out[3:6].copy(), out[6:9].copy()
 
 
+def tile_owner_map(w, h, num_gpus):
+    """StaticWorkDistribution::getSamplePixel over all GPUs and samples -> (owner[h, w], pixels enumerated twice)"""
+    L = lib()
+    L.ref_tile_owner_map.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p]
+    owner = np.zeros((h, w), np.int32)
+    twice = L.ref_tile_owner_map(w, h, num_gpus, owner.ctypes.data)
+    return owner, int(twice)
+
+
 def tree_load(pkg, directory, cap=1 << 20):
     """classTree::tree_load run in `directory` (reads tree_eye.txt / tree_light.txt) -> (eye tree_node[], light tree_node[])"""
     eye, light = np.zeros(cap, pkg.TREE_NODE), np.zeros(cap, pkg.TREE_NODE)

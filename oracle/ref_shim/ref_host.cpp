@@ -232,6 +232,28 @@ REF_API void ref_camera_uvw(const float* eye, const float* lookat, const float* 
     for (int k = 0; k < 3; k++) { out[3 * k] = v[k].x; out[3 * k + 1] = v[k].y; out[3 * k + 2] = v[k].z; }
 }
 
+// StaticWorkDistribution (sutil/WorkDistribution.h:34-91), the multi-GPU tile layout the reference ships: owner[y * w + x] = the GPU whose
+// getSamplePixel enumeration contains the pixel.  Returns the number of pixels enumerated twice (0 for a partition); pixels no GPU
+// enumerates keep -1.
+#include <sutil/WorkDistribution.h>
+REF_API int ref_tile_owner_map(int w, int h, int num_gpus, int* owner) {
+    for (int i = 0; i < w * h; i++) owner[i] = -1;
+    int twice = 0;
+    for (int g = 0; g < num_gpus; g++) {
+        StaticWorkDistribution d;
+        d.setRasterSize(w, h);
+        d.setNumGPUs(num_gpus);
+        const int n = d.numSamples(g);
+        for (int s = 0; s < n; s++) {
+            const int2 p = d.getSamplePixel(g, s);
+            if (p.x < 0 || p.y < 0 || p.x >= w || p.y >= h) continue;
+            if (owner[p.y * w + p.x] != -1) twice++;
+            owner[p.y * w + p.x] = g;
+        }
+    }
+    return twice;
+}
+
 // classTree::tree_load(eye, light) (classTree_host.h:15-60): reads tree_eye.txt / tree_light.txt from the working directory.  Run in `dir`
 // to check the files host/train_state.cpp writes.  Returns 0, or -1 when a tree exceeds `cap` / the directory cannot be entered.
 REF_API int ref_tree_load(const char* dir, spc_tree_node* eye, int* n_eye, spc_tree_node* light, int* n_light, int cap) {

@@ -7,6 +7,7 @@ import socket
 import sys
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -103,3 +104,24 @@ def test_shard_plan_partitions_the_work():
         assert False, "20000 does not divide by 3"
     except AssertionError as ex:
         assert "divide" in str(ex)
+
+
+def test_tile_partition_formula_is_the_reference_work_distribution():
+    """The GPU test of spc_set_tile_partition (tests/test_pipeline_gpu.py) checks that rank g renders exactly the pixels with
+    ((x // 8) - (y // 4)) mod G == g.  Here that closed form is compared with the reference's own StaticWorkDistribution
+    (sutil/WorkDistribution.h:34-91, compiled from the reference tree): its getSamplePixel enumeration over all GPUs is a partition of
+    the image with exactly that ownership, also when the image is no multiple of the tile strip."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("spc_ref_py", os.path.join(root, "oracle", "ref_py.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    if not (ref.available() and hasattr(ref.lib(), "ref_tile_owner_map")):
+        pytest.skip("oracle/_ref/libref_host.so without ref_tile_owner_map (built where /root/reference exists)")
+    for w, h in ((1920, 1080), (3840, 2160), (96, 64), (100, 37), (7, 5), (1, 1), (64, 3)):
+        for G in (1, 2, 3, 4, 8):
+            owner, twice = ref.tile_owner_map(w, h, G)
+            yy, xx = np.mgrid[0:h, 0:w]
+            assert twice == 0 and (owner >= 0).all(), (w, h, G)
+            assert np.array_equal(owner, (xx // 8 - yy // 4) % G), (w, h, G)
