@@ -97,8 +97,9 @@ def make_quad_light(light_id, corner, v1, v2, emission, div_level, ss_base):
     corner = np.asarray(corner, f)
     u = np.asarray(v1, f) - corner
     v = np.asarray(v2, f) - corner
-    n = np.cross(u, v).astype(f)
-    area = f(np.sqrt(np.dot(n, n)))
+    # cross / length in the scalar fp32 order of the reference's vec_math.h (and of host/host_scene.cpp): numpy's dot may sum differently
+    n = np.asarray([u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]], f)
+    area = f(np.sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]))
     L = np.zeros(1, LIGHT)
     L["type"] = LIGHT_QUAD
     L["id"] = light_id
