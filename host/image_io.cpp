@@ -4,6 +4,7 @@
 #include <cctype>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace spchost {
@@ -135,6 +136,64 @@ bool write_pfm_from_float4(const std::string& path, const float* accum4, int wid
     }
     const bool ok = !ferror(f);
     return fclose(f) == 0 && ok;
+}
+
+bool read_pfm_rgb(const std::string& path, std::vector<float>& rgb, int& width, int& height, std::string& err) {
+    std::vector<uint8_t> d;
+    if (!read_file(path, d)) {
+        err = "cannot read " + path;
+        return false;
+    }
+    // header: "PF\n<w> <h>\n<scale>\n" (any whitespace between the tokens, one whitespace byte after the scale)
+    size_t p = 0;
+    auto token = [&](std::string& t) {
+        while (p < d.size() && isspace(d[p])) p++;
+        t.clear();
+        while (p < d.size() && !isspace(d[p]) && t.size() < 32) t.push_back((char)d[p++]);
+        return !t.empty();
+    };
+    std::string magic, sw, sh, ss;
+    if (!token(magic) || magic != "PF" || !token(sw) || !token(sh) || !token(ss)) {
+        err = "not a colour PFM file: " + path;
+        return false;
+    }
+    p++;
+    const long w = strtol(sw.c_str(), nullptr, 10), h = strtol(sh.c_str(), nullptr, 10);
+    const double scale = strtod(ss.c_str(), nullptr);
+    if (w <= 0 || h <= 0 || w > (1 << 16) || h > (1 << 16) || scale == 0.0 || p + (size_t)w * h * 12 > d.size()) {
+        err = "bad PFM header or truncated data: " + path;
+        return false;
+    }
+    width = (int)w;
+    height = (int)h;
+    rgb.resize((size_t)w * h * 3);
+    const bool big_endian = scale > 0.0;
+    for (size_t i = 0; i < rgb.size(); i++) {
+        uint8_t b[4];
+        memcpy(b, d.data() + p + 4 * i, 4);
+        if (big_endian) {
+            const uint8_t t0 = b[0], t1 = b[1];
+            b[0] = b[3]; b[1] = b[2]; b[2] = t1; b[3] = t0;
+        }
+        memcpy(&rgb[i], b, 4);
+    }
+    return true;
+}
+
+double rel_mse(const std::vector<float>& img, const std::vector<float>& ref, size_t* skipped) {
+    double sum = 0.0;
+    size_t n = 0, bad = 0;
+    const size_t m = img.size() < ref.size() ? img.size() : ref.size();
+    for (size_t i = 0; i < m; i++) {
+        const double r = ref[i], e = (double)img[i] - r;
+        const double t = e * e / (r * r + 1e-2);
+        if (std::isfinite(t)) {
+            sum += t;
+            n++;
+        } else bad++;
+    }
+    if (skipped) *skipped = bad;
+    return n ? sum / (double)n : 0.0;
 }
 
 }  // namespace spchost

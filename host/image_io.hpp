@@ -28,6 +28,11 @@ bool write_rgba8_cache(const std::string& path, const ImageRGBA8& img);
 // PPM is written top row first (flipped), PFM bottom row first (its native order, negative scale = little endian).
 bool write_ppm_from_uchar4(const std::string& path, const uint32_t* frame, int width, int height);
 bool write_pfm_from_float4(const std::string& path, const float* accum4, int width, int height);
+// colour PFM ("PF", little or big endian) back in: rgb = width * height * 3 floats, bottom row first as in the file
+bool read_pfm_rgb(const std::string& path, std::vector<float>& rgb, int& width, int& height, std::string& err);
+// relMSE of an image against a reference image, the error metric of BASELINE.json / SURVEY.md section 8d:
+// mean over pixels and channels of (I - R)^2 / (R^2 + 0.01); non-finite terms are skipped and counted in *skipped
+double rel_mse(const std::vector<float>& img, const std::vector<float>& ref, size_t* skipped);
 // 8-bit RGB PNG of the frame buffer (top row first; deflate by the system zlib, filter 0), for viewers that do not read PPM
 bool write_png_from_uchar4(const std::string& path, const uint32_t* frame, int width, int height);
 

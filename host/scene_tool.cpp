@@ -3,6 +3,7 @@
 //   spc_scene_tool info    <file.spcscene> <out.txt>                                    cache -> one summary line (loader check)
 //   spc_scene_tool state   <in_prefix> <out_prefix> <K>                                 trained state (tree_eye/tree_light/Q/E .txt) read and re-written
 //   spc_scene_tool camera  <file.spcscene> <out.txt> <width> <height>                   eye, U, V, W of the launch parameters (Camera::UVWFrame check)
+//   spc_scene_tool relmse  <image.pfm> <reference.pfm>                                  relMSE of a render against a reference image (stdout)
 //   spc_scene_tool decode  <image> <out.rgba8>                                          JPEG/PNG/PNM -> raw RGBA8 cache
 //   spc_scene_tool png     <image> <out.png>                                            re-encode through the driver's PNG writer
 //   spc_scene_tool scene   <file.scene> <out.txt> [data-root]                          parsed .scene as text (LoadScene check)
@@ -47,6 +48,16 @@ int main(int argc, char** argv) {
         if (!load_train_state(argv[2], atoi(argv[4]), st, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
         if (!save_train_state(argv[3], st)) { fprintf(stderr, "cannot write %s*.txt\n", argv[3]); return 1; }
         printf("%zu + %zu tree nodes, %zu Q, %zu Gamma\n", st.eye_tree.size(), st.light_tree.size(), st.Q.size(), st.gamma.size());
+        return 0;
+    }
+    if (cmd == "relmse") {   // the error metric of the equal-time comparisons: mean((I - R)^2 / (R^2 + 0.01)) over two .pfm files of the driver
+        std::vector<float> a, b;
+        int wa, ha, wb, hb;
+        if (!read_pfm_rgb(argv[2], a, wa, ha, err) || !read_pfm_rgb(argv[3], b, wb, hb, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        if (wa != wb || ha != hb) { fprintf(stderr, "image sizes differ: %dx%d vs %dx%d\n", wa, ha, wb, hb); return 1; }
+        size_t skipped = 0;
+        const double e = rel_mse(a, b, &skipped);
+        printf("relMSE %.9g over %dx%d pixels (%zu non-finite terms skipped)\n", e, wa, ha, skipped);
         return 0;
     }
     if (cmd == "camera") {

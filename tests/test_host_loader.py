@@ -397,3 +397,29 @@ def test_quad_lights_of_any_orientation_match_the_cpp_loader(tool, pkg, tmp_path
     assert s2.lights.shape == sc.lights.shape
     for k in ("corner", "u", "v", "normal", "area", "emission", "divLevel", "ssBase", "id", "type"):
         assert np.ascontiguousarray(sc.lights[k]).tobytes() == np.ascontiguousarray(s2.lights[k]).tobytes(), k
+
+
+def test_relmse_tool_reads_the_driver_s_pfm(tool, tmp_path):
+    """spc_scene_tool relmse: the metric of BASELINE.json (mean((I - R)^2 / (R^2 + 0.01))) over two colour PFM files as the driver
+    writes them (little endian) or as other tools write them (big endian); NaN pixels are skipped and counted"""
+    rng = np.random.default_rng(12)
+    h, w = 17, 23
+    ref = (rng.random((h, w, 3)) * 2).astype(np.float32)
+    img = (ref + rng.normal(0, 0.05, ref.shape)).astype(np.float32)
+    img[3, 4, 1] = np.nan
+
+    def write(path, a, big):
+        with open(path, "wb") as f:
+            f.write(b"PF\n%d %d\n%s\n" % (w, h, b"1.0" if big else b"-1.0"))
+            f.write(a.astype(">f4" if big else "<f4").tobytes())
+    write(tmp_path / "img.pfm", img, False)
+    write(tmp_path / "ref.pfm", ref, True)
+    r = run(tool, "relmse", str(tmp_path / "img.pfm"), str(tmp_path / "ref.pfm"))
+    t = (img.astype(np.float64) - ref) ** 2 / (ref.astype(np.float64) ** 2 + 1e-2)
+    want = t[np.isfinite(t)].mean()
+    got = float(r.stdout.split()[1])
+    assert abs(got - want) <= 1e-7 * want and "(1 non-finite terms skipped)" in r.stdout and "%dx%d" % (w, h) in r.stdout
+    write(tmp_path / "small.pfm", ref[:5], False)
+    (tmp_path / "small.pfm").write_bytes((tmp_path / "small.pfm").read_bytes().replace(b"23 17", b"23 5", 1))
+    bad = subprocess.run([tool, "relmse", str(tmp_path / "img.pfm"), str(tmp_path / "small.pfm")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "sizes differ" in bad.stderr
