@@ -70,6 +70,7 @@ void usage(const char* argv0) {
     fprintf(stderr,
             "Usage  : %s --scene <file.scene> | --cache <file.spcscene> [options]\n"
             "         --dim=<width>x<height>      image dimensions; defaults to 1920x1000\n"
+            "         --no-gl-interop             accepted for command-line compatibility with the reference (output goes to files)\n"
             "         --data-root <dir>           directory the .scene's file names are relative to\n"
             "         --frames <n>                subframes to accumulate per rank (default 16)\n"
             "         --host-trees                build the classification trees on the host (the reference's way; default: on the GPU)\n"
@@ -111,6 +112,7 @@ bool parse_args(int argc, char** argv, Options& o) {
             return argv[++i];
         };
         if (a == "--help" || a == "-h") return false;
+        else if (a == "--no-gl-interop") {}   // the reference's third option (optixPathTracer.cpp:702): accepted, there is no GL interop to disable
         else if (a.rfind("--dim=", 0) == 0) { if (!parse_dimensions(a.c_str() + 6, o.width, o.height)) throw std::runtime_error("Failed to parse width, height from string '" + a.substr(6) + "'"); }
         else if (a == "--scene") o.scene = need("--scene");
         else if (a == "--cache") o.cache = need("--cache");
