@@ -2,7 +2,7 @@
 //
 // In:  textures named by `albedoTex` in a .scene file, decoded to RGBA8 exactly as the reference hands them to
 //      CUDA (scene_shift.cpp:36-56: stbi_load(name, &w, &h, &ch, STBI_rgb_alpha), 8 bit, 4 channels, first row = top).
-//      Formats: baseline JPEG and PNG (what the shipped scene uses), binary PPM/PGM, and this repo's own raw
+//      Formats: baseline and progressive JPEG, PNG (what the shipped scene uses), binary PPM/PGM, and this repo's own raw
 //      cache "<file>.rgba8" (magic "SPCRGBA8", int32 w, int32 h, w*h*4 bytes).
 // Out: what replaces the GL display of the reference (sutil::GLDisplay / CUDAOutputBuffer, optixPathTracer.cpp:638-651):
 //      the tone-mapped uchar4 frame buffer as a binary PPM and the float4 accumulation buffer as a PFM.
