@@ -722,10 +722,8 @@ def main():
     if args.watchdog < 0:
         args.watchdog = 1800 if args.workload == "large" else 900
     if args.watchdog > 0:
-        # two stages: the headline part (process group, scene, timed region, e2e, oracle leg: normally well under a minute) gets a
-        # third of the budget, so that a rank stuck in the very first collective says so early; re-armed for the rest below
         import faulthandler
-        faulthandler.dump_traceback_later(max(60, args.watchdog // 3) if args.impl == "ours" else args.watchdog, exit=True)
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -907,10 +905,6 @@ def main():
                              "sample": "first %d rays of each of the 3 sets (%d rays, %.1f s) on the oracle port" % (ns, cpu_n, cpu_s)},
         }
     rebind_affinity()
-    if args.watchdog > 0:
-        import faulthandler
-        faulthandler.cancel_dump_traceback_later()
-        faulthandler.dump_traceback_later(args.watchdog, exit=True)
 
     # The headline line is complete at this point (rank 0 holds it); the SPCBPT section below is an extra key.  It runs under a
     # guard: an exception in it (single GPU) or a hang in it (any N) must not take the headline down.
